@@ -1,0 +1,198 @@
+// api.cu -- the extern "C" surface declared in include/b200_clover.h, plus the few precision-independent kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "engine_impl.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+__global__ void set_scalars_kernel(double* scal, int* status, ScalarSet s) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int i = 0; i < s.n; ++i) scal[s.slots[i]] = s.vals[i];
+    if (s.reset_status) for (int i = 0; i < ST_COUNT; ++i) status[i] = 0;
+  }
+}
+
+template <typename C2>
+__device__ void scale_planes_body(C2* p, int nplanes, size_t stride, size_t off, int count, double f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  for (int k = 0; k < nplanes; ++k) {
+    C2 v = p[(size_t)k * stride + off + i];
+    v.x = (decltype(v.x))(v.x * f); v.y = (decltype(v.y))(v.y * f);
+    p[(size_t)k * stride + off + i] = v;
+  }
+}
+__global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
+__global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
+
+__global__ void __launch_bounds__(BLAS_BLOCK) sum_double_kernel(const double* x, size_t n, ReduceBuf red, double* dst) {
+  double s[1] = {0.0};
+  for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) s[0] += x[i];
+  grid_reduce<1, BLAS_BLOCK>(s, red, FinStore{dst, 1});
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define CHECK_CTX(c)                                                     \
+  do {                                                                   \
+    if (!(c) || !(c)->eng) { set_error("null b200_ctx"); return B200_ERR_ARG; } \
+  } while (0)
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err; }
+const char* b200_version(void) { return "b200-clover 0.1 (sm_100a)"; }
+
+int b200_create(b200_ctx** out, int device, const int global_dims[4], const int proc_grid[4], const int proc_coord[4],
+                const b200_comm* comm, int prec) {
+  if (!out || !global_dims) { set_error("b200_create: null argument"); return B200_ERR_ARG; }
+  *out = nullptr;
+  if (prec != B200_DOUBLE && prec != B200_SINGLE) { set_error("prec must be B200_SINGLE (4) or B200_DOUBLE (8)"); return B200_ERR_ARG; }
+  Config c;
+  memset(&c, 0, sizeof(c));
+  c.device = device; c.prec = prec;
+  for (int i = 0; i < 4; ++i) {
+    c.gdims[i] = global_dims[i];
+    c.pgrid[i] = proc_grid ? proc_grid[i] : 1;
+    c.pcoord[i] = proc_coord ? proc_coord[i] : 0;
+    if (c.gdims[i] < 2 || c.gdims[i] % 2) { set_error("global lattice extent %d (dim %d) must be even", c.gdims[i], i); return B200_ERR_ARG; }
+    if (c.pcoord[i] < 0 || c.pcoord[i] >= c.pgrid[i]) { set_error("proc_coord out of range"); return B200_ERR_ARG; }
+  }
+  c.have_comm = comm != nullptr;
+  if (comm) c.comm = *comm;
+  EngineBase* e = (prec == B200_DOUBLE) ? make_engine_double(c) : make_engine_float(c);
+  int rc = e->init();
+  if (rc) { delete e; return rc; }
+  b200_ctx* ctx = new b200_ctx;
+  ctx->eng = e;
+  *out = ctx;
+  return B200_OK;
+}
+
+void b200_destroy(b200_ctx* ctx) {
+  if (!ctx) return;
+  delete ctx->eng;
+  delete ctx;
+}
+
+int b200_load_gauge(b200_ctx* ctx, const void* const u[4], int host_prec, const double aniso_coeff[4], int t_boundary, int reconstruct) {
+  CHECK_CTX(ctx);
+  if (!u) { set_error("null gauge array"); return B200_ERR_ARG; }
+  const double one[4] = {1, 1, 1, 1};
+  return ctx->eng->load_gauge(u, host_prec, aniso_coeff ? aniso_coeff : one, t_boundary, reconstruct);
+}
+int b200_load_clover(b200_ctx* ctx, const void* clov, const void* invclov, int host_prec) { CHECK_CTX(ctx); return ctx->eng->load_clover(clov, invclov, host_prec); }
+int b200_make_clover(b200_ctx* ctx, double diag_mass, double clov_r, double clov_t, int aniso, int t_dir) { CHECK_CTX(ctx); return ctx->eng->make_clover(diag_mass, clov_r, clov_t, aniso, t_dir); }
+int b200_get_clover(b200_ctx* ctx, void* clov, void* invclov, int host_prec) { CHECK_CTX(ctx); return ctx->eng->get_clover(clov, invclov, host_prec); }
+int b200_clover_logdet(b200_ctx* ctx, double* out) { CHECK_CTX(ctx); if (!out) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->clover_logdet(out); }
+
+int b200_field_alloc(b200_ctx* ctx, b200_field** f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_alloc(f); }
+void b200_field_free(b200_ctx* ctx, b200_field* f) { if (ctx && ctx->eng) ctx->eng->field_free(f); }
+int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_upload(f, host, host_prec); }
+int b200_field_download(b200_ctx* ctx, const b200_field* f, void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_download(f, host, host_prec); }
+int b200_field_zero(b200_ctx* ctx, b200_field* f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_zero(f); }
+
+int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb) { CHECK_CTX(ctx); return ctx->eng->dslash(out, in, isign, out_cb); }
+int b200_dev_clover_apply(b200_ctx* ctx, b200_field* out, const b200_field* in, int cb, int inverse) { CHECK_CTX(ctx); return ctx->eng->clover_apply(out, in, cb, inverse); }
+int b200_dev_clover_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign) { CHECK_CTX(ctx); return ctx->eng->matpc(out, in, isign); }
+int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* r) { CHECK_CTX(ctx); if (!x || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->norm2(x, r); }
+int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double r[2]) { CHECK_CTX(ctx); if (!x || !y || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->inner(x, y, r); }
+int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return ctx->eng->invert(psi, chi, solver, rsd, max_iter, info);
+}
+int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver) {
+  CHECK_CTX(ctx);
+  if (!psi || !chi || psi == chi) { set_error("bad field argument"); return B200_ERR_ARG; }
+  if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
+  return ctx->eng->iterate_begin(psi, chi, solver);
+}
+int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter) {
+  CHECK_CTX(ctx);
+  if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
+  return ctx->eng->iterate(solver, n_iter);
+}
+
+// ---- host-pointer entry points: upload -> device op -> download -------------------------------------------
+namespace {
+struct TmpFields {
+  b200_ctx* ctx; b200_field* f[3] = {nullptr, nullptr, nullptr};
+  explicit TmpFields(b200_ctx* c) : ctx(c) {}
+  int get(int n) { for (int i = 0; i < n; ++i) { int rc = ctx->eng->field_alloc(&f[i]); if (rc) return rc; } return 0; }
+  ~TmpFields() { for (auto p : f) if (p) ctx->eng->field_free(p); }
+};
+}  // namespace
+
+int b200_dslash(b200_ctx* ctx, void* out, const void* in, int host_prec, int isign, int out_cb) {
+  CHECK_CTX(ctx);
+  TmpFields t(ctx); int rc = t.get(2); if (rc) return rc;
+  if ((rc = ctx->eng->field_upload(t.f[0], in, host_prec))) return rc;
+  if ((rc = ctx->eng->dslash(t.f[1], t.f[0], isign, out_cb))) return rc;
+  return ctx->eng->field_download(t.f[1], out, host_prec);
+}
+int b200_clover_apply(b200_ctx* ctx, void* out, const void* in, int host_prec, int cb, int inverse) {
+  CHECK_CTX(ctx);
+  TmpFields t(ctx); int rc = t.get(2); if (rc) return rc;
+  if ((rc = ctx->eng->field_upload(t.f[0], in, host_prec))) return rc;
+  if ((rc = ctx->eng->clover_apply(t.f[1], t.f[0], cb, inverse))) return rc;
+  return ctx->eng->field_download(t.f[1], out, host_prec);
+}
+int b200_clover_matpc(b200_ctx* ctx, void* out, const void* in, int host_prec, int isign) {
+  CHECK_CTX(ctx);
+  TmpFields t(ctx); int rc = t.get(2); if (rc) return rc;
+  if ((rc = ctx->eng->field_upload(t.f[0], in, host_prec))) return rc;
+  if ((rc = ctx->eng->matpc(t.f[1], t.f[0], isign))) return rc;
+  return ctx->eng->field_download(t.f[1], out, host_prec);
+}
+int b200_invert(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int solver, double rsd, int max_iter, b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  if (!psi || !chi || !info) { set_error("b200_invert: null pointer"); return B200_ERR_ARG; }
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaSetDevice(ctx->eng->cfg.device));
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, ctx->eng->stream));
+  TmpFields t(ctx); int rc = t.get(2);
+  if (!rc) rc = ctx->eng->field_upload(t.f[0], chi, host_prec);
+  if (!rc) rc = ctx->eng->field_upload(t.f[1], psi, host_prec);
+  if (!rc) rc = ctx->eng->invert(t.f[1], t.f[0], solver, rsd, max_iter, info);
+  if (!rc || rc == B200_ERR_BREAKDOWN) { int r2 = ctx->eng->field_download(t.f[1], psi, host_prec); if (!rc) rc = r2; }
+  cudaEventRecord(e1, ctx->eng->stream); cudaEventSynchronize(e1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  info->secs_total = ms * 1e-3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+int b200_qprop(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter, b200_solve_info* infos) {
+  CHECK_CTX(ctx);
+  return ctx->eng->qprop(psi, chi, host_prec, nrhs, solver, rsd, max_iter, infos);
+}
+
+void* b200_stream(b200_ctx* ctx) { return (ctx && ctx->eng) ? (void*)ctx->eng->stream : nullptr; }
+int b200_sync(b200_ctx* ctx) { CHECK_CTX(ctx); return ctx->eng->sync(); }
+long long b200_launch_count(b200_ctx* ctx) { return (ctx && ctx->eng) ? ctx->eng->launches : -1; }
+int b200_host_alloc(void** p, size_t bytes) {
+  if (!p) { set_error("null pointer"); return B200_ERR_ARG; }
+  B200_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+  return B200_OK;
+}
+void b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+int b200_local_volume(const b200_ctx* ctx, int local_dims[4]) {
+  if (!ctx || !ctx->eng) { set_error("null b200_ctx"); return B200_ERR_ARG; }
+  for (int i = 0; i < 4; ++i) local_dims[i] = ctx->eng->cfg.ldims[i];
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// common.cuh -- shared types of the B200 clover engine (device layout, geometry, small complex algebra).
+//
+// Device layout ("site-major SoA"): every field is a set of PLANES of complex numbers, one plane
+// per internal index, each plane holding one checkerboard's sites in QDP++ cb2 order
+//   idx = ((t*Lz+z)*Ly+y)*(Lx/2) + x/2
+// so that consecutive threads (= consecutive idx) load consecutive 16-byte (fp64) complex numbers:
+//   fermion  C[12][Vh]              plane = spin*3+colour
+//   gauge    C[4][2][9][Vh]         [mu][parity][row*3+col]   (aniso factor folded in, BC phases as given)
+//   clover   C[2][36][Vh]           [parity][block*18 + {3 diag pairs, 15 offd}]
+// Vh = local checkerboard volume.  Plane stride == Vh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+template <typename R> struct CT;
+template <> struct CT<double> { typedef double2 type; };
+template <> struct CT<float> { typedef float2 type; };
+template <typename R> using Cx = typename CT<R>::type;
+
+template <typename R> __host__ __device__ __forceinline__ Cx<R> mk(R x, R y) { Cx<R> r; r.x = x; r.y = y; return r; }
+
+__device__ __forceinline__ double2 ldg(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ float2 ldg(const float2* p) { return __ldg(p); }
+
+// complex helpers (all on Cx<R>)
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) { C r; r.x = a.x*b.x - a.y*b.y; r.y = a.x*b.y + a.y*b.x; return r; }
+// acc += a*b
+template <typename C> __device__ __forceinline__ void cmac(C& acc, C a, C b) {
+  acc.x += a.x*b.x; acc.x -= a.y*b.y; acc.y += a.x*b.y; acc.y += a.y*b.x;
+}
+// acc += conj(a)*b
+template <typename C> __device__ __forceinline__ void cmac_conj(C& acc, C a, C b) {
+  acc.x += a.x*b.x; acc.x += a.y*b.y; acc.y += a.x*b.y; acc.y -= a.y*b.x;
+}
+
+struct Geom {
+  int Lxh, Ly, Lz, Lt;  // local extents (x halved by checkerboarding)
+  int Vh;               // local checkerboard volume = plane stride
+  int S3h;              // sites per time slice per checkerboard = Lxh*Ly*Lz
+  int tsplit;           // 1 if T is split across ranks (ghost faces instead of wrap-around in t)
+};
+
+// Device-resident scalars of the solvers (double, one array per context).
+enum ScalarSlot {
+  S_RSDSQ = 0,   // stopping threshold |r|^2 <= / < rsd_sq
+  S_C, S_D, S_CP, S_A, S_B,                       // CG: c=|r_{k-1}|^2, d=|Mp|^2, cp=|r_k|^2, a=c/d, b=cp/c
+  S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM,       // BiCGStab rho, rho_prev
+  S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM,
+  S_RNORM,                                        // BiCGStab |r|^2
+  S_TMP0, S_TMP1, S_TMP2, S_TMP3,                 // generic reduction results (norm2 / inner)
+  S_COUNT = 32
+};
+// Integer status block
+enum StatusSlot {
+  ST_STOP = 0,      // 0 while iterating; else the iteration at which the recurrence residual converged
+  ST_BREAKDOWN,     // BiCGStab breakdown code (1 rho=0, 2 <r0|v>=0, 3 |t|=0)
+  ST_COUNT = 8
+};
+
+}  // namespace b200

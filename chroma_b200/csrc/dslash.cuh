@@ -1,0 +1,371 @@
+// dslash.cuh -- the hot kernels: Wilson hopping term with fused clover / solver epilogues.
+//
+// One thread per target-checkerboard site.  Per site the thread gathers 8 neighbour spinors
+// (12 x 128-bit loads each, coalesced across the warp because idx is the fastest index of every
+// plane), spin-projects them to half spinors while loading, multiplies by the 3x3 link
+// (9 x 128-bit loads, or 6 with 12-real reconstruction), reconstructs and accumulates -- the same
+// grouping of operations as the reference site loop (cpp_dslash_scalar_64bit.cc:105-213 with the site
+// ops of cpp_dslash_scalar_64bit_c.h and su3_mult / su3_adj_mult of cpp_dslash_matvec64bit_c.h) --
+// and then runs one of the fused epilogues:
+//
+//   EPI_DSLASH   out = D in                                       (Dslash<REAL>::operator())
+//   EPI_AINV     out = A^-1 D in                                  (pass 1 of CloverSchur4D, cpp_clover_scalar_64bit.cc:137-237)
+//   EPI_M        out = A x - 1/4 D in                             (pass 2, :248-377; eoprec_clover_linop_w.cc:167-171)
+//   EPI_M_NORM   EPI_M and |out|^2                    -> CG d     (invcg2.cc:162-165)
+//   EPI_M_CG     r -= a (A x - 1/4 D in), |r|^2       -> CG cp    (invcg2.cc:170-182; M^dag M p is never stored)
+//   EPI_M_DOTR0  EPI_M and <r0|out>                   -> BiCGStab alpha   (invbicgstab.cc:101-114)
+//   EPI_M_DOTX   EPI_M and <out|x>, |out|^2           -> BiCGStab omega   (invbicgstab.cc:126-140)
+//
+// Neighbour indices come from coordinate arithmetic (no shift table in HBM; replaces ShiftTable,
+// shift_table_scalar.h:10-147).  The arithmetic is HBM-bound: 1320 flop per (48+8G) reals moved.
+#pragma once
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace b200 {
+
+enum Epilogue { EPI_DSLASH = 0, EPI_AINV, EPI_M, EPI_M_NORM, EPI_M_CG, EPI_M_DOTR0, EPI_M_DOTX };
+
+template <typename R>
+struct DslashArgs {
+  typedef Cx<R> C;
+  const C* in;      // source checkerboard field (parity 1-parity)
+  C* out;           // result (target parity); unused by EPI_M_CG
+  const C* gauge;   // C[4][2][NG][Vh]
+  const C* clov;    // clover planes of the TARGET parity (A_oo or A_ee^-1): C[36][Vh]
+  const C* x;       // EPI_M*: the field A acts on (target parity)
+  C* r;             // EPI_M_CG: residual, updated in place
+  const C* r0;      // EPI_M_DOTR0: shadow residual
+  // T-split ghost faces (half spinors, C[6][S3h]); only read when g.tsplit
+  const C* ghost_fwd;   // (1 -/+ g3) psi(x+t) projected by the +t neighbour rank, for sites at t = Lt-1
+  const C* ghost_bwd;   // U_t^dag (1 +/- g3) psi(x-t) projected AND multiplied by the -t rank, for sites at t = 0
+  double* scal;     // device scalars (ScalarSlot)
+  int* status;      // device status (StatusSlot)
+  ReduceBuf red;
+  Geom g;
+  int parity;       // target parity
+  int isign;        // +1: D, -1: D^dagger
+  int idx_begin;    // first target site of this launch
+  int idx_count;    // number of target sites of this launch
+  int iter;         // solver iteration this launch belongs to (for the stop flag)
+  int check_stop;   // 1: return immediately if status[ST_STOP] != 0
+};
+
+// ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
+template <typename R, int MU>
+__device__ __forceinline__ void load_project(Cx<R> h0[3], Cx<R> h1[3], const Cx<R>* __restrict__ p, int stride, R sg) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const Cx<R> a0 = ldg(p + (0 * 3 + c) * (size_t)stride);
+    const Cx<R> a1 = ldg(p + (1 * 3 + c) * (size_t)stride);
+    const Cx<R> a2 = ldg(p + (2 * 3 + c) * (size_t)stride);
+    const Cx<R> a3 = ldg(p + (3 * 3 + c) * (size_t)stride);
+    if (MU == 0) {          // h0 = a0 + sg*i*a3, h1 = a1 + sg*i*a2
+      h0[c] = mk<R>(a0.x - sg * a3.y, a0.y + sg * a3.x);
+      h1[c] = mk<R>(a1.x - sg * a2.y, a1.y + sg * a2.x);
+    } else if (MU == 1) {   // h0 = a0 - sg*a3, h1 = a1 + sg*a2
+      h0[c] = mk<R>(a0.x - sg * a3.x, a0.y - sg * a3.y);
+      h1[c] = mk<R>(a1.x + sg * a2.x, a1.y + sg * a2.y);
+    } else if (MU == 2) {   // h0 = a0 + sg*i*a2, h1 = a1 - sg*i*a3
+      h0[c] = mk<R>(a0.x - sg * a2.y, a0.y + sg * a2.x);
+      h1[c] = mk<R>(a1.x + sg * a3.y, a1.y - sg * a3.x);
+    } else {                // h0 = a0 + sg*a2, h1 = a1 + sg*a3
+      h0[c] = mk<R>(a0.x + sg * a2.x, a0.y + sg * a2.y);
+      h1[c] = mk<R>(a1.x + sg * a3.x, a1.y + sg * a3.y);
+    }
+  }
+}
+
+// ---- reconstruct the lower two spin components and accumulate ------------------------------------
+template <typename R, int MU>
+__device__ __forceinline__ void recons_acc(Cx<R> acc[12], const Cx<R> r0[3], const Cx<R> r1[3], R sg) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    acc[c].x += r0[c].x;     acc[c].y += r0[c].y;
+    acc[3 + c].x += r1[c].x; acc[3 + c].y += r1[c].y;
+    if (MU == 0) {          // r2 = -sg*i*r1, r3 = -sg*i*r0
+      acc[6 + c].x += sg * r1[c].y; acc[6 + c].y -= sg * r1[c].x;
+      acc[9 + c].x += sg * r0[c].y; acc[9 + c].y -= sg * r0[c].x;
+    } else if (MU == 1) {   // r2 = sg*r1, r3 = -sg*r0
+      acc[6 + c].x += sg * r1[c].x; acc[6 + c].y += sg * r1[c].y;
+      acc[9 + c].x -= sg * r0[c].x; acc[9 + c].y -= sg * r0[c].y;
+    } else if (MU == 2) {   // r2 = -sg*i*r0, r3 = +sg*i*r1
+      acc[6 + c].x += sg * r0[c].y; acc[6 + c].y -= sg * r0[c].x;
+      acc[9 + c].x -= sg * r1[c].y; acc[9 + c].y += sg * r1[c].x;
+    } else {                // r2 = sg*r0, r3 = sg*r1
+      acc[6 + c].x += sg * r0[c].x; acc[6 + c].y += sg * r0[c].y;
+      acc[9 + c].x += sg * r1[c].x; acc[9 + c].y += sg * r1[c].y;
+    }
+  }
+}
+
+// ---- link load (18 reals, or 12 + third-row reconstruction) --------------------------------------
+template <typename R, bool RECON12>
+__device__ __forceinline__ void load_link(Cx<R> U[9], const Cx<R>* __restrict__ p, int stride) {
+  constexpr int NG = RECON12 ? 6 : 9;
+#pragma unroll
+  for (int k = 0; k < NG; ++k) U[k] = ldg(p + k * (size_t)stride);
+  if (RECON12) {
+    // row2 = conj(row0 x row1): exact for SU(3); non-unit factors (anisotropy, -1 boundary phase)
+    // are carried separately by the caller (see load_gauge in api.cu).
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+      Cx<R> t = csub(cmul(U[c1], U[3 + c2]), cmul(U[c2], U[3 + c1]));
+      U[6 + c] = mk<R>(t.x, -t.y);
+    }
+  }
+}
+
+template <typename R, bool ADJ>
+__device__ __forceinline__ void su3_mul(Cx<R> r0[3], Cx<R> r1[3], const Cx<R> U[9], const Cx<R> h0[3], const Cx<R> h1[3]) {
+#pragma unroll
+  for (int row = 0; row < 3; ++row) {
+    Cx<R> s0 = mk<R>(0, 0), s1 = mk<R>(0, 0);
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      if (!ADJ) { cmac(s0, U[row * 3 + col], h0[col]); cmac(s1, U[row * 3 + col], h1[col]); }
+      else      { cmac_conj(s0, U[col * 3 + row], h0[col]); cmac_conj(s1, U[col * 3 + row], h1[col]); }
+    }
+    r0[row] = s0; r1[row] = s1;
+  }
+}
+
+// One hop: acc += recons( U(or U^dag) * project(psi_nbr) ).
+template <typename R, int MU, bool ADJ, bool RECON12>
+__device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi_nbr, const Cx<R>* __restrict__ link,
+                                    int stride, R sg, R scale) {
+  Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
+  load_project<R, MU>(h0, h1, psi_nbr, stride, sg);
+  load_link<R, RECON12>(U, link, stride);
+  if (RECON12) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
+  }
+  su3_mul<R, ADJ>(r0, r1, U, h0, h1);
+  recons_acc<R, MU>(acc, r0, r1, sg);
+}
+
+// Per-direction scale factors used only with RECON12 (anisotropy * boundary sign), see api.cu.
+struct LinkScale {
+  double aniso[4];    // aniso_coeff[mu]
+  int bc_t;           // +1 / -1: phase on links U_t at global t = Lt_global-1
+  int t_is_last;      // 1 if this rank holds the global last time slice
+};
+
+// The Wilson hopping term for one target site.  (xh,y,z,t) are its checkerboard coordinates.
+template <typename R, bool RECON12>
+__device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx) {
+  typedef Cx<R> C;
+  const Geom& g = a.g;
+  const int stride = g.Vh;
+  int q = idx;
+  const int xh = q % g.Lxh; q /= g.Lxh;
+  const int y = q % g.Ly;   q /= g.Ly;
+  const int z = q % g.Lz;
+  const int t = q / g.Lz;
+  const int p = a.parity;
+  const int r = (y + z + t + p) & 1;      // x = 2*xh + r
+  constexpr int NG = RECON12 ? 6 : 9;
+  const size_t gplane = (size_t)NG * stride;
+  const C* __restrict__ Uf = a.gauge + (size_t)p * gplane + idx;         // forward links live on the target parity
+  const C* __restrict__ Ub = a.gauge + (size_t)(1 - p) * gplane;          // backward links on the source parity
+  const size_t gmu = 2 * gplane;
+  const C* __restrict__ in = a.in;
+  const R s = (R)a.isign;
+
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = mk<R>(0, 0);
+
+  // x direction: neighbours have the same idx or idx +/- 1 within the row
+  {
+    const int xf = r ? (xh + 1 == g.Lxh ? idx - (g.Lxh - 1) : idx + 1) : idx;
+    const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
+    hop<R, 0, false, RECON12>(acc, in + xf, Uf + 0 * gmu, stride, -s, (R)ls.aniso[0]);
+    hop<R, 0, true, RECON12>(acc, in + xb, Ub + 0 * gmu + xb, stride, s, (R)ls.aniso[0]);
+  }
+  {
+    const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
+    const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
+    hop<R, 1, false, RECON12>(acc, in + yf, Uf + 1 * gmu, stride, -s, (R)ls.aniso[1]);
+    hop<R, 1, true, RECON12>(acc, in + yb, Ub + 1 * gmu + yb, stride, s, (R)ls.aniso[1]);
+  }
+  {
+    const int sz = g.Ly * g.Lxh;
+    const int zf = (z + 1 == g.Lz) ? idx - (g.Lz - 1) * sz : idx + sz;
+    const int zb = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
+    hop<R, 2, false, RECON12>(acc, in + zf, Uf + 2 * gmu, stride, -s, (R)ls.aniso[2]);
+    hop<R, 2, true, RECON12>(acc, in + zb, Ub + 2 * gmu + zb, stride, s, (R)ls.aniso[2]);
+  }
+  {
+    const int st = g.S3h;
+    const bool last = (t + 1 == g.Lt), first = (t == 0);
+    const int tf = last ? idx - (g.Lt - 1) * st : idx + st;
+    const int tb = first ? idx + (g.Lt - 1) * st : idx - st;
+    R scf = (R)ls.aniso[3], scb = (R)ls.aniso[3];
+    if (RECON12) {   // the -1 of an antiperiodic boundary sits on U_t(t_global = last): forward hop from the last
+                     // slice, backward hop into slice 0 (its link lives on the last slice)
+      if (ls.t_is_last && last) scf *= (R)ls.bc_t;
+      if (ls.t_is_last && first && !g.tsplit) scb *= (R)ls.bc_t;
+    }
+    if (g.tsplit && last) {
+      // half spinor already projected by the +t neighbour rank: only the link multiply is left
+      C h0[3], h1[3], U[9], r0[3], r1[3];
+      const C* __restrict__ gp = a.ghost_fwd + (idx - (g.Lt - 1) * st);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { h0[c] = ldg(gp + (size_t)c * st); h1[c] = ldg(gp + (size_t)(3 + c) * st); }
+      load_link<R, RECON12>(U, Uf + 3 * gmu, stride);
+      if (RECON12) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { h0[c].x *= scf; h0[c].y *= scf; h1[c].x *= scf; h1[c].y *= scf; }
+      }
+      su3_mul<R, false>(r0, r1, U, h0, h1);
+      recons_acc<R, 3>(acc, r0, r1, -s);
+    } else {
+      hop<R, 3, false, RECON12>(acc, in + tf, Uf + 3 * gmu, stride, -s, scf);
+    }
+    if (g.tsplit && first) {
+      // U^dag (1 +/- g3) psi computed by the -t neighbour rank (it owns that link): just reconstruct
+      C r0[3], r1[3];
+      const C* __restrict__ gp = a.ghost_bwd + idx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { r0[c] = ldg(gp + (size_t)c * st); r1[c] = ldg(gp + (size_t)(3 + c) * st); }
+      recons_acc<R, 3>(acc, r0, r1, s);
+    } else {
+      hop<R, 3, true, RECON12>(acc, in + tb, Ub + 3 * gmu + tb, stride, s, scb);
+    }
+  }
+}
+
+// ---- clover: one 6x6 Hermitian block times 6 complex --------------------------------------------
+// out[i] = d_i in[i] + sum_{j<i} o_{k(i,j)} in[j] + sum_{j>i} conj(o_{k(j,i)}) in[j], k = i(i-1)/2+j
+// (applySiteLoop, clover_term_qdp_w.h:1606-1634).  cl points at plane 0 of the block for this site.
+template <typename R>
+__device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], const Cx<R>* __restrict__ cl, int stride) {
+  const Cx<R> d01 = ldg(cl), d23 = ldg(cl + (size_t)stride), d45 = ldg(cl + 2 * (size_t)stride);
+  out[0] = mk<R>(d01.x * in[0].x, d01.x * in[0].y);
+  out[1] = mk<R>(d01.y * in[1].x, d01.y * in[1].y);
+  out[2] = mk<R>(d23.x * in[2].x, d23.x * in[2].y);
+  out[3] = mk<R>(d23.y * in[3].x, d23.y * in[3].y);
+  out[4] = mk<R>(d45.x * in[4].x, d45.x * in[4].y);
+  out[5] = mk<R>(d45.y * in[5].x, d45.y * in[5].y);
+  int k = 0;
+#pragma unroll
+  for (int i = 1; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      const Cx<R> o = ldg(cl + (size_t)(3 + k) * stride);
+      cmac(out[i], o, in[j]);
+      cmac_conj(out[j], o, in[i]);
+      ++k;
+    }
+  }
+}
+
+// ---- finalisers: run in one thread after the grid-wide (and cross-GPU) sum -----------------------
+struct FinNone { __device__ void operator()(const double*) const {} };
+// CG: d = |M p|^2  ->  a = c/d   (invcg2.cc:165,174)
+struct FinCgD {
+  double* scal;
+  __device__ void operator()(const double* t) const { scal[S_D] = t[0]; scal[S_A] = scal[S_C] / t[0]; }
+};
+// CG: cp = |r|^2  ->  b = cp/c, c <- cp, convergence flag (invcg2.cc:182-216)
+struct FinCgCp {
+  double* scal; int* status; int iter; int check;
+  __device__ void operator()(const double* t) const {
+    const double cp = t[0], c = scal[S_C];
+    scal[S_CP] = cp; scal[S_B] = cp / c; scal[S_C] = cp;
+    if (check && status[ST_STOP] == 0 && cp <= scal[S_RSDSQ]) status[ST_STOP] = iter;
+  }
+};
+// BiCGStab: ctmp = <r0|v>  ->  alpha = rho/ctmp (invbicgstab.cc:106-114)
+struct FinBiAlpha {
+  double* scal; int* status;
+  __device__ void operator()(const double* t) const {
+    const double cr = t[0], ci = t[1];
+    if (cr == 0.0 && ci == 0.0) { if (status[ST_BREAKDOWN] == 0) status[ST_BREAKDOWN] = 2; return; }
+    const double rr = scal[S_RHO_RE], ri = scal[S_RHO_IM], d = cr * cr + ci * ci;
+    scal[S_ALPHA_RE] = (rr * cr + ri * ci) / d;
+    scal[S_ALPHA_IM] = (ri * cr - rr * ci) / d;
+  }
+};
+// BiCGStab: omega = <t|r> / |t|^2 (invbicgstab.cc:130-140)
+struct FinBiOmega {
+  double* scal; int* status;
+  __device__ void operator()(const double* t) const {
+    const double tn = t[2];
+    if (tn == 0.0) { if (status[ST_BREAKDOWN] == 0) status[ST_BREAKDOWN] = 3; return; }
+    scal[S_OMEGA_RE] = t[0] / tn; scal[S_OMEGA_IM] = t[1] / tn;
+  }
+};
+
+template <typename R, int EPI, bool RECON12, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
+  typedef Cx<R> C;
+  if (a.check_stop && a.status[ST_STOP] != 0) return;
+  const int stride = a.g.Vh;
+  const int local = blockIdx.x * BLOCK + threadIdx.x;
+  const bool active = local < a.idx_count;
+  const int idx = a.idx_begin + (active ? local : 0);
+  double red[3] = {0.0, 0.0, 0.0};
+
+  if (active) {
+    C acc[12];
+    dslash_site<R, RECON12>(acc, a, ls, idx);
+
+    if (EPI == EPI_DSLASH) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) a.out[(size_t)k * stride + idx] = acc[k];
+    } else if (EPI == EPI_AINV) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        C o[6];
+        clover_block<R>(o, acc + 6 * b, a.clov + (size_t)(18 * b) * stride + idx, stride);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.out[(size_t)(6 * b + k) * stride + idx] = o[k];
+      }
+    } else {
+      // all EPI_M* variants: m = A x - 1/4 D in
+      R cg_a = 0;
+      if (EPI == EPI_M_CG) cg_a = (R)a.scal[S_A];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        C xi[6], o[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xi[k] = ldg(a.x + (size_t)(6 * b + k) * stride + idx);
+        clover_block<R>(o, xi, a.clov + (size_t)(18 * b) * stride + idx, stride);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          C m = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
+          const size_t off = (size_t)(6 * b + k) * stride + idx;
+          if (EPI == EPI_M_CG) {
+            C rv = a.r[off];
+            rv.x -= cg_a * m.x; rv.y -= cg_a * m.y;
+            a.r[off] = rv;
+            red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+          } else {
+            a.out[off] = m;
+            if (EPI == EPI_M_NORM) red[0] += (double)m.x * m.x + (double)m.y * m.y;
+            if (EPI == EPI_M_DOTR0) {
+              const C q = ldg(a.r0 + off);
+              red[0] += (double)q.x * m.x + (double)q.y * m.y;   // <r0|m> = conj(r0) m
+              red[1] += (double)q.x * m.y - (double)q.y * m.x;
+            }
+            if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
+              red[0] += (double)m.x * xi[k].x + (double)m.y * xi[k].y;
+              red[1] += (double)m.x * xi[k].y - (double)m.y * xi[k].x;
+              red[2] += (double)m.x * m.x + (double)m.y * m.y;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal});
+  if (EPI == EPI_M_CG) grid_reduce<1, BLOCK>(red, a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status});
+  if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status});
+}
+
+}  // namespace b200

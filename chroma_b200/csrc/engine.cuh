@@ -1,0 +1,86 @@
+// engine.cuh -- host-side engine: device state, kernel launchers and the CG / BiCGStab drivers.
+//
+// Everything the plugin needs after construction happens on one CUDA stream; solver scalars never
+// leave the device, the host only polls a status word every ITER_BATCH iterations (pipelined so the
+// poll never drains the GPU).  The drivers follow InvCG2_a (lib/actions/ferm/invert/invcg2.cc:70-232)
+// and InvBiCGStab_a (invbicgstab.cc:10-202) step by step; the shells follow
+// LinOpSysSolverCG::operator() (syssolver_linop_cg.h:57-96) and LinOpSysSolverBiCGStab::operator()
+// (syssolver_linop_bicgstab.h:57-95).
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+
+#include "../../include/b200_clover.h"
+#include "common.cuh"
+
+struct b200_field {
+  void* d;        // device planes C[12][Vh]
+  size_t bytes;
+  int prec;
+};
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return B200_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+struct Config {
+  int device;
+  int gdims[4], pgrid[4], pcoord[4], ldims[4];
+  int prec;
+  b200_comm comm;
+  bool have_comm;
+};
+
+// Precision-independent interface the C ABI talks to.
+class EngineBase {
+ public:
+  virtual ~EngineBase() {}
+  virtual int init() = 0;
+  virtual int load_gauge(const void* const u[4], int host_prec, const double aniso[4], int t_boundary, int recon) = 0;
+  virtual int load_clover(const void* clov, const void* invclov, int host_prec) = 0;
+  virtual int make_clover(double diag_mass, double cr, double ct, int aniso, int t_dir) = 0;
+  virtual int get_clover(void* clov, void* invclov, int host_prec) = 0;
+  virtual int clover_logdet(double* out) = 0;
+  virtual int field_alloc(b200_field** f) = 0;
+  virtual void field_free(b200_field* f) = 0;
+  virtual int field_upload(b200_field* f, const void* host, int host_prec) = 0;
+  virtual int field_download(const b200_field* f, void* host, int host_prec) = 0;
+  virtual int field_zero(b200_field* f) = 0;
+  virtual int dslash(b200_field* out, const b200_field* in, int isign, int out_cb) = 0;
+  virtual int clover_apply(b200_field* out, const b200_field* in, int cb, int inverse) = 0;
+  virtual int matpc(b200_field* out, const b200_field* in, int isign) = 0;
+  virtual int norm2(const b200_field* x, double* r) = 0;
+  virtual int inner(const b200_field* x, const b200_field* y, double r[2]) = 0;
+  virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) = 0;
+  virtual int iterate_begin(b200_field* psi, const b200_field* chi, int solver) = 0;
+  virtual int iterate(int solver, int n_iter) = 0;
+  virtual int qprop(void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter,
+                    b200_solve_info* infos) = 0;
+  virtual int sync() = 0;
+
+  Config cfg;
+  Geom g;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+};
+
+EngineBase* make_engine_double(const Config& c);
+EngineBase* make_engine_float(const Config& c);
+
+}  // namespace b200
+
+struct b200_ctx {
+  b200::EngineBase* eng;
+};

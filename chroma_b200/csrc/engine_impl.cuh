@@ -1,0 +1,649 @@
+// engine_impl.cuh -- Engine<R>: templated on the device precision (double / float).
+#pragma once
+#include <algorithm>
+#include <cstdarg>
+
+#include "engine.cuh"
+#include "dslash.cuh"
+#include "blas.cuh"
+#include "pack.cuh"
+#include "clover_setup.cuh"
+#include "halo.cuh"
+
+namespace b200 {
+
+constexpr int DSLASH_BLOCK = 128;
+constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
+constexpr size_t STAGING_BYTES = 256u << 20;
+
+template <typename R, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) clover_kernel(const Cx<R>* __restrict__ in, Cx<R>* __restrict__ out,
+                                                      const Cx<R>* __restrict__ clov, int Vh) {
+  const int idx = blockIdx.x * BLOCK + threadIdx.x;
+  if (idx >= Vh) return;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    Cx<R> xi[6], o[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) xi[k] = ldg(in + (size_t)(6 * b + k) * Vh + idx);
+    clover_block<R>(o, xi, clov + (size_t)(18 * b) * Vh + idx, Vh);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) out[(size_t)(6 * b + k) * Vh + idx] = o[k];
+  }
+}
+
+struct ScalarSet { int n; int slots[12]; double vals[12]; int reset_status; };
+__global__ void set_scalars_kernel(double* scal, int* status, ScalarSet s);
+__global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f);
+__global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f);
+
+template <typename R>
+class Engine : public EngineBase {
+ public:
+  typedef Cx<R> C;
+  explicit Engine(const Config& c) { cfg = c; }
+  ~Engine() override { destroy(); }
+
+  // ------------------------------------------------------------------ state
+  C* gauge = nullptr;       // [4][2][NG][Vh]
+  int recon = 0;            // 18 / 12 once loaded
+  double aniso_[4] = {1, 1, 1, 1};
+  int t_boundary_ = 1;
+  LinkScale ls{};
+  C* clov = nullptr;        // [2][36][Vh]
+  C* invclov = nullptr;     // [36][Vh]  (cb 0)
+  double* tr_log = nullptr; // [Vh] log|det A_ee| per even site (make_clover only)
+  bool have_trlog = false;
+  double* scal = nullptr; int* status = nullptr;
+  double* partial = nullptr; unsigned int* ticket = nullptr; int partial_cap = 0;
+  double* h_scal = nullptr; int* h_status = nullptr;   // pinned; h_status has 2 slots
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
+  void* staging = nullptr;
+  b200_field* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  Halo<R> halo;
+  int blas_grid = 148 * 8;
+  // fixed-iteration (benchmark) state
+  C* it_psi = nullptr; const C* it_chi = nullptr; int it_k = 0;
+
+  size_t nelem() const { return (size_t)12 * g.Vh; }
+
+  // ------------------------------------------------------------------ lifecycle
+  int init() override {
+    for (int i = 0; i < 4; ++i) {
+      if (cfg.pgrid[i] < 1 || cfg.gdims[i] % cfg.pgrid[i] != 0) { set_error("global dim %d not divisible by grid", i); return B200_ERR_ARG; }
+      cfg.ldims[i] = cfg.gdims[i] / cfg.pgrid[i];
+      // checkerboarding needs even GLOBAL dims (shift_table_scalar.cc:23-28); we also need even LOCAL dims so
+      // that local parity == global parity on every rank (cf. cpp_dslash_parscalar_64bit.cc:187-212)
+      if (cfg.ldims[i] % 2 != 0 || cfg.ldims[i] < 2) { set_error("local lattice extent %d (dim %d) must be even and >= 2", cfg.ldims[i], i); return B200_ERR_ARG; }
+    }
+    if (cfg.pgrid[0] != 1 || cfg.pgrid[1] != 1 || cfg.pgrid[2] != 1) { set_error("only a T split of the process grid is supported"); return B200_ERR_ARG; }
+    if (cfg.pgrid[3] > 8) { set_error("at most 8 ranks in T"); return B200_ERR_ARG; }
+    if (cfg.pgrid[3] > 1 && !cfg.have_comm) { set_error("a b200_comm is required for a split lattice"); return B200_ERR_COMM; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: this engine has no CPU fallback"); return B200_ERR_CUDA; }
+    B200_CUDA(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major < 10) { set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); return B200_ERR_CUDA; }
+    blas_grid = prop.multiProcessorCount * 8;
+    g.Lxh = cfg.ldims[0] / 2; g.Ly = cfg.ldims[1]; g.Lz = cfg.ldims[2]; g.Lt = cfg.ldims[3];
+    g.S3h = g.Lxh * g.Ly * g.Lz;
+    g.Vh = g.S3h * g.Lt;
+    g.tsplit = cfg.pgrid[3] > 1 ? 1 : 0;
+    B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaMalloc(&scal, sizeof(double) * S_COUNT));
+    B200_CUDA(cudaMalloc(&status, sizeof(int) * ST_COUNT));
+    B200_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * S_COUNT, stream));
+    B200_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * ST_COUNT, stream));
+    partial_cap = std::max((g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK + 8, blas_grid);
+    B200_CUDA(cudaMalloc(&partial, sizeof(double) * 4 * (size_t)partial_cap));
+    B200_CUDA(cudaMalloc(&ticket, sizeof(unsigned int)));
+    B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
+    B200_CUDA(cudaHostAlloc(&h_scal, sizeof(double) * S_COUNT, cudaHostAllocDefault));
+    B200_CUDA(cudaHostAlloc(&h_status, sizeof(int) * ST_COUNT * 2, cudaHostAllocDefault));
+    for (int i = 0; i < 2; ++i) B200_CUDA(cudaEventCreateWithFlags(&ev_poll[i], cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreate(&ev_t0));
+    B200_CUDA(cudaEventCreate(&ev_t1));
+    B200_CUDA(cudaMalloc(&staging, STAGING_BYTES));
+    if (g.tsplit) { int rc = halo.init(cfg, g, stream); if (rc) return rc; }
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+
+  void destroy() {
+    if (!stream) return;
+    cudaSetDevice(cfg.device);
+    cudaStreamSynchronize(stream);
+    halo.destroy();
+    for (auto& f : ws) if (f) { field_free(f); f = nullptr; }
+    cudaFree(gauge); cudaFree(clov); cudaFree(invclov); cudaFree(tr_log);
+    cudaFree(scal); cudaFree(status); cudaFree(partial); cudaFree(ticket); cudaFree(staging);
+    cudaFreeHost(h_scal); cudaFreeHost(h_status);
+    for (int i = 0; i < 2; ++i) if (ev_poll[i]) cudaEventDestroy(ev_poll[i]);
+    if (ev_t0) cudaEventDestroy(ev_t0);
+    if (ev_t1) cudaEventDestroy(ev_t1);
+    cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+
+  int sync() override { B200_CUDA(cudaSetDevice(cfg.device)); B200_CUDA(cudaStreamSynchronize(stream)); return B200_OK; }
+
+  int launched(const char* what) {
+    ++launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("launch of %s failed: %s", what, cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    return B200_OK;
+  }
+
+  ReduceBuf make_red(int block_offset, int total_blocks) {
+    ReduceBuf rb;
+    rb.partial = partial; rb.ticket = ticket; rb.block_offset = block_offset; rb.total_blocks = total_blocks;
+    rb.peer = halo.peer_reduce();
+    return rb;
+  }
+
+  // ------------------------------------------------------------------ host <-> device reordering
+  template <typename H, int NR, int NPL, typename Map>
+  int upload_aos(const H* src, int nsites, C* dst, size_t stride, Map map, double scale) {
+    const size_t rec = (size_t)NR * sizeof(H);
+    int chunk = (int)std::min<size_t>((size_t)nsites, (STAGING_BYTES / rec) / PACK_SITES * PACK_SITES);
+    for (int off = 0; off < nsites; off += chunk) {
+      const int n = std::min(chunk, nsites - off);
+      B200_CUDA(cudaMemcpyAsync(staging, (const char*)src + (size_t)off * rec, (size_t)n * rec, cudaMemcpyHostToDevice, stream));
+      aos_to_soa_kernel<H, R, NR, NPL, Map><<<(n + PACK_SITES - 1) / PACK_SITES, PACK_BLOCK, 0, stream>>>(
+          (const H*)staging, dst, n, stride, (size_t)off, map, scale);
+      int rc = launched("aos_to_soa"); if (rc) return rc;
+      // the staging buffer is reused by the next chunk: same stream, so ordering is implicit
+    }
+    return B200_OK;
+  }
+  template <typename H, int NR, int NPL, typename Map>
+  int download_aos(H* dst, int nsites, const C* src, size_t stride, Map map) {
+    const size_t rec = (size_t)NR * sizeof(H);
+    int chunk = (int)std::min<size_t>((size_t)nsites, (STAGING_BYTES / rec) / PACK_SITES * PACK_SITES);
+    for (int off = 0; off < nsites; off += chunk) {
+      const int n = std::min(chunk, nsites - off);
+      soa_to_aos_kernel<H, R, NR, NPL, Map><<<(n + PACK_SITES - 1) / PACK_SITES, PACK_BLOCK, 0, stream>>>(
+          (H*)staging, src, n, stride, (size_t)off, map);
+      int rc = launched("soa_to_aos"); if (rc) return rc;
+      B200_CUDA(cudaMemcpyAsync((char*)dst + (size_t)off * rec, staging, (size_t)n * rec, cudaMemcpyDeviceToHost, stream));
+    }
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+
+  int load_gauge(const void* const u[4], int host_prec, const double aniso[4], int t_boundary, int recon_) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (recon_ != B200_RECONS_NONE && recon_ != B200_RECONS_12) { set_error("reconstruct must be 18 or 12"); return B200_ERR_ARG; }
+    if (host_prec != B200_SINGLE && host_prec != B200_DOUBLE) { set_error("host_prec must be 4 or 8"); return B200_ERR_ARG; }
+    if (t_boundary != 1 && t_boundary != -1) { set_error("t_boundary must be +1 or -1"); return B200_ERR_ARG; }
+    for (int mu = 0; mu < 4; ++mu) if (!u[mu]) { set_error("null gauge pointer"); return B200_ERR_ARG; }
+    const int NG = recon_ / 2;
+    if (gauge) { cudaFree(gauge); gauge = nullptr; }
+    B200_CUDA(cudaMalloc(&gauge, sizeof(C) * 8 * (size_t)NG * g.Vh));
+    recon = recon_; t_boundary_ = t_boundary;
+    const bool last_rank = cfg.pcoord[3] == cfg.pgrid[3] - 1;
+    for (int mu = 0; mu < 4; ++mu) {
+      aniso_[mu] = aniso[mu];
+      ls.aniso[mu] = aniso[mu];
+      for (int par = 0; par < 2; ++par) {
+        C* dst = gauge + (size_t)(mu * 2 + par) * NG * g.Vh;
+        int rc;
+        const double sc = (recon == 18) ? aniso[mu] : 1.0;
+        if (host_prec == B200_DOUBLE) {
+          const double* src = (const double*)u[mu] + (size_t)par * g.Vh * 18;
+          rc = (recon == 18) ? upload_aos<double, 18, 9>(src, g.Vh, dst, (size_t)g.Vh, MapIdentity(), sc)
+                             : upload_aos<double, 18, 6>(src, g.Vh, dst, (size_t)g.Vh, MapIdentity(), sc);
+        } else {
+          const float* src = (const float*)u[mu] + (size_t)par * g.Vh * 18;
+          rc = (recon == 18) ? upload_aos<float, 18, 9>(src, g.Vh, dst, (size_t)g.Vh, MapIdentity(), sc)
+                             : upload_aos<float, 18, 6>(src, g.Vh, dst, (size_t)g.Vh, MapIdentity(), sc);
+        }
+        if (rc) return rc;
+        if (recon == 12 && mu == 3 && t_boundary == -1 && last_rank) {
+          // strip the antiperiodic phase so that rows 0,1 are rows of an SU(3) matrix again; the kernel
+          // re-applies it (LinkScale::bc_t), as the QUDA / QPhiX adapters do
+          // (syssolver_linop_clover_quda_w.h:147-156, syssolver_linop_clover_qphix_w.h:107-116)
+          scale_planes_kernel<<<(g.S3h + 255) / 256, 256, 0, stream>>>(dst, 6, (size_t)g.Vh, (size_t)(g.Lt - 1) * g.S3h, g.S3h, -1.0);
+          rc = launched("scale_planes"); if (rc) return rc;
+        }
+      }
+    }
+    ls.bc_t = t_boundary;
+    ls.t_is_last = last_rank ? 1 : 0;
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+
+  int load_clover(const void* clov_h, const void* invclov_h, int host_prec) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!clov_h || !invclov_h) { set_error("null clover pointer"); return B200_ERR_ARG; }
+    if (host_prec != B200_SINGLE && host_prec != B200_DOUBLE) { set_error("host_prec must be 4 or 8"); return B200_ERR_ARG; }
+    int rc = alloc_clover(); if (rc) return rc;
+    for (int par = 0; par < 2; ++par) {
+      C* dst = clov + (size_t)par * 36 * g.Vh;
+      if (host_prec == B200_DOUBLE) rc = upload_aos<double, 72, 36>((const double*)clov_h + (size_t)par * g.Vh * 72, g.Vh, dst, (size_t)g.Vh, MapClover(), 1.0);
+      else rc = upload_aos<float, 72, 36>((const float*)clov_h + (size_t)par * g.Vh * 72, g.Vh, dst, (size_t)g.Vh, MapClover(), 1.0);
+      if (rc) return rc;
+    }
+    if (host_prec == B200_DOUBLE) rc = upload_aos<double, 72, 36>((const double*)invclov_h, g.Vh, invclov, (size_t)g.Vh, MapClover(), 1.0);
+    else rc = upload_aos<float, 72, 36>((const float*)invclov_h, g.Vh, invclov, (size_t)g.Vh, MapClover(), 1.0);
+    if (rc) return rc;
+    have_trlog = false;
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+
+  int alloc_clover() {
+    if (!clov) B200_CUDA(cudaMalloc(&clov, sizeof(C) * 72 * (size_t)g.Vh));
+    if (!invclov) B200_CUDA(cudaMalloc(&invclov, sizeof(C) * 36 * (size_t)g.Vh));
+    if (!tr_log) B200_CUDA(cudaMalloc(&tr_log, sizeof(double) * (size_t)g.Vh));
+    return B200_OK;
+  }
+
+  int make_clover(double diag_mass, double cr, double ct, int aniso, int t_dir) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!gauge) { set_error("b200_make_clover: load the gauge field first"); return B200_ERR_STATE; }
+    if (t_dir < 0 || t_dir > 3) { set_error("t_dir out of range"); return B200_ERR_ARG; }
+    int rc = alloc_clover(); if (rc) return rc;
+    CloverSetupArgs<R> a;
+    a.gauge = gauge; a.recon12 = (recon == 12); a.g = g;
+    for (int mu = 0; mu < 4; ++mu) a.inv_aniso[mu] = (recon == 18) ? 1.0 / aniso_[mu] : 1.0;
+    a.bc_t = (recon == 12) ? t_boundary_ : 1; a.t_is_last = ls.t_is_last;
+    a.diag_mass = diag_mass; a.cr = cr; a.ct = ct; a.aniso = aniso; a.t_dir = t_dir;
+    a.ghost_links = g.tsplit ? halo.gauge_ghost() : nullptr;
+    if (g.tsplit) { rc = halo.exchange_gauge_ghost(gauge, recon, launches); if (rc) return rc; }
+    for (int par = 0; par < 2; ++par) {
+      a.parity = par; a.clov_out = clov + (size_t)par * 36 * g.Vh;
+      make_clover_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(a);
+      rc = launched("make_clover"); if (rc) return rc;
+    }
+    B200_CUDA(cudaMemcpyAsync(invclov, clov, sizeof(C) * 36 * (size_t)g.Vh, cudaMemcpyDeviceToDevice, stream));
+    ldagdlinv_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov, tr_log, g.Vh);
+    rc = launched("ldagdlinv"); if (rc) return rc;
+    have_trlog = true;
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+
+  int get_clover(void* clov_h, void* invclov_h, int host_prec) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!clov) { set_error("no clover term loaded"); return B200_ERR_STATE; }
+    int rc = B200_OK;
+    if (clov_h) for (int par = 0; par < 2 && !rc; ++par) {
+      const C* src = clov + (size_t)par * 36 * g.Vh;
+      if (host_prec == B200_DOUBLE) rc = download_aos<double, 72, 36>((double*)clov_h + (size_t)par * g.Vh * 72, g.Vh, src, (size_t)g.Vh, MapClover());
+      else rc = download_aos<float, 72, 36>((float*)clov_h + (size_t)par * g.Vh * 72, g.Vh, src, (size_t)g.Vh, MapClover());
+    }
+    if (invclov_h && !rc) {
+      if (host_prec == B200_DOUBLE) rc = download_aos<double, 72, 36>((double*)invclov_h, g.Vh, invclov, (size_t)g.Vh, MapClover());
+      else rc = download_aos<float, 72, 36>((float*)invclov_h, g.Vh, invclov, (size_t)g.Vh, MapClover());
+    }
+    return rc;
+  }
+
+  int clover_logdet(double* out) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!have_trlog) { set_error("tr log is only available after b200_make_clover"); return B200_ERR_STATE; }
+    sum_double_kernel<<<blas_grid, BLAS_BLOCK, 0, stream>>>(tr_log, (size_t)g.Vh, make_red(0, blas_grid), scal + S_TMP0);
+    int rc = launched("sum_double"); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    *out = h_scal[S_TMP0];
+    return B200_OK;
+  }
+
+  // ------------------------------------------------------------------ fields
+  int field_alloc(b200_field** f) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    b200_field* p = new b200_field;
+    p->bytes = sizeof(C) * nelem(); p->prec = sizeof(R); p->d = nullptr;
+    cudaError_t e = cudaMalloc(&p->d, p->bytes);
+    if (e != cudaSuccess) { delete p; set_error("cudaMalloc(%zu) failed: %s", sizeof(C) * nelem(), cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    cudaMemsetAsync(p->d, 0, p->bytes, stream);
+    *f = p;
+    return B200_OK;
+  }
+  void field_free(b200_field* f) override { if (f) { cudaSetDevice(cfg.device); cudaStreamSynchronize(stream); cudaFree(f->d); delete f; } }
+  int field_zero(b200_field* f) override { B200_CUDA(cudaSetDevice(cfg.device)); B200_CUDA(cudaMemsetAsync(f->d, 0, f->bytes, stream)); return B200_OK; }
+  int field_upload(b200_field* f, const void* host, int host_prec) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!f || !host) { set_error("null pointer"); return B200_ERR_ARG; }
+    if (host_prec == B200_DOUBLE) return upload_aos<double, 24, 12>((const double*)host, g.Vh, (C*)f->d, (size_t)g.Vh, MapIdentity(), 1.0);
+    if (host_prec == B200_SINGLE) return upload_aos<float, 24, 12>((const float*)host, g.Vh, (C*)f->d, (size_t)g.Vh, MapIdentity(), 1.0);
+    set_error("host_prec must be 4 or 8"); return B200_ERR_ARG;
+  }
+  int field_download(const b200_field* f, void* host, int host_prec) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!f || !host) { set_error("null pointer"); return B200_ERR_ARG; }
+    if (host_prec == B200_DOUBLE) return download_aos<double, 24, 12>((double*)host, g.Vh, (const C*)f->d, (size_t)g.Vh, MapIdentity());
+    if (host_prec == B200_SINGLE) return download_aos<float, 24, 12>((float*)host, g.Vh, (const C*)f->d, (size_t)g.Vh, MapIdentity());
+    set_error("host_prec must be 4 or 8"); return B200_ERR_ARG;
+  }
+
+  int need_ws(int n) {
+    for (int i = 0; i < n; ++i) if (!ws[i]) { int rc = field_alloc(&ws[i]); if (rc) return rc; }
+    return B200_OK;
+  }
+  C* W(int i) { return (C*)ws[i]->d; }
+
+  // ------------------------------------------------------------------ kernel launchers
+  template <int EPI>
+  int launch_dslash(DslashArgs<R>& a) {
+    a.gauge = gauge; a.scal = scal; a.status = status; a.g = g;
+    int rc;
+    if (g.tsplit) {
+      // pack + send both time faces over NVLink, run the interior while they fly, then the two boundary slices
+      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, launches); if (rc) return rc;
+      a.ghost_fwd = halo.ghost_fwd(); a.ghost_bwd = halo.ghost_bwd();
+      const int nb_int = (g.Vh - 2 * g.S3h + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+      const int nb_face = (g.S3h + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+      const int total = nb_int + 2 * nb_face;
+      if (g.Lt > 2) {
+        a.idx_begin = g.S3h; a.idx_count = g.Vh - 2 * g.S3h; a.red = make_red(0, total);
+        rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
+      }
+      rc = halo.wait(launches); if (rc) return rc;
+      a.idx_begin = 0; a.idx_count = g.S3h; a.red = make_red(nb_int, total);
+      rc = launch_one<EPI>(a, nb_face); if (rc) return rc;
+      a.idx_begin = g.Vh - g.S3h; a.idx_count = g.S3h; a.red = make_red(nb_int + nb_face, total);
+      return launch_one<EPI>(a, nb_face);
+    }
+    a.ghost_fwd = nullptr; a.ghost_bwd = nullptr;
+    a.idx_begin = 0; a.idx_count = g.Vh;
+    const int blocks = (g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+    a.red = make_red(0, blocks);
+    return launch_one<EPI>(a, blocks);
+  }
+  template <int EPI>
+  int launch_one(const DslashArgs<R>& a, int blocks) {
+    if (blocks <= 0) return B200_OK;
+    if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
+    else dslash_kernel<R, EPI, false, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
+    return launched("dslash_kernel");
+  }
+
+  int ready() {
+    if (!gauge) { set_error("gauge field not loaded"); return B200_ERR_STATE; }
+    if (!clov || !invclov) { set_error("clover term not loaded"); return B200_ERR_STATE; }
+    return B200_OK;
+  }
+
+  // out = M in (isign=+1) / M^dag in (-1) with one of the EPI_M* epilogues; te is the even temporary
+  int apply_M(C* out, const C* in, int isign, int epi, C* r, const C* r0, int iter, int check) {
+    DslashArgs<R> a{};
+    a.in = in; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign; a.iter = iter; a.check_stop = check;
+    int rc = launch_dslash<EPI_AINV>(a); if (rc) return rc;
+    DslashArgs<R> b{};
+    b.in = W(0); b.out = out; b.clov = clov + (size_t)36 * g.Vh; b.x = in; b.r = r; b.r0 = r0;
+    b.parity = 1; b.isign = isign; b.iter = iter; b.check_stop = check;
+    switch (epi) {
+      case EPI_M: return launch_dslash<EPI_M>(b);
+      case EPI_M_NORM: return launch_dslash<EPI_M_NORM>(b);
+      case EPI_M_CG: return launch_dslash<EPI_M_CG>(b);
+      case EPI_M_DOTR0: return launch_dslash<EPI_M_DOTR0>(b);
+      case EPI_M_DOTX: return launch_dslash<EPI_M_DOTX>(b);
+    }
+    set_error("bad epilogue"); return B200_ERR_ARG;
+  }
+
+  int dslash(b200_field* out, const b200_field* in, int isign, int out_cb) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!gauge) { set_error("gauge field not loaded"); return B200_ERR_STATE; }
+    if ((isign != 1 && isign != -1) || (out_cb != 0 && out_cb != 1) || !out || !in || out == in) { set_error("b200_dslash: bad argument"); return B200_ERR_ARG; }
+    DslashArgs<R> a{};
+    a.in = (const C*)in->d; a.out = (C*)out->d; a.parity = out_cb; a.isign = isign;
+    return launch_dslash<EPI_DSLASH>(a);
+  }
+
+  int clover_apply(b200_field* out, const b200_field* in, int cb, int inverse) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!clov) { set_error("clover term not loaded"); return B200_ERR_STATE; }
+    if ((cb != 0 && cb != 1) || !out || !in || out == in) { set_error("b200_clover_apply: bad argument"); return B200_ERR_ARG; }
+    if (inverse && cb != 0) { set_error("only the cb-0 inverse exists (invclov.choles(0), eoprec_clover_linop_w.cc:30)"); return B200_ERR_ARG; }
+    const C* cl = inverse ? invclov : clov + (size_t)cb * 36 * g.Vh;
+    clover_kernel<R, 128><<<(g.Vh + 127) / 128, 128, 0, stream>>>((const C*)in->d, (C*)out->d, cl, g.Vh);
+    return launched("clover_kernel");
+  }
+
+  int matpc(b200_field* out, const b200_field* in, int isign) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = ready(); if (rc) return rc;
+    if ((isign != 1 && isign != -1) || !out || !in || out == in) { set_error("b200_clover_matpc: bad argument"); return B200_ERR_ARG; }
+    rc = need_ws(1); if (rc) return rc;
+    return apply_M((C*)out->d, (const C*)in->d, isign, EPI_M, nullptr, nullptr, 0, 0);
+  }
+
+  int fetch_scalars() {
+    B200_CUDA(cudaMemcpyAsync(h_scal, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+  int set_scalars(const ScalarSet& s) {
+    set_scalars_kernel<<<1, 32, 0, stream>>>(scal, status, s);
+    return launched("set_scalars");
+  }
+
+  int norm2_dev(const C* x, int slot) {
+    norm2_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(x, nelem(), make_red(0, blas_grid), scal + slot);
+    return launched("norm2");
+  }
+  int xmy_norm_dev(C* out, C* out2, const C* x, const C* y, int slot) {
+    xmy_norm_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(out, out2, x, y, nelem(), make_red(0, blas_grid), scal + slot);
+    return launched("xmy_norm");
+  }
+  int axpby_dev(C* out, double a, const C* x, double b, const C* y) {
+    axpby_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(out, a, x, b, y, nelem());
+    return launched("axpby");
+  }
+
+  int norm2(const b200_field* x, double* r) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = norm2_dev((const C*)x->d, S_TMP0); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    *r = h_scal[S_TMP0];
+    return B200_OK;
+  }
+  int inner(const b200_field* x, const b200_field* y, double r[2]) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    inner_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>((const C*)x->d, (const C*)y->d, nelem(), make_red(0, blas_grid), scal + S_TMP0);
+    int rc = launched("inner"); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    r[0] = h_scal[S_TMP0]; r[1] = h_scal[S_TMP1];
+    return B200_OK;
+  }
+
+  // ------------------------------------------------------------------ solver loops
+  BlasCtl ctl(int iter, int check) {
+    BlasCtl c; c.scal = scal; c.status = status; c.red = make_red(0, blas_grid); c.iter = iter; c.check_stop = check;
+    return c;
+  }
+
+  // one CG iteration, invcg2.cc:158-220.  workspace: W(1)=mp, W(2)=p, W(3)=r
+  int cg_iteration(C* psi, int k, int check) {
+    int rc = apply_M(W(1), W(2), +1, EPI_M_NORM, nullptr, nullptr, k, check); if (rc) return rc;      // mp = M p, d, a
+    rc = apply_M(nullptr, W(1), -1, EPI_M_CG, W(3), nullptr, k, check); if (rc) return rc;            // r -= a M^dag mp, cp, b
+    cg_update_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(psi, W(2), W(3), nelem(), ctl(k, check));
+    return launched("cg_update");
+  }
+  // one BiCGStab iteration, invbicgstab.cc:74-170.  W(1)=r, W(2)=r0, W(3)=p, W(4)=v, W(5)=t
+  int bicg_iteration(C* psi, int k, int check) {
+    bicg_p_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(W(3), W(1), W(4), nelem(), ctl(k, check));
+    int rc = launched("bicg_p"); if (rc) return rc;
+    rc = apply_M(W(4), W(3), +1, EPI_M_DOTR0, nullptr, W(2), k, check); if (rc) return rc;            // v = M p, alpha
+    bicg_s_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(W(1), W(4), nelem(), ctl(k, check));
+    rc = launched("bicg_s"); if (rc) return rc;
+    rc = apply_M(W(5), W(1), +1, EPI_M_DOTX, nullptr, nullptr, k, check); if (rc) return rc;          // t = M r, omega
+    bicg_update_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(psi, W(1), W(3), W(5), W(2), nelem(), ctl(k, check));
+    return launched("bicg_update");
+  }
+
+  // InvCG2_a set-up (invcg2.cc:100-150): returns chi_sq, cp in h_scal[S_TMP0], h_scal[S_TMP1]
+  int cg_begin(C* psi, const C* chi) {
+    int rc = norm2_dev(chi, S_TMP0); if (rc) return rc;
+    rc = apply_M(W(1), psi, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+    rc = apply_M(W(4), W(1), -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+    rc = xmy_norm_dev(W(3), W(2), chi, W(4), S_TMP1); if (rc) return rc;     // r = chi - M^dag M psi ; p = r ; cp
+    return fetch_scalars();
+  }
+  // InvBiCGStab_a set-up (invbicgstab.cc:31-71)
+  int bicg_begin(C* psi, const C* chi) {
+    int rc = norm2_dev(chi, S_TMP0); if (rc) return rc;
+    rc = apply_M(W(2), psi, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+    rc = xmy_norm_dev(W(1), W(2), chi, W(2), S_TMP1); if (rc) return rc;     // r = r0 = chi - M psi ; |r|^2 = <r0|r>
+    B200_CUDA(cudaMemsetAsync(W(3), 0, sizeof(C) * nelem(), stream));
+    B200_CUDA(cudaMemsetAsync(W(4), 0, sizeof(C) * nelem(), stream));
+    return fetch_scalars();
+  }
+
+  int poll_loop(C* psi, int solver, int max_iter, int* n_count, int* converged, int* breakdown) {
+    int k = 1, slot = 0, prev = -1;
+    bool done = false;
+    *breakdown = 0;
+    while (k <= max_iter && !done) {
+      const int n = std::min(ITER_BATCH, max_iter - k + 1);
+      for (int i = 0; i < n; ++i) {
+        int rc = (solver == B200_SOLVER_CG) ? cg_iteration(psi, k + i, 1) : bicg_iteration(psi, k + i, 1);
+        if (rc) return rc;
+      }
+      B200_CUDA(cudaMemcpyAsync(h_status + slot * ST_COUNT, status, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, stream));
+      B200_CUDA(cudaEventRecord(ev_poll[slot], stream));
+      if (prev >= 0) {
+        B200_CUDA(cudaEventSynchronize(ev_poll[prev]));
+        if (h_status[prev * ST_COUNT + ST_STOP] != 0 || h_status[prev * ST_COUNT + ST_BREAKDOWN] != 0) done = true;
+      }
+      prev = slot; slot ^= 1; k += n;
+    }
+    B200_CUDA(cudaStreamSynchronize(stream));
+    const int* st = h_status + prev * ST_COUNT;   // the last copy enqueued reflects the final state
+    *breakdown = st[ST_BREAKDOWN];
+    *converged = st[ST_STOP] != 0;
+    *n_count = st[ST_STOP] != 0 ? st[ST_STOP] : max_iter;
+    return B200_OK;
+  }
+
+  int invert(b200_field* psi_f, const b200_field* chi_f, int solver, double rsd, int max_iter, b200_solve_info* info) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = ready(); if (rc) return rc;
+    if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0)) { set_error("b200_invert: bad argument"); return B200_ERR_ARG; }
+    if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
+    rc = need_ws(7); if (rc) return rc;
+    C* psi = (C*)psi_f->d; const C* chi = (const C*)chi_f->d;
+    memset(info, 0, sizeof(*info));
+    B200_CUDA(cudaEventRecord(ev_t0, stream));
+    int n_count = 0, converged = 0, breakdown = 0;
+    double flops_iter;
+    if (solver == B200_SOLVER_CG) {
+      flops_iter = 2.0 * 3792.0 + 240.0;
+      // chi_tmp = M^dag chi (syssolver_linop_cg.h:65-66) -> W(6)
+      rc = apply_M(W(6), chi, -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+      rc = cg_begin(psi, W(6)); if (rc) return rc;
+      const double chi_sq = h_scal[S_TMP0], cp = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
+      info->rsd_sq_iter = cp;
+      if (cp <= rsd_sq) { n_count = 0; converged = 1; }          // invcg2.cc:136-146
+      else {
+        ScalarSet s{}; s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = rsd_sq; s.slots[1] = S_C; s.vals[1] = cp; s.reset_status = 1;
+        rc = set_scalars(s); if (rc) return rc;
+        rc = poll_loop(psi, solver, max_iter, &n_count, &converged, &breakdown); if (rc) return rc;
+      }
+    } else {
+      flops_iter = 2.0 * 3792.0 + 960.0;
+      rc = bicg_begin(psi, chi); if (rc) return rc;
+      const double chi_sq = h_scal[S_TMP0], rr = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
+      info->rsd_sq_iter = rr;
+      ScalarSet s{}; s.reset_status = 1; s.n = 11;
+      const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
+      const double vl[11] = {rsd_sq, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};   // beta_1 = (rho_1/1)(1/1)
+      for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+      if (rr == 0.0) breakdown = 1;                                // rho = <r0|r> = 0 (invbicgstab.cc:80-83)
+      else {
+        rc = set_scalars(s); if (rc) return rc;
+        rc = poll_loop(psi, solver, max_iter, &n_count, &converged, &breakdown); if (rc) return rc;
+      }
+    }
+    B200_CUDA(cudaEventRecord(ev_t1, stream));
+    // true residual with M, as both shells do (syssolver_linop_cg.h:80-87)
+    rc = apply_M(W(1), psi, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+    rc = xmy_norm_dev(nullptr, nullptr, chi, W(1), S_TMP2); if (rc) return rc;
+    rc = norm2_dev(chi, S_TMP3); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    float ms = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms, ev_t0, ev_t1));
+    info->n_count = n_count; info->converged = converged;
+    info->resid = sqrt(h_scal[S_TMP2]);
+    info->rel_resid = h_scal[S_TMP3] > 0 ? info->resid / sqrt(h_scal[S_TMP3]) : 0.0;
+    if (n_count > 0) info->rsd_sq_iter = (solver == B200_SOLVER_CG) ? h_scal[S_CP] : h_scal[S_RNORM];
+    info->secs = ms * 1e-3; info->secs_total = info->secs;
+    const double gvol = (double)g.Vh * cfg.pgrid[3];
+    info->gflops = info->secs > 0 ? flops_iter * gvol * n_count / info->secs * 1e-9 : 0.0;
+    if (breakdown) { set_error("BiCGStab breakdown (code %d) at iteration <= %d", breakdown, n_count); return B200_ERR_BREAKDOWN; }
+    return B200_OK;
+  }
+
+  int iterate_begin(b200_field* psi_f, const b200_field* chi_f, int solver) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = ready(); if (rc) return rc;
+    rc = need_ws(7); if (rc) return rc;
+    it_psi = (C*)psi_f->d; it_chi = (const C*)chi_f->d; it_k = 0;
+    ScalarSet s{}; s.reset_status = 1;
+    if (solver == B200_SOLVER_CG) {
+      rc = cg_begin(it_psi, it_chi); if (rc) return rc;
+      s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = 0.0; s.slots[1] = S_C; s.vals[1] = h_scal[S_TMP1];
+    } else {
+      rc = bicg_begin(it_psi, it_chi); if (rc) return rc;
+      const double rr = h_scal[S_TMP1];
+      s.n = 11;
+      const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
+      const double vl[11] = {0.0, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};
+      for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+    }
+    return set_scalars(s);
+  }
+  int iterate(int solver, int n_iter) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!it_psi) { set_error("b200_dev_iterate: call b200_dev_iterate_begin first"); return B200_ERR_STATE; }
+    for (int i = 0; i < n_iter; ++i) {
+      ++it_k;
+      int rc = (solver == B200_SOLVER_CG) ? cg_iteration(it_psi, it_k, 0) : bicg_iteration(it_psi, it_k, 0);
+      if (rc) return rc;
+    }
+    return B200_OK;
+  }
+
+  // ------------------------------------------------------------------ full-lattice propagator (section 8f, rank 1)
+  // PrecFermActQprop::operator() (eoprec_fermact_qprop.cc:41-80) inside the 12-colour-spin loop of
+  // quarkProp4_a (quarkprop4_w.cc:70-117), all on the device.  evenOddLinOp = -1/2 D (eoprec_clover_linop_w.cc:98-133).
+  int qprop(void* psi_h, const void* chi_h, int host_prec, int nrhs, int solver, double rsd, int max_iter,
+            b200_solve_info* infos) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = ready(); if (rc) return rc;
+    if (!psi_h || !chi_h || !infos || nrhs < 1) { set_error("b200_qprop: bad argument"); return B200_ERR_ARG; }
+    if (host_prec != B200_SINGLE && host_prec != B200_DOUBLE) { set_error("host_prec must be 4 or 8"); return B200_ERR_ARG; }
+    rc = need_ws(7); if (rc) return rc;
+    b200_field *chi_e = nullptr, *chi_o = nullptr, *psi_o = nullptr, *t1 = nullptr, *t2 = nullptr;
+    if ((rc = field_alloc(&chi_e)) || (rc = field_alloc(&chi_o)) || (rc = field_alloc(&psi_o)) || (rc = field_alloc(&t1)) || (rc = field_alloc(&t2))) return rc;
+    const size_t cbbytes = (size_t)g.Vh * 24 * host_prec;
+    for (int i = 0; i < nrhs && !rc; ++i) {
+      const char* ch = (const char*)chi_h + (size_t)i * 2 * cbbytes;
+      char* ph = (char*)psi_h + (size_t)i * 2 * cbbytes;
+      if ((rc = field_upload(chi_e, ch, host_prec))) break;
+      if ((rc = field_upload(chi_o, ch + cbbytes, host_prec))) break;
+      if ((rc = field_upload(psi_o, ph + cbbytes, host_prec))) break;
+      // chi' = chi_o - D_oe A_ee^-1 chi_e = chi_o + 1/2 Dslash(A_ee^-1 chi_e)
+      if ((rc = clover_apply(t1, chi_e, 0, 1))) break;
+      if ((rc = dslash(t2, t1, +1, 1))) break;
+      if ((rc = axpby_dev((C*)t1->d, 1.0, (const C*)chi_o->d, 0.5, (const C*)t2->d))) break;
+      rc = invert(psi_o, t1, solver, rsd, max_iter, &infos[i]);
+      if (rc) break;
+      // psi_e = A_ee^-1 (chi_e - D_eo psi_o) = A_ee^-1 (chi_e + 1/2 Dslash psi_o)
+      if ((rc = dslash(t1, psi_o, +1, 0))) break;
+      if ((rc = axpby_dev((C*)t2->d, 1.0, (const C*)chi_e->d, 0.5, (const C*)t1->d))) break;
+      if ((rc = clover_apply(t1, t2, 0, 1))) break;
+      if ((rc = field_download(t1, ph, host_prec))) break;
+      if ((rc = field_download(psi_o, ph + cbbytes, host_prec))) break;
+    }
+    field_free(chi_e); field_free(chi_o); field_free(psi_o); field_free(t1); field_free(t2);
+    return rc;
+  }
+};
+
+}  // namespace b200

@@ -1,0 +1,108 @@
+// reduce.cuh -- deterministic block reduction + "last block finalises" pattern used by every fused
+// solver kernel.  Each block writes one partial per reduced quantity; the block that draws the last
+// ticket sums the partials in a fixed order (so the result does not depend on block scheduling),
+// optionally combines across GPUs through NVLink peer mailboxes, and hands the totals to a finaliser
+// functor that derives the solver scalars (alpha, beta, ...) ON THE DEVICE -- the host never sees them.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// Cross-GPU reduction mailboxes (peer-mapped).  See comm.cuh for how they are wired up.
+struct PeerReduce {
+  int nranks;           // 1 => single GPU, nothing to do
+  int rank;
+  unsigned long long* seq;  // device counter: number of cross-GPU reductions done so far on this rank
+  double* mailbox[8];       // mailbox[r] = rank r's mailbox base (peer pointer), layout [slot 2][src rank 8][4 values + seq]
+};
+
+struct ReduceBuf {
+  double* partial;       // [N][total_blocks]
+  unsigned int* ticket;  // zero between kernels
+  int block_offset;      // first partial slot of this launch (a step may be split into several launches)
+  int total_blocks;      // blocks over all launches of the step
+  PeerReduce peer;
+};
+
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v, double* smem /* [BLOCK/32] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < BLOCK / 32; ++i) s += smem[i];   // every thread sums in the same fixed order
+  return s;
+}
+
+// Combine `vals[N]` (N<=4) across ranks in fixed rank order.  Executed by ONE thread of the last block.
+// Each rank writes its values + a sequence tag into every peer's mailbox (slot = seq&1), then polls its
+// own mailbox until all N ranks' tags match.  Two slots suffice because a rank cannot start reduction
+// s+2 before every peer has finished reading reduction s (they all needed this rank's s+1 contribution).
+template <int N>
+__device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, double vals[N]) {
+  if (pr.nranks <= 1) return;
+  const unsigned long long s = *pr.seq + 1ull;
+  const int slot = (int)(s & 1ull);
+  for (int dst = 0; dst < pr.nranks; ++dst) {
+    volatile double* mb = pr.mailbox[dst] + ((size_t)slot * 8 + pr.rank) * 8;
+    for (int k = 0; k < N; ++k) mb[k] = vals[k];
+  }
+  __threadfence_system();
+  for (int dst = 0; dst < pr.nranks; ++dst) {
+    volatile unsigned long long* tag =
+        (volatile unsigned long long*)(pr.mailbox[dst] + ((size_t)slot * 8 + pr.rank) * 8 + 4);
+    *tag = s;
+  }
+  __threadfence_system();
+  double tot[N];
+  for (int k = 0; k < N; ++k) tot[k] = 0.0;
+  for (int src = 0; src < pr.nranks; ++src) {
+    volatile double* mb = pr.mailbox[pr.rank] + ((size_t)slot * 8 + src) * 8;
+    volatile unsigned long long* tag = (volatile unsigned long long*)(mb + 4);
+    while (*tag != s) { }
+    __threadfence_system();
+    for (int k = 0; k < N; ++k) tot[k] += mb[k];
+  }
+  for (int k = 0; k < N; ++k) vals[k] = tot[k];
+  *pr.seq = s;
+}
+
+// v[N]: this thread's contributions.  fin(tot) runs in exactly one thread of the whole step.
+template <int N, int BLOCK, typename Fin>
+__device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fin fin) {
+  __shared__ double smem[BLOCK / 32];
+  __shared__ bool is_last;
+  double s[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) s[k] = block_sum<BLOCK>(v[k], smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + rb.block_offset + blockIdx.x] = s[k];
+    __threadfence();
+    unsigned int t = atomicAdd(rb.ticket, 1u);
+    is_last = (t == (unsigned int)rb.total_blocks - 1u);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double tot[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double acc = 0.0;
+      for (int b = threadIdx.x; b < rb.total_blocks; b += BLOCK) acc += __ldcg(rb.partial + (size_t)k * rb.total_blocks + b);
+      tot[k] = block_sum<BLOCK>(acc, smem);
+    }
+    if (threadIdx.x == 0) {
+      peer_allreduce<N>(rb.peer, tot);
+      fin(tot);
+      *rb.ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace b200

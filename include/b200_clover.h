@@ -1,0 +1,178 @@
+/*
+ * b200_clover.h -- C ABI of the B200-native even-odd preconditioned Wilson-clover engine.
+ *
+ * This is the drop-in boundary behind Chroma's solver-plugin surface: the adapter class
+ * LinOpSysSolverB200Clover (chroma_adapter/) registered in TheLinOpFermSystemSolverFactory as
+ * "B200_CLOVER_INVERTER" binds exactly these entry points, the way the QUDA adapter binds
+ * loadGaugeQuda / loadCloverQuda / invertQuda / freeGaugeQuda
+ * (lib/actions/ferm/invert/quda_solvers/syssolver_linop_clover_quda_w.h:523,552,573-574 and
+ *  syssolver_linop_clover_quda_w.cc:98), and the way the CPU wrappers bind the Dslash C ABI
+ * init_sse_su3dslash / sse_su3dslash_wilson / free_sse_su3dslash
+ * (other_libs/sse_wilson_dslash/include/sse_dslash.h:13-36).  All citations are relative to
+ * the Chroma tree.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only, no C++ / torch / QDP++ types, no exceptions.
+ *  - Every function returns 0 on success, a B200_ERR_* code otherwise; b200_last_error() gives text.
+ *  - "Host" pointers are ordinary host memory in QDP++'s native layout:
+ *      site order  cb2: idx = cb*Vh + ((t*Lz+z)*Ly+y)*(Lx/2) + x/2, cb = (x+y+z+t)&1, on the LOCAL
+ *                  lattice of this rank (shift_table_scalar.cc:155-214)
+ *      fermion     REAL[Vh][spin 4][colour 3][re,im] for ONE checkerboard, i.e. what
+ *                  &psi.elem(rb[cb].start()).elem(0).elem(0).real() points at
+ *                  (syssolver_linop_clover_quda_w.cc:76,85)
+ *      gauge       u[mu] = REAL[V][row 3][col 3][re,im], mu = 0..3, fermion boundary phases already
+ *                  multiplied in (state->getLinks(); simple_fermbc.h:87-103), NOT transposed, NOT
+ *                  anisotropy-scaled (syssolver_linop_clover_quda_w.h:514-516)
+ *      clover      PrimitiveClovTriang<REAL>[V]: diag[2][6] then offd[2][15][re,im], 72 reals/site
+ *                  (clover_term_qdp_w.h:19-24)
+ *    host_prec says whether REAL is float (B200_SINGLE) or double (B200_DOUBLE).
+ *  - "dev" entry points work on device-resident checkerboard fields (b200_field) in the engine's
+ *    site-major SoA layout; they exist so a caller can keep vectors on the GPU between calls
+ *    (the way QUDA's BUILD_QUDA_DEVIFACE_SPINOR path does, syssolver_linop_clover_quda_w.cc:78-92).
+ *  - The operator is Chroma's ASYMMETRIC even-odd preconditioned clover operator on the odd
+ *    checkerboard, M = A_oo - 1/4 D_oe A_ee^-1 D_eo (eoprec_clover_linop_w.cc:142-187), so that
+ *    the adapter's residual check with Chroma's own linop passes.
+ *  - There is no CPU fallback: every entry point fails with B200_ERR_CUDA if no sm_100 device.
+ */
+#ifndef B200_CLOVER_H
+#define B200_CLOVER_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_field b200_field; /* one device-resident checkerboard fermion */
+
+enum { B200_SINGLE = 4, B200_DOUBLE = 8 };            /* bytes per real */
+enum { B200_RECONS_NONE = 18, B200_RECONS_12 = 12 };   /* reals stored per link; enum_quda_io.h:77-80 */
+enum { B200_SOLVER_CG = 0, B200_SOLVER_BICGSTAB = 1 }; /* enum_quda_io.h:21-26 */
+enum { B200_PLUS = 1, B200_MINUS = -1 };               /* enum PlusMinus */
+
+enum {
+  B200_OK = 0,
+  B200_ERR_ARG = 1,       /* bad argument (odd dimension, null pointer, unknown enum ...) */
+  B200_ERR_CUDA = 2,      /* CUDA runtime error / no usable device */
+  B200_ERR_STATE = 3,     /* call out of order (e.g. solve before gauge/clover are loaded) */
+  B200_ERR_BREAKDOWN = 4, /* BiCGStab breakdown (rho = 0, <r0|v> = 0, |t| = 0); invbicgstab.cc:80-83,109-112,133-136 */
+  B200_ERR_COMM = 5       /* multi-GPU bootstrap failed */
+};
+
+/* Host-side collectives the caller lends the engine for the ONE-TIME multi-GPU bootstrap (exchange of
+ * CUDA IPC handles).  In Chroma these are two QMP/MPI calls; in the Python harness torch.distributed.
+ * The hot path never calls them: halos and global sums travel GPU-to-GPU over NVLink peer memory. */
+typedef struct {
+  int rank, size;
+  /* gather `bytes` bytes from every rank into recv (size*bytes), rank order */
+  int (*allgather)(void* user, const void* send, void* recv, size_t bytes);
+  int (*barrier)(void* user);
+  void* user;
+} b200_comm;
+
+typedef struct {
+  int n_count;          /* iterations, as SystemSolverResults_t::n_count (lib/syssolver.h:16-23) */
+  int converged;        /* 1 if the recurrence residual met rsd_target */
+  double resid;         /* |chi - M psi| recomputed with M, as syssolver_linop_cg.h:80-87 */
+  double rel_resid;     /* resid / |chi| */
+  double rsd_sq_iter;   /* last recurrence |r|^2 (invcg2.cc:182 / invbicgstab.cc:160) */
+  double secs;          /* device time of the iteration loop (CUDA events) */
+  double secs_total;    /* including host<->device copies of chi / psi when host pointers were given */
+  double gflops;        /* Chroma's flop count / secs: CG 2*M + 240, BiCGStab 2*M + 960 per site-iter */
+} b200_solve_info;
+
+const char* b200_last_error(void);
+const char* b200_version(void);
+
+/* Create an engine context on CUDA device `device` for a local lattice.  global_dims/proc_grid/
+ * proc_coord describe the 4-D domain decomposition the way Layout::lattSize()/logicalSize()/
+ * nodeCoord do; comm may be NULL when the grid is 1x1x1x1.  This round splits T only.
+ * prec = B200_DOUBLE or B200_SINGLE chooses the device storage + arithmetic precision (reductions
+ * are always accumulated in double).  Replaces initQuda (lib/init/chroma_init.cc:250). */
+int b200_create(b200_ctx** ctx, int device, const int global_dims[4], const int proc_grid[4],
+                const int proc_coord[4], const b200_comm* comm, int prec);
+void b200_destroy(b200_ctx* ctx); /* freeGaugeQuda/freeCloverQuda/endQuda, syssolver_linop_clover_quda_w.h:570-575 */
+
+/* Upload the four link fields.  aniso_coeff[mu] multiplies U_mu inside the hopping term only
+ * (makeFermCoeffs, lib/io/aniso_io.cc:63-80; lwldslash_w_cppd.cc:115-121); pass {1,1,1,1} (or NULL) if isotropic.
+ * t_boundary (+1 / -1) says which phase the fermion BC multiplied into U_t on the last global time slice; it is
+ * only used with B200_RECONS_12, where the phase is stripped on upload and re-applied in the kernel, like the
+ * QUDA / QPhiX adapters do (syssolver_linop_clover_quda_w.h:147-156, syssolver_linop_clover_qphix_w.h:107-116).
+ * Replaces loadGaugeQuda (syssolver_linop_clover_quda_w.h:523) and CPPWilsonDslashD::create +
+ * qdp_pack_gauge (lwldslash_w_cppd.cc:96-149, qdp_packer_nopad.cc:7-21). */
+int b200_load_gauge(b200_ctx* ctx, const void* const u[4], int host_prec, const double aniso_coeff[4],
+                    int t_boundary, int reconstruct);
+
+/* Either hand over Chroma's clover term and its cb-0 inverse (both PrimitiveClovTriang[V], as
+ * clov.getTriBuffer()/invclov.getTriBuffer() give them) -- replaces loadCloverQuda
+ * (syssolver_linop_clover_quda_w.h:552) ... */
+int b200_load_clover(b200_ctx* ctx, const void* clov_tri, const void* invclov_tri, int host_prec);
+/* ... or let the GPU build both from the loaded links: field strength (lib/meas/glue/mesfield.cc:44-74),
+ * makeClov (clover_term_qdp_w.h:398-553) and the per-site LDL^dagger inverse on cb 0 (:619-846).
+ * diag_mass, clov_r, clov_t are the values QDPCloverTermT::create derives (:263-278):
+ * diag_mass = 1 + 3*(nu/xi_0 | 1) + Mass, clov_r = clovCoeffR/2 (/xi_0 if aniso), clov_t = clovCoeffT/2.
+ * Needs the UN-scaled links, so call b200_load_gauge first (it keeps what this needs). */
+int b200_make_clover(b200_ctx* ctx, double diag_mass, double clov_r, double clov_t, int aniso, int t_dir);
+/* Read back what b200_make_clover / b200_load_clover hold (PrimitiveClovTriang<double>[V]); for tests. */
+int b200_get_clover(b200_ctx* ctx, void* clov_tri, void* invclov_tri, int host_prec);
+/* sum over cb-0 sites of log|det A_ee| from the LDL^dagger pass (tr_log_diag, clover_term_qdp_w.h:737) */
+int b200_clover_logdet(b200_ctx* ctx, double* tr_log_ee);
+
+/* Wilson hopping term on one checkerboard: out (parity out_cb) = D in (parity 1-out_cb).
+ * Replaces Dslash<REAL>::operator() (cpp_dslash_scalar.h:20-105; cpp_dslash_scalar_64bit.cc:35-65)
+ * as called from CPPWilsonDslashD::apply (lwldslash_w_cppd.cc:174-215). */
+int b200_dslash(b200_ctx* ctx, void* out_cb_host, const void* in_cb_host, int host_prec, int isign, int out_cb);
+/* Clover term (inverse = 0) or its cb-0 inverse (inverse = 1) on checkerboard cb:
+ * QDPCloverTermT::apply (clover_term_qdp_w.h:2138-2160). */
+int b200_clover_apply(b200_ctx* ctx, void* out_cb_host, const void* in_cb_host, int host_prec, int cb, int inverse);
+/* out_odd = M in_odd (isign=+1) or M^dagger in_odd (-1): EvenOddPrecCloverLinOp::operator()
+ * (eoprec_clover_linop_w.cc:142-187); also what CloverSchur4D fuses (cpp_clover_scalar_64bit.cc:65-102). */
+int b200_clover_matpc(b200_ctx* ctx, void* out_odd_host, const void* in_odd_host, int host_prec, int isign);
+
+/* Solve M psi = chi on the odd checkerboard.  psi holds the initial guess on entry, the solution on exit.
+ * solver = B200_SOLVER_CG:       LinOpSysSolverCG (syssolver_linop_cg.h:57-96): chi' = M^dag chi, then
+ *                                InvCG2_a on M^dag M (invcg2.cc:70-232), stop |r|^2 <= rsd^2 |chi'|^2.
+ * solver = B200_SOLVER_BICGSTAB: LinOpSysSolverBiCGStab (syssolver_linop_bicgstab.h:57-95) ->
+ *                                InvBiCGStab_a (invbicgstab.cc:10-202), stop |r|^2 < rsd^2 |chi|^2.
+ * Replaces invertQuda (syssolver_linop_clover_quda_w.cc:98).  Non-convergence is NOT an error: the call
+ * returns 0 with info->converged = 0 and n_count = max_iter, like invcg2.cc:222-228. */
+int b200_invert(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec, int solver,
+                double rsd_target, int max_iter, b200_solve_info* info);
+
+/* Full-lattice propagator solve for nrhs right-hand sides (the sequential 12 spin-colour loop of
+ * quarkprop4_w.cc:70-117 with the even-odd source preparation and solution reconstruction of
+ * eoprec_fermact_qprop.cc:41-80 done on the device).  chi/psi: REAL[nrhs][V][4][3][2]. */
+int b200_qprop(b200_ctx* ctx, void* psi_full_host, const void* chi_full_host, int host_prec, int nrhs, int solver,
+               double rsd_target, int max_iter, b200_solve_info* infos);
+
+/* ---- device-resident interface ------------------------------------------------------------- */
+int b200_field_alloc(b200_ctx* ctx, b200_field** f);
+void b200_field_free(b200_ctx* ctx, b200_field* f);
+int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* cb_host, int host_prec);
+int b200_field_download(b200_ctx* ctx, const b200_field* f, void* cb_host, int host_prec);
+int b200_field_zero(b200_ctx* ctx, b200_field* f);
+int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb);
+int b200_dev_clover_apply(b200_ctx* ctx, b200_field* out, const b200_field* in, int cb, int inverse);
+int b200_dev_clover_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign);
+int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* result);
+int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double result[2]); /* <x|y> = sum conj(x) y */
+int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd_target,
+                    int max_iter, b200_solve_info* info);
+/* Benchmark leg: set up the solver recurrences (r, p, ... as the solver's own preamble does), then run exactly
+ * n_iter iterations of the loop body per call with the convergence test disabled. */
+int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver);
+int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter);
+
+/* ---- plumbing -------------------------------------------------------------------------------- */
+void* b200_stream(b200_ctx* ctx);              /* cudaStream_t the engine launches on (for event timing) */
+int b200_sync(b200_ctx* ctx);
+long long b200_launch_count(b200_ctx* ctx);    /* kernels launched by the engine since creation */
+int b200_host_alloc(void** p, size_t bytes);   /* pinned host memory (optional, speeds up host<->device copies) */
+void b200_host_free(void* p);
+int b200_local_volume(const b200_ctx* ctx, int local_dims[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_CLOVER_H */

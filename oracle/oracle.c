@@ -1,0 +1,747 @@
+/*
+ * oracle.c -- CPU restatement of Chroma's even-odd preconditioned Wilson-clover path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under chroma_b200/ may call, link or load this
+ * file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * arm use it, and only as the checker / CPU baseline -- never as the product path.
+ *
+ * Every function cites the reference lines (relative to /root/reference) it follows.
+ * Data layouts are the ones QDP++ hands to the solver plugin:
+ *   site order   "cb2": idx = cb*Vh + ((t*Lz+z)*Ly+y)*(Lx/2) + x/2, cb=(x+y+z+t)&1
+ *                (other_libs/cpp_wilson_dslash/lib/shift_table_scalar.cc:155-214)
+ *   fermion      double[V][spin 4][colour 3][re,im]
+ *   gauge        four arrays u[mu] = double[V][row 3][col 3][re,im]
+ *   packed gauge double[V][mu 4][col 3][row 3][re,im]  (transposed links,
+ *                other_libs/cpp_wilson_dslash/lib/qdp_packer_nopad.cc:13-19)
+ *   clover       per site: diag[2][6] reals then offd[2][15] complex = 72 reals
+ *                (lib/actions/ferm/linop/clover_term_qdp_w.h:19-24)
+ *
+ * Parity pinning: orc_dslash and orc_clover_apply are checked against the reference's
+ * own Dslash<double> / CloverSchur4D<double> compiled unmodified into oracle/_ref
+ * (tests/test_oracle_vs_ref.py).  The clover build, LDL^dagger inverse and the solver
+ * loops are restated-and-self-consistent (A*A^-1=1, gamma5-hermiticity, free field,
+ * constant abelian field strength): the reference holds no golden vectors for them
+ * that can be reproduced without QDP++'s RNG.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NC 3
+#define SPINOR 24   /* reals per site */
+#define LINK 18
+#define CLOV 72
+
+typedef struct { double re, im; } cplx;
+
+static inline cplx c_mul(cplx a, cplx b) { cplx r = { a.re*b.re - a.im*b.im, a.re*b.im + a.im*b.re }; return r; }
+static inline cplx c_conj(cplx a) { cplx r = { a.re, -a.im }; return r; }
+static inline cplx c_add(cplx a, cplx b) { cplx r = { a.re+b.re, a.im+b.im }; return r; }
+static inline cplx c_sub(cplx a, cplx b) { cplx r = { a.re-b.re, a.im-b.im }; return r; }
+static inline cplx c_timesI(cplx a) { cplx r = { -a.im, a.re }; return r; }
+static inline cplx c_neg(cplx a) { cplx r = { -a.re, -a.im }; return r; }
+/* complex division as std::complex / RComplex do it (textbook formula) */
+static inline cplx c_div(cplx a, cplx b) {
+  double d = b.re*b.re + b.im*b.im;
+  cplx r = { (a.re*b.re + a.im*b.im)/d, (a.im*b.re - a.re*b.im)/d };
+  return r;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Geometry: QDP++ cb2 layout, restated from shift_table_scalar.cc:155-214    */
+/* ------------------------------------------------------------------------- */
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+int orc_site_index(const int L[4], const int c[4]) {
+  int V = L[0]*L[1]*L[2]*L[3];
+  int cb = (c[0]+c[1]+c[2]+c[3]) & 1;
+  return ((c[3]*L[2]+c[2])*L[1]+c[1])*(L[0]/2) + c[0]/2 + cb*(V/2);
+}
+
+void orc_site_coords(const int L[4], int idx, int c[4]) {
+  int V = L[0]*L[1]*L[2]*L[3], Vh = V/2, Lxh = L[0]/2;
+  int cb = idx / Vh, r = idx % Vh;
+  int xh = r % Lxh; r /= Lxh;
+  c[1] = r % L[1]; r /= L[1];
+  c[2] = r % L[2]; r /= L[2];
+  c[3] = r;
+  c[0] = 2*xh + ((cb + c[1] + c[2] + c[3]) & 1);
+}
+
+static inline int nbr(const int L[4], const int c[4], int mu, int dir) {
+  int n[4] = { c[0], c[1], c[2], c[3] };
+  n[mu] = (c[mu] + dir + L[mu]) % L[mu];
+  return orc_site_index(L, n);
+}
+
+/* neighbour tables: fwd[4*site+mu], bwd[4*site+mu] (shift_table_scalar.cc:118-147) */
+static void build_tables(const int L[4], int** fwd_out, int** bwd_out) {
+  int V = L[0]*L[1]*L[2]*L[3];
+  int* fwd = (int*)malloc(sizeof(int)*4*(size_t)V);
+  int* bwd = (int*)malloc(sizeof(int)*4*(size_t)V);
+#pragma omp parallel for
+  for (int s = 0; s < V; ++s) {
+    int c[4]; orc_site_coords(L, s, c);
+    for (int mu = 0; mu < 4; ++mu) { fwd[4*s+mu] = nbr(L, c, mu, +1); bwd[4*s+mu] = nbr(L, c, mu, -1); }
+  }
+  *fwd_out = fwd; *bwd_out = bwd;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Boundary phases and anisotropy factors folded into the links               */
+/* ------------------------------------------------------------------------- */
+/* lib/actions/ferm/fermbcs/simple_fermbc.h:87-103: u[m] *= boundary[m] on x_m = L_m-1 */
+void orc_apply_fermbc(const int L[4], double* const u[4], const int boundary[4]) {
+  int V = L[0]*L[1]*L[2]*L[3];
+  for (int mu = 0; mu < 4; ++mu) {
+    if (boundary[mu] == 1) continue;
+#pragma omp parallel for
+    for (int s = 0; s < V; ++s) {
+      int c[4]; orc_site_coords(L, s, c);
+      if (c[mu] == L[mu]-1)
+        for (int k = 0; k < LINK; ++k) u[mu][(size_t)s*LINK+k] *= (double)boundary[mu];
+    }
+  }
+}
+
+/* lwldslash_w_cppd.cc:115-121 (u[mu] *= coeffs[mu]) followed by
+ * qdp_packer_nopad.cc:13-19 (u_tmp[mu+4*ix] = transpose(u[mu](ix))) */
+void orc_pack_gauge(const int L[4], const double* const u[4], const double coeffs[4], double* packed) {
+  int V = L[0]*L[1]*L[2]*L[3];
+#pragma omp parallel for
+  for (int s = 0; s < V; ++s)
+    for (int mu = 0; mu < 4; ++mu) {
+      const double* in = u[mu] + (size_t)s*LINK;
+      double* out = packed + ((size_t)s*4 + mu)*LINK;
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+        out[(c*3+r)*2+0] = coeffs[mu]*in[(r*3+c)*2+0];
+        out[(c*3+r)*2+1] = coeffs[mu]*in[(r*3+c)*2+1];
+      }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Wilson hopping term                                                        */
+/* ------------------------------------------------------------------------- */
+/* su3_mult: res[s][row] = sum_col u[col][row]*h[s][col]  (cpp_dslash_matvec64bit_c.h:14-150)
+ * su3_adj_mult: res[s][row] = sum_col conj(u[row][col])*h[s][col]  (:152-296)
+ * with u the PACKED (transposed) link. */
+static inline void su3_mult(cplx res[2][3], const double* u, cplx h[2][3]) {
+  for (int s = 0; s < 2; ++s)
+    for (int row = 0; row < 3; ++row) {
+      cplx acc = {0.0, 0.0};
+      for (int col = 0; col < 3; ++col) {
+        cplx m = { u[(col*3+row)*2], u[(col*3+row)*2+1] };
+        acc = c_add(acc, c_mul(m, h[s][col]));
+      }
+      res[s][row] = acc;
+    }
+}
+static inline void su3_adj_mult(cplx res[2][3], const double* u, cplx h[2][3]) {
+  for (int s = 0; s < 2; ++s)
+    for (int row = 0; row < 3; ++row) {
+      cplx acc = {0.0, 0.0};
+      for (int col = 0; col < 3; ++col) {
+        cplx m = { u[(row*3+col)*2], -u[(row*3+col)*2+1] };
+        acc = c_add(acc, c_mul(m, h[s][col]));
+      }
+      res[s][row] = acc;
+    }
+}
+
+/* Spin projection (1 + sgn*gamma_mu) onto the upper two components and the matching
+ * reconstruction of the lower two, DeGrand-Rossi basis, restated from
+ * cpp_dslash_scalar_64bit_c.h:33-1190 (one inline function per direction/sign there). */
+static inline void project(cplx h[2][3], const double* a, int mu, int sgn) {
+  const cplx* A = (const cplx*)a; /* A[spin*3+colour] */
+  for (int c = 0; c < 3; ++c) {
+    cplx a0 = A[c], a1 = A[3+c], a2 = A[6+c], a3 = A[9+c];
+    switch (mu) {
+      case 0: /* (1-g0): a0 - i a3, a1 - i a2 */
+        if (sgn < 0) { h[0][c] = c_sub(a0, c_timesI(a3)); h[1][c] = c_sub(a1, c_timesI(a2)); }
+        else         { h[0][c] = c_add(a0, c_timesI(a3)); h[1][c] = c_add(a1, c_timesI(a2)); }
+        break;
+      case 1: /* (1-g1): a0 + a3, a1 - a2 */
+        if (sgn < 0) { h[0][c] = c_add(a0, a3); h[1][c] = c_sub(a1, a2); }
+        else         { h[0][c] = c_sub(a0, a3); h[1][c] = c_add(a1, a2); }
+        break;
+      case 2: /* (1-g2): a0 - i a2, a1 + i a3 */
+        if (sgn < 0) { h[0][c] = c_sub(a0, c_timesI(a2)); h[1][c] = c_add(a1, c_timesI(a3)); }
+        else         { h[0][c] = c_add(a0, c_timesI(a2)); h[1][c] = c_sub(a1, c_timesI(a3)); }
+        break;
+      default: /* (1-g3): a0 - a2, a1 - a3 */
+        if (sgn < 0) { h[0][c] = c_sub(a0, a2); h[1][c] = c_sub(a1, a3); }
+        else         { h[0][c] = c_add(a0, a2); h[1][c] = c_add(a1, a3); }
+        break;
+    }
+  }
+}
+static inline void recons_add(cplx* out, cplx r[2][3], int mu, int sgn) {
+  for (int c = 0; c < 3; ++c) {
+    cplx r0 = r[0][c], r1 = r[1][c], r2, r3;
+    switch (mu) {
+      case 0: if (sgn < 0) { r2 = c_timesI(r1); r3 = c_timesI(r0); }
+              else { r2 = c_neg(c_timesI(r1)); r3 = c_neg(c_timesI(r0)); } break;
+      case 1: if (sgn < 0) { r2 = c_neg(r1); r3 = r0; }
+              else { r2 = r1; r3 = c_neg(r0); } break;
+      case 2: if (sgn < 0) { r2 = c_timesI(r0); r3 = c_neg(c_timesI(r1)); }
+              else { r2 = c_neg(c_timesI(r0)); r3 = c_timesI(r1); } break;
+      default: if (sgn < 0) { r2 = c_neg(r0); r3 = c_neg(r1); }
+              else { r2 = r0; r3 = r1; } break;
+    }
+    out[c]   = c_add(out[c],   r0);
+    out[3+c] = c_add(out[3+c], r1);
+    out[6+c] = c_add(out[6+c], r2);
+    out[9+c] = c_add(out[9+c], r3);
+  }
+}
+
+typedef struct {
+  int L[4]; int V, Vh;
+  int *fwd, *bwd;
+} orc_geom;
+
+orc_geom* orc_geom_create(const int L[4]) {
+  orc_geom* g = (orc_geom*)calloc(1, sizeof(orc_geom));
+  for (int i = 0; i < 4; ++i) g->L[i] = L[i];
+  g->V = L[0]*L[1]*L[2]*L[3]; g->Vh = g->V/2;
+  build_tables(L, &g->fwd, &g->bwd);
+  return g;
+}
+void orc_geom_free(orc_geom* g) { if (g) { free(g->fwd); free(g->bwd); free(g); } }
+
+/* Dslash<double>::operator()(res, psi, u, isign, cb): cb is the SOURCE checkerboard, the
+ * loop runs over target sites of parity 1-cb (cpp_dslash_scalar_64bit.cc:35-65, 69-214;
+ * lwldslash_w_cppd.cc:196-205).  isign=+1: forward hop (1-g_mu) U_mu(x) psi(x+mu),
+ * backward hop (1+g_mu) U_mu(x-mu)^dag psi(x-mu); isign=-1 swaps the projector signs
+ * (lwldslash_w.h:252-295). */
+void orc_dslash(const orc_geom* g, double* res, const double* psi, const double* packed_u, int isign, int cb) {
+  int Vh = g->Vh, tcb = 1 - cb;
+#pragma omp parallel for
+  for (int i = 0; i < Vh; ++i) {
+    int ix = tcb*Vh + i;
+    cplx acc[12]; memset(acc, 0, sizeof(acc));
+    for (int mu = 0; mu < 4; ++mu) {
+      cplx h[2][3], r[2][3];
+      int f = g->fwd[4*ix+mu], b = g->bwd[4*ix+mu];
+      project(h, psi + (size_t)f*SPINOR, mu, -isign);
+      su3_mult(r, packed_u + ((size_t)ix*4+mu)*LINK, h);
+      recons_add(acc, r, mu, -isign);
+      project(h, psi + (size_t)b*SPINOR, mu, +isign);
+      su3_adj_mult(r, packed_u + ((size_t)b*4+mu)*LINK, h);
+      recons_add(acc, r, mu, +isign);
+    }
+    memcpy(res + (size_t)ix*SPINOR, acc, sizeof(acc));
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Field strength: lib/meas/glue/mesfield.cc:44-74                             */
+/* ------------------------------------------------------------------------- */
+static inline void m_mul(cplx* r, const cplx* a, const cplx* b) {          /* r = a b */
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    cplx s = {0,0};
+    for (int k = 0; k < 3; ++k) s = c_add(s, c_mul(a[i*3+k], b[k*3+j]));
+    r[i*3+j] = s;
+  }
+}
+static inline void m_mul_adj(cplx* r, const cplx* a, const cplx* b) {      /* r = a b^dag */
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    cplx s = {0,0};
+    for (int k = 0; k < 3; ++k) s = c_add(s, c_mul(a[i*3+k], c_conj(b[j*3+k])));
+    r[i*3+j] = s;
+  }
+}
+static inline void m_adj_mul(cplx* r, const cplx* a, const cplx* b) {      /* r = a^dag b */
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    cplx s = {0,0};
+    for (int k = 0; k < 3; ++k) s = c_add(s, c_mul(c_conj(a[k*3+i]), b[k*3+j]));
+    r[i*3+j] = s;
+  }
+}
+
+/* f[offset] for (mu<nu) in the order (0,1),(0,2),(0,3),(1,2),(1,3),(2,3); f is [6][V][3][3][2]. */
+void orc_mesfield(const orc_geom* g, const double* const u[4], double* f) {
+  int V = g->V;
+  cplx* t2 = (cplx*)malloc(sizeof(cplx)*9*(size_t)V);  /* adj(tmp_0)*tmp_1            */
+  cplx* t3 = (cplx*)malloc(sizeof(cplx)*9*(size_t)V);  /* tmp_0*adj(tmp_1), 2nd stage  */
+  cplx* t4 = (cplx*)malloc(sizeof(cplx)*9*(size_t)V);  /* adj(tmp_1)*tmp_0, 2nd stage  */
+  int offset = 0;
+  for (int mu = 0; mu < 3; ++mu)
+    for (int nu = mu+1; nu < 4; ++nu, ++offset) {
+      cplx* F = (cplx*)(f + (size_t)offset*V*LINK);
+      const cplx* Um = (const cplx*)u[mu];
+      const cplx* Un = (const cplx*)u[nu];
+#pragma omp parallel for
+      for (int s = 0; s < V; ++s) {
+        const cplx* tmp_3 = Un + 9*(size_t)g->fwd[4*s+mu];   /* shift(u[nu],FORWARD,mu) */
+        const cplx* tmp_4 = Um + 9*(size_t)g->fwd[4*s+nu];   /* shift(u[mu],FORWARD,nu) */
+        cplx tmp_0[9], tmp_1[9];
+        m_mul(tmp_0, Un + 9*(size_t)s, tmp_4);               /* u[nu]*tmp_4 */
+        m_mul(tmp_1, Um + 9*(size_t)s, tmp_3);               /* u[mu]*tmp_3 */
+        m_mul_adj(F + 9*(size_t)s, tmp_1, tmp_0);            /* f = tmp_1*adj(tmp_0) */
+        m_adj_mul(t2 + 9*(size_t)s, tmp_0, tmp_1);           /* tmp_2 = adj(tmp_0)*tmp_1 */
+        cplx a[9], b[9];
+        m_mul_adj(a, tmp_4, tmp_3);                          /* tmp_1 = tmp_4*adj(tmp_3) */
+        m_adj_mul(b, Un + 9*(size_t)s, Um + 9*(size_t)s);    /* tmp_0 = adj(u[nu])*u[mu] */
+        m_mul_adj(t3 + 9*(size_t)s, b, a);                   /* tmp_0*adj(tmp_1) */
+        m_adj_mul(t4 + 9*(size_t)s, a, b);                   /* adj(tmp_1)*tmp_0 */
+      }
+#pragma omp parallel for
+      for (int s = 0; s < V; ++s) {
+        int sbn = g->bwd[4*s+nu], sbm = g->bwd[4*s+mu];
+        int sbnm = g->bwd[4*sbn+mu];                          /* shift(shift(.,BACKWARD,nu),BACKWARD,mu) */
+        cplx* Fs = F + 9*(size_t)s;
+        for (int k = 0; k < 9; ++k) {
+          Fs[k] = c_add(Fs[k], t2[9*(size_t)sbnm+k]);
+          Fs[k] = c_add(Fs[k], t3[9*(size_t)sbn+k]);
+          Fs[k] = c_add(Fs[k], t4[9*(size_t)sbm+k]);
+        }
+        cplx adjF[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) adjF[i*3+j] = c_conj(Fs[j*3+i]);
+        for (int k = 0; k < 9; ++k) { Fs[k] = c_sub(Fs[k], adjF[k]); Fs[k].re *= 0.125; Fs[k].im *= 0.125; }
+      }
+    }
+  free(t2); free(t3); free(t4);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Clover term: coefficients, makeClov, LDL^dag inverse, apply                 */
+/* ------------------------------------------------------------------------- */
+/* QDPCloverTermT::create, clover_term_qdp_w.h:263-278: clovCoeffR *= 0.5/xi_0 (aniso) or 0.5,
+ * clovCoeffT *= 0.5, diag_mass = 1 + (Nd-1)*(nu/xi_0 | 1) + Mass. out = {diag_mass, cR, cT}. */
+void orc_clover_coeffs(double Mass, double clovCoeffR, double clovCoeffT, int anisoP, double xi_0, double nu, double out[3]) {
+  double ff = anisoP ? 1.0/xi_0 : 1.0;
+  out[1] = clovCoeffR * 0.5 * ff;
+  out[2] = clovCoeffT * 0.5;
+  double fm = anisoP ? nu/xi_0 : 1.0;
+  out[0] = 1.0 + 3.0*fm + Mass;
+}
+
+/* makeFermCoeffs, lib/io/aniso_io.cc:63-80 */
+void orc_ferm_coeffs(int anisoP, int t_dir, double xi_0, double nu, double out[4]) {
+  for (int mu = 0; mu < 4; ++mu) out[mu] = (anisoP && mu != t_dir) ? nu/xi_0 : 1.0;
+}
+
+/* makeClov + makeClovSiteLoop, clover_term_qdp_w.h:398-553; getCloverCoeff :1524-1544.
+ * tri is [V][72]: diag[0][0..5], diag[1][0..5], offd[0][0..14][2], offd[1][0..14][2]. */
+void orc_make_clov(const orc_geom* g, const double* f, double diag_mass, double cR, double cT,
+                   int anisoP, int t_dir, double* tri) {
+  int V = g->V;
+  static const int pmu[6] = {0,0,0,1,1,2}, pnu[6] = {1,2,3,2,3,3};
+  double coef[6];
+  for (int k = 0; k < 6; ++k)
+    coef[k] = (anisoP && (pmu[k] == t_dir || pnu[k] == t_dir)) ? cT : cR;
+#pragma omp parallel for
+  for (int site = 0; site < V; ++site) {
+    cplx F[6][9];
+    for (int k = 0; k < 6; ++k) {
+      const cplx* fk = (const cplx*)(f + ((size_t)k*V + site)*LINK);
+      for (int e = 0; e < 9; ++e) { F[k][e].re = fk[e].re*coef[k]; F[k][e].im = fk[e].im*coef[k]; }
+    }
+    double* diag0 = tri + (size_t)site*CLOV;
+    double* diag1 = diag0 + 6;
+    cplx* offd0 = (cplx*)(diag0 + 12);
+    cplx* offd1 = offd0 + 15;
+    for (int i = 0; i < 6; ++i) { diag0[i] = diag_mass; diag1[i] = diag_mass; }
+    for (int i = 0; i < NC; ++i) {
+      cplx c0 = c_sub(F[5][i*3+i], F[0][i*3+i]);
+      diag0[i] += c0.im; diag0[i+NC] -= c0.im;
+      cplx c1 = c_add(F[5][i*3+i], F[0][i*3+i]);
+      diag1[i] -= c1.im; diag1[i+NC] += c1.im;
+    }
+    for (int i = 1; i < NC; ++i)
+      for (int j = 0; j < i; ++j) {
+        int eij = i*(i-1)/2 + j, etmp = (i+NC)*(i+NC-1)/2 + j + NC;
+        offd0[eij] = c_timesI(c_sub(F[0][i*3+j], F[5][i*3+j]));
+        offd0[etmp] = c_neg(offd0[eij]);
+        offd1[eij] = c_timesI(c_add(F[5][i*3+j], F[0][i*3+j]));
+        offd1[etmp] = c_neg(offd1[eij]);
+      }
+    for (int i = 0; i < NC; ++i)
+      for (int j = 0; j < NC; ++j) {
+        int eij = (i+NC)*(i+NC-1)/2 + j;
+        cplx E_minus = c_add(c_timesI(F[2][i*3+j]), F[4][i*3+j]);
+        cplx B_minus = c_sub(c_timesI(F[3][i*3+j]), F[1][i*3+j]);
+        offd0[eij] = c_sub(B_minus, E_minus);
+        offd1[eij] = c_add(E_minus, B_minus);
+      }
+  }
+}
+
+/* ldagdlinv / LDagDLInvSiteLoop, clover_term_qdp_w.h:619-846: in-place LDL^dag factorisation
+ * (Golub & van Loan alg. 4.1.2) and inversion of both 6x6 blocks on checkerboard cb.
+ * tr_log_diag (length V, may be NULL) receives sum log|d_i| on the sites touched. */
+void orc_ldagdlinv(const orc_geom* g, double* tri, int cb, double* tr_log_diag) {
+  int Vh = g->Vh;
+  const int N = 6;
+#pragma omp parallel for
+  for (int ss = 0; ss < Vh; ++ss) {
+    int site = cb*Vh + ss;
+    double tl = 0.0;
+    for (int block = 0; block < 2; ++block) {
+      double* d_ptr = tri + (size_t)site*CLOV + 6*block;
+      cplx* o_ptr = (cplx*)(tri + (size_t)site*CLOV + 12) + 15*block;
+      double inv_d[6], diag_g[6]; cplx inv_offd[15], v[6];
+      for (int i = 0; i < N; ++i) inv_d[i] = d_ptr[i];
+      for (int i = 0; i < 15; ++i) inv_offd[i] = o_ptr[i];
+      for (int j = 0; j < N; ++j) {
+        for (int i = 0; i < j; ++i) {
+          int eji = j*(j-1)/2 + i;
+          cplx Aii = { inv_d[i], 0.0 };
+          v[i] = c_mul(Aii, c_conj(inv_offd[eji]));
+        }
+        v[j].re = inv_d[j]; v[j].im = 0.0;
+        for (int k = 0; k < j; ++k) {
+          int ejk = j*(j-1)/2 + k;
+          v[j] = c_sub(v[j], c_mul(inv_offd[ejk], v[k]));
+        }
+        inv_d[j] = v[j].re;
+        for (int k = j+1; k < N; ++k) {
+          int ekj = k*(k-1)/2 + j;
+          for (int l = 0; l < j; ++l) {
+            int ekl = k*(k-1)/2 + l;
+            inv_offd[ekj] = c_sub(inv_offd[ekj], c_mul(inv_offd[ekl], v[l]));
+          }
+          inv_offd[ekj] = c_div(inv_offd[ekj], v[j]);
+        }
+      }
+      for (int i = 0; i < N; ++i) { diag_g[i] = 1.0/inv_d[i]; tl += log(fabs(inv_d[i])); }
+      for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < k; ++i) { v[i].re = 0; v[i].im = 0; }
+        v[k].re = diag_g[k]; v[k].im = 0.0;
+        for (int i = k+1; i < N; ++i) {
+          v[i].re = 0; v[i].im = 0;
+          for (int j = k; j < i; ++j) {
+            int eij = i*(i-1)/2 + j;
+            cplx dj = { inv_d[j], 0.0 };
+            v[i] = c_sub(v[i], c_mul(c_mul(inv_offd[eij], dj), v[j]));
+          }
+          v[i].re *= diag_g[i]; v[i].im *= diag_g[i];
+        }
+        for (int i = N-2; i >= k; --i)
+          for (int j = i+1; j < N; ++j) {
+            int eji = j*(j-1)/2 + i;
+            v[i] = c_sub(v[i], c_mul(c_conj(inv_offd[eji]), v[j]));
+          }
+        inv_d[k] = v[k].re;
+        for (int i = k+1; i < N; ++i) inv_offd[i*(i-1)/2 + k] = v[i];
+      }
+      for (int i = 0; i < N; ++i) d_ptr[i] = inv_d[i];
+      for (int i = 0; i < 15; ++i) o_ptr[i] = inv_offd[i];
+    }
+    if (tr_log_diag) tr_log_diag[site] = tl;
+  }
+}
+
+/* applySiteLoop, clover_term_qdp_w.h:1562-1634: chi = (L + D + L^dag) psi on checkerboard cb. */
+static inline void clover_site_apply(double* chi, const double* psi, const double* tri) {
+  const int n = 6;
+  cplx* cchi = (cplx*)chi; const cplx* ppsi = (const cplx*)psi;
+  const double* diag0 = tri; const double* diag1 = tri + 6;
+  const cplx* off0 = (const cplx*)(tri + 12); const cplx* off1 = off0 + 15;
+  cplx out[12];
+  for (int i = 0; i < n; ++i) {
+    out[i].re = diag0[i]*ppsi[i].re;     out[i].im = diag0[i]*ppsi[i].im;
+    out[n+i].re = diag1[i]*ppsi[n+i].re; out[n+i].im = diag1[i]*ppsi[n+i].im;
+  }
+  int kij = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) {
+      out[i]   = c_add(out[i],   c_mul(off0[kij], ppsi[j]));
+      out[j]   = c_add(out[j],   c_mul(c_conj(off0[kij]), ppsi[i]));
+      out[n+i] = c_add(out[n+i], c_mul(off1[kij], ppsi[n+j]));
+      out[n+j] = c_add(out[n+j], c_mul(c_conj(off1[kij]), ppsi[n+i]));
+      ++kij;
+    }
+  memcpy(cchi, out, sizeof(out));
+}
+
+void orc_clover_apply(const orc_geom* g, double* chi, const double* psi, const double* tri, int cb) {
+  int Vh = g->Vh;
+#pragma omp parallel for
+  for (int ss = 0; ss < Vh; ++ss) {
+    size_t site = (size_t)cb*Vh + ss;
+    clover_site_apply(chi + site*SPINOR, psi + site*SPINOR, tri + site*CLOV);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* EvenOddPrecCloverLinOp                                                      */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  orc_geom* g;
+  double* packed_u;   /* aniso-folded, transposed links */
+  double* clov;       /* A on both checkerboards */
+  double* invclov;    /* copy of A with cb 0 inverted (A_ee^-1) */
+  double* tmp1; double* tmp2;
+  double* tr_log_diag;
+} orc_op;
+
+/* EvenOddPrecCloverLinOp::create, eoprec_clover_linop_w.cc:19-39: clov.create (mesField +
+ * makeClov on the BC-modified links), invclov = copy, invclov.choles(0), D.create (aniso
+ * factors folded into the links, then packed).  u[] must already carry the fermion BC phases
+ * (state->getLinks()). */
+orc_op* orc_op_create(const int L[4], const double* const u[4], double Mass, double clovCoeffR,
+                      double clovCoeffT, int anisoP, int t_dir, double xi_0, double nu) {
+  orc_op* op = (orc_op*)calloc(1, sizeof(orc_op));
+  op->g = orc_geom_create(L);
+  size_t V = (size_t)op->g->V;
+  double cc[3], fc[4];
+  orc_clover_coeffs(Mass, clovCoeffR, clovCoeffT, anisoP, xi_0, nu, cc);
+  orc_ferm_coeffs(anisoP, t_dir, xi_0, nu, fc);
+  op->packed_u = (double*)malloc(sizeof(double)*V*4*LINK);
+  orc_pack_gauge(L, u, fc, op->packed_u);
+  double* f = (double*)malloc(sizeof(double)*6*V*LINK);
+  orc_mesfield(op->g, u, f);
+  op->clov = (double*)malloc(sizeof(double)*V*CLOV);
+  orc_make_clov(op->g, f, cc[0], cc[1], cc[2], anisoP, t_dir, op->clov);
+  free(f);
+  op->invclov = (double*)malloc(sizeof(double)*V*CLOV);
+  memcpy(op->invclov, op->clov, sizeof(double)*V*CLOV);
+  op->tr_log_diag = (double*)calloc(V, sizeof(double));
+  orc_ldagdlinv(op->g, op->invclov, 0, op->tr_log_diag);
+  op->tmp1 = (double*)calloc(V*SPINOR, sizeof(double));
+  op->tmp2 = (double*)calloc(V*SPINOR, sizeof(double));
+  return op;
+}
+void orc_op_free(orc_op* op) {
+  if (!op) return;
+  orc_geom_free(op->g); free(op->packed_u); free(op->clov); free(op->invclov);
+  free(op->tmp1); free(op->tmp2); free(op->tr_log_diag); free(op);
+}
+const double* orc_op_clov(const orc_op* op) { return op->clov; }
+const double* orc_op_invclov(const orc_op* op) { return op->invclov; }
+const double* orc_op_packed_gauge(const orc_op* op) { return op->packed_u; }
+const orc_geom* orc_op_geom(const orc_op* op) { return op->g; }
+
+/* D.apply(chi, psi, isign, cb): cb is the TARGET checkerboard here, the library call gets
+ * source_cb = 1-cb (lwldslash_w_cppd.cc:196-205). */
+void orc_op_dslash(const orc_op* op, double* chi, const double* psi, int isign, int cb) {
+  orc_dslash(op->g, chi, psi, op->packed_u, isign, 1 - cb);
+}
+
+/* EvenOddPrecCloverLinOp::operator(), eoprec_clover_linop_w.cc:142-187 (no twisted mass):
+ * tmp1 = D_eo psi; tmp2 = A_ee^-1 tmp1; tmp1 = D_oe tmp2; chi = A_oo psi; chi -= 1/4 tmp1.
+ * Fields are full-lattice arrays; only the odd half of chi is written. */
+void orc_op_apply(orc_op* op, double* chi, const double* psi, int isign) {
+  int Vh = op->g->Vh;
+  orc_op_dslash(op, op->tmp1, psi, isign, 0);
+  orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 0);
+  orc_op_dslash(op, op->tmp1, op->tmp2, isign, 1);
+  orc_clover_apply(op->g, chi, psi, op->clov, 1);
+  double* c = chi + (size_t)Vh*SPINOR; const double* t = op->tmp1 + (size_t)Vh*SPINOR;
+  size_t n = (size_t)Vh*SPINOR;
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) c[i] += -0.25*t[i];
+}
+
+/* ------------------------------------------------------------------------- */
+/* Subset BLAS on rb[1] (odd half of a full-lattice array)                     */
+/* ------------------------------------------------------------------------- */
+static double norm2_odd(const orc_geom* g, const double* x) {
+  size_t n = (size_t)g->Vh*SPINOR; const double* p = x + n; double s = 0;
+#pragma omp parallel for reduction(+:s)
+  for (size_t i = 0; i < n; ++i) s += p[i]*p[i];
+  return s;
+}
+static cplx inner_odd(const orc_geom* g, const double* x, const double* y) {  /* <x|y> = sum conj(x) y */
+  size_t n = (size_t)g->Vh*12; const cplx* a = (const cplx*)x + n; const cplx* b = (const cplx*)y + n;
+  double sr = 0, si = 0;
+#pragma omp parallel for reduction(+:sr,si)
+  for (size_t i = 0; i < n; ++i) { sr += a[i].re*b[i].re + a[i].im*b[i].im; si += a[i].re*b[i].im - a[i].im*b[i].re; }
+  cplx r = { sr, si }; return r;
+}
+double orc_norm2_odd(const orc_geom* g, const double* x) { return norm2_odd(g, x); }
+void orc_inner_odd(const orc_geom* g, const double* x, const double* y, double out[2]) {
+  cplx r = inner_odd(g, x, y); out[0] = r.re; out[1] = r.im;
+}
+
+/* ------------------------------------------------------------------------- */
+/* InvCG2_a, lib/actions/ferm/invert/invcg2.cc:70-232                          */
+/* ------------------------------------------------------------------------- */
+/* Solves (M^dag M) psi = chi on rb[1]. Returns n_count; *resid as the reference sets it.
+ * max_iter_timing: if >0, never tests convergence (used for fixed-iteration CPU timing). */
+int orc_invcg2(orc_op* op, const double* chi, double* psi, double RsdCG, int MaxCG, double* resid) {
+  const orc_geom* g = op->g;
+  size_t V = (size_t)g->V, n = (size_t)g->Vh*SPINOR, off = n;
+  double* mp = (double*)calloc(V*SPINOR, sizeof(double));
+  double* mmp = (double*)calloc(V*SPINOR, sizeof(double));
+  double* p = (double*)calloc(V*SPINOR, sizeof(double));
+  double* r = (double*)calloc(V*SPINOR, sizeof(double));
+  int n_count = MaxCG;
+  double chi_sq = norm2_odd(g, chi);
+  double rsd_sq = (RsdCG*RsdCG)*chi_sq;
+  orc_op_apply(op, mp, psi, +1);
+  orc_op_apply(op, mmp, mp, -1);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) r[off+i] = chi[off+i] - mmp[off+i];
+  double cp = norm2_odd(g, r);
+  memcpy(p + off, r + off, n*sizeof(double));
+  if (cp <= rsd_sq) { *resid = sqrt(cp); n_count = 0; goto done; }
+  {
+    double a, b, c, d;
+    int k;
+    for (k = 1; k <= MaxCG; ++k) {
+      c = cp;
+      orc_op_apply(op, mp, p, +1);
+      d = norm2_odd(g, mp);
+      orc_op_apply(op, mmp, mp, -1);
+      a = c/d;
+#pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) r[off+i] -= a*mmp[off+i];
+      cp = norm2_odd(g, r);
+#pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) psi[off+i] += a*p[off+i];
+      if (cp <= rsd_sq) {
+        n_count = k;
+        orc_op_apply(op, mp, psi, +1);
+        orc_op_apply(op, mmp, mp, -1);
+        double s = 0;
+#pragma omp parallel for reduction(+:s)
+        for (size_t i = 0; i < n; ++i) { double t = chi[off+i] - mmp[off+i]; s += t*t; }
+        *resid = sqrt(s);
+        goto done;
+      }
+      b = cp/c;
+#pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) p[off+i] = r[off+i] + b*p[off+i];
+    }
+    n_count = MaxCG; *resid = sqrt(cp);
+  }
+done:
+  free(mp); free(mmp); free(p); free(r);
+  return n_count;
+}
+
+/* LinOpSysSolverCG::operator(), syssolver_linop_cg.h:57-96: chi_tmp = M^dag chi; InvCG2;
+ * resid = |chi - M psi|.  Returns n_count; out[0] = resid, out[1] = relative resid. */
+int orc_solve_cg(orc_op* op, const double* chi, double* psi, double RsdCG, int MaxCG, double out[2]) {
+  const orc_geom* g = op->g;
+  size_t V = (size_t)g->V, n = (size_t)g->Vh*SPINOR, off = n;
+  double* chi_tmp = (double*)calloc(V*SPINOR, sizeof(double));
+  double dummy;
+  orc_op_apply(op, chi_tmp, chi, -1);
+  int n_count = orc_invcg2(op, chi_tmp, psi, RsdCG, MaxCG, &dummy);
+  orc_op_apply(op, chi_tmp, psi, +1);
+  double s = 0;
+#pragma omp parallel for reduction(+:s)
+  for (size_t i = 0; i < n; ++i) { double t = chi[off+i] - chi_tmp[off+i]; s += t*t; }
+  out[0] = sqrt(s); out[1] = out[0]/sqrt(norm2_odd(g, chi));
+  free(chi_tmp);
+  return n_count;
+}
+
+/* ------------------------------------------------------------------------- */
+/* InvBiCGStab_a, lib/actions/ferm/invert/invbicgstab.cc:10-202                */
+/* ------------------------------------------------------------------------- */
+/* Returns n_count (MaxBiCGStab if not converged), -1 on breakdown (the reference aborts). */
+int orc_invbicgstab(orc_op* op, const double* chi, double* psi, double Rsd, int MaxIter, int isign, double* resid) {
+  const orc_geom* g = op->g;
+  size_t V = (size_t)g->V, n = (size_t)g->Vh*12, off = n;
+  cplx* r  = (cplx*)calloc(V*12, sizeof(cplx));
+  cplx* r0 = (cplx*)calloc(V*12, sizeof(cplx));
+  cplx* p  = (cplx*)calloc(V*12, sizeof(cplx));
+  cplx* v  = (cplx*)calloc(V*12, sizeof(cplx));
+  cplx* t  = (cplx*)calloc(V*12, sizeof(cplx));
+  cplx* ps = (cplx*)psi; const cplx* ch = (const cplx*)chi;
+  int n_count = MaxIter; int convP = 0;
+  *resid = 0.0;
+  double chi_sq = norm2_odd(g, chi);
+  double rsd_sq = Rsd*Rsd*chi_sq;
+  orc_op_apply(op, (double*)r0, psi, isign);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) { r[off+i] = c_sub(ch[off+i], r0[off+i]); r0[off+i] = r[off+i]; }
+  cplx rho, rho_prev = {1,0}, alpha = {1,0}, omega = {1,0};
+  for (int k = 1; k <= MaxIter && !convP; ++k) {
+    rho = inner_odd(g, (double*)r0, (double*)r);
+    if (rho.re == 0 && rho.im == 0) { n_count = -1; break; }
+    cplx beta = c_mul(c_div(rho, rho_prev), c_div(alpha, omega));
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) {
+      cplx tmp = c_sub(p[off+i], c_mul(omega, v[off+i]));
+      p[off+i] = c_add(r[off+i], c_mul(beta, tmp));
+    }
+    orc_op_apply(op, (double*)v, (double*)p, isign);
+    cplx ctmp = inner_odd(g, (double*)r0, (double*)v);
+    if (ctmp.re == 0 && ctmp.im == 0) { n_count = -1; break; }
+    alpha = c_div(rho, ctmp);
+    rho_prev = rho;
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) r[off+i] = c_sub(r[off+i], c_mul(alpha, v[off+i]));
+    orc_op_apply(op, (double*)t, (double*)r, isign);
+    double t_norm = norm2_odd(g, (double*)t);
+    if (t_norm == 0) { n_count = -1; break; }
+    omega = inner_odd(g, (double*)t, (double*)r);
+    omega.re /= t_norm; omega.im /= t_norm;
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) {
+      cplx tmp = c_add(ps[off+i], c_mul(omega, r[off+i]));
+      ps[off+i] = c_add(tmp, c_mul(alpha, p[off+i]));
+      r[off+i] = c_sub(r[off+i], c_mul(omega, t[off+i]));
+    }
+    double r_norm = norm2_odd(g, (double*)r);
+    if (r_norm < rsd_sq) { convP = 1; *resid = sqrt(r_norm); n_count = k; }
+  }
+  free(r); free(r0); free(p); free(v); free(t);
+  return n_count;
+}
+
+/* LinOpSysSolverBiCGStab::operator(), syssolver_linop_bicgstab.h:57-95 */
+int orc_solve_bicgstab(orc_op* op, const double* chi, double* psi, double Rsd, int MaxIter, double out[2]) {
+  const orc_geom* g = op->g;
+  size_t V = (size_t)g->V, n = (size_t)g->Vh*SPINOR, off = n;
+  double dummy;
+  int n_count = orc_invbicgstab(op, chi, psi, Rsd, MaxIter, +1, &dummy);
+  double* tmp = (double*)calloc(V*SPINOR, sizeof(double));
+  orc_op_apply(op, tmp, psi, +1);
+  double s = 0;
+#pragma omp parallel for reduction(+:s)
+  for (size_t i = 0; i < n; ++i) { double t = chi[off+i] - tmp[off+i]; s += t*t; }
+  out[0] = sqrt(s); out[1] = out[0]/sqrt(norm2_odd(g, chi));
+  free(tmp);
+  return n_count;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Full-lattice source preparation / solution reconstruction                   */
+/* (lib/actions/ferm/qprop/eoprec_fermact_qprop.cc:41-80) -- "next" row (f1)    */
+/* ------------------------------------------------------------------------- */
+/* chi'_o = chi_o - D_oe A_ee^-1 chi_e  (the caller's unprec operator carries the -1/2 on D:
+ * evenOddLinOp = -1/2 D_eo, eoprec_clover_linop_w.cc:98-133) */
+void orc_qprop_prepare(orc_op* op, double* chi_prime, const double* chi) {
+  int Vh = op->g->Vh; size_t n = (size_t)Vh*SPINOR;
+  orc_clover_apply(op->g, op->tmp1, chi, op->invclov, 0);
+  orc_op_dslash(op, op->tmp2, op->tmp1, +1, 1);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) chi_prime[n+i] = chi[n+i] + 0.5*op->tmp2[n+i];
+}
+/* psi_e = A_ee^-1 (chi_e - D_eo psi_o), with D_eo = -1/2 Dslash */
+void orc_qprop_reconstruct(orc_op* op, double* psi, const double* chi) {
+  int Vh = op->g->Vh; size_t n = (size_t)Vh*SPINOR;
+  orc_op_dslash(op, op->tmp1, psi, +1, 0);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) op->tmp2[i] = chi[i] + 0.5*op->tmp1[i];
+  orc_clover_apply(op->g, psi, op->tmp2, op->invclov, 0);
+}
+/* Unpreconditioned operator on the full lattice: (A - 1/2 D) psi
+ * (lib/eoprec_linop.h unprecLinOp: chi_e = A_ee psi_e + D_eo psi_o etc.) */
+void orc_unprec_apply(orc_op* op, double* chi, const double* psi, int isign) {
+  size_t n = (size_t)op->g->V*SPINOR;
+  orc_clover_apply(op->g, chi, psi, op->clov, 0);
+  orc_clover_apply(op->g, chi, psi, op->clov, 1);
+  orc_op_dslash(op, op->tmp1, psi, isign, 0);
+  orc_op_dslash(op, op->tmp1, psi, isign, 1);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) chi[i] -= 0.5*op->tmp1[i];
+}

@@ -1,0 +1,311 @@
+"""ctypes/numpy front-end of the CPU oracle (oracle/oracle.c) and of the reference build (oracle/_ref).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / reference arm.  Nothing under chroma_b200/ imports this module.
+
+Array conventions (QDP++ order):
+  spinor  float64[V, 4, 3, 2]      gauge  float64[4, V, 3, 3, 2]      clover  float64[V, 72]
+  site index = cb2: cb*Vh + ((t*Lz+z)*Ly+y)*(Lx/2) + x/2
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+c_int4 = C.c_int * 4
+c_dbl_p = C.POINTER(C.c_double)
+c_flt_p = C.POINTER(C.c_float)
+
+
+def build(force=False):
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) or \
+            os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < os.path.getmtime(os.path.join(_HERE, "oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/other_libs/cpp_wilson_dslash/lib"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def _p(a):
+    return a.ctypes.data_as(c_dbl_p)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        L.orc_geom_create.restype = C.c_void_p
+        L.orc_op_create.restype = C.c_void_p
+        L.orc_op_geom.restype = C.c_void_p
+        L.orc_op_clov.restype = c_dbl_p
+        L.orc_op_invclov.restype = c_dbl_p
+        L.orc_op_packed_gauge.restype = c_dbl_p
+        L.orc_norm2_odd.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def have_ref():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_dslash.so"))
+
+
+def ref():
+    """The reference's own Dslash<double|float> / CloverSchur4D<double> (oracle/_ref/libref_dslash.so)."""
+    global _REF
+    if _REF is None:
+        R = C.CDLL(os.path.join(_HERE, "_ref", "libref_dslash.so"))
+        for n in ("ref_dslash_create_d", "ref_dslash_create_f", "ref_clover_create_d"):
+            getattr(R, n).restype = C.c_void_p
+        _REF = R
+    return _REF
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def site_index(L, c):
+    return lib().orc_site_index(c_int4(*L), c_int4(*c))
+
+
+def site_coords_all(L):
+    """int array [V,4] of (x,y,z,t) for every cb2 site index (vectorised restatement of orc_site_coords)."""
+    Lx, Ly, Lz, Lt = L
+    V = Lx * Ly * Lz * Lt
+    Vh, Lxh = V // 2, Lx // 2
+    idx = np.arange(V)
+    cb, r = idx // Vh, idx % Vh
+    xh = r % Lxh
+    r //= Lxh
+    y = r % Ly
+    r //= Ly
+    z = r % Lz
+    t = r // Lz
+    x = 2 * xh + ((cb + y + z + t) & 1)
+    return np.stack([x, y, z, t], axis=1)
+
+
+class Geom:
+    def __init__(self, L):
+        self.L = tuple(L)
+        self.V = int(np.prod(L))
+        self.Vh = self.V // 2
+        self.h = C.c_void_p(lib().orc_geom_create(c_int4(*L)))
+
+    def __del__(self):
+        try:
+            lib().orc_geom_free(self.h)
+        except Exception:
+            pass
+
+
+def apply_fermbc(L, u, boundary):
+    u = np.ascontiguousarray(u, dtype=np.float64).copy()
+    ptrs = (c_dbl_p * 4)(*[_p(u[m]) for m in range(4)])
+    lib().orc_apply_fermbc(c_int4(*L), ptrs, c_int4(*boundary))
+    return u
+
+
+def pack_gauge(L, u, coeffs=(1.0, 1.0, 1.0, 1.0)):
+    V = int(np.prod(L))
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty((V, 4, 3, 3, 2), dtype=np.float64)
+    ptrs = (c_dbl_p * 4)(*[_p(u[m]) for m in range(4)])
+    lib().orc_pack_gauge(c_int4(*L), ptrs, (C.c_double * 4)(*coeffs), _p(out))
+    return out
+
+
+def dslash(geom, psi, packed_u, isign, source_cb):
+    """Restated Dslash<double>::operator(): writes the (1-source_cb) half, other half zero."""
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    res = np.zeros_like(psi)
+    lib().orc_dslash(geom.h, _p(res), _p(psi), _p(packed_u), C.c_int(isign), C.c_int(source_cb))
+    return res
+
+
+def mesfield(geom, u):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    f = np.empty((6, geom.V, 3, 3, 2), dtype=np.float64)
+    ptrs = (c_dbl_p * 4)(*[_p(u[m]) for m in range(4)])
+    lib().orc_mesfield(geom.h, ptrs, _p(f))
+    return f
+
+
+def clover_coeffs(Mass, clovCoeffR, clovCoeffT, anisoP=False, xi_0=1.0, nu=1.0):
+    out = (C.c_double * 3)()
+    lib().orc_clover_coeffs(C.c_double(Mass), C.c_double(clovCoeffR), C.c_double(clovCoeffT), C.c_int(int(anisoP)),
+                            C.c_double(xi_0), C.c_double(nu), out)
+    return tuple(out)
+
+
+def make_clov(geom, f, diag_mass, cR, cT, anisoP=False, t_dir=3):
+    tri = np.empty((geom.V, 72), dtype=np.float64)
+    lib().orc_make_clov(geom.h, _p(f), C.c_double(diag_mass), C.c_double(cR), C.c_double(cT), C.c_int(int(anisoP)),
+                        C.c_int(t_dir), _p(tri))
+    return tri
+
+
+def ldagdlinv(geom, tri, cb):
+    out = np.ascontiguousarray(tri, dtype=np.float64).copy()
+    trlog = np.zeros(geom.V, dtype=np.float64)
+    lib().orc_ldagdlinv(geom.h, _p(out), C.c_int(cb), _p(trlog))
+    return out, trlog
+
+
+def clover_apply(geom, psi, tri, cb):
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    chi = np.zeros_like(psi)
+    lib().orc_clover_apply(geom.h, _p(chi), _p(psi), _p(tri), C.c_int(cb))
+    return chi
+
+
+def norm2_odd(geom, x):
+    return lib().orc_norm2_odd(geom.h, _p(np.ascontiguousarray(x)))
+
+
+class Op:
+    """Restated EvenOddPrecCloverLinOp (eoprec_clover_linop_w.cc:19-39, 142-187).
+    u: float64[4,V,3,3,2] links WITH fermion boundary phases already applied."""
+
+    def __init__(self, L, u, Mass, clovCoeffR, clovCoeffT=None, anisoP=False, t_dir=3, xi_0=1.0, nu=1.0):
+        if clovCoeffT is None:
+            clovCoeffT = clovCoeffR
+        self.L = tuple(L)
+        self.V = int(np.prod(L))
+        self.Vh = self.V // 2
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        ptrs = (c_dbl_p * 4)(*[_p(u[m]) for m in range(4)])
+        self.h = C.c_void_p(lib().orc_op_create(c_int4(*L), ptrs, C.c_double(Mass), C.c_double(clovCoeffR),
+                                                C.c_double(clovCoeffT), C.c_int(int(anisoP)), C.c_int(t_dir),
+                                                C.c_double(xi_0), C.c_double(nu)))
+        self.geom_h = C.c_void_p(lib().orc_op_geom(self.h))
+
+    def __del__(self):
+        try:
+            lib().orc_op_free(self.h)
+        except Exception:
+            pass
+
+    def _arr(self, ptr, shape):
+        return np.ctypeslib.as_array(ptr, shape=shape)
+
+    @property
+    def clov(self):
+        return self._arr(lib().orc_op_clov(self.h), (self.V, 72))
+
+    @property
+    def invclov(self):
+        return self._arr(lib().orc_op_invclov(self.h), (self.V, 72))
+
+    @property
+    def packed_gauge(self):
+        return self._arr(lib().orc_op_packed_gauge(self.h), (self.V, 4, 3, 3, 2))
+
+    def dslash(self, psi, isign, target_cb):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        chi = np.zeros_like(psi)
+        lib().orc_op_dslash(self.h, _p(chi), _p(psi), C.c_int(isign), C.c_int(target_cb))
+        return chi
+
+    def apply(self, psi, isign=+1):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        chi = np.zeros_like(psi)
+        lib().orc_op_apply(self.h, _p(chi), _p(psi), C.c_int(isign))
+        return chi
+
+    def unprec_apply(self, psi, isign=+1):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        chi = np.zeros_like(psi)
+        lib().orc_unprec_apply(self.h, _p(chi), _p(psi), C.c_int(isign))
+        return chi
+
+    def qprop_prepare(self, chi):
+        chi = np.ascontiguousarray(chi, dtype=np.float64)
+        out = np.zeros_like(chi)
+        lib().orc_qprop_prepare(self.h, _p(out), _p(chi))
+        return out
+
+    def qprop_reconstruct(self, psi, chi):
+        psi = np.ascontiguousarray(psi, dtype=np.float64).copy()
+        lib().orc_qprop_reconstruct(self.h, _p(psi), _p(np.ascontiguousarray(chi)))
+        return psi
+
+    def invcg2(self, chi, psi0, rsd, maxit):
+        psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+        resid = C.c_double()
+        n = lib().orc_invcg2(self.h, _p(np.ascontiguousarray(chi)), _p(psi), C.c_double(rsd), C.c_int(maxit), C.byref(resid))
+        return psi, n, resid.value
+
+    def solve_cg(self, chi, psi0, rsd, maxit):
+        psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+        out = (C.c_double * 2)()
+        n = lib().orc_solve_cg(self.h, _p(np.ascontiguousarray(chi)), _p(psi), C.c_double(rsd), C.c_int(maxit), out)
+        return psi, n, out[0], out[1]
+
+    def solve_bicgstab(self, chi, psi0, rsd, maxit):
+        psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+        out = (C.c_double * 2)()
+        n = lib().orc_solve_bicgstab(self.h, _p(np.ascontiguousarray(chi)), _p(psi), C.c_double(rsd), C.c_int(maxit), out)
+        return psi, n, out[0], out[1]
+
+
+# --------------------------------------------------------------------------- reference build
+class RefDslash:
+    """Reference CPlusPlusWilsonDslash::Dslash<double|float> (cpp_dslash_scalar.h:20-105)."""
+
+    def __init__(self, L, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        self.sfx = "d" if self.dtype == np.float64 else "f"
+        self.h = C.c_void_p(getattr(ref(), "ref_dslash_create_" + self.sfx)(c_int4(*L)))
+
+    def __call__(self, psi, packed_u, isign, source_cb):
+        psi = np.ascontiguousarray(psi, dtype=self.dtype)
+        u = np.ascontiguousarray(packed_u, dtype=self.dtype)
+        res = np.zeros_like(psi)
+        getattr(ref(), "ref_dslash_apply_" + self.sfx)(self.h, C.c_void_p(res.ctypes.data), C.c_void_p(psi.ctypes.data),
+                                                        C.c_void_p(u.ctypes.data), C.c_int(isign), C.c_int(source_cb))
+        return res
+
+    def __del__(self):
+        try:
+            getattr(ref(), "ref_dslash_free_" + self.sfx)(self.h)
+        except Exception:
+            pass
+
+
+def tri_to_ref_clover(tri):
+    """Chroma PrimitiveClovTriang [V,72] -> cpp_clover CloverTerm [V,2,{diag[8],off_diag[16][2]}] (80 reals),
+    same k = i(i-1)/2+j order (cpp_clover_types.h:8-27)."""
+    V = tri.shape[0]
+    out = np.zeros((V, 2, 40), dtype=tri.dtype)
+    for b in range(2):
+        out[:, b, 0:6] = tri[:, 6 * b:6 * b + 6]
+        out[:, b, 8:38] = tri[:, 12 + 30 * b:12 + 30 * b + 30]
+    return out
+
+
+class RefCloverSchur:
+    """Reference CPlusPlusClover::CloverSchur4D<double> (cpp_clover_scalar.h). Run with OMP_NUM_THREADS=1
+    (its two site loops are not separated by a barrier)."""
+
+    def __init__(self, L):
+        self.h = C.c_void_p(ref().ref_clover_create_d(c_int4(*L)))
+
+    def __call__(self, psi, packed_u, clov80, invclov80, isign):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        res = np.zeros_like(psi)
+        ref().ref_clover_apply_d(self.h, _p(res), _p(psi), _p(np.ascontiguousarray(packed_u)),
+                                 _p(np.ascontiguousarray(clov80)), _p(np.ascontiguousarray(invclov80)), C.c_int(isign))
+        return res
+
+    def __del__(self):
+        try:
+            ref().ref_clover_free_d(self.h)
+        except Exception:
+            pass
