@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): <= 1e-13 relative per site in fp64, <= 1e-6 in fp32, for the hopping term, the clover
+apply / inverse and the full even-odd operator; solvers reach the same target residual with iteration counts within a
+few percent of the CPU restatement of InvCG2 / InvBiCGStab.  Procedure mirrors the reference's own differential tests
+(other_libs/cpp_wilson_dslash/tests/testDslashFull.cc:70-97, mainprogs/tests/t_lwldslash_sse.cc:217-241,
+mainprogs/tests/symm_prec_tests.cc:210-249).
+"""
+import numpy as np
+import pytest
+
+from chroma_b200 import fields
+from chroma_b200 import lib as L
+from chroma_b200.solver import (CloverFermActParams, AnisoParam, Context, LinOpSysSolverB200Clover, SolverFailure,
+                                SysSolverB200CloverParams)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-13, "single": 1e-6}
+NP = {"double": np.float64, "single": np.float32}
+LATTICES = [(4, 4, 4, 8), (6, 4, 2, 4), (8, 8, 8, 8), (16, 8, 8, 12)]
+
+
+def rel_site_err(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(a.shape[0], -1)
+    b = np.asarray(b, dtype=np.float64).reshape(b.shape[0], -1)
+    nb = np.linalg.norm(b, axis=1)
+    m = nb > 0
+    return float((np.linalg.norm(a - b, axis=1)[m] / nb[m]).max())
+
+
+def setup(oracle, latt, prec="double", gauge="random", recon=L.B200_RECONS_NONE, aniso=False, bc=(1, 1, 1, -1), gpu_clover=False):
+    u = fields.random_gauge(latt, seed=11) if gauge == "random" else fields.weak_gauge(latt, seed=11)
+    u = fields.apply_bc(latt, u, bc)
+    an = dict(anisoP=True, t_dir=3, xi_0=2.464, nu=0.95) if aniso else {}
+    cR, cT = (0.91, 1.07) if aniso else (1.0, 1.0)
+    op = oracle.Op(latt, u, 0.1, cR, cT, **an)
+    cp = CloverFermActParams(Mass=0.1, clovCoeffR=cR, clovCoeffT=cT, anisoParam=AnisoParam(**an))
+    ctx = Context(latt, prec=prec)
+    ctx.load_gauge(u.astype(NP[prec]) if prec == "single" else u, aniso_coeff=cp.ferm_coeffs(), t_boundary=bc[3], reconstruct=recon)
+    if gpu_clover:
+        ctx.make_clover(*cp.derived(), aniso=aniso, t_dir=3)
+    else:
+        ctx.load_clover(op.clov.copy(), op.invclov.copy())
+    return u, op, ctx, cp
+
+
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("latt", LATTICES)
+def test_dslash_parity(oracle, latt, prec):
+    u, op, ctx, _ = setup(oracle, latt, prec)
+    psi = fields.gaussian_fermion(latt, seed=12)
+    Vh = ctx.Vh
+    for isign in (+1, -1):
+        for out_cb in (0, 1):
+            want = op.dslash(psi, isign, out_cb)[out_cb * Vh:(out_cb + 1) * Vh]
+            src = psi[(1 - out_cb) * Vh:(2 - out_cb) * Vh].astype(NP[prec])
+            got = ctx.dslash(src, isign, out_cb)
+            assert rel_site_err(got, want) < TOL[prec], (isign, out_cb)
+    ctx.close()
+
+
+@pytest.mark.parametrize("recon", [L.B200_RECONS_NONE, L.B200_RECONS_12])
+@pytest.mark.parametrize("aniso", [False, True])
+def test_dslash_parity_aniso_recon(oracle, recon, aniso):
+    latt = (8, 4, 4, 8)
+    u, op, ctx, _ = setup(oracle, latt, "double", recon=recon, aniso=aniso)
+    psi = fields.gaussian_fermion(latt, seed=12)
+    Vh = ctx.Vh
+    for isign in (+1, -1):
+        for out_cb in (0, 1):
+            want = op.dslash(psi, isign, out_cb)[out_cb * Vh:(out_cb + 1) * Vh]
+            got = ctx.dslash(psi[(1 - out_cb) * Vh:(2 - out_cb) * Vh], isign, out_cb)
+            assert rel_site_err(got, want) < 2e-13, (isign, out_cb)
+    ctx.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "single"])
+def test_clover_apply_and_inverse_parity(oracle, prec):
+    latt = (8, 4, 4, 8)
+    u, op, ctx, _ = setup(oracle, latt, prec)
+    g = oracle.Geom(latt)
+    psi = fields.gaussian_fermion(latt, seed=14)
+    Vh = ctx.Vh
+    for cb in (0, 1):
+        want = oracle.clover_apply(g, psi, op.clov, cb)[cb * Vh:(cb + 1) * Vh]
+        got = ctx.clover_apply(psi[cb * Vh:(cb + 1) * Vh].astype(NP[prec]), cb, inverse=False)
+        assert rel_site_err(got, want) < TOL[prec]
+    want = oracle.clover_apply(g, psi, op.invclov, 0)[:Vh]
+    got = ctx.clover_apply(psi[:Vh].astype(NP[prec]), 0, inverse=True)
+    assert rel_site_err(got, want) < TOL[prec]
+    with pytest.raises(L.B200Error):
+        ctx.clover_apply(psi[Vh:].astype(NP[prec]), 1, inverse=True)     # only the cb-0 inverse exists
+    ctx.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("latt", LATTICES)
+def test_matpc_parity(oracle, latt, prec):
+    """M and M^dagger against EvenOddPrecCloverLinOp::operator() restated (eoprec_clover_linop_w.cc:142-187)."""
+    u, op, ctx, _ = setup(oracle, latt, prec)
+    psi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    for isign in (+1, -1):
+        want = op.apply(psi, isign)[Vh:]
+        got = ctx.matpc(psi[Vh:].astype(NP[prec]), isign)
+        # the operator has a 4.1-ish diagonal and O(8) hopping part: same per-site criterion
+        assert rel_site_err(got, want) < 2 * TOL[prec], isign
+    ctx.close()
+
+
+def test_matpc_parity_aniso_recon12(oracle):
+    latt = (8, 4, 4, 8)
+    u, op, ctx, _ = setup(oracle, latt, "double", recon=L.B200_RECONS_12, aniso=True)
+    psi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    for isign in (+1, -1):
+        assert rel_site_err(ctx.matpc(psi[Vh:], isign), op.apply(psi, isign)[Vh:]) < 3e-13
+    ctx.close()
+
+
+@pytest.mark.parametrize("recon", [L.B200_RECONS_NONE, L.B200_RECONS_12])
+@pytest.mark.parametrize("aniso", [False, True])
+def test_gpu_built_clover_matches_restated_build(oracle, recon, aniso):
+    """b200_make_clover (field strength + makeClov + LDL^dagger inverse on the GPU) against the restated
+    mesField / makeClov / ldagdlinv (mesfield.cc:44-74, clover_term_qdp_w.h:416-519, 636-815)."""
+    latt = (6, 4, 4, 8)
+    u, op, ctx, cp = setup(oracle, latt, "double", recon=recon, aniso=aniso, gpu_clover=True)
+    clov, inv = ctx.get_clover()
+    assert np.abs(clov - op.clov).max() < 1e-13
+    assert np.abs(inv - op.invclov[:ctx.Vh]).max() < 1e-12
+    g = oracle.Geom(latt)
+    _, trlog = oracle.ldagdlinv(g, op.clov, 0)
+    assert abs(ctx.clover_logdet() - trlog[:ctx.Vh].sum()) < 1e-9 * abs(trlog.sum())
+    ctx.close()
+
+
+def test_device_fields_norm_inner_hermiticity(oracle):
+    """Device-resident interface + <chi, M psi> = <M^dag chi, psi> on the GPU (t_precact_4d.cc:83-104)."""
+    latt = (8, 8, 4, 4)
+    u, op, ctx, _ = setup(oracle, latt, "double")
+    Vh = ctx.Vh
+    a = fields.gaussian_fermion(latt, seed=20)[Vh:]
+    b = fields.gaussian_fermion(latt, seed=21)[Vh:]
+    fa, fb, fm, fn = ctx.field(a), ctx.field(b), ctx.field(), ctx.field()
+    assert np.array_equal(fa.download(), a)                     # AoS -> SoA -> AoS round trip is exact
+    assert abs(ctx.dev_norm2(fa) - np.sum(a * a)) < 1e-12 * np.sum(a * a)
+    ca, cb_ = a[..., 0] + 1j * a[..., 1], b[..., 0] + 1j * b[..., 1]
+    assert abs(ctx.dev_inner(fa, fb) - np.vdot(ca, cb_)) < 1e-11 * abs(np.vdot(ca, cb_))
+    ctx.dev_matpc(fm, fb, +1)
+    ctx.dev_matpc(fn, fa, -1)
+    lhs, rhs = ctx.dev_inner(fa, fm), ctx.dev_inner(fn, fb)
+    assert abs(lhs - rhs) < 1e-11 * abs(lhs)
+    ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["CG", "BICGSTAB"])
+@pytest.mark.parametrize("prec,rsd", [("double", 1e-8), ("single", 1e-5)])
+def test_solver_matches_cpu_restatement(oracle, solver, prec, rsd):
+    """BASELINE configs[0] on the GPU: 8^4 weak field, Mass 0.1, clovCoeff 1, antiperiodic T.  Same target residual;
+    iteration count within a few percent of InvCG2_a / InvBiCGStab_a restated on the CPU."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, prec, gauge="weak")
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    if solver == "CG":
+        psi_ref, n_ref, resid_ref, rel_ref = op.solve_cg(chi, np.zeros_like(chi), rsd, 2000)
+        code = L.B200_SOLVER_CG
+    else:
+        psi_ref, n_ref, resid_ref, rel_ref = op.solve_bicgstab(chi, np.zeros_like(chi), rsd, 2000)
+        code = L.B200_SOLVER_BICGSTAB
+    psi, info = ctx.invert(chi[Vh:].astype(NP[prec]), None, solver=code, rsd=rsd, max_iter=2000)
+    assert info.converged == 1
+    assert abs(info.n_count - n_ref) <= max(2, 0.05 * n_ref), (info.n_count, n_ref)
+    # true residual, recomputed with the CPU operator
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - op.apply(full, +1)
+    rel = np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(chi[Vh:] ** 2))
+    assert rel < (10 * rsd if prec == "double" else 50 * rsd)
+    if prec == "double":
+        assert abs(info.rel_resid - rel) < 1e-3 * rel + 1e-14
+        assert rel_site_err(psi, psi_ref[Vh:]) < 1e-6         # both solve to 1e-8: solutions agree to ~cond * 1e-8
+    ctx.close()
+
+
+def test_plugin_mirror_drop_in(oracle):
+    """LinOpSysSolverB200Clover used the way quarkprop4_w.cc:86-109 uses a LinOpSystemSolver: XML-like params in,
+    (psi, chi) -> {n_count, resid}; GPU-built clover; non-convergence raises unless SilentFail (.h:634-644)."""
+    latt = (8, 8, 8, 8)
+    u = fields.apply_bc(latt, fields.weak_gauge(latt, seed=11))
+    op = oracle.Op(latt, u, 0.1, 1.0)
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = chi.shape[0] // 2
+    p = SysSolverB200CloverParams(CloverParams=CloverFermActParams(Mass=0.1, clovCoeffR=1.0, clovCoeffT=1.0),
+                                  RsdTarget=1e-8, MaxIter=1000, SolverType="BICGSTAB", AntiPeriodicT=True)
+    S = LinOpSysSolverB200Clover(latt, u, p)
+    psi = np.zeros((Vh, 4, 3, 2))
+    res = S(psi, chi[Vh:])
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - op.apply(full, +1)
+    assert np.sqrt(np.sum(r[Vh:] ** 2)) == pytest.approx(res.resid, rel=1e-3)
+    assert res.resid / np.sqrt(np.sum(chi[Vh:] ** 2)) < 1e-7 and res.n_count > 0
+    S.close()
+    p2 = SysSolverB200CloverParams(CloverParams=p.CloverParams, RsdTarget=1e-10, MaxIter=3, SolverType="CG")
+    S2 = LinOpSysSolverB200Clover(latt, u, p2)
+    with pytest.raises(SolverFailure):
+        S2(np.zeros((Vh, 4, 3, 2)), chi[Vh:])
+    p2.SilentFail = True
+    assert S2(np.zeros((Vh, 4, 3, 2)), chi[Vh:]).n_count == 3
+    S2.close()
+
+
+def test_qprop_full_lattice(oracle):
+    """12 spin-colour point sources through b200_qprop == the unpreconditioned system solved (eoprec_fermact_qprop.cc:41-80)."""
+    latt = (4, 4, 4, 8)
+    u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
+    srcs = np.stack([fields.point_source(latt, s, c) for s in range(4) for c in range(3)])
+    sol, infos = ctx.qprop(srcs, solver=L.B200_SOLVER_CG, rsd=1e-10, max_iter=500)
+    for i in range(12):
+        r = op.unprec_apply(sol[i], +1) - srcs[i]
+        assert np.linalg.norm(r) / np.linalg.norm(srcs[i]) < 1e-8
+        assert infos[i].converged == 1
+    ctx.close()
+
+
+def test_error_behaviour():
+    """Bad arguments fail loudly with a code and a message (no exceptions cross the C ABI)."""
+    lib = L.load()
+    with pytest.raises(L.B200Error) as e:
+        Context((5, 4, 4, 4))                       # odd global extent (shift_table_scalar.cc:23-28)
+    assert e.value.code == L.B200_ERR_ARG
+    ctx = Context((4, 4, 4, 4))
+    f = ctx.field()
+    g2 = ctx.field()
+    with pytest.raises(L.B200Error) as e:
+        ctx.dev_dslash(f, g2, +1, 0)                # gauge not loaded
+    assert e.value.code == L.B200_ERR_STATE
+    u = fields.unit_gauge((4, 4, 4, 4))
+    ctx.load_gauge(u)
+    with pytest.raises(L.B200Error) as e:
+        ctx.dev_matpc(f, g2, +1)                    # clover not loaded
+    assert e.value.code == L.B200_ERR_STATE
+    with pytest.raises(L.B200Error) as e:
+        ctx.dev_dslash(f, g2, 0, 0)                 # isign must be +-1
+    assert e.value.code == L.B200_ERR_ARG
+    ctx.close()
