@@ -108,6 +108,7 @@ int b200_field_zero(b200_ctx* ctx, b200_field* f) { CHECK_CTX(ctx); if (!f) { se
 int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb) { CHECK_CTX(ctx); return ctx->eng->dslash(out, in, isign, out_cb); }
 int b200_dev_clover_apply(b200_ctx* ctx, b200_field* out, const b200_field* in, int cb, int inverse) { CHECK_CTX(ctx); return ctx->eng->clover_apply(out, in, cb, inverse); }
 int b200_dev_clover_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign) { CHECK_CTX(ctx); return ctx->eng->matpc(out, in, isign); }
+int b200_dev_time_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) { CHECK_CTX(ctx); if (!ms) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->time_matpc(out, in, isign, reps, ms); }
 int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* r) { CHECK_CTX(ctx); if (!x || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->norm2(x, r); }
 int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double r[2]) { CHECK_CTX(ctx); if (!x || !y || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->inner(x, y, r); }
 int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) {

@@ -61,6 +61,7 @@ class EngineBase {
   virtual int dslash(b200_field* out, const b200_field* in, int isign, int out_cb) = 0;
   virtual int clover_apply(b200_field* out, const b200_field* in, int cb, int inverse) = 0;
   virtual int matpc(b200_field* out, const b200_field* in, int isign) = 0;
+  virtual int time_matpc(b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) = 0;
   virtual int norm2(const b200_field* x, double* r) = 0;
   virtual int inner(const b200_field* x, const b200_field* y, double r[2]) = 0;
   virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) = 0;

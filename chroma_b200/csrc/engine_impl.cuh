@@ -413,6 +413,36 @@ class Engine : public EngineBase {
     return apply_M((C*)out->d, (const C*)in->d, isign, EPI_M, nullptr, nullptr, 0, 0);
   }
 
+  int time_matpc(b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = ready(); if (rc) return rc;
+    if ((isign != 1 && isign != -1) || !out || !in || out == in || reps < 1) { set_error("b200_dev_time_matpc: bad argument"); return B200_ERR_ARG; }
+    if (g.tsplit) { set_error("b200_dev_time_matpc: single-GPU measurement only"); return B200_ERR_ARG; }
+    rc = need_ws(1); if (rc) return rc;
+    cudaEvent_t e[3];
+    for (auto& x : e) B200_CUDA(cudaEventCreate(&x));
+    double acc[2] = {0, 0};
+    for (int i = 0; i < reps; ++i) {
+      DslashArgs<R> a{};
+      a.in = (const C*)in->d; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign;
+      DslashArgs<R> b{};
+      b.in = W(0); b.out = (C*)out->d; b.clov = clov + (size_t)36 * g.Vh; b.x = (const C*)in->d; b.parity = 1; b.isign = isign;
+      B200_CUDA(cudaEventRecord(e[0], stream));
+      rc = launch_dslash<EPI_AINV>(a); if (rc) return rc;
+      B200_CUDA(cudaEventRecord(e[1], stream));
+      rc = launch_dslash<EPI_M>(b); if (rc) return rc;
+      B200_CUDA(cudaEventRecord(e[2], stream));
+      B200_CUDA(cudaEventSynchronize(e[2]));
+      float t0 = 0, t1 = 0;
+      B200_CUDA(cudaEventElapsedTime(&t0, e[0], e[1]));
+      B200_CUDA(cudaEventElapsedTime(&t1, e[1], e[2]));
+      acc[0] += t0; acc[1] += t1;
+    }
+    for (auto& x : e) cudaEventDestroy(x);
+    ms[0] = acc[0] / reps; ms[1] = acc[1] / reps;
+    return B200_OK;
+  }
+
   int fetch_scalars() {
     B200_CUDA(cudaMemcpyAsync(h_scal, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));

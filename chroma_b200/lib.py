@@ -69,6 +69,7 @@ SYMBOLS = {
     "b200_dev_dslash": (_i, [_vp, _vp, _vp, _i, _i]),
     "b200_dev_clover_apply": (_i, [_vp, _vp, _vp, _i, _i]),
     "b200_dev_clover_matpc": (_i, [_vp, _vp, _vp, _i]),
+    "b200_dev_time_matpc": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_d)]),
     "b200_dev_norm2": (_i, [_vp, _vp, C.POINTER(_d)]),
     "b200_dev_inner": (_i, [_vp, _vp, _vp, C.POINTER(_d)]),
     "b200_dev_invert": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),

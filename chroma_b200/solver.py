@@ -173,6 +173,11 @@ class Context:
     def dev_matpc(self, out, inp, isign=+1):
         L.check(self.lib.b200_dev_clover_matpc(self.h, out.h, inp.h, int(isign)))
 
+    def dev_time_matpc(self, out, inp, isign=+1, reps=10):
+        ms = (C.c_double * 2)()
+        L.check(self.lib.b200_dev_time_matpc(self.h, out.h, inp.h, int(isign), int(reps), ms))
+        return ms[0], ms[1]
+
     def dev_norm2(self, x):
         r = C.c_double()
         L.check(self.lib.b200_dev_norm2(self.h, x.h, C.byref(r)))

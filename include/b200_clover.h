@@ -164,6 +164,11 @@ int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int s
 int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver);
 int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter);
 
+/* Measurement aid: run M (isign) `reps` times and return the average device time in milliseconds of each of its
+ * two kernels separately (CUDA events around every launch): ms[0] = fused A_ee^-1 D_eo, ms[1] = fused
+ * A_oo x - 1/4 D_oe t.  Used by bench.py for the roofline line. */
+int b200_dev_time_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int reps, double ms[2]);
+
 /* ---- plumbing -------------------------------------------------------------------------------- */
 void* b200_stream(b200_ctx* ctx);              /* cudaStream_t the engine launches on (for event timing) */
 int b200_sync(b200_ctx* ctx);

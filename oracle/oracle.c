@@ -745,3 +745,71 @@ void orc_unprec_apply(orc_op* op, double* chi, const double* psi, int isign) {
 #pragma omp parallel for
   for (size_t i = 0; i < n; ++i) chi[i] -= 0.5*op->tmp1[i];
 }
+
+/* ------------------------------------------------------------------------- */
+/* CPU baseline support (bench.py): optional hook that routes the hopping term */
+/* through the reference's own Dslash<double> (oracle/_ref), and a fixed-count  */
+/* CG loop timer.                                                              */
+/* ------------------------------------------------------------------------- */
+typedef void (*orc_dslash_hook_fn)(void* handle, double* res, double* psi, double* packed_u, int isign, int source_cb);
+static orc_dslash_hook_fn g_hook = 0;
+static void* g_hook_handle = 0;
+void orc_set_dslash_hook(orc_dslash_hook_fn fn, void* handle) { g_hook = fn; g_hook_handle = handle; }
+
+static void bench_dslash(orc_op* op, double* chi, const double* psi, int isign, int cb) {
+  if (g_hook) g_hook(g_hook_handle, chi, (double*)psi, op->packed_u, isign, 1 - cb);
+  else orc_op_dslash(op, chi, psi, isign, cb);
+}
+static void bench_apply(orc_op* op, double* chi, const double* psi, int isign) {
+  int Vh = op->g->Vh;
+  bench_dslash(op, op->tmp1, psi, isign, 0);
+  orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 0);
+  bench_dslash(op, op->tmp1, op->tmp2, isign, 1);
+  orc_clover_apply(op->g, chi, psi, op->clov, 1);
+  double* c = chi + (size_t)Vh*SPINOR; const double* t = op->tmp1 + (size_t)Vh*SPINOR;
+  size_t n = (size_t)Vh*SPINOR;
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) c[i] += -0.25*t[i];
+}
+
+/* n_warm untimed + n_timed timed iterations of the InvCG2_a loop body (invcg2.cc:158-220), convergence test off.
+ * Also times n_timed applications of M alone.  out = {secs per CG iteration, secs per M apply}. */
+void orc_cg_bench(orc_op* op, const double* chi, int n_warm, int n_timed, double out[2]) {
+  const orc_geom* g = op->g;
+  size_t V = (size_t)g->V, n = (size_t)g->Vh*SPINOR, off = n;
+  double* mp = (double*)calloc(V*SPINOR, sizeof(double));
+  double* mmp = (double*)calloc(V*SPINOR, sizeof(double));
+  double* p = (double*)calloc(V*SPINOR, sizeof(double));
+  double* r = (double*)calloc(V*SPINOR, sizeof(double));
+  double* psi = (double*)calloc(V*SPINOR, sizeof(double));
+  memcpy(r + off, chi + off, n*sizeof(double));
+  memcpy(p + off, chi + off, n*sizeof(double));
+  double cp = norm2_odd(g, r), t0 = 0.0;
+  for (int k = 0; k < n_warm + n_timed; ++k) {
+#ifdef _OPENMP
+    if (k == n_warm) t0 = omp_get_wtime();
+#endif
+    double c = cp;
+    bench_apply(op, mp, p, +1);
+    double d = norm2_odd(g, mp);
+    bench_apply(op, mmp, mp, -1);
+    double a = c/d;
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) r[off+i] -= a*mmp[off+i];
+    cp = norm2_odd(g, r);
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) psi[off+i] += a*p[off+i];
+    double b = cp/c;
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) p[off+i] = r[off+i] + b*p[off+i];
+  }
+#ifdef _OPENMP
+  out[0] = (omp_get_wtime() - t0)/n_timed;
+  t0 = omp_get_wtime();
+  for (int k = 0; k < n_timed; ++k) bench_apply(op, mp, p, +1);
+  out[1] = (omp_get_wtime() - t0)/n_timed;
+#else
+  out[0] = out[1] = 0.0;
+#endif
+  free(mp); free(mmp); free(p); free(r); free(psi);
+}

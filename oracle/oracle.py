@@ -309,3 +309,23 @@ class RefCloverSchur:
             ref().ref_clover_free_d(self.h)
         except Exception:
             pass
+
+
+def cg_bench(op, chi, n_warm, n_timed, use_reference_dslash=True):
+    """Seconds per CG iteration / per M apply on the host cores (bench.py's CPU arm).  With use_reference_dslash the
+    hopping term is the reference's own Dslash<double> from oracle/_ref; clover apply and BLAS are the restatement
+    (they live in QDP++-dependent files that cannot be compiled here)."""
+    kind = "port"
+    keep = None
+    if use_reference_dslash and have_ref():
+        rd = RefDslash(op.L, np.float64)
+        fn = ref().ref_dslash_apply_d
+        lib().orc_set_dslash_hook(C.cast(fn, C.c_void_p), rd.h)
+        kind, keep = "reference", rd
+    else:
+        lib().orc_set_dslash_hook(None, None)
+    out = (C.c_double * 2)()
+    lib().orc_cg_bench(op.h, _p(np.ascontiguousarray(chi)), C.c_int(n_warm), C.c_int(n_timed), out)
+    lib().orc_set_dslash_hook(None, None)
+    del keep
+    return out[0], out[1], kind
