@@ -17,6 +17,10 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++",
 ]
+# tuning knobs (defaults live in the sources): B200_DSLASH_BLOCK, B200_DSLASH_MINBLOCKS
+for _k in ("B200_DSLASH_BLOCK", "B200_DSLASH_MINBLOCKS"):
+    if os.environ.get(_k):
+        FLAGS += ["-D%s=%s" % (_k, os.environ[_k])]
 
 
 def _newest_source_mtime():

@@ -24,6 +24,58 @@ template <typename R> __host__ __device__ __forceinline__ Cx<R> mk(R x, R y) { C
 __device__ __forceinline__ double2 ldg(const double2* p) { return __ldg(p); }
 __device__ __forceinline__ float2 ldg(const float2* p) { return __ldg(p); }
 
+// ---- L2 residency control -------------------------------------------------------------------------
+// One time slice of gauge + clover + output streams ~117 MB through the 126 MB L2 at 48^3 (fp64) while the
+// neighbour spinors of that slice (10.6 MB) are re-read up to 8 times over three slices.  Streams are therefore
+// loaded/stored with an evict-first policy (and no L1 allocation), neighbour spinors with evict-last, so that the
+// re-reads are served by L2 instead of HBM (ncu: 13% excess DRAM reads without this).
+// sm_100 only takes the direct .L2::evict_* qualifiers on 256-bit accesses; 128/64-bit ones need a createpolicy
+// descriptor + .L2::cache_hint.
+struct L2Policy { uint64_t keep, stream; };
+__device__ __forceinline__ L2Policy make_l2_policy() {
+  L2Policy p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  return p;
+}
+__device__ __forceinline__ double2 ld_keep(const double2* p, uint64_t pol) {
+  double2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_keep(const float2* p, uint64_t pol) {
+  float2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p, uint64_t pol) {
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p, uint64_t pol) {
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+// read-modify-write streams (the CG residual) must not use the non-coherent path
+__device__ __forceinline__ double2 ld_stream_rw(const double2* p, uint64_t pol) {
+  double2 v;
+  asm("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_stream_rw(const float2* p, uint64_t pol) {
+  float2 v;
+  asm("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_stream(double2* p, double2 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_stream(float2* p, float2 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+
 // complex helpers (all on Cx<R>)
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }

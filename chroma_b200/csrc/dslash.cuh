@@ -53,13 +53,13 @@ struct DslashArgs {
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
 template <typename R, int MU>
-__device__ __forceinline__ void load_project(Cx<R> h0[3], Cx<R> h1[3], const Cx<R>* __restrict__ p, int stride, R sg) {
+__device__ __forceinline__ void load_project(Cx<R> h0[3], Cx<R> h1[3], const Cx<R>* __restrict__ p, int stride, R sg, uint64_t keep) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const Cx<R> a0 = ldg(p + (0 * 3 + c) * (size_t)stride);
-    const Cx<R> a1 = ldg(p + (1 * 3 + c) * (size_t)stride);
-    const Cx<R> a2 = ldg(p + (2 * 3 + c) * (size_t)stride);
-    const Cx<R> a3 = ldg(p + (3 * 3 + c) * (size_t)stride);
+    const Cx<R> a0 = ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a1 = ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a2 = ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a3 = ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
     if (MU == 0) {          // h0 = a0 + sg*i*a3, h1 = a1 + sg*i*a2
       h0[c] = mk<R>(a0.x - sg * a3.y, a0.y + sg * a3.x);
       h1[c] = mk<R>(a1.x - sg * a2.y, a1.y + sg * a2.x);
@@ -101,10 +101,10 @@ __device__ __forceinline__ void recons_acc(Cx<R> acc[12], const Cx<R> r0[3], con
 
 // ---- link load (18 reals, or 12 + third-row reconstruction) --------------------------------------
 template <typename R, bool RECON12>
-__device__ __forceinline__ void load_link(Cx<R> U[9], const Cx<R>* __restrict__ p, int stride) {
+__device__ __forceinline__ void load_link(Cx<R> U[9], const Cx<R>* __restrict__ p, int stride, uint64_t strm) {
   constexpr int NG = RECON12 ? 6 : 9;
 #pragma unroll
-  for (int k = 0; k < NG; ++k) U[k] = ldg(p + k * (size_t)stride);
+  for (int k = 0; k < NG; ++k) U[k] = ld_stream(p + k * (size_t)stride, strm);
   if (RECON12) {
     // row2 = conj(row0 x row1): exact for SU(3); non-unit factors (anisotropy, -1 boundary phase)
     // are carried separately by the caller (see load_gauge in api.cu).
@@ -134,10 +134,10 @@ __device__ __forceinline__ void su3_mul(Cx<R> r0[3], Cx<R> r1[3], const Cx<R> U[
 // One hop: acc += recons( U(or U^dag) * project(psi_nbr) ).
 template <typename R, int MU, bool ADJ, bool RECON12>
 __device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi_nbr, const Cx<R>* __restrict__ link,
-                                    int stride, R sg, R scale) {
+                                    int stride, R sg, R scale, const L2Policy& pol) {
   Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
-  load_project<R, MU>(h0, h1, psi_nbr, stride, sg);
-  load_link<R, RECON12>(U, link, stride);
+  load_project<R, MU>(h0, h1, psi_nbr, stride, sg, pol.keep);
+  load_link<R, RECON12>(U, link, stride, pol.stream);
   if (RECON12) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
@@ -155,7 +155,7 @@ struct LinkScale {
 
 // The Wilson hopping term for one target site.  (xh,y,z,t) are its checkerboard coordinates.
 template <typename R, bool RECON12>
-__device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx) {
+__device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol) {
   typedef Cx<R> C;
   const Geom& g = a.g;
   const int stride = g.Vh;
@@ -181,21 +181,21 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
   {
     const int xf = r ? (xh + 1 == g.Lxh ? idx - (g.Lxh - 1) : idx + 1) : idx;
     const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
-    hop<R, 0, false, RECON12>(acc, in + xf, Uf + 0 * gmu, stride, -s, (R)ls.aniso[0]);
-    hop<R, 0, true, RECON12>(acc, in + xb, Ub + 0 * gmu + xb, stride, s, (R)ls.aniso[0]);
+    hop<R, 0, false, RECON12>(acc, in + xf, Uf + 0 * gmu, stride, -s, (R)ls.aniso[0], pol);
+    hop<R, 0, true, RECON12>(acc, in + xb, Ub + 0 * gmu + xb, stride, s, (R)ls.aniso[0], pol);
   }
   {
     const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
     const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
-    hop<R, 1, false, RECON12>(acc, in + yf, Uf + 1 * gmu, stride, -s, (R)ls.aniso[1]);
-    hop<R, 1, true, RECON12>(acc, in + yb, Ub + 1 * gmu + yb, stride, s, (R)ls.aniso[1]);
+    hop<R, 1, false, RECON12>(acc, in + yf, Uf + 1 * gmu, stride, -s, (R)ls.aniso[1], pol);
+    hop<R, 1, true, RECON12>(acc, in + yb, Ub + 1 * gmu + yb, stride, s, (R)ls.aniso[1], pol);
   }
   {
     const int sz = g.Ly * g.Lxh;
     const int zf = (z + 1 == g.Lz) ? idx - (g.Lz - 1) * sz : idx + sz;
     const int zb = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
-    hop<R, 2, false, RECON12>(acc, in + zf, Uf + 2 * gmu, stride, -s, (R)ls.aniso[2]);
-    hop<R, 2, true, RECON12>(acc, in + zb, Ub + 2 * gmu + zb, stride, s, (R)ls.aniso[2]);
+    hop<R, 2, false, RECON12>(acc, in + zf, Uf + 2 * gmu, stride, -s, (R)ls.aniso[2], pol);
+    hop<R, 2, true, RECON12>(acc, in + zb, Ub + 2 * gmu + zb, stride, s, (R)ls.aniso[2], pol);
   }
   {
     const int st = g.S3h;
@@ -213,8 +213,8 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       C h0[3], h1[3], U[9], r0[3], r1[3];
       const C* __restrict__ gp = a.ghost_fwd + (idx - (g.Lt - 1) * st);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { h0[c] = ldg(gp + (size_t)c * st); h1[c] = ldg(gp + (size_t)(3 + c) * st); }
-      load_link<R, RECON12>(U, Uf + 3 * gmu, stride);
+      for (int c = 0; c < 3; ++c) { h0[c] = ld_stream(gp + (size_t)c * st, pol.stream); h1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
+      load_link<R, RECON12>(U, Uf + 3 * gmu, stride, pol.stream);
       if (RECON12) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { h0[c].x *= scf; h0[c].y *= scf; h1[c].x *= scf; h1[c].y *= scf; }
@@ -222,17 +222,17 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       su3_mul<R, false>(r0, r1, U, h0, h1);
       recons_acc<R, 3>(acc, r0, r1, -s);
     } else {
-      hop<R, 3, false, RECON12>(acc, in + tf, Uf + 3 * gmu, stride, -s, scf);
+      hop<R, 3, false, RECON12>(acc, in + tf, Uf + 3 * gmu, stride, -s, scf, pol);
     }
     if (g.tsplit && first) {
       // U^dag (1 +/- g3) psi computed by the -t neighbour rank (it owns that link): just reconstruct
       C r0[3], r1[3];
       const C* __restrict__ gp = a.ghost_bwd + idx;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { r0[c] = ldg(gp + (size_t)c * st); r1[c] = ldg(gp + (size_t)(3 + c) * st); }
+      for (int c = 0; c < 3; ++c) { r0[c] = ld_stream(gp + (size_t)c * st, pol.stream); r1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
       recons_acc<R, 3>(acc, r0, r1, s);
     } else {
-      hop<R, 3, true, RECON12>(acc, in + tb, Ub + 3 * gmu + tb, stride, s, scb);
+      hop<R, 3, true, RECON12>(acc, in + tb, Ub + 3 * gmu + tb, stride, s, scb, pol);
     }
   }
 }
@@ -241,8 +241,8 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
 // out[i] = d_i in[i] + sum_{j<i} o_{k(i,j)} in[j] + sum_{j>i} conj(o_{k(j,i)}) in[j], k = i(i-1)/2+j
 // (applySiteLoop, clover_term_qdp_w.h:1606-1634).  cl points at plane 0 of the block for this site.
 template <typename R>
-__device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], const Cx<R>* __restrict__ cl, int stride) {
-  const Cx<R> d01 = ldg(cl), d23 = ldg(cl + (size_t)stride), d45 = ldg(cl + 2 * (size_t)stride);
+__device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], const Cx<R>* __restrict__ cl, int stride, uint64_t strm) {
+  const Cx<R> d01 = ld_stream(cl, strm), d23 = ld_stream(cl + (size_t)stride, strm), d45 = ld_stream(cl + 2 * (size_t)stride, strm);
   out[0] = mk<R>(d01.x * in[0].x, d01.x * in[0].y);
   out[1] = mk<R>(d01.y * in[1].x, d01.y * in[1].y);
   out[2] = mk<R>(d23.x * in[2].x, d23.x * in[2].y);
@@ -254,7 +254,7 @@ __device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], co
   for (int i = 1; i < 6; ++i) {
 #pragma unroll
     for (int j = 0; j < i; ++j) {
-      const Cx<R> o = ldg(cl + (size_t)(3 + k) * stride);
+      const Cx<R> o = ld_stream(cl + (size_t)(3 + k) * stride, strm);
       cmac(out[i], o, in[j]);
       cmac_conj(out[j], o, in[i]);
       ++k;
@@ -299,8 +299,11 @@ struct FinBiOmega {
   }
 };
 
+#ifndef B200_DSLASH_MINBLOCKS
+#define B200_DSLASH_MINBLOCKS 1
+#endif
 template <typename R, int EPI, bool RECON12, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
+__global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
   typedef Cx<R> C;
   if (a.check_stop && a.status[ST_STOP] != 0) return;
   const int stride = a.g.Vh;
@@ -310,54 +313,71 @@ __global__ void __launch_bounds__(BLOCK) dslash_kernel(const DslashArgs<R> a, co
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {
+    const L2Policy pol = make_l2_policy();
     C acc[12];
-    dslash_site<R, RECON12>(acc, a, ls, idx);
+    dslash_site<R, RECON12>(acc, a, ls, idx, pol);
 
     if (EPI == EPI_DSLASH) {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) a.out[(size_t)k * stride + idx] = acc[k];
+      for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, acc[k], pol.stream);
     } else if (EPI == EPI_AINV) {
+      C o[12];
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        C o[6];
-        clover_block<R>(o, acc + 6 * b, a.clov + (size_t)(18 * b) * stride + idx, stride);
+      for (int b = 0; b < 2; ++b) clover_block<R>(o + 6 * b, acc + 6 * b, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) a.out[(size_t)(6 * b + k) * stride + idx] = o[k];
-      }
+      for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, o[k], pol.stream);
     } else {
-      // all EPI_M* variants: m = A x - 1/4 D in
-      R cg_a = 0;
-      if (EPI == EPI_M_CG) cg_a = (R)a.scal[S_A];
+      // all EPI_M* variants: m = A x - 1/4 D in.  Every load is issued before the first store (the stores are
+      // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
+      // and would cost one exposed DRAM round trip each.
+      C m[12], ex[12];
+      if (EPI == EPI_M_CG) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ex[k] = ld_stream_rw(a.r + (size_t)k * stride + idx, pol.stream);
+      }
+      if (EPI == EPI_M_DOTR0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ex[k] = ld_stream(a.r0 + (size_t)k * stride + idx, pol.stream);
+      }
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         C xi[6], o[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) xi[k] = ldg(a.x + (size_t)(6 * b + k) * stride + idx);
-        clover_block<R>(o, xi, a.clov + (size_t)(18 * b) * stride + idx, stride);
+        for (int k = 0; k < 6; ++k) xi[k] = ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
+        clover_block<R>(o, xi, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-          C m = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
-          const size_t off = (size_t)(6 * b + k) * stride + idx;
-          if (EPI == EPI_M_CG) {
-            C rv = a.r[off];
-            rv.x -= cg_a * m.x; rv.y -= cg_a * m.y;
-            a.r[off] = rv;
-            red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
-          } else {
-            a.out[off] = m;
-            if (EPI == EPI_M_NORM) red[0] += (double)m.x * m.x + (double)m.y * m.y;
-            if (EPI == EPI_M_DOTR0) {
-              const C q = ldg(a.r0 + off);
-              red[0] += (double)q.x * m.x + (double)q.y * m.y;   // <r0|m> = conj(r0) m
-              red[1] += (double)q.x * m.y - (double)q.y * m.x;
-            }
-            if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
-              red[0] += (double)m.x * xi[k].x + (double)m.y * xi[k].y;
-              red[1] += (double)m.x * xi[k].y - (double)m.y * xi[k].x;
-              red[2] += (double)m.x * m.x + (double)m.y * m.y;
-            }
+          m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
+          if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
+            const C mm = m[6 * b + k];
+            red[0] += (double)mm.x * xi[k].x + (double)mm.y * xi[k].y;
+            red[1] += (double)mm.x * xi[k].y - (double)mm.y * xi[k].x;
+            red[2] += (double)mm.x * mm.x + (double)mm.y * mm.y;
           }
         }
+      }
+      if (EPI == EPI_M_CG) {
+        const R cg_a = (R)a.scal[S_A];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          C rv = ex[k];
+          rv.x -= cg_a * m[k].x; rv.y -= cg_a * m[k].y;
+          red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+          m[k] = rv;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st_stream(a.r + (size_t)k * stride + idx, m[k], pol.stream);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          if (EPI == EPI_M_NORM) red[0] += (double)m[k].x * m[k].x + (double)m[k].y * m[k].y;
+          if (EPI == EPI_M_DOTR0) {                             // <r0|m> = conj(r0) m
+            red[0] += (double)ex[k].x * m[k].x + (double)ex[k].y * m[k].y;
+            red[1] += (double)ex[k].x * m[k].y - (double)ex[k].y * m[k].x;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, m[k], pol.stream);
       }
     }
   }

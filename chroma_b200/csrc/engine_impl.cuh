@@ -12,7 +12,10 @@
 
 namespace b200 {
 
-constexpr int DSLASH_BLOCK = 128;
+#ifndef B200_DSLASH_BLOCK
+#define B200_DSLASH_BLOCK 128
+#endif
+constexpr int DSLASH_BLOCK = B200_DSLASH_BLOCK;
 constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
 constexpr size_t STAGING_BYTES = 256u << 20;
 
@@ -26,7 +29,7 @@ __global__ void __launch_bounds__(BLOCK) clover_kernel(const Cx<R>* __restrict__
     Cx<R> xi[6], o[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) xi[k] = ldg(in + (size_t)(6 * b + k) * Vh + idx);
-    clover_block<R>(o, xi, clov + (size_t)(18 * b) * Vh + idx, Vh);
+    clover_block<R>(o, xi, clov + (size_t)(18 * b) * Vh + idx, Vh, make_l2_policy().stream);
 #pragma unroll
     for (int k = 0; k < 6; ++k) out[(size_t)(6 * b + k) * Vh + idx] = o[k];
   }
