@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(BLAS_BLOCK) cg_update_kernel(Cx<R>* __restrict
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) bicg_p_kernel(Cx<R>* __restrict__ p, const Cx<R>* __restrict__ r,
                                                            const Cx<R>* __restrict__ v, size_t n, BlasCtl c) {
-  if (c.check_stop && c.status[ST_STOP] != 0) return;
+  if (c.check_stop && (c.status[ST_STOP] != 0 || c.status[ST_BREAKDOWN] != 0)) return;
   const Cx<R> beta = mk<R>((R)c.scal[S_BETA_RE], (R)c.scal[S_BETA_IM]);
   const Cx<R> omega = mk<R>((R)c.scal[S_OMEGA_RE], (R)c.scal[S_OMEGA_IM]);
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(BLAS_BLOCK) bicg_p_kernel(Cx<R>* __restrict__ 
 // invbicgstab.cc:122
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) bicg_s_kernel(Cx<R>* __restrict__ r, const Cx<R>* __restrict__ v, size_t n, BlasCtl c) {
-  if (c.check_stop && c.status[ST_STOP] != 0) return;
+  if (c.check_stop && (c.status[ST_STOP] != 0 || c.status[ST_BREAKDOWN] != 0)) return;
   const Cx<R> alpha = mk<R>((R)c.scal[S_ALPHA_RE], (R)c.scal[S_ALPHA_IM]);
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK)
     r[i] = csub(r[i], cmul(alpha, v[i]));
@@ -94,7 +94,7 @@ template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) bicg_update_kernel(Cx<R>* __restrict__ psi, Cx<R>* __restrict__ r,
                                                                 const Cx<R>* __restrict__ p, const Cx<R>* __restrict__ t,
                                                                 const Cx<R>* __restrict__ r0, size_t n, BlasCtl c) {
-  if (c.check_stop && c.status[ST_STOP] != 0) return;
+  if (c.check_stop && (c.status[ST_STOP] != 0 || c.status[ST_BREAKDOWN] != 0)) return;
   const Cx<R> alpha = mk<R>((R)c.scal[S_ALPHA_RE], (R)c.scal[S_ALPHA_IM]);
   const Cx<R> omega = mk<R>((R)c.scal[S_OMEGA_RE], (R)c.scal[S_OMEGA_IM]);
   double red[3] = {0.0, 0.0, 0.0};
@@ -138,8 +138,7 @@ __global__ void __launch_bounds__(BLAS_BLOCK) inner_kernel(const Cx<R>* __restri
 
 // out = x - y ; optional copies of out into out2 ; |out|^2 -> dst   (r = chi - A psi ; p = r / r0 = r)
 template <typename R>
-__global__ void __launch_bounds__(BLAS_BLOCK) xmy_norm_kernel(Cx<R>* __restrict__ out, Cx<R>* __restrict__ out2,
-                                                             const Cx<R>* __restrict__ x, const Cx<R>* __restrict__ y, size_t n,
+__global__ void __launch_bounds__(BLAS_BLOCK) xmy_norm_kernel(Cx<R>* out, Cx<R>* out2, const Cx<R>* x, const Cx<R>* y, size_t n,
                                                              ReduceBuf red, double* dst) {
   double s[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {

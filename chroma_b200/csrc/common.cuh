@@ -109,8 +109,11 @@ enum ScalarSlot {
 // Integer status block
 enum StatusSlot {
   ST_STOP = 0,      // 0 while iterating; else the iteration at which the recurrence residual converged
-  ST_BREAKDOWN,     // BiCGStab breakdown code (1 rho=0, 2 <r0|v>=0, 3 |t|=0)
+  ST_BREAKDOWN,     // BiCGStab breakdown code (1 rho=0, 2 <r0|v>=0, 3 |t|=0); 90/91 = peer wait timed out (halo / reduction)
   ST_COUNT = 8
 };
+
+// Spin-wait budget for peer flags (SM clock cycles, ~5 s): a lost peer must not hang the GPU forever.
+constexpr long long PEER_SPIN_CYCLES = 10000000000LL;
 
 }  // namespace b200

@@ -47,6 +47,8 @@ struct DslashArgs {
   int isign;        // +1: D, -1: D^dagger
   int idx_begin;    // first target site of this launch
   int idx_count;    // number of target sites of this launch
+  int idx_begin2;   // optional second range (both boundary time slices in one launch) ...
+  int idx_count2;   // ... of this many sites
   int iter;         // solver iteration this launch belongs to (for the stop flag)
   int check_stop;   // 1: return immediately if status[ST_STOP] != 0
 };
@@ -305,11 +307,11 @@ struct FinBiOmega {
 template <typename R, int EPI, bool RECON12, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
   typedef Cx<R> C;
-  if (a.check_stop && a.status[ST_STOP] != 0) return;
+  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
   const int stride = a.g.Vh;
   const int local = blockIdx.x * BLOCK + threadIdx.x;
-  const bool active = local < a.idx_count;
-  const int idx = a.idx_begin + (active ? local : 0);
+  const bool active = local < a.idx_count + a.idx_count2;
+  const int idx = !active ? a.idx_begin : (local < a.idx_count ? a.idx_begin + local : a.idx_begin2 + (local - a.idx_count));
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {

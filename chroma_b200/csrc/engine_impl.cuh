@@ -108,7 +108,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
     B200_CUDA(cudaMalloc(&staging, STAGING_BYTES));
-    if (g.tsplit) { int rc = halo.init(cfg, g, stream); if (rc) return rc; }
+    if (g.tsplit) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
@@ -255,7 +255,8 @@ class Engine : public EngineBase {
     a.bc_t = (recon == 12) ? t_boundary_ : 1; a.t_is_last = ls.t_is_last;
     a.diag_mass = diag_mass; a.cr = cr; a.ct = ct; a.aniso = aniso; a.t_dir = t_dir;
     a.ghost_links = g.tsplit ? halo.gauge_ghost() : nullptr;
-    if (g.tsplit) { rc = halo.exchange_gauge_ghost(gauge, recon, launches); if (rc) return rc; }
+    a.parity = 0; a.clov_out = nullptr;
+    if (g.tsplit) { rc = halo.exchange_gauge_ghost(a, launches); if (rc) return rc; }
     for (int par = 0; par < 2; ++par) {
       a.parity = par; a.clov_out = clov + (size_t)par * 36 * g.Vh;
       make_clover_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(a);
@@ -335,24 +336,23 @@ class Engine : public EngineBase {
     a.gauge = gauge; a.scal = scal; a.status = status; a.g = g;
     int rc;
     if (g.tsplit) {
-      // pack + send both time faces over NVLink, run the interior while they fly, then the two boundary slices
+      // pack + send both time faces over NVLink, run the interior while they fly, then both boundary slices
       rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, launches); if (rc) return rc;
       a.ghost_fwd = halo.ghost_fwd(); a.ghost_bwd = halo.ghost_bwd();
-      const int nb_int = (g.Vh - 2 * g.S3h + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
-      const int nb_face = (g.S3h + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
-      const int total = nb_int + 2 * nb_face;
-      if (g.Lt > 2) {
-        a.idx_begin = g.S3h; a.idx_count = g.Vh - 2 * g.S3h; a.red = make_red(0, total);
+      const int n_int = g.Vh - 2 * g.S3h;
+      const int nb_int = (n_int + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+      const int nb_face = (2 * g.S3h + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+      const int total = nb_int + nb_face;
+      if (n_int > 0) {
+        a.idx_begin = g.S3h; a.idx_count = n_int; a.idx_begin2 = 0; a.idx_count2 = 0; a.red = make_red(0, total);
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
-      rc = halo.wait(launches); if (rc) return rc;
-      a.idx_begin = 0; a.idx_count = g.S3h; a.red = make_red(nb_int, total);
-      rc = launch_one<EPI>(a, nb_face); if (rc) return rc;
-      a.idx_begin = g.Vh - g.S3h; a.idx_count = g.S3h; a.red = make_red(nb_int + nb_face, total);
+      rc = halo.wait(a.check_stop ? status : nullptr, launches); if (rc) return rc;
+      a.idx_begin = 0; a.idx_count = g.S3h; a.idx_begin2 = g.Vh - g.S3h; a.idx_count2 = g.S3h; a.red = make_red(nb_int, total);
       return launch_one<EPI>(a, nb_face);
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr;
-    a.idx_begin = 0; a.idx_count = g.Vh;
+    a.idx_begin = 0; a.idx_count = g.Vh; a.idx_begin2 = 0; a.idx_count2 = 0;
     const int blocks = (g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
     a.red = make_red(0, blocks);
     return launch_one<EPI>(a, blocks);
@@ -608,6 +608,7 @@ class Engine : public EngineBase {
     info->secs = ms * 1e-3; info->secs_total = info->secs;
     const double gvol = (double)g.Vh * cfg.pgrid[3];
     info->gflops = info->secs > 0 ? flops_iter * gvol * n_count / info->secs * 1e-9 : 0.0;
+    if (breakdown >= 90) { set_error("multi-GPU peer wait timed out (code %d: 90 = halo flag, 91 = reduction mailbox)", breakdown); return B200_ERR_COMM; }
     if (breakdown) { set_error("BiCGStab breakdown (code %d) at iteration <= %d", breakdown, n_count); return B200_ERR_BREAKDOWN; }
     return B200_OK;
   }

@@ -14,6 +14,7 @@ struct PeerReduce {
   int rank;
   unsigned long long* seq;  // device counter: number of cross-GPU reductions done so far on this rank
   double* mailbox[8];       // mailbox[r] = rank r's mailbox base (peer pointer), layout [slot 2][src rank 8][4 values + seq]
+  int* status;              // device status block (ST_BREAKDOWN = 91 on timeout)
 };
 
 struct ReduceBuf {
@@ -63,7 +64,10 @@ __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, double vals
   for (int src = 0; src < pr.nranks; ++src) {
     volatile double* mb = pr.mailbox[pr.rank] + ((size_t)slot * 8 + src) * 8;
     volatile unsigned long long* tag = (volatile unsigned long long*)(mb + 4);
-    while (*tag != s) { }
+    const long long t0 = clock64();
+    while (*tag != s) {
+      if (clock64() - t0 > PEER_SPIN_CYCLES) { if (pr.status) pr.status[ST_BREAKDOWN] = 91; break; }
+    }
     __threadfence_system();
     for (int k = 0; k < N; ++k) tot[k] += mb[k];
   }
