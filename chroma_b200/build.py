@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200clover.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ["api.cu", "engine_d.cu", "engine_f.cu"]
+SOURCES = ["api.cu", "engine_d.cu", "engine_f.cu", "engine_mixed.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

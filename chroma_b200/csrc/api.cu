@@ -36,8 +36,9 @@ __device__ void scale_planes_body(C2* p, int nplanes, size_t stride, size_t off,
 __global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
 __global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
 
-__global__ void wait_flags_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long seq, int* status, int check_stop) {
+__global__ void wait_flags_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long seq, int* status, int check_stop, int run_if) {
   if (check_stop && status && (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0)) return;
+  if (run_if && status && status[run_if] == 0) return;
   const volatile unsigned long long* v0 = f0;
   const volatile unsigned long long* v1 = f1;
   const long long t0 = clock64();
@@ -61,6 +62,39 @@ using namespace b200;
   do {                                                                   \
     if (!(c) || !(c)->eng) { set_error("null b200_ctx"); return B200_ERR_ARG; } \
   } while (0)
+
+// ---- host-pointer entry points: upload -> device op -> download -------------------------------------------
+namespace {
+struct TmpFields {
+  b200_ctx* ctx; b200_field* f[3] = {nullptr, nullptr, nullptr};
+  explicit TmpFields(b200_ctx* c) : ctx(c) {}
+  int get(int n) { for (int i = 0; i < n; ++i) { int rc = ctx->eng->field_alloc(&f[i]); if (rc) return rc; } return 0; }
+  ~TmpFields() { for (auto p : f) if (p) ctx->eng->field_free(p); }
+};
+}  // namespace
+
+namespace {
+// upload chi, psi0 -> device solve -> download psi; secs_total covers the lot
+template <typename Solve>
+int host_solve(b200_ctx* ctx, void* psi, const void* chi, int host_prec, b200_solve_info* info, Solve solve) {
+  if (!psi || !chi || !info) { set_error("b200_invert: null pointer"); return B200_ERR_ARG; }
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaSetDevice(ctx->eng->cfg.device));
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, ctx->eng->stream));
+  TmpFields t(ctx); int rc = t.get(2);
+  if (!rc) rc = ctx->eng->field_upload(t.f[0], chi, host_prec);
+  if (!rc) rc = ctx->eng->field_upload(t.f[1], psi, host_prec);
+  if (!rc) rc = solve(t.f[1], t.f[0]);
+  if (!rc || rc == B200_ERR_BREAKDOWN) { int r2 = ctx->eng->field_download(t.f[1], psi, host_prec); if (!rc) rc = r2; }
+  cudaEventRecord(e1, ctx->eng->stream); cudaEventSynchronize(e1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  info->secs_total = ms * 1e-3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
+}
+}  // namespace
+
 
 extern "C" {
 
@@ -89,12 +123,14 @@ int b200_create(b200_ctx** out, int device, const int global_dims[4], const int 
   if (rc) { delete e; return rc; }
   b200_ctx* ctx = new b200_ctx;
   ctx->eng = e;
+  ctx->sloppy = nullptr;
   *out = ctx;
   return B200_OK;
 }
 
 void b200_destroy(b200_ctx* ctx) {
   if (!ctx) return;
+  delete ctx->sloppy;   // first: it borrows the main engine's stream and scalar block
   delete ctx->eng;
   delete ctx;
 }
@@ -124,7 +160,16 @@ int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* r) { CHECK_CTX(ct
 int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double r[2]) { CHECK_CTX(ctx); if (!x || !y || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->inner(x, y, r); }
 int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) {
   CHECK_CTX(ctx);
-  return ctx->eng->invert(psi, chi, solver, rsd, max_iter, info);
+  return ctx->eng->invert(psi, chi, solver, rsd, max_iter, 0, info);
+}
+int b200_dev_invert_mdagm(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return ctx->eng->invert(psi, chi, solver, rsd, max_iter, 1, info);
+}
+int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd, double delta, int max_iter, int mdagm,
+                             b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return reliable_solve(ctx->eng, &ctx->sloppy, psi, chi, rsd, delta, max_iter, mdagm, info);
 }
 int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver) {
   CHECK_CTX(ctx);
@@ -137,16 +182,6 @@ int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter) {
   if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
   return ctx->eng->iterate(solver, n_iter);
 }
-
-// ---- host-pointer entry points: upload -> device op -> download -------------------------------------------
-namespace {
-struct TmpFields {
-  b200_ctx* ctx; b200_field* f[3] = {nullptr, nullptr, nullptr};
-  explicit TmpFields(b200_ctx* c) : ctx(c) {}
-  int get(int n) { for (int i = 0; i < n; ++i) { int rc = ctx->eng->field_alloc(&f[i]); if (rc) return rc; } return 0; }
-  ~TmpFields() { for (auto p : f) if (p) ctx->eng->field_free(p); }
-};
-}  // namespace
 
 int b200_dslash(b200_ctx* ctx, void* out, const void* in, int host_prec, int isign, int out_cb) {
   CHECK_CTX(ctx);
@@ -171,21 +206,17 @@ int b200_clover_matpc(b200_ctx* ctx, void* out, const void* in, int host_prec, i
 }
 int b200_invert(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int solver, double rsd, int max_iter, b200_solve_info* info) {
   CHECK_CTX(ctx);
-  if (!psi || !chi || !info) { set_error("b200_invert: null pointer"); return B200_ERR_ARG; }
-  cudaEvent_t e0, e1;
-  B200_CUDA(cudaSetDevice(ctx->eng->cfg.device));
-  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
-  B200_CUDA(cudaEventRecord(e0, ctx->eng->stream));
-  TmpFields t(ctx); int rc = t.get(2);
-  if (!rc) rc = ctx->eng->field_upload(t.f[0], chi, host_prec);
-  if (!rc) rc = ctx->eng->field_upload(t.f[1], psi, host_prec);
-  if (!rc) rc = ctx->eng->invert(t.f[1], t.f[0], solver, rsd, max_iter, info);
-  if (!rc || rc == B200_ERR_BREAKDOWN) { int r2 = ctx->eng->field_download(t.f[1], psi, host_prec); if (!rc) rc = r2; }
-  cudaEventRecord(e1, ctx->eng->stream); cudaEventSynchronize(e1);
-  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
-  info->secs_total = ms * 1e-3;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return rc;
+  return host_solve(ctx, psi, chi, host_prec, info, [&](b200_field* p, b200_field* c) { return ctx->eng->invert(p, c, solver, rsd, max_iter, 0, info); });
+}
+int b200_invert_mdagm(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int solver, double rsd, int max_iter, b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return host_solve(ctx, psi, chi, host_prec, info, [&](b200_field* p, b200_field* c) { return ctx->eng->invert(p, c, solver, rsd, max_iter, 1, info); });
+}
+int b200_invert_reliable(b200_ctx* ctx, void* psi, const void* chi, int host_prec, double rsd, double delta, int max_iter, int mdagm,
+                         b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return host_solve(ctx, psi, chi, host_prec, info,
+                    [&](b200_field* p, b200_field* c) { return reliable_solve(ctx->eng, &ctx->sloppy, p, c, rsd, delta, max_iter, mdagm, info); });
 }
 int b200_qprop(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter, b200_solve_info* infos) {
   CHECK_CTX(ctx);

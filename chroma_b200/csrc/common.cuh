@@ -104,12 +104,16 @@ enum ScalarSlot {
   S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM,
   S_RNORM,                                        // BiCGStab |r|^2
   S_TMP0, S_TMP1, S_TMP2, S_TMP3,                 // generic reduction results (norm2 / inner)
+  S_R0NORM, S_MAXRX, S_MAXRR, S_DELTA,            // reliable updates (reliable_cg.cc:68-73,115-121)
   S_COUNT = 32
 };
 // Integer status block
 enum StatusSlot {
   ST_STOP = 0,      // 0 while iterating; else the iteration at which the recurrence residual converged
   ST_BREAKDOWN,     // BiCGStab breakdown code (1 rho=0, 2 <r0|v>=0, 3 |t|=0); 90/91 = peer wait timed out (halo / reduction)
+  ST_UPD_R,         // reliable updates: this iteration replaces the residual with the fp64 one (updateR, reliable_cg.cc:120)
+  ST_UPD_X,         // ... and folds the accumulated fp32 solution into psi (updateX, :119)
+  ST_NUPD,          // number of residual replacements done
   ST_COUNT = 8
 };
 

@@ -15,6 +15,7 @@
 //   EPI_M_CG     r -= a (A x - 1/4 D in), |r|^2       -> CG cp    (invcg2.cc:170-182; M^dag M p is never stored)
 //   EPI_M_DOTR0  EPI_M and <r0|out>                   -> BiCGStab alpha   (invbicgstab.cc:101-114)
 //   EPI_M_DOTX   EPI_M and <out|x>, |out|^2           -> BiCGStab omega   (invbicgstab.cc:126-140)
+//   EPI_M_CGREL  EPI_M_CG whose finaliser also takes the reliable-update decisions (reliable_cg.cc:113-121)
 //
 // Neighbour indices come from coordinate arithmetic (no shift table in HBM; replaces ShiftTable,
 // shift_table_scalar.h:10-147).  The arithmetic is HBM-bound: 1320 flop per (48+8G) reals moved.
@@ -24,7 +25,7 @@
 
 namespace b200 {
 
-enum Epilogue { EPI_DSLASH = 0, EPI_AINV, EPI_M, EPI_M_NORM, EPI_M_CG, EPI_M_DOTR0, EPI_M_DOTX };
+enum Epilogue { EPI_DSLASH = 0, EPI_AINV, EPI_M, EPI_M_NORM, EPI_M_CG, EPI_M_DOTR0, EPI_M_DOTX, EPI_M_CGREL };
 
 template <typename R>
 struct DslashArgs {
@@ -51,6 +52,7 @@ struct DslashArgs {
   int idx_count2;   // ... of this many sites
   int iter;         // solver iteration this launch belongs to (for the stop flag)
   int check_stop;   // 1: return immediately if status[ST_STOP] != 0
+  int run_if;       // != 0: status slot that must be non-zero for this launch to do anything (predicated launch)
 };
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
@@ -280,6 +282,29 @@ struct FinCgCp {
     if (check && status[ST_STOP] == 0 && cp <= scal[S_RSDSQ]) status[ST_STOP] = iter;
   }
 };
+// Reliable-update CG: cp = |r|^2 of the fp32 recurrence; decide on the device whether this iteration replaces the
+// residual (updateR) and folds the partial solution into psi (updateX) -- reliable_cg.cc:113-121.  When it does,
+// b, c and the convergence test are left to the finaliser of the replacement kernel (FinRelReplace, mixed.cuh).
+struct FinRelCp {
+  double* scal; int* status; int iter; int check;
+  __device__ void operator()(const double* t) const {
+    const double cp = t[0], rnorm = sqrt(cp);
+    double maxrx = scal[S_MAXRX], maxrr = scal[S_MAXRR];
+    const double r0 = scal[S_R0NORM], delta = scal[S_DELTA];
+    if (rnorm > maxrx) maxrx = rnorm;
+    if (rnorm > maxrr) maxrr = rnorm;
+    scal[S_MAXRX] = maxrx; scal[S_MAXRR] = maxrr;
+    const bool upd_x = (rnorm < delta * r0) && (r0 <= maxrx);
+    const bool upd_r = ((rnorm < delta * maxrr) && (r0 <= maxrr)) || upd_x;
+    status[ST_UPD_R] = upd_r ? 1 : 0; status[ST_UPD_X] = upd_x ? 1 : 0;
+    scal[S_CP] = cp;
+    if (!upd_r) {
+      const double c = scal[S_C];
+      scal[S_B] = cp / c; scal[S_C] = cp;
+      if (check && status[ST_STOP] == 0 && cp < scal[S_RSDSQ]) status[ST_STOP] = iter;   // strict <, reliable_cg.cc:163
+    }
+  }
+};
 // BiCGStab: ctmp = <r0|v>  ->  alpha = rho/ctmp (invbicgstab.cc:106-114)
 struct FinBiAlpha {
   double* scal; int* status;
@@ -308,6 +333,7 @@ template <typename R, int EPI, bool RECON12, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
   typedef Cx<R> C;
   if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  if (a.run_if && a.status[a.run_if] == 0) return;
   const int stride = a.g.Vh;
   const int local = blockIdx.x * BLOCK + threadIdx.x;
   const bool active = local < a.idx_count + a.idx_count2;
@@ -333,7 +359,7 @@ __global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(co
       // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
       // and would cost one exposed DRAM round trip each.
       C m[12], ex[12];
-      if (EPI == EPI_M_CG) {
+      if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
 #pragma unroll
         for (int k = 0; k < 12; ++k) ex[k] = ld_stream_rw(a.r + (size_t)k * stride + idx, pol.stream);
       }
@@ -358,7 +384,7 @@ __global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(co
           }
         }
       }
-      if (EPI == EPI_M_CG) {
+      if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
         const R cg_a = (R)a.scal[S_A];
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
@@ -386,6 +412,7 @@ __global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(co
 
   if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal});
   if (EPI == EPI_M_CG) grid_reduce<1, BLOCK>(red, a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_CGREL) grid_reduce<1, BLOCK>(red, a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status});
   if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status});
 }

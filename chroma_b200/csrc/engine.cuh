@@ -64,7 +64,7 @@ class EngineBase {
   virtual int time_matpc(b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) = 0;
   virtual int norm2(const b200_field* x, double* r) = 0;
   virtual int inner(const b200_field* x, const b200_field* y, double r[2]) = 0;
-  virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) = 0;
+  virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, int mdagm, b200_solve_info* info) = 0;
   virtual int iterate_begin(b200_field* psi, const b200_field* chi, int solver) = 0;
   virtual int iterate(int solver, int n_iter) = 0;
   virtual int qprop(void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter,
@@ -77,6 +77,10 @@ class EngineBase {
   long long launches = 0;
 };
 
+// Mixed-precision reliable-update CG (engine_mixed.cu): hi must be the fp64 engine; *lo_slot is created on first use.
+int reliable_solve(EngineBase* hi, EngineBase** lo_slot, b200_field* psi, const b200_field* chi, double rsd, double delta,
+                   int max_iter, int mdagm, b200_solve_info* info);
+
 EngineBase* make_engine_double(const Config& c);
 EngineBase* make_engine_float(const Config& c);
 
@@ -84,4 +88,5 @@ EngineBase* make_engine_float(const Config& c);
 
 struct b200_ctx {
   b200::EngineBase* eng;
+  b200::EngineBase* sloppy;   // fp32 twin of an fp64 engine, made on demand by b200_invert_reliable
 };

@@ -65,6 +65,8 @@ class Engine : public EngineBase {
   b200_field* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Halo<R> halo;
   int blas_grid = 148 * 8;
+  bool owns_stream = true, owns_scalars = true;   // false once a mixed-precision partner lent us its stream / scalar block
+  long long operator_epoch = 0;                   // bumped whenever gauge or clover change (the fp32 twin re-syncs on it)
   // fixed-iteration (benchmark) state
   C* it_psi = nullptr; const C* it_chi = nullptr; int it_k = 0;
 
@@ -120,12 +122,13 @@ class Engine : public EngineBase {
     halo.destroy();
     for (auto& f : ws) if (f) { field_free(f); f = nullptr; }
     cudaFree(gauge); cudaFree(clov); cudaFree(invclov); cudaFree(tr_log);
-    cudaFree(scal); cudaFree(status); cudaFree(partial); cudaFree(ticket); cudaFree(staging);
+    if (owns_scalars) { cudaFree(scal); cudaFree(status); }
+    cudaFree(partial); cudaFree(ticket); cudaFree(staging);
     cudaFreeHost(h_scal); cudaFreeHost(h_status);
     for (int i = 0; i < 2; ++i) if (ev_poll[i]) cudaEventDestroy(ev_poll[i]);
     if (ev_t0) cudaEventDestroy(ev_t0);
     if (ev_t1) cudaEventDestroy(ev_t1);
-    cudaStreamDestroy(stream);
+    if (owns_stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
 
@@ -214,6 +217,7 @@ class Engine : public EngineBase {
     }
     ls.bc_t = t_boundary;
     ls.t_is_last = last_rank ? 1 : 0;
+    ++operator_epoch;
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
@@ -233,6 +237,7 @@ class Engine : public EngineBase {
     else rc = upload_aos<float, 72, 36>((const float*)invclov_h, g.Vh, invclov, (size_t)g.Vh, MapClover(), 1.0);
     if (rc) return rc;
     have_trlog = false;
+    ++operator_epoch;
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
@@ -266,6 +271,7 @@ class Engine : public EngineBase {
     ldagdlinv_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov, tr_log, g.Vh);
     rc = launched("ldagdlinv"); if (rc) return rc;
     have_trlog = true;
+    ++operator_epoch;
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
@@ -337,7 +343,7 @@ class Engine : public EngineBase {
     int rc;
     if (g.tsplit) {
       // pack + send both time faces over NVLink, run the interior while they fly, then both boundary slices
-      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, launches); if (rc) return rc;
+      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, launches); if (rc) return rc;
       a.ghost_fwd = halo.ghost_fwd(); a.ghost_bwd = halo.ghost_bwd();
       const int n_int = g.Vh - 2 * g.S3h;
       const int nb_int = (n_int + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
@@ -347,7 +353,7 @@ class Engine : public EngineBase {
         a.idx_begin = g.S3h; a.idx_count = n_int; a.idx_begin2 = 0; a.idx_count2 = 0; a.red = make_red(0, total);
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
-      rc = halo.wait(a.check_stop ? status : nullptr, launches); if (rc) return rc;
+      rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, launches); if (rc) return rc;
       a.idx_begin = 0; a.idx_count = g.S3h; a.idx_begin2 = g.Vh - g.S3h; a.idx_count2 = g.S3h; a.red = make_red(nb_int, total);
       return launch_one<EPI>(a, nb_face);
     }
@@ -372,14 +378,15 @@ class Engine : public EngineBase {
   }
 
   // out = M in (isign=+1) / M^dag in (-1) with one of the EPI_M* epilogues; te is the even temporary
-  int apply_M(C* out, const C* in, int isign, int epi, C* r, const C* r0, int iter, int check) {
+  int apply_M(C* out, const C* in, int isign, int epi, C* r, const C* r0, int iter, int check, int run_if = 0) {
     DslashArgs<R> a{};
-    a.in = in; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign; a.iter = iter; a.check_stop = check;
+    a.in = in; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign; a.iter = iter; a.check_stop = check; a.run_if = run_if;
     int rc = launch_dslash<EPI_AINV>(a); if (rc) return rc;
     DslashArgs<R> b{};
     b.in = W(0); b.out = out; b.clov = clov + (size_t)36 * g.Vh; b.x = in; b.r = r; b.r0 = r0;
-    b.parity = 1; b.isign = isign; b.iter = iter; b.check_stop = check;
+    b.parity = 1; b.isign = isign; b.iter = iter; b.check_stop = check; b.run_if = run_if;
     switch (epi) {
+      case EPI_M_CGREL: return launch_dslash<EPI_M_CGREL>(b);
       case EPI_M: return launch_dslash<EPI_M>(b);
       case EPI_M_NORM: return launch_dslash<EPI_M_NORM>(b);
       case EPI_M_CG: return launch_dslash<EPI_M_CG>(b);
@@ -499,13 +506,13 @@ class Engine : public EngineBase {
     return launched("cg_update");
   }
   // one BiCGStab iteration, invbicgstab.cc:74-170.  W(1)=r, W(2)=r0, W(3)=p, W(4)=v, W(5)=t
-  int bicg_iteration(C* psi, int k, int check) {
+  int bicg_iteration(C* psi, int k, int check, int isign = +1) {
     bicg_p_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(W(3), W(1), W(4), nelem(), ctl(k, check));
     int rc = launched("bicg_p"); if (rc) return rc;
-    rc = apply_M(W(4), W(3), +1, EPI_M_DOTR0, nullptr, W(2), k, check); if (rc) return rc;            // v = M p, alpha
+    rc = apply_M(W(4), W(3), isign, EPI_M_DOTR0, nullptr, W(2), k, check); if (rc) return rc;         // v = M p, alpha
     bicg_s_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(W(1), W(4), nelem(), ctl(k, check));
     rc = launched("bicg_s"); if (rc) return rc;
-    rc = apply_M(W(5), W(1), +1, EPI_M_DOTX, nullptr, nullptr, k, check); if (rc) return rc;          // t = M r, omega
+    rc = apply_M(W(5), W(1), isign, EPI_M_DOTX, nullptr, nullptr, k, check); if (rc) return rc;       // t = M r, omega
     bicg_update_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(psi, W(1), W(3), W(5), W(2), nelem(), ctl(k, check));
     return launched("bicg_update");
   }
@@ -519,23 +526,23 @@ class Engine : public EngineBase {
     return fetch_scalars();
   }
   // InvBiCGStab_a set-up (invbicgstab.cc:31-71)
-  int bicg_begin(C* psi, const C* chi) {
+  int bicg_begin(C* psi, const C* chi, int isign = +1) {
     int rc = norm2_dev(chi, S_TMP0); if (rc) return rc;
-    rc = apply_M(W(2), psi, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+    rc = apply_M(W(2), psi, isign, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
     rc = xmy_norm_dev(W(1), W(2), chi, W(2), S_TMP1); if (rc) return rc;     // r = r0 = chi - M psi ; |r|^2 = <r0|r>
     B200_CUDA(cudaMemsetAsync(W(3), 0, sizeof(C) * nelem(), stream));
     B200_CUDA(cudaMemsetAsync(W(4), 0, sizeof(C) * nelem(), stream));
     return fetch_scalars();
   }
 
-  int poll_loop(C* psi, int solver, int max_iter, int* n_count, int* converged, int* breakdown) {
+  int poll_loop(C* psi, int solver, int max_iter, int* n_count, int* converged, int* breakdown, int isign = +1) {
     int k = 1, slot = 0, prev = -1;
     bool done = false;
     *breakdown = 0;
     while (k <= max_iter && !done) {
       const int n = std::min(ITER_BATCH, max_iter - k + 1);
       for (int i = 0; i < n; ++i) {
-        int rc = (solver == B200_SOLVER_CG) ? cg_iteration(psi, k + i, 1) : bicg_iteration(psi, k + i, 1);
+        int rc = (solver == B200_SOLVER_CG) ? cg_iteration(psi, k + i, 1) : bicg_iteration(psi, k + i, 1, isign);
         if (rc) return rc;
       }
       B200_CUDA(cudaMemcpyAsync(h_status + slot * ST_COUNT, status, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, stream));
@@ -554,7 +561,61 @@ class Engine : public EngineBase {
     return B200_OK;
   }
 
-  int invert(b200_field* psi_f, const b200_field* chi_f, int solver, double rsd, int max_iter, b200_solve_info* info) override {
+  // InvCG2_a (invcg2.cc:70-232): solve M^dag M psi = rhs.  Uses W(0..4).
+  int run_cg(C* psi, const C* rhs, double rsd, int max_iter, int* n_count, int* converged, double* rsd_sq_iter) {
+    int rc = cg_begin(psi, rhs); if (rc) return rc;
+    const double chi_sq = h_scal[S_TMP0], cp = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
+    *rsd_sq_iter = cp; *n_count = 0; *converged = 0;
+    if (cp <= rsd_sq) { *converged = 1; return B200_OK; }          // invcg2.cc:136-146
+    ScalarSet s{}; s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = rsd_sq; s.slots[1] = S_C; s.vals[1] = cp; s.reset_status = 1;
+    rc = set_scalars(s); if (rc) return rc;
+    int breakdown = 0;
+    rc = poll_loop(psi, B200_SOLVER_CG, max_iter, n_count, converged, &breakdown); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    if (*n_count > 0) *rsd_sq_iter = h_scal[S_CP];
+    if (breakdown >= 90) return comm_timeout(breakdown);
+    return B200_OK;
+  }
+  // InvBiCGStab_a (invbicgstab.cc:10-202): solve M psi = rhs (isign=+1) or M^dag psi = rhs (-1).  Uses W(0..5).
+  int run_bicg(C* psi, const C* rhs, int isign, double rsd, int max_iter, int* n_count, int* converged, double* rsd_sq_iter) {
+    int rc = bicg_begin(psi, rhs, isign); if (rc) return rc;
+    const double chi_sq = h_scal[S_TMP0], rr = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
+    *rsd_sq_iter = rr; *n_count = 0; *converged = 0;
+    ScalarSet s{}; s.reset_status = 1; s.n = 11;
+    const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
+    const double vl[11] = {rsd_sq, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};   // beta_1 = (rho_1/1)(1/1)
+    for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+    int breakdown = 0;
+    if (rr == 0.0) breakdown = 1;                                // rho = <r0|r> = 0 (invbicgstab.cc:80-83)
+    else {
+      rc = set_scalars(s); if (rc) return rc;
+      rc = poll_loop(psi, B200_SOLVER_BICGSTAB, max_iter, n_count, converged, &breakdown, isign); if (rc) return rc;
+      rc = fetch_scalars(); if (rc) return rc;
+      if (*n_count > 0) *rsd_sq_iter = h_scal[S_RNORM];
+    }
+    if (breakdown >= 90) return comm_timeout(breakdown);
+    if (breakdown) { set_error("BiCGStab breakdown (code %d) at iteration <= %d", breakdown, *n_count); return B200_ERR_BREAKDOWN; }
+    return B200_OK;
+  }
+  int comm_timeout(int code) {
+    set_error("multi-GPU peer wait timed out (code %d: 90 = halo flag, 91 = reduction mailbox)", code);
+    return B200_ERR_COMM;
+  }
+
+  // True residual of the shells: |chi - M psi| (syssolver_linop_cg.h:80-87) or |chi - M^dag M psi| (syssolver_mdagm_cg.h:75-82)
+  int true_residual(const C* psi, const C* chi, int mdagm, b200_solve_info* info) {
+    int rc = apply_M(W(1), psi, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+    const C* mpsi = W(1);
+    if (mdagm) { rc = apply_M(W(2), W(1), -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc; mpsi = W(2); }
+    rc = xmy_norm_dev(nullptr, nullptr, chi, mpsi, S_TMP2); if (rc) return rc;
+    rc = norm2_dev(chi, S_TMP3); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    info->resid = sqrt(h_scal[S_TMP2]);
+    info->rel_resid = h_scal[S_TMP3] > 0 ? info->resid / sqrt(h_scal[S_TMP3]) : 0.0;
+    return B200_OK;
+  }
+
+  int invert(b200_field* psi_f, const b200_field* chi_f, int solver, double rsd, int max_iter, int mdagm, b200_solve_info* info) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
     if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0)) { set_error("b200_invert: bad argument"); return B200_ERR_ARG; }
@@ -563,54 +624,38 @@ class Engine : public EngineBase {
     C* psi = (C*)psi_f->d; const C* chi = (const C*)chi_f->d;
     memset(info, 0, sizeof(*info));
     B200_CUDA(cudaEventRecord(ev_t0, stream));
-    int n_count = 0, converged = 0, breakdown = 0;
-    double flops_iter;
+    int n_count = 0, converged = 0;
+    double flops_iter, rsq = 0.0;
     if (solver == B200_SOLVER_CG) {
       flops_iter = 2.0 * 3792.0 + 240.0;
-      // chi_tmp = M^dag chi (syssolver_linop_cg.h:65-66) -> W(6)
-      rc = apply_M(W(6), chi, -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
-      rc = cg_begin(psi, W(6)); if (rc) return rc;
-      const double chi_sq = h_scal[S_TMP0], cp = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
-      info->rsd_sq_iter = cp;
-      if (cp <= rsd_sq) { n_count = 0; converged = 1; }          // invcg2.cc:136-146
-      else {
-        ScalarSet s{}; s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = rsd_sq; s.slots[1] = S_C; s.vals[1] = cp; s.reset_status = 1;
-        rc = set_scalars(s); if (rc) return rc;
-        rc = poll_loop(psi, solver, max_iter, &n_count, &converged, &breakdown); if (rc) return rc;
+      const C* rhs = chi;
+      if (!mdagm) {   // chi_tmp = M^dag chi (syssolver_linop_cg.h:65-66) -> W(6)
+        rc = apply_M(W(6), chi, -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+        rhs = W(6);
       }
-    } else {
+      rc = run_cg(psi, rhs, rsd, max_iter, &n_count, &converged, &rsq);
+    } else if (!mdagm) {
       flops_iter = 2.0 * 3792.0 + 960.0;
-      rc = bicg_begin(psi, chi); if (rc) return rc;
-      const double chi_sq = h_scal[S_TMP0], rr = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
-      info->rsd_sq_iter = rr;
-      ScalarSet s{}; s.reset_status = 1; s.n = 11;
-      const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
-      const double vl[11] = {rsd_sq, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};   // beta_1 = (rho_1/1)(1/1)
-      for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
-      if (rr == 0.0) breakdown = 1;                                // rho = <r0|r> = 0 (invbicgstab.cc:80-83)
-      else {
-        rc = set_scalars(s); if (rc) return rc;
-        rc = poll_loop(psi, solver, max_iter, &n_count, &converged, &breakdown); if (rc) return rc;
-      }
+      rc = run_bicg(psi, chi, +1, rsd, max_iter, &n_count, &converged, &rsq);
+    } else {
+      // two-step solve, syssolver_mdagm_bicgstab.h:62-110: Y = M psi; M^dag Y = chi; M psi = Y
+      flops_iter = 2.0 * 3792.0 + 960.0;
+      int n1 = 0, c1 = 0;
+      rc = apply_M(W(6), psi, +1, EPI_M, nullptr, nullptr, 0, 0);
+      if (!rc) rc = run_bicg(W(6), chi, -1, rsd, max_iter, &n1, &c1, &rsq);
+      if (!rc) rc = run_bicg(psi, W(6), +1, rsd, max_iter, &n_count, &converged, &rsq);
+      n_count += n1; converged = converged && c1;
     }
+    info->n_count = n_count; info->converged = converged; info->rsd_sq_iter = rsq;
+    if (rc && rc != B200_ERR_BREAKDOWN) return rc;
     B200_CUDA(cudaEventRecord(ev_t1, stream));
-    // true residual with M, as both shells do (syssolver_linop_cg.h:80-87)
-    rc = apply_M(W(1), psi, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
-    rc = xmy_norm_dev(nullptr, nullptr, chi, W(1), S_TMP2); if (rc) return rc;
-    rc = norm2_dev(chi, S_TMP3); if (rc) return rc;
-    rc = fetch_scalars(); if (rc) return rc;
+    int rc2 = true_residual(psi, chi, mdagm, info); if (rc2) return rc2;
     float ms = 0.f;
     B200_CUDA(cudaEventElapsedTime(&ms, ev_t0, ev_t1));
-    info->n_count = n_count; info->converged = converged;
-    info->resid = sqrt(h_scal[S_TMP2]);
-    info->rel_resid = h_scal[S_TMP3] > 0 ? info->resid / sqrt(h_scal[S_TMP3]) : 0.0;
-    if (n_count > 0) info->rsd_sq_iter = (solver == B200_SOLVER_CG) ? h_scal[S_CP] : h_scal[S_RNORM];
     info->secs = ms * 1e-3; info->secs_total = info->secs;
     const double gvol = (double)g.Vh * cfg.pgrid[3];
     info->gflops = info->secs > 0 ? flops_iter * gvol * n_count / info->secs * 1e-9 : 0.0;
-    if (breakdown >= 90) { set_error("multi-GPU peer wait timed out (code %d: 90 = halo flag, 91 = reduction mailbox)", breakdown); return B200_ERR_COMM; }
-    if (breakdown) { set_error("BiCGStab breakdown (code %d) at iteration <= %d", breakdown, n_count); return B200_ERR_BREAKDOWN; }
-    return B200_OK;
+    return rc;
   }
 
   int iterate_begin(b200_field* psi_f, const b200_field* chi_f, int solver) override {
@@ -623,7 +668,7 @@ class Engine : public EngineBase {
       rc = cg_begin(it_psi, it_chi); if (rc) return rc;
       s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = 0.0; s.slots[1] = S_C; s.vals[1] = h_scal[S_TMP1];
     } else {
-      rc = bicg_begin(it_psi, it_chi); if (rc) return rc;
+      rc = bicg_begin(it_psi, it_chi, +1); if (rc) return rc;
       const double rr = h_scal[S_TMP1];
       s.n = 11;
       const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
@@ -666,7 +711,7 @@ class Engine : public EngineBase {
       if ((rc = clover_apply(t1, chi_e, 0, 1))) break;
       if ((rc = dslash(t2, t1, +1, 1))) break;
       if ((rc = axpby_dev((C*)t1->d, 1.0, (const C*)chi_o->d, 0.5, (const C*)t2->d))) break;
-      rc = invert(psi_o, t1, solver, rsd, max_iter, &infos[i]);
+      rc = invert(psi_o, t1, solver, rsd, max_iter, 0, &infos[i]);
       if (rc) break;
       // psi_e = A_ee^-1 (chi_e - D_eo psi_o) = A_ee^-1 (chi_e + 1/2 Dslash psi_o)
       if ((rc = dslash(t1, psi_o, +1, 0))) break;

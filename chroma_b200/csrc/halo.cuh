@@ -16,6 +16,8 @@
 //   boundary      dslash kernel on slices 0 and Lt-1, reading the ghost half spinors.
 // Two slots are enough: a rank can only start packing Dslash n+2 after it finished the boundary of n+1, which
 // needed the neighbour's pack n+1, which the neighbour issued after ITS boundary kernel of n had read slot n&1.
+// Predicated Dslashes (run_if, used by the reliable-update solver) are skipped by ALL ranks or by none (the flag is
+// derived from a global sum) and always come in groups of four, so executed Dslashes still alternate slots.
 #pragma once
 #include <vector>
 
@@ -42,6 +44,7 @@ struct PackArgs {
   unsigned long long seq;
   unsigned int* ticket;
   const int* status;    // may be null
+  const int* pred;      // may be null: status word that must be non-zero for this launch to run (predicated Dslash)
   Geom g;
   int src_par, isign, recon12;
   double scale_b;       // RECON12 only: aniso[3] * (bc_t if this rank owns the global last slice)
@@ -51,6 +54,7 @@ template <typename R, bool RECON12>
 __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   typedef Cx<R> C;
   if (a.status && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  if (a.pred && *a.pred == 0) return;
   const Geom& g = a.g;
   const int tid = blockIdx.x * 128 + threadIdx.x;
   const int stride = g.Vh, st = g.S3h;
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   }
 }
 
-__global__ void wait_flags_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long seq, int* status, int check_stop);
+__global__ void wait_flags_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long seq, int* status, int check_stop, int run_if);
 
 // One-time push of the boundary link slices needed by the field-strength (clover leaves reach x +/- t):
 // face 0 of the receiver = slice t=-1 (sender's last slice), face 1 = slice t=Lt (sender's first slice).
@@ -215,7 +219,7 @@ class Halo {
   }
 
   // Pack + send both faces of `in` for the Dslash that targets `parity`.
-  int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, long long& launches) {
+  int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, int run_if, long long& launches) {
     ++seq;
     const int slot = (int)(seq & 1);
     PackArgs<R> a;
@@ -224,7 +228,7 @@ class Halo {
     a.to_fwd = ghost_ptr(peer[fwd], slot, 1);
     a.flag_bwd = flag_ptr(peer[bwd], slot, 0);
     a.flag_fwd = flag_ptr(peer[fwd], slot, 1);
-    a.seq = seq; a.ticket = ticket; a.status = status; a.g = g;
+    a.seq = seq; a.ticket = ticket; a.status = status; a.pred = run_if ? status_dev + run_if : nullptr; a.g = g;
     a.src_par = 1 - parity; a.isign = isign; a.recon12 = recon == 12;
     a.scale_b = ls.aniso[3] * (ls.t_is_last ? (double)ls.bc_t : 1.0);
     const int blocks = (2 * g.S3h + 127) / 128;
@@ -236,9 +240,9 @@ class Halo {
     return B200_OK;
   }
 
-  int wait(const int* status, long long& launches) {
+  int wait(const int* status, int run_if, long long& launches) {
     const int slot = (int)(seq & 1);
-    wait_flags_kernel<<<1, 1, 0, stream>>>(flag_ptr(arena, slot, 0), flag_ptr(arena, slot, 1), seq, status_dev, status ? 1 : 0);
+    wait_flags_kernel<<<1, 1, 0, stream>>>(flag_ptr(arena, slot, 0), flag_ptr(arena, slot, 1), seq, status_dev, status ? 1 : 0, run_if);
     ++launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("wait_flags launch failed: %s", cudaGetErrorString(e)); return B200_ERR_CUDA; }

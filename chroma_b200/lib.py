@@ -60,6 +60,8 @@ SYMBOLS = {
     "b200_clover_apply": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "b200_clover_matpc": (_i, [_vp, _vp, _vp, _i, _i]),
     "b200_invert": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
+    "b200_invert_mdagm": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
+    "b200_invert_reliable": (_i, [_vp, _vp, _vp, _i, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
     "b200_qprop": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_field_alloc": (_i, [_vp, C.POINTER(_vp)]),
     "b200_field_free": (None, [_vp, _vp]),
@@ -73,6 +75,8 @@ SYMBOLS = {
     "b200_dev_norm2": (_i, [_vp, _vp, C.POINTER(_d)]),
     "b200_dev_inner": (_i, [_vp, _vp, _vp, C.POINTER(_d)]),
     "b200_dev_invert": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),
+    "b200_dev_invert_mdagm": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),
+    "b200_dev_invert_reliable": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
     "b200_dev_iterate_begin": (_i, [_vp, _vp, _vp, _i]),
     "b200_dev_iterate": (_i, [_vp, _i, _i]),
     "b200_stream": (_vp, [_vp]),

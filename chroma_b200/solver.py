@@ -148,6 +148,23 @@ class Context:
         L.check(rc)
         return psi.reshape(self.Vh, 4, 3, 2), info
 
+    def invert_mdagm(self, chi_odd, psi0_odd=None, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
+        """Solve M^dag M psi = chi (the HMC-side shells)."""
+        chi_odd = np.ascontiguousarray(chi_odd)
+        psi = np.zeros_like(chi_odd) if psi0_odd is None else np.ascontiguousarray(psi0_odd, dtype=chi_odd.dtype).copy()
+        info = L.SolveInfo()
+        L.check(self.lib.b200_invert_mdagm(self.h, _ptr(psi), _ptr(chi_odd), _prec_of(chi_odd), int(solver), float(rsd), int(max_iter), C.byref(info)))
+        return psi.reshape(self.Vh, 4, 3, 2), info
+
+    def invert_reliable(self, chi_odd, psi0_odd=None, rsd=1e-8, delta=0.1, max_iter=1000, mdagm=False):
+        """Mixed-precision reliable-update CG (fp32 inner, fp64 outer); the context must be double precision."""
+        chi_odd = np.ascontiguousarray(chi_odd)
+        psi = np.zeros_like(chi_odd) if psi0_odd is None else np.ascontiguousarray(psi0_odd, dtype=chi_odd.dtype).copy()
+        info = L.SolveInfo()
+        L.check(self.lib.b200_invert_reliable(self.h, _ptr(psi), _ptr(chi_odd), _prec_of(chi_odd), float(rsd), float(delta), int(max_iter),
+                                              int(bool(mdagm)), C.byref(info)))
+        return psi.reshape(self.Vh, 4, 3, 2), info
+
     def qprop(self, chi_full, psi0_full=None, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
         """chi_full: [nrhs, V, 4, 3, 2] full-lattice sources -> full-lattice solutions of the UNPRECONDITIONED operator."""
         chi_full = np.ascontiguousarray(chi_full)
@@ -191,6 +208,16 @@ class Context:
     def dev_invert(self, psi, chi, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
         info = L.SolveInfo()
         L.check(self.lib.b200_dev_invert(self.h, psi.h, chi.h, int(solver), float(rsd), int(max_iter), C.byref(info)))
+        return info
+
+    def dev_invert_mdagm(self, psi, chi, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
+        info = L.SolveInfo()
+        L.check(self.lib.b200_dev_invert_mdagm(self.h, psi.h, chi.h, int(solver), float(rsd), int(max_iter), C.byref(info)))
+        return info
+
+    def dev_invert_reliable(self, psi, chi, rsd=1e-8, delta=0.1, max_iter=1000, mdagm=False):
+        info = L.SolveInfo()
+        L.check(self.lib.b200_dev_invert_reliable(self.h, psi.h, chi.h, float(rsd), float(delta), int(max_iter), int(bool(mdagm)), C.byref(info)))
         return info
 
     def dev_iterate_begin(self, psi, chi, solver):

@@ -140,6 +140,25 @@ int b200_clover_matpc(b200_ctx* ctx, void* out_odd_host, const void* in_odd_host
 int b200_invert(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec, int solver,
                 double rsd_target, int max_iter, b200_solve_info* info);
 
+/* Solve M^dag M psi = chi on the odd checkerboard -- the HMC-side shells (TheMdagMFermSystemSolverFactory,
+ * syssolver_mdagm_factory.h:30-39; call site two_flavor_monomial_w.h:74-87).
+ * solver = B200_SOLVER_CG:       MdagMSysSolverCG::operator() (syssolver_mdagm_cg.h:59-94): InvCG2_a on chi itself.
+ * solver = B200_SOLVER_BICGSTAB: MdagMSysSolverBiCGStab::operator() (syssolver_mdagm_bicgstab.h:62-110): Y = M psi,
+ *                                solve M^dag Y = chi (InvBiCGStab isign = MINUS), then M psi = Y (PLUS);
+ *                                n_count is the sum of both solves.
+ * info->resid = |chi - M^dag M psi|.  Replaces invertQuda as called from syssolver_mdagm_clover_quda_w.h. */
+int b200_invert_mdagm(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec, int solver,
+                      double rsd_target, int max_iter, b200_solve_info* info);
+
+/* Mixed-precision reliable-update CG for M psi = chi (normal equations, like B200_SOLVER_CG): fp32 inner iterations,
+ * fp64 residual replacement and group-wise solution updates, RelInvCG_a (lib/actions/ferm/invert/reliable_cg.cc:10-190)
+ * behind the shell of LinOpSysSolverReliableCGClover (syssolver_linop_rel_cg_clover.h:41-165; XML: RsdTarget, Delta,
+ * MaxIter, syssolver_rel_cg_clover_params.cc).  Needs a context created with B200_DOUBLE; the fp32 copy of the gauge
+ * and clover fields is made on the device at the first call.  mdagm != 0 solves M^dag M psi = chi instead (no M^dag chi
+ * preparation; resid = |chi - M^dag M psi|).  info->n_count counts inner iterations. */
+int b200_invert_reliable(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec, double rsd_target,
+                         double delta, int max_iter, int mdagm, b200_solve_info* info);
+
 /* Full-lattice propagator solve for nrhs right-hand sides (the sequential 12 spin-colour loop of
  * quarkprop4_w.cc:70-117 with the even-odd source preparation and solution reconstruction of
  * eoprec_fermact_qprop.cc:41-80 done on the device).  chi/psi: REAL[nrhs][V][4][3][2]. */
@@ -159,6 +178,10 @@ int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* result);
 int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double result[2]); /* <x|y> = sum conj(x) y */
 int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd_target,
                     int max_iter, b200_solve_info* info);
+int b200_dev_invert_mdagm(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd_target,
+                          int max_iter, b200_solve_info* info);
+int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd_target, double delta,
+                             int max_iter, int mdagm, b200_solve_info* info);
 /* Benchmark leg: set up the solver recurrences (r, p, ... as the solver's own preamble does), then run exactly
  * n_iter iterations of the loop body per call with the convergence test disabled. */
 int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver);

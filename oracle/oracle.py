@@ -254,6 +254,94 @@ class Op:
         n = lib().orc_solve_bicgstab(self.h, _p(np.ascontiguousarray(chi)), _p(psi), C.c_double(rsd), C.c_int(maxit), out)
         return psi, n, out[0], out[1]
 
+    def invbicgstab(self, chi, psi0, rsd, maxit, isign=+1):
+        """InvBiCGStab_a with an explicit isign (invbicgstab.cc:10-202)."""
+        psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+        resid = C.c_double()
+        n = lib().orc_invbicgstab(self.h, _p(np.ascontiguousarray(chi)), _p(psi), C.c_double(rsd), C.c_int(maxit), C.c_int(isign), C.byref(resid))
+        return psi, n, resid.value
+
+    def _mdagm_resid(self, chi, psi):
+        r = chi - self.apply(self.apply(psi, +1), -1)
+        return float(np.sqrt(np.sum(r[self.Vh:] ** 2)))
+
+    def solve_mdagm_cg(self, chi, psi0, rsd, maxit):
+        """MdagMSysSolverCG::operator() (syssolver_mdagm_cg.h:59-94): InvCG2 on chi itself; resid = |chi - M^dag M psi|."""
+        psi, n, _ = self.invcg2(chi, psi0, rsd, maxit)
+        return psi, n, self._mdagm_resid(chi, psi)
+
+    def solve_mdagm_bicgstab(self, chi, psi0, rsd, maxit):
+        """MdagMSysSolverBiCGStab::operator() (syssolver_mdagm_bicgstab.h:62-110): Y = M psi; M^dag Y = chi; M psi = Y."""
+        Y = self.apply(psi0, +1)
+        Y, n1, _ = self.invbicgstab(chi, Y, rsd, maxit, -1)
+        psi, n2, _ = self.invbicgstab(Y, psi0, rsd, maxit, +1)
+        return psi, n1 + n2, self._mdagm_resid(chi, psi)
+
+    def solve_reliable_cg(self, chi, psi0, rsd, delta, maxit, mdagm=False):
+        """RelInvCG_a<double, float> (lib/actions/ferm/invert/reliable_cg.cc:10-190) behind the CGNE shell of
+        LinOpSysSolverReliableCGClover (syssolver_linop_rel_cg_clover.h:118-150).  The fp32 operator AF is emulated
+        as round_to_float(M(float vector)) with M evaluated in double -- the rounding of the vectors, which is what
+        drives the reliable-update logic, is exact; the internal rounding of an fp32 Dslash is not modelled.
+        Returns (psi, iterations [1-based count; the reference reports its 0-based loop index], n_updates, resid)."""
+        f32 = lambda a: a.astype(np.float32).astype(np.float64)   # noqa: E731
+        Vh = self.Vh
+        n2 = lambda a: float(np.sum(a[Vh:] ** 2))                 # noqa: E731
+        rhs = chi if mdagm else self.apply(chi, -1)
+        psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+        chi_norm = n2(rhs)
+        rsd_sq = rsd * rsd * chi_norm
+        b = np.zeros_like(psi)
+        b[Vh:] = (rhs - self.apply(self.apply(psi, +1), -1))[Vh:]
+        x = np.zeros_like(psi)
+        r = f32(b)
+        r_sq = n2(r)
+        rNorm = np.sqrt(r_sq)
+        r0Norm = maxrx = maxrr = rNorm
+        p = np.zeros_like(psi)
+        c = 1.0
+        n_upd = 0
+        iters = maxit
+        for k in range(maxit):
+            if k == 0:
+                p = r.copy()
+            else:
+                beta = np.float32(r_sq / c)
+                p = f32(r + float(beta) * p)
+            c = r_sq
+            mp = f32(self.apply(p, +1))
+            d = n2(mp)
+            mmp = f32(self.apply(mp, -1))
+            a = float(np.float32(c / d))
+            x = f32(x + a * p)
+            r = f32(r - a * mmp)
+            r_sq = n2(r)
+            rNorm = np.sqrt(r_sq)
+            maxrx = max(maxrx, rNorm)
+            maxrr = max(maxrr, rNorm)
+            updateX = rNorm < delta * r0Norm and r0Norm <= maxrx
+            updateR = (rNorm < delta * maxrr and r0Norm <= maxrr) or updateX
+            if updateR:
+                n_upd += 1
+                r_d = np.zeros_like(psi)
+                r_d[Vh:] = (b - self.apply(self.apply(x, +1), -1))[Vh:]
+                r = f32(r_d)
+                r_sq = n2(r_d)
+                rNorm = np.sqrt(r_sq)
+                maxrr = rNorm
+                if updateX:
+                    psi[Vh:] += x[Vh:]
+                    x[:] = 0
+                    b = r_d
+                    r0Norm = maxrx = rNorm
+            if r_sq < rsd_sq:
+                psi[Vh:] += x[Vh:]
+                iters = k + 1
+                break
+        else:
+            psi[Vh:] += x[Vh:]
+        resid = self._mdagm_resid(chi, psi) if mdagm else float(np.sqrt(n2(chi - self.apply(psi, +1))))
+        return psi, iters, n_upd, resid
+
 
 # --------------------------------------------------------------------------- reference build
 class RefDslash:

@@ -184,6 +184,72 @@ def test_solver_matches_cpu_restatement(oracle, solver, prec, rsd):
     ctx.close()
 
 
+@pytest.mark.parametrize("solver", ["CG", "BICGSTAB"])
+def test_mdagm_solver(oracle, solver):
+    """HMC-side shells: M^dag M psi = chi by CG (syssolver_mdagm_cg.h:59-94) and two-step BiCGStab
+    (syssolver_mdagm_bicgstab.h:62-110); iteration counts against the CPU restatement, true residual of the normal system."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, "double", gauge="weak")
+    chi = fields.gaussian_fermion(latt, seed=14, cb=1)
+    Vh = ctx.Vh
+    rsd = 1e-8
+    if solver == "CG":
+        psi_ref, n_ref, resid_ref = op.solve_mdagm_cg(chi, np.zeros_like(chi), rsd, 2000)
+        code = L.B200_SOLVER_CG
+    else:
+        psi_ref, n_ref, resid_ref = op.solve_mdagm_bicgstab(chi, np.zeros_like(chi), rsd, 2000)
+        code = L.B200_SOLVER_BICGSTAB
+    psi, info = ctx.invert_mdagm(chi[Vh:], None, solver=code, rsd=rsd, max_iter=2000)
+    assert info.converged == 1
+    assert abs(info.n_count - n_ref) <= max(2, 0.05 * n_ref), (info.n_count, n_ref)
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - op.apply(op.apply(full, +1), -1)
+    res = np.sqrt(np.sum(r[Vh:] ** 2))
+    assert res / np.sqrt(np.sum(chi[Vh:] ** 2)) < 50 * rsd
+    assert abs(info.resid - res) < 1e-3 * res + 1e-13
+    assert rel_site_err(psi, psi_ref[Vh:]) < 1e-5
+    ctx.close()
+
+
+@pytest.mark.parametrize("mdagm", [False, True])
+@pytest.mark.parametrize("delta", [0.1, 0.01])
+def test_reliable_cg_mixed_precision(oracle, delta, mdagm):
+    """RelInvCG_a (reliable_cg.cc:10-190) with fp32 inner / fp64 outer: reaches the fp64 target residual that a pure
+    fp32 solve cannot, with an iteration count within a few percent (+2) of the CPU restatement of the same algorithm
+    and of plain fp64 CG; at least one residual replacement must have happened."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, "double", gauge="weak")
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    rsd = 1e-10
+    psi_ref, n_ref, nupd_ref, resid_ref = op.solve_reliable_cg(chi, np.zeros_like(chi), rsd, delta, 2000, mdagm=mdagm)
+    psi, info = ctx.invert_reliable(chi[Vh:], None, rsd=rsd, delta=delta, max_iter=2000, mdagm=mdagm)
+    assert info.converged == 1
+    assert abs(info.n_count - n_ref) <= max(3, 0.08 * n_ref), (info.n_count, n_ref)
+    if mdagm:
+        _, n64, _ = op.solve_mdagm_cg(chi, np.zeros_like(chi), rsd, 2000)
+    else:
+        _, n64, _, _ = op.solve_cg(chi, np.zeros_like(chi), rsd, 2000)
+    assert info.n_count <= 1.15 * n64 + 3, (info.n_count, n64)
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - (op.apply(op.apply(full, +1), -1) if mdagm else op.apply(full, +1))
+    rel = np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(chi[Vh:] ** 2))
+    assert rel < 20 * rsd, rel                                  # far below what fp32 alone can reach (~1e-6)
+    assert abs(info.rel_resid - rel) < 1e-2 * rel + 1e-14
+    assert rel_site_err(psi, psi_ref[Vh:]) < 1e-6
+    # the second call reuses the fp32 twin; a float context must refuse
+    psi2, info2 = ctx.invert_reliable(chi[Vh:], None, rsd=rsd, delta=delta, max_iter=2000, mdagm=mdagm)
+    assert info2.n_count == info.n_count and np.array_equal(psi2, psi)
+    ctx.close()
+    u, op, ctxf, cp = setup(oracle, latt, "single", gauge="weak")
+    with pytest.raises(L.B200Error) as e:
+        ctxf.invert_reliable(chi[Vh:].astype(np.float32), None, rsd=1e-6, delta=0.1, max_iter=10)
+    assert e.value.code == L.B200_ERR_ARG
+    ctxf.close()
+
+
 def test_plugin_mirror_drop_in(oracle):
     """LinOpSysSolverB200Clover used the way quarkprop4_w.cc:86-109 uses a LinOpSystemSolver: XML-like params in,
     (psi, chi) -> {n_count, resid}; GPU-built clover; non-convergence raises unless SilentFail (.h:634-644)."""

@@ -384,3 +384,25 @@ def test_qprop_solves_unprec_system(oracle):
     psi = op.qprop_reconstruct(psi_o, chi)
     r = op.unprec_apply(psi, +1) - chi
     assert np.linalg.norm(r) / np.linalg.norm(chi) < 1e-8
+
+
+def test_mdagm_and_reliable_restatements(oracle):
+    """The HMC-side shells and the reliable-update CG restatement solve what they claim (true residual of the normal
+    system / of M psi = chi at a tolerance fp32 alone cannot reach), with iteration counts close to plain CG."""
+    L = (4, 4, 4, 8)
+    u = fields.apply_bc(L, fields.weak_gauge(L, seed=11))
+    op = oracle.Op(L, u, 0.1, 1.0)
+    chi = fields.gaussian_fermion(L, seed=12, cb=1)
+    Vh = chi.shape[0] // 2
+    z = np.zeros_like(chi)
+    nchi = np.sqrt(np.sum(chi[Vh:] ** 2))
+    psi, n_cg, res = op.solve_mdagm_cg(chi, z, 1e-9, 500)
+    assert 0 < n_cg < 500 and res / nchi < 1e-7
+    psi2, n_bi, res2 = op.solve_mdagm_bicgstab(chi, z, 1e-9, 500)
+    assert 0 < n_bi < 500 and res2 / nchi < 1e-7
+    assert np.abs(psi - psi2)[Vh:].max() < 1e-6
+    _, n64, _, _ = op.solve_cg(chi, z, 1e-10, 500)
+    for delta in (0.1, 0.01):
+        psi3, n_rel, n_upd, res3 = op.solve_reliable_cg(chi, z, 1e-10, delta, 500)
+        assert n_upd >= 1 and res3 / nchi < 2e-9
+        assert abs(n_rel - n64) <= 0.15 * n64 + 3, (n_rel, n64)
