@@ -1,0 +1,157 @@
+// -*- C++ -*-
+/*! \file
+ *  \brief RAII holder of a b200_ctx for one (gauge field, clover parameters) pair; shared by the LinOp and MdagM
+ *         B200 system solvers.  All numerics happen behind the C ABI of include/b200_clover.h -- this file only
+ *         hands QDP++ pointers across, exactly where the QUDA adapter hands them to loadGaugeQuda / loadCloverQuda /
+ *         invertQuda (quda_solvers/syssolver_linop_clover_quda_w.h:514-552, syssolver_linop_clover_quda_w.cc:76-98).
+ */
+#ifndef __B200_CLOVER_ENGINE_H__
+#define __B200_CLOVER_ENGINE_H__
+
+#include "chromabase.h"
+#include "handle.h"
+#include "state.h"
+#include "io/aniso_io.h"
+#include "actions/ferm/invert/b200_solvers/syssolver_b200_clover_params.h"
+
+#include <b200_clover.h>
+#include <cstring>
+#include <vector>
+
+namespace Chroma
+{
+  namespace B200Glue
+  {
+    //! b200_comm callbacks on top of QDP++'s global sums (used ONCE, to swap CUDA IPC handles between the ranks)
+    inline int allgather(void*, const void* send, void* recv, size_t bytes)
+    {
+      const int nodes = Layout::numNodes(), me = Layout::nodeNumber();
+      std::vector<int> buf(static_cast<size_t>(nodes) * bytes, 0);
+      const unsigned char* s = static_cast<const unsigned char*>(send);
+      for (size_t i = 0; i < bytes; ++i) buf[static_cast<size_t>(me) * bytes + i] = s[i];
+      QDPInternal::globalSumArray(buf.data(), static_cast<int>(buf.size()));
+      unsigned char* r = static_cast<unsigned char*>(recv);
+      for (size_t i = 0; i < buf.size(); ++i) r[i] = static_cast<unsigned char>(buf[i]);
+      return 0;
+    }
+    inline int barrier(void*)
+    {
+      int one = 1;
+      QDPInternal::globalSum(one);
+      return 0;
+    }
+  }
+
+  class B200CloverEngine
+  {
+  public:
+    typedef LatticeFermion T;
+    typedef LatticeColorMatrix U;
+    typedef multi1d<LatticeColorMatrix> Q;
+    typedef WordType<T>::Type_t REALT;
+
+    B200CloverEngine(Handle< FermState<T,Q,Q> > state, const SysSolverB200CloverParams& p) : ctx(0), invParam(p)
+    {
+      host_prec = (sizeof(REALT) == 4) ? B200_SINGLE : B200_DOUBLE;
+      int dev_prec = host_prec;
+      if (p.precision == B200_PREC_SINGLE) dev_prec = B200_SINGLE;
+      if (p.precision == B200_PREC_DOUBLE) dev_prec = B200_DOUBLE;
+      mixed = (dev_prec == B200_DOUBLE) &&
+              (p.sloppyPrecision == B200_PREC_SINGLE || p.solverType == B200_RELIABLE_CG_SOLVER);
+      if (p.solverType == B200_RELIABLE_CG_SOLVER && dev_prec != B200_DOUBLE) {
+        QDPIO::cerr << "B200_CLOVER_INVERTER: RELIABLE_CG needs CudaPrecision DOUBLE" << std::endl;
+        QDP_abort(1);
+      }
+
+      // geometry: the engine splits T only (one rank per GPU inside one NVSwitch box)
+      int gdims[4], grid[4], coord[4];
+      const multi1d<int>& machsize = Layout::logicalSize();
+      const multi1d<int>& mycoord = Layout::nodeCoord();
+      for (int mu = 0; mu < Nd; ++mu) {
+        gdims[mu] = Layout::lattSize()[mu];
+        grid[mu] = machsize[mu];
+        coord[mu] = mycoord[mu];
+      }
+      b200_comm comm;
+      comm.rank = coord[3]; comm.size = grid[3];
+      comm.allgather = B200Glue::allgather; comm.barrier = B200Glue::barrier; comm.user = 0;
+      int device = p.device;
+      if (device < 0) {
+        const int ndev = b200_device_count();
+        if (ndev <= 0) fail("no CUDA device visible");
+        device = Layout::nodeNumber() % ndev;
+      }
+      check(b200_create(&ctx, device, gdims, grid, coord, Layout::numNodes() > 1 ? &comm : 0, dev_prec), "b200_create");
+
+      // links: state->getLinks() already carry the fermion BC phases (simple_fermbc.h:87-103); they go over UNSCALED,
+      // the anisotropy factors of the hopping term travel separately (makeFermCoeffs, io/aniso_io.cc:63-80)
+      const Q& links = state->getLinks();
+      const void* gauge[4];
+      for (int mu = 0; mu < Nd; ++mu)
+        gauge[mu] = (const void*)&(links[mu].elem(all.start()).elem().elem(0,0).real());
+      double cf[4] = {1.0, 1.0, 1.0, 1.0};
+      const AnisoParam_t& aniso = p.CloverParams.anisoParam;
+      if (aniso.anisoP) {
+        multi1d<Real> c = makeFermCoeffs(aniso);
+        for (int mu = 0; mu < Nd; ++mu) cf[mu] = toDouble(c[mu]);
+      }
+      check(b200_load_gauge(ctx, gauge, host_prec, cf, p.AntiPeriodicT ? -1 : +1,
+                            p.reconstruct == B200_RECONS_12_T ? B200_RECONS_12 : B200_RECONS_NONE), "b200_load_gauge");
+
+      // clover term and its even-even inverse are built on the GPU from those links with the coefficients
+      // QDPCloverTermT::create derives (clover_term_qdp_w.h:263-278) -- no host-side CloverTerm is needed
+      double ff = 1.0, fm = 1.0;
+      if (aniso.anisoP) { ff = 1.0 / toDouble(aniso.xi_0); fm = toDouble(aniso.nu) / toDouble(aniso.xi_0); }
+      const double diag_mass = 1.0 + (Nd - 1) * fm + toDouble(p.CloverParams.Mass);
+      const double clov_r = 0.5 * ff * toDouble(p.CloverParams.clovCoeffR);
+      const double clov_t = 0.5 * toDouble(p.CloverParams.clovCoeffT);
+      check(b200_make_clover(ctx, diag_mass, clov_r, clov_t, aniso.anisoP ? 1 : 0, aniso.t_dir), "b200_make_clover");
+    }
+
+    ~B200CloverEngine() { if (ctx) b200_destroy(ctx); }
+
+    //! psi, chi live on rb[1]; cb2 layout makes that one contiguous block starting at rb[1].start()
+    b200_solve_info solve(T& psi, const T& chi, bool mdagm) const
+    {
+      void* out = (void*)&(psi.elem(rb[1].start()).elem(0).elem(0).real());
+      const void* in = (const void*)&(chi.elem(rb[1].start()).elem(0).elem(0).real());
+      b200_solve_info info;
+      std::memset(&info, 0, sizeof(info));
+      const double rsd = toDouble(invParam.RsdTarget);
+      int rc;
+      if (mixed && invParam.solverType != B200_BICGSTAB_SOLVER)
+        rc = b200_invert_reliable(ctx, out, in, host_prec, rsd, toDouble(invParam.Delta), invParam.MaxIter, mdagm ? 1 : 0, &info);
+      else {
+        const int solver = invParam.solverType == B200_BICGSTAB_SOLVER ? B200_SOLVER_BICGSTAB : B200_SOLVER_CG;
+        rc = mdagm ? b200_invert_mdagm(ctx, out, in, host_prec, solver, rsd, invParam.MaxIter, &info)
+                   : b200_invert(ctx, out, in, host_prec, solver, rsd, invParam.MaxIter, &info);
+      }
+      check(rc, "b200_invert");
+      if (invParam.verboseP)
+        QDPIO::cout << "B200_CLOVER_SOLVER: time=" << info.secs << " s\tPerformance=" << info.gflops
+                    << " GFLOPS\tTotal Time (incl. copies)=" << info.secs_total << " s" << std::endl;
+      return info;
+    }
+
+  private:
+    void fail(const char* what) const
+    {
+      QDPIO::cerr << "B200_CLOVER_INVERTER: " << what << std::endl;
+      QDP_abort(1);
+    }
+    void check(int rc, const char* call) const
+    {
+      if (rc != B200_OK) {
+        QDPIO::cerr << "B200_CLOVER_INVERTER: " << call << " failed (" << rc << "): " << b200_last_error() << std::endl;
+        QDP_abort(1);
+      }
+    }
+
+    b200_ctx* ctx;
+    const SysSolverB200CloverParams invParam;
+    int host_prec;
+    bool mixed;
+  };
+}
+
+#endif

@@ -1,0 +1,42 @@
+/*! \file
+ *  \brief Registration of B200_CLOVER_INVERTER in TheLinOpFermSystemSolverFactory
+ */
+#include "chroma_config.h"
+
+#ifdef BUILD_B200
+
+#include "actions/ferm/invert/syssolver_linop_factory.h"
+#include "actions/ferm/invert/syssolver_linop_aggregate.h"
+#include "actions/ferm/invert/b200_solvers/syssolver_linop_clover_b200_w.h"
+
+namespace Chroma
+{
+  namespace LinOpSysSolverB200CloverEnv
+  {
+    namespace
+    {
+      const std::string name("B200_CLOVER_INVERTER");
+      bool registered = false;
+    }
+
+    LinOpSystemSolver<LatticeFermion>* createFerm(XMLReader& xml_in,
+                                                  const std::string& path,
+                                                  Handle< FermState< LatticeFermion, multi1d<LatticeColorMatrix>, multi1d<LatticeColorMatrix> > > state,
+                                                  Handle< LinearOperator<LatticeFermion> > A)
+    {
+      return new LinOpSysSolverB200Clover(A, state, SysSolverB200CloverParams(xml_in, path));
+    }
+
+    bool registerAll()
+    {
+      bool success = true;
+      if (!registered) {
+        success &= Chroma::TheLinOpFermSystemSolverFactory::Instance().registerObject(name, createFerm);
+        registered = true;
+      }
+      return success;
+    }
+  }
+}
+
+#endif

@@ -100,6 +100,7 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_err; }
 const char* b200_version(void) { return "b200-clover 0.1 (sm_100a)"; }
+int b200_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 
 int b200_create(b200_ctx** out, int device, const int global_dims[4], const int proc_grid[4], const int proc_coord[4],
                 const b200_comm* comm, int prec) {

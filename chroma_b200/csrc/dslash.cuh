@@ -329,8 +329,11 @@ struct FinBiOmega {
 #ifndef B200_DSLASH_MINBLOCKS
 #define B200_DSLASH_MINBLOCKS 1
 #endif
+#ifndef B200_DSLASH_MINBLOCKS_F
+#define B200_DSLASH_MINBLOCKS_F 4   // fp32: 64-bit loads need 4 CTAs/SM in flight (tuned on B200: 1 -> 80 %, 3 -> 96 %, 4 -> 100 % of HBM peak)
+#endif
 template <typename R, int EPI, bool RECON12, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, B200_DSLASH_MINBLOCKS) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
+__global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS)) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
   typedef Cx<R> C;
   if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
   if (a.run_if && a.status[a.run_if] == 0) return;

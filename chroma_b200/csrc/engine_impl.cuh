@@ -15,7 +15,10 @@ namespace b200 {
 #ifndef B200_DSLASH_BLOCK
 #define B200_DSLASH_BLOCK 128
 #endif
-constexpr int DSLASH_BLOCK = B200_DSLASH_BLOCK;
+#ifndef B200_DSLASH_BLOCK_F
+#define B200_DSLASH_BLOCK_F 128
+#endif
+constexpr int DSLASH_BLOCK_MAX = B200_DSLASH_BLOCK > B200_DSLASH_BLOCK_F ? B200_DSLASH_BLOCK : B200_DSLASH_BLOCK_F;
 constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
 constexpr size_t STAGING_BYTES = 256u << 20;
 
@@ -44,6 +47,7 @@ template <typename R>
 class Engine : public EngineBase {
  public:
   typedef Cx<R> C;
+  static constexpr int DSLASH_BLOCK = sizeof(R) == 4 ? B200_DSLASH_BLOCK_F : B200_DSLASH_BLOCK;   // tuned per precision
   explicit Engine(const Config& c) { cfg = c; }
   ~Engine() override { destroy(); }
 

@@ -49,6 +49,7 @@ _i4 = C.POINTER(C.c_int)
 SYMBOLS = {
     "b200_last_error": (C.c_char_p, []),
     "b200_version": (C.c_char_p, []),
+    "b200_device_count": (_i, []),
     "b200_create": (_i, [C.POINTER(_vp), _i, _i4, _i4, _i4, C.POINTER(Comm), _i]),
     "b200_destroy": (None, [_vp]),
     "b200_load_gauge": (_i, [_vp, C.POINTER(_vp), _i, C.POINTER(_d), _i, _i]),

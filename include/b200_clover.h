@@ -84,6 +84,7 @@ typedef struct {
 
 const char* b200_last_error(void);
 const char* b200_version(void);
+int b200_device_count(void);   /* CUDA devices visible to this process (<= 0: none); for rank -> device mapping */
 
 /* Create an engine context on CUDA device `device` for a local lattice.  global_dims/proc_grid/
  * proc_coord describe the 4-D domain decomposition the way Layout::lattSize()/logicalSize()/

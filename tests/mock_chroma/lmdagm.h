@@ -1,0 +1,15 @@
+#ifndef MOCK_LMDAGM_H
+#define MOCK_LMDAGM_H
+#include "linearop.h"
+#include "handle.h"
+namespace Chroma {
+template <typename T> class MdagMLinOp : public LinearOperator<T> {   // lib/actions/ferm/linop/lmdagm.h
+ public:
+  MdagMLinOp(Handle< LinearOperator<T> > A_) : A(A_) {}
+  void operator()(T&, const T&, enum PlusMinus) const {}
+  const Subset& subset() const { return A->subset(); }
+ private:
+  Handle< LinearOperator<T> > A;
+};
+}
+#endif
