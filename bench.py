@@ -155,15 +155,23 @@ class Clocks:
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def torch_weak_gauge(latt_local, t0_global, latt_global, seed, eps, device):
-    """Smooth SU(3) field, generated on the GPU per time slab (same recipe as fields.weak_gauge: Gram-Schmidt of 1+eps*G)."""
+    """Smooth SU(3) field, generated on the GPU (same recipe as fields.weak_gauge: Gram-Schmidt of 1+eps*G).  The random
+    stream is keyed by (seed, mu, GLOBAL time slice, checkerboard), so every rank count sees the same global field."""
     import torch
     V = int(np.prod(latt_local))
+    Vh = V // 2
+    lt = latt_local[3]
+    s3h = Vh // lt
     out = np.empty((4, V, 3, 3, 2), dtype=np.float64)
     eye = torch.eye(3, dtype=torch.complex128, device=device)
+    gen = torch.Generator(device=device)
     for mu in range(4):
-        gen = torch.Generator(device=device)
-        gen.manual_seed(seed * 1000 + mu * 10 + 7 + 100003 * t0_global)
-        g = torch.randn((V, 3, 3, 2), generator=gen, device=device, dtype=torch.float64)
+        g = torch.empty((V, 3, 3, 2), device=device, dtype=torch.float64)
+        for cb in range(2):
+            for t in range(lt):
+                gen.manual_seed(((seed * 4 + mu) * 2 + cb) * 100003 + (t0_global + t))
+                lo = cb * Vh + t * s3h
+                g[lo:lo + s3h] = torch.randn((s3h, 3, 3, 2), generator=gen, device=device, dtype=torch.float64)
         m = eye + eps * torch.view_as_complex(g)
         r0 = m[:, 0, :]
         r0 = r0 / torch.linalg.norm(r0, dim=-1, keepdim=True)
@@ -176,6 +184,20 @@ def torch_weak_gauge(latt_local, t0_global, latt_global, seed, eps, device):
         del g, m, u, r0, r1, r2
     torch.cuda.empty_cache()
     return out
+
+
+def torch_gaussian_source(latt_local, t0_global, seed, device, dtype):
+    """Gaussian odd-checkerboard source keyed by (seed, GLOBAL time slice): identical for every rank count."""
+    import torch
+    Vh = int(np.prod(latt_local)) // 2
+    lt = latt_local[3]
+    s3h = Vh // lt
+    gen = torch.Generator(device=device)
+    out = torch.empty((Vh, 4, 3, 2), device=device, dtype=torch.float64)
+    for t in range(lt):
+        gen.manual_seed(seed * 100003 + 7 + (t0_global + t))
+        out[t * s3h:(t + 1) * s3h] = torch.randn((s3h, 4, 3, 2), generator=gen, device=device, dtype=torch.float64)
+    return out.to(dtype).cpu().pin_memory()
 
 
 def apply_bc_local(u, latt_local, is_last_rank):
@@ -258,9 +280,7 @@ def run_b200(args):
     Vh = ctx.Vh
     Vh_global = Vh * world
     npdt = np.float64 if args.prec == "double" else np.float32
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(12 + 7919 * rank)
-    chi_host = torch.randn((Vh, 4, 3, 2), generator=gen, device=dev, dtype=torch.float64).to(torch.float64 if args.prec == "double" else torch.float32).cpu().pin_memory()
+    chi_host = torch_gaussian_source(latt_local, rank * lt, 12, dev, torch.float64 if args.prec == "double" else torch.float32)
     psi_host = torch.zeros_like(chi_host).pin_memory()
     chi_np, psi_np = chi_host.numpy(), psi_host.numpy()
     t_setup = time.time() - t_setup
@@ -373,6 +393,20 @@ def run_b200(args):
         barrier()
         solve = {"solver": args.solver, "seconds": max_over_ranks(inf.secs), "iterations": inf.n_count, "converged": bool(inf.converged),
                  "rel_resid": inf.rel_resid, "gflops": flop_iter * Vh_global * inf.n_count / max(inf.secs, 1e-9) * 1e-9}
+        if args.prec == "double":
+            # the same system by mixed-precision reliable-update CG (fp32 inner, fp64 outer; reliable_cg.cc)
+            psi3 = ctx.field(np.zeros_like(chi_np))
+            barrier()
+            ctx.dev_invert_reliable(psi3, chi_f, rsd=1e-8, delta=0.1, max_iter=50)      # builds the fp32 twin (untimed)
+            solve["mixed_precision_cg"] = []
+            for delta in (0.1, 0.01):
+                psi3.zero()
+                barrier()
+                inf = ctx.dev_invert_reliable(psi3, chi_f, rsd=1e-8, delta=delta, max_iter=10000)
+                barrier()
+                solve["mixed_precision_cg"].append({"delta": delta, "seconds": max_over_ranks(inf.secs), "iterations": inf.n_count,
+                                                    "fp64_residual_replacements": inf.n_updates, "converged": bool(inf.converged),
+                                                    "rel_resid": inf.rel_resid})
 
     clocks.stop()
     ck = clocks.summary(wall0, t_clock_end)

@@ -231,7 +231,7 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   B200_CUDA(cudaEventRecord(hi.ev_t1, st));
   rc = hi.fetch_scalars(); if (rc) return rc;
   if (n_count > 0) info->rsd_sq_iter = hi.h_scal[S_CP];
-  info->n_count = n_count; info->converged = converged;
+  info->n_count = n_count; info->converged = converged; info->n_updates = n_upd;
   rc = hi.true_residual(psi, chi, mdagm, info); if (rc) return rc;
   float ms = 0.f;
   B200_CUDA(cudaEventElapsedTime(&ms, hi.ev_t0, hi.ev_t1));

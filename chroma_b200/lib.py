@@ -28,7 +28,8 @@ class B200Error(RuntimeError):
 
 class SolveInfo(C.Structure):
     _fields_ = [("n_count", C.c_int), ("converged", C.c_int), ("resid", C.c_double), ("rel_resid", C.c_double),
-                ("rsd_sq_iter", C.c_double), ("secs", C.c_double), ("secs_total", C.c_double), ("gflops", C.c_double)]
+                ("rsd_sq_iter", C.c_double), ("secs", C.c_double), ("secs_total", C.c_double), ("gflops", C.c_double),
+                ("n_updates", C.c_int), ("reserved", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -80,6 +80,8 @@ typedef struct {
   double secs;          /* device time of the iteration loop (CUDA events) */
   double secs_total;    /* including host<->device copies of chi / psi when host pointers were given */
   double gflops;        /* Chroma's flop count / secs: CG 2*M + 240, BiCGStab 2*M + 960 per site-iter */
+  int n_updates;        /* b200_invert_reliable: number of fp64 residual replacements (0 for the other solvers) */
+  int reserved;
 } b200_solve_info;
 
 const char* b200_last_error(void);

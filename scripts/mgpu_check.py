@@ -106,6 +106,34 @@ def main():
         print("[rank %d] %-8s iters %d (cpu %d) true rel resid %.3e reported %.3e %s" %
               (rank, name, info.n_count, n_ref, rel, info.rel_resid, "ok" if good else "FAIL"), flush=True)
 
+    # ---- HMC-side normal-equation solve and mixed-precision reliable-update CG (predicated fp64 launches across ranks)
+    def gather_full(sol):
+        full = np.zeros_like(podd)
+        parts = [None] * world
+        dist.all_gather_object(parts, sol.astype(np.float64))
+        for r in range(world):
+            full[Vh + r * lt * s3h: Vh + (r + 1) * lt * s3h] = parts[r]
+        return full
+
+    _, n_ref, _ = op.solve_mdagm_cg(podd, np.zeros_like(podd), rsd, 2000)
+    sol, info = ctx.invert_mdagm(slab_cb(podd, 1).astype(npdt), None, solver=L.B200_SOLVER_CG, rsd=rsd, max_iter=2000)
+    full = gather_full(sol)
+    res = podd - op.apply(op.apply(full, +1), -1)
+    rel = np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(podd[Vh:] ** 2))
+    good = info.converged == 1 and abs(info.n_count - n_ref) <= max(2, 0.05 * n_ref) and rel < 50 * rsd
+    ok &= good
+    print("[rank %d] MdagM CG iters %d (cpu %d) true rel resid %.3e %s" % (rank, info.n_count, n_ref, rel, "ok" if good else "FAIL"), flush=True)
+    if prec == "double":
+        _, n_ref, nupd, _ = op.solve_reliable_cg(podd, np.zeros_like(podd), 1e-10, 0.1, 2000)
+        sol, info = ctx.invert_reliable(slab_cb(podd, 1), None, rsd=1e-10, delta=0.1, max_iter=2000)
+        full = gather_full(sol)
+        res = podd - op.apply(full, +1)
+        rel = np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(podd[Vh:] ** 2))
+        good = info.converged == 1 and abs(info.n_count - n_ref) <= max(3, 0.08 * n_ref) and rel < 2e-9
+        ok &= good
+        print("[rank %d] reliable CG iters %d (cpu %d, %d updates) true rel resid %.3e %s" %
+              (rank, info.n_count, n_ref, nupd, rel, "ok" if good else "FAIL"), flush=True)
+
     ctx.close()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

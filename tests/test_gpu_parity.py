@@ -232,6 +232,7 @@ def test_reliable_cg_mixed_precision(oracle, delta, mdagm):
     else:
         _, n64, _, _ = op.solve_cg(chi, np.zeros_like(chi), rsd, 2000)
     assert info.n_count <= 1.15 * n64 + 3, (info.n_count, n64)
+    assert info.n_updates >= 1 and abs(info.n_updates - nupd_ref) <= 2, (info.n_updates, nupd_ref)
     full = np.zeros_like(chi)
     full[Vh:] = psi
     r = chi - (op.apply(op.apply(full, +1), -1) if mdagm else op.apply(full, +1))
