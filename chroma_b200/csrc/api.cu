@@ -18,8 +18,11 @@ void set_error(const char* fmt, ...) {
 
 __global__ void set_scalars_kernel(double* scal, int* status, ScalarSet s) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    scal += s.rhs * S_COUNT; status += s.rhs * ST_COUNT;
     for (int i = 0; i < s.n; ++i) scal[s.slots[i]] = s.vals[i];
     if (s.reset_status) for (int i = 0; i < ST_COUNT; ++i) status[i] = 0;
+    if (s.reset_status == 2) status[ST_STOP] = -1;        // already converged: no iteration may touch this right-hand side
+    if (s.reset_status == 3) status[ST_BREAKDOWN] = 1;    // rho = 0 before the first iteration
   }
 }
 
@@ -151,6 +154,10 @@ int b200_field_alloc(b200_ctx* ctx, b200_field** f) { CHECK_CTX(ctx); if (!f) { 
 void b200_field_free(b200_ctx* ctx, b200_field* f) { if (ctx && ctx->eng) ctx->eng->field_free(f); }
 int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_upload(f, host, host_prec); }
 int b200_field_download(b200_ctx* ctx, const b200_field* f, void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_download(f, host, host_prec); }
+int b200_mfield_alloc(b200_ctx* ctx, int nrhs, b200_field** f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_alloc(f, nrhs); }
+int b200_mfield_upload(b200_ctx* ctx, b200_field* f, int irhs, const void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_upload(f, host, host_prec, irhs); }
+int b200_mfield_download(b200_ctx* ctx, const b200_field* f, int irhs, void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_download(f, host, host_prec, irhs); }
+int b200_field_nrhs(const b200_field* f) { return f ? f->nrhs : 0; }
 int b200_field_zero(b200_ctx* ctx, b200_field* f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_zero(f); }
 
 int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb) { CHECK_CTX(ctx); return ctx->eng->dslash(out, in, isign, out_cb); }

@@ -16,16 +16,29 @@ namespace b200 {
 
 constexpr int BLAS_BLOCK = 256;
 
+// Batched (multi-RHS) launches use gridDim.y = number of right-hand sides: blockIdx.y picks the field (fstride
+// elements apart), the scalar / status block and the reduction slots of that right-hand side.  gridDim.y = 1 is the
+// ordinary single-RHS launch.
 struct BlasCtl {
   double* scal; int* status; ReduceBuf red;
   int iter; int check_stop;
+  size_t fstride;
+  template <int N>
+  __device__ __forceinline__ BlasCtl for_rhs(int rhs) const {
+    BlasCtl c = *this;
+    c.scal += rhs * S_COUNT; c.status += rhs * ST_COUNT;
+    if (N > 0) c.red = red.template for_rhs<(N > 0 ? N : 1)>(rhs);
+    return c;
+  }
 };
 
 // ---------------------------------------------------------------- CG: psi += a p ; p = r + b p
 // invcg2.cc:185 and :220.  On the converging iteration psi is still updated, p is not.
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) cg_update_kernel(Cx<R>* __restrict__ psi, Cx<R>* __restrict__ p,
-                                                              const Cx<R>* __restrict__ r, size_t n, BlasCtl c) {
+                                                              const Cx<R>* __restrict__ r, size_t n, BlasCtl c0) {
+  const BlasCtl c = c0.template for_rhs<0>(blockIdx.y);
+  psi += blockIdx.y * c.fstride; p += blockIdx.y * c.fstride; r += blockIdx.y * c.fstride;
   int stop = c.check_stop ? c.status[ST_STOP] : 0;
   if (stop != 0 && stop < c.iter) return;
   const bool conv = (stop == c.iter) && stop != 0;
@@ -46,7 +59,9 @@ __global__ void __launch_bounds__(BLAS_BLOCK) cg_update_kernel(Cx<R>* __restrict
 // invbicgstab.cc:87-97
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) bicg_p_kernel(Cx<R>* __restrict__ p, const Cx<R>* __restrict__ r,
-                                                           const Cx<R>* __restrict__ v, size_t n, BlasCtl c) {
+                                                           const Cx<R>* __restrict__ v, size_t n, BlasCtl c0) {
+  const BlasCtl c = c0.template for_rhs<0>(blockIdx.y);
+  p += blockIdx.y * c.fstride; r += blockIdx.y * c.fstride; v += blockIdx.y * c.fstride;
   if (c.check_stop && (c.status[ST_STOP] != 0 || c.status[ST_BREAKDOWN] != 0)) return;
   const Cx<R> beta = mk<R>((R)c.scal[S_BETA_RE], (R)c.scal[S_BETA_IM]);
   const Cx<R> omega = mk<R>((R)c.scal[S_OMEGA_RE], (R)c.scal[S_OMEGA_IM]);
@@ -59,7 +74,9 @@ __global__ void __launch_bounds__(BLAS_BLOCK) bicg_p_kernel(Cx<R>* __restrict__ 
 // ---------------------------------------------------------------- BiCGStab: r -= alpha v   (s overlaps r)
 // invbicgstab.cc:122
 template <typename R>
-__global__ void __launch_bounds__(BLAS_BLOCK) bicg_s_kernel(Cx<R>* __restrict__ r, const Cx<R>* __restrict__ v, size_t n, BlasCtl c) {
+__global__ void __launch_bounds__(BLAS_BLOCK) bicg_s_kernel(Cx<R>* __restrict__ r, const Cx<R>* __restrict__ v, size_t n, BlasCtl c0) {
+  const BlasCtl c = c0.template for_rhs<0>(blockIdx.y);
+  r += blockIdx.y * c.fstride; v += blockIdx.y * c.fstride;
   if (c.check_stop && (c.status[ST_STOP] != 0 || c.status[ST_BREAKDOWN] != 0)) return;
   const Cx<R> alpha = mk<R>((R)c.scal[S_ALPHA_RE], (R)c.scal[S_ALPHA_IM]);
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK)
@@ -93,7 +110,9 @@ struct FinBiUpdate {
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) bicg_update_kernel(Cx<R>* __restrict__ psi, Cx<R>* __restrict__ r,
                                                                 const Cx<R>* __restrict__ p, const Cx<R>* __restrict__ t,
-                                                                const Cx<R>* __restrict__ r0, size_t n, BlasCtl c) {
+                                                                const Cx<R>* __restrict__ r0, size_t n, BlasCtl c0) {
+  const BlasCtl c = c0.template for_rhs<3>(blockIdx.y);
+  psi += blockIdx.y * c.fstride; r += blockIdx.y * c.fstride; p += blockIdx.y * c.fstride; t += blockIdx.y * c.fstride; r0 += blockIdx.y * c.fstride;
   if (c.check_stop && (c.status[ST_STOP] != 0 || c.status[ST_BREAKDOWN] != 0)) return;
   const Cx<R> alpha = mk<R>((R)c.scal[S_ALPHA_RE], (R)c.scal[S_ALPHA_IM]);
   const Cx<R> omega = mk<R>((R)c.scal[S_OMEGA_RE], (R)c.scal[S_OMEGA_IM]);
@@ -116,7 +135,9 @@ __global__ void __launch_bounds__(BLAS_BLOCK) bicg_update_kernel(Cx<R>* __restri
 struct FinStore { double* dst; int n; __device__ void operator()(const double* t) const { for (int k = 0; k < n; ++k) dst[k] = t[k]; } };
 
 template <typename R>
-__global__ void __launch_bounds__(BLAS_BLOCK) norm2_kernel(const Cx<R>* __restrict__ x, size_t n, ReduceBuf red, double* dst) {
+__global__ void __launch_bounds__(BLAS_BLOCK) norm2_kernel(const Cx<R>* __restrict__ x, size_t n, ReduceBuf red0, double* dst, size_t fstride) {
+  const ReduceBuf red = red0.template for_rhs<1>(blockIdx.y);
+  x += blockIdx.y * fstride; dst += blockIdx.y * S_COUNT;
   double s[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
     const Cx<R> v = x[i]; s[0] += (double)v.x * v.x + (double)v.y * v.y;
@@ -126,7 +147,9 @@ __global__ void __launch_bounds__(BLAS_BLOCK) norm2_kernel(const Cx<R>* __restri
 
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) inner_kernel(const Cx<R>* __restrict__ x, const Cx<R>* __restrict__ y, size_t n,
-                                                          ReduceBuf red, double* dst) {
+                                                          ReduceBuf red0, double* dst, size_t fstride) {
+  const ReduceBuf red = red0.template for_rhs<2>(blockIdx.y);
+  x += blockIdx.y * fstride; y += blockIdx.y * fstride; dst += blockIdx.y * S_COUNT;
   double s[2] = {0.0, 0.0};
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
     const Cx<R> a = x[i], b = y[i];
@@ -139,7 +162,11 @@ __global__ void __launch_bounds__(BLAS_BLOCK) inner_kernel(const Cx<R>* __restri
 // out = x - y ; optional copies of out into out2 ; |out|^2 -> dst   (r = chi - A psi ; p = r / r0 = r)
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) xmy_norm_kernel(Cx<R>* out, Cx<R>* out2, const Cx<R>* x, const Cx<R>* y, size_t n,
-                                                             ReduceBuf red, double* dst) {
+                                                             ReduceBuf red0, double* dst, size_t fstride) {
+  const ReduceBuf red = red0.template for_rhs<1>(blockIdx.y);
+  if (out) out += blockIdx.y * fstride;
+  if (out2) out2 += blockIdx.y * fstride;
+  x += blockIdx.y * fstride; y += blockIdx.y * fstride; dst += blockIdx.y * S_COUNT;
   double s[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
     const Cx<R> v = csub(x[i], y[i]);
@@ -153,7 +180,8 @@ __global__ void __launch_bounds__(BLAS_BLOCK) xmy_norm_kernel(Cx<R>* out, Cx<R>*
 // out = a*x + b*y (real a,b from the host; setup only)
 template <typename R>
 __global__ void __launch_bounds__(BLAS_BLOCK) axpby_kernel(Cx<R>* __restrict__ out, double a, const Cx<R>* __restrict__ x, double b,
-                                                          const Cx<R>* __restrict__ y, size_t n) {
+                                                          const Cx<R>* __restrict__ y, size_t n, size_t fstride) {
+  out += blockIdx.y * fstride; x += blockIdx.y * fstride; y += blockIdx.y * fstride;
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
     const Cx<R> xv = x[i], yv = y[i];
     out[i] = mk<R>((R)(a * xv.x + b * yv.x), (R)(a * xv.y + b * yv.y));

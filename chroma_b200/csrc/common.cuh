@@ -58,6 +58,21 @@ __device__ __forceinline__ float2 ld_stream(const float2* p, uint64_t pol) {
   asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+// Multi-RHS kernels: the 12 right-hand sides of a CTA read the SAME links / clover blocks, so those loads allocate in L1
+// (plain ld.global.nc, default L2 policy) and the first warp's miss serves the other eleven; the spinors, which are
+// private to one right-hand side, bypass L1 so they cannot evict the shared operator data.
+__device__ __forceinline__ double2 ld_op(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ float2 ld_op(const float2* p) { return __ldg(p); }
+__device__ __forceinline__ double2 ld_keep_nol1(const double2* p, uint64_t pol) {
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float2 ld_keep_nol1(const float2* p, uint64_t pol) {
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
 // read-modify-write streams (the CG residual) must not use the non-coherent path
 __device__ __forceinline__ double2 ld_stream_rw(const double2* p, uint64_t pol) {
   double2 v;
@@ -96,7 +111,11 @@ struct Geom {
   int tsplit;           // 1 if T is split across ranks (ghost faces instead of wrap-around in t)
 };
 
-// Device-resident scalars of the solvers (double, one array per context).
+// Right-hand sides solved in lockstep by the batched (multi-RHS) kernels: the 12 spin-colour sources of a propagator
+// (quarkprop4_w.cc:70-117).  Every right-hand side owns one ScalarSlot block and one StatusSlot block.
+constexpr int MAX_RHS = 12;
+
+// Device-resident scalars of the solvers (double, one block of S_COUNT per right-hand side).
 enum ScalarSlot {
   S_RSDSQ = 0,   // stopping threshold |r|^2 <= / < rsd_sq
   S_C, S_D, S_CP, S_A, S_B,                       // CG: c=|r_{k-1}|^2, d=|Mp|^2, cp=|r_k|^2, a=c/d, b=cp/c

@@ -53,17 +53,21 @@ struct DslashArgs {
   int iter;         // solver iteration this launch belongs to (for the stop flag)
   int check_stop;   // 1: return immediately if status[ST_STOP] != 0
   int run_if;       // != 0: status slot that must be non-zero for this launch to do anything (predicated launch)
+  // multi-RHS launches (dslash_mrhs_kernel): in/out/x/r/r0 point at right-hand side 0 of `nrhs` consecutive fields
+  int nrhs;
+  size_t fstride;   // elements between consecutive right-hand sides of a batched field (12*Vh)
+  size_t gstride;   // same for the ghost faces (6*S3h)
 };
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
-template <typename R, int MU>
+template <typename R, int MU, bool MR = false>
 __device__ __forceinline__ void load_project(Cx<R> h0[3], Cx<R> h1[3], const Cx<R>* __restrict__ p, int stride, R sg, uint64_t keep) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const Cx<R> a0 = ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a1 = ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a2 = ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a3 = ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a0 = MR ? ld_keep_nol1(p + (0 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a1 = MR ? ld_keep_nol1(p + (1 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a2 = MR ? ld_keep_nol1(p + (2 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a3 = MR ? ld_keep_nol1(p + (3 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
     if (MU == 0) {          // h0 = a0 + sg*i*a3, h1 = a1 + sg*i*a2
       h0[c] = mk<R>(a0.x - sg * a3.y, a0.y + sg * a3.x);
       h1[c] = mk<R>(a1.x - sg * a2.y, a1.y + sg * a2.x);
@@ -104,11 +108,11 @@ __device__ __forceinline__ void recons_acc(Cx<R> acc[12], const Cx<R> r0[3], con
 }
 
 // ---- link load (18 reals, or 12 + third-row reconstruction) --------------------------------------
-template <typename R, bool RECON12>
+template <typename R, bool RECON12, bool MR = false>
 __device__ __forceinline__ void load_link(Cx<R> U[9], const Cx<R>* __restrict__ p, int stride, uint64_t strm) {
   constexpr int NG = RECON12 ? 6 : 9;
 #pragma unroll
-  for (int k = 0; k < NG; ++k) U[k] = ld_stream(p + k * (size_t)stride, strm);
+  for (int k = 0; k < NG; ++k) U[k] = MR ? ld_op(p + k * (size_t)stride) : ld_stream(p + k * (size_t)stride, strm);
   if (RECON12) {
     // row2 = conj(row0 x row1): exact for SU(3); non-unit factors (anisotropy, -1 boundary phase)
     // are carried separately by the caller (see load_gauge in api.cu).
@@ -136,12 +140,12 @@ __device__ __forceinline__ void su3_mul(Cx<R> r0[3], Cx<R> r1[3], const Cx<R> U[
 }
 
 // One hop: acc += recons( U(or U^dag) * project(psi_nbr) ).
-template <typename R, int MU, bool ADJ, bool RECON12>
+template <typename R, int MU, bool ADJ, bool RECON12, bool MR = false>
 __device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi_nbr, const Cx<R>* __restrict__ link,
                                     int stride, R sg, R scale, const L2Policy& pol) {
   Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
-  load_project<R, MU>(h0, h1, psi_nbr, stride, sg, pol.keep);
-  load_link<R, RECON12>(U, link, stride, pol.stream);
+  load_project<R, MU, MR>(h0, h1, psi_nbr, stride, sg, pol.keep);
+  load_link<R, RECON12, MR>(U, link, stride, pol.stream);
   if (RECON12) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
@@ -158,7 +162,7 @@ struct LinkScale {
 };
 
 // The Wilson hopping term for one target site.  (xh,y,z,t) are its checkerboard coordinates.
-template <typename R, bool RECON12>
+template <typename R, bool RECON12, bool MR = false>
 __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol) {
   typedef Cx<R> C;
   const Geom& g = a.g;
@@ -185,21 +189,21 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
   {
     const int xf = r ? (xh + 1 == g.Lxh ? idx - (g.Lxh - 1) : idx + 1) : idx;
     const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
-    hop<R, 0, false, RECON12>(acc, in + xf, Uf + 0 * gmu, stride, -s, (R)ls.aniso[0], pol);
-    hop<R, 0, true, RECON12>(acc, in + xb, Ub + 0 * gmu + xb, stride, s, (R)ls.aniso[0], pol);
+    hop<R, 0, false, RECON12, MR>(acc, in + xf, Uf + 0 * gmu, stride, -s, (R)ls.aniso[0], pol);
+    hop<R, 0, true, RECON12, MR>(acc, in + xb, Ub + 0 * gmu + xb, stride, s, (R)ls.aniso[0], pol);
   }
   {
     const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
     const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
-    hop<R, 1, false, RECON12>(acc, in + yf, Uf + 1 * gmu, stride, -s, (R)ls.aniso[1], pol);
-    hop<R, 1, true, RECON12>(acc, in + yb, Ub + 1 * gmu + yb, stride, s, (R)ls.aniso[1], pol);
+    hop<R, 1, false, RECON12, MR>(acc, in + yf, Uf + 1 * gmu, stride, -s, (R)ls.aniso[1], pol);
+    hop<R, 1, true, RECON12, MR>(acc, in + yb, Ub + 1 * gmu + yb, stride, s, (R)ls.aniso[1], pol);
   }
   {
     const int sz = g.Ly * g.Lxh;
     const int zf = (z + 1 == g.Lz) ? idx - (g.Lz - 1) * sz : idx + sz;
     const int zb = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
-    hop<R, 2, false, RECON12>(acc, in + zf, Uf + 2 * gmu, stride, -s, (R)ls.aniso[2], pol);
-    hop<R, 2, true, RECON12>(acc, in + zb, Ub + 2 * gmu + zb, stride, s, (R)ls.aniso[2], pol);
+    hop<R, 2, false, RECON12, MR>(acc, in + zf, Uf + 2 * gmu, stride, -s, (R)ls.aniso[2], pol);
+    hop<R, 2, true, RECON12, MR>(acc, in + zb, Ub + 2 * gmu + zb, stride, s, (R)ls.aniso[2], pol);
   }
   {
     const int st = g.S3h;
@@ -218,7 +222,7 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       const C* __restrict__ gp = a.ghost_fwd + (idx - (g.Lt - 1) * st);
 #pragma unroll
       for (int c = 0; c < 3; ++c) { h0[c] = ld_stream(gp + (size_t)c * st, pol.stream); h1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
-      load_link<R, RECON12>(U, Uf + 3 * gmu, stride, pol.stream);
+      load_link<R, RECON12, MR>(U, Uf + 3 * gmu, stride, pol.stream);
       if (RECON12) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { h0[c].x *= scf; h0[c].y *= scf; h1[c].x *= scf; h1[c].y *= scf; }
@@ -226,7 +230,7 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       su3_mul<R, false>(r0, r1, U, h0, h1);
       recons_acc<R, 3>(acc, r0, r1, -s);
     } else {
-      hop<R, 3, false, RECON12>(acc, in + tf, Uf + 3 * gmu, stride, -s, scf, pol);
+      hop<R, 3, false, RECON12, MR>(acc, in + tf, Uf + 3 * gmu, stride, -s, scf, pol);
     }
     if (g.tsplit && first) {
       // U^dag (1 +/- g3) psi computed by the -t neighbour rank (it owns that link): just reconstruct
@@ -236,7 +240,7 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       for (int c = 0; c < 3; ++c) { r0[c] = ld_stream(gp + (size_t)c * st, pol.stream); r1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
       recons_acc<R, 3>(acc, r0, r1, s);
     } else {
-      hop<R, 3, true, RECON12>(acc, in + tb, Ub + 3 * gmu + tb, stride, s, scb, pol);
+      hop<R, 3, true, RECON12, MR>(acc, in + tb, Ub + 3 * gmu + tb, stride, s, scb, pol);
     }
   }
 }
@@ -244,9 +248,11 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
 // ---- clover: one 6x6 Hermitian block times 6 complex --------------------------------------------
 // out[i] = d_i in[i] + sum_{j<i} o_{k(i,j)} in[j] + sum_{j>i} conj(o_{k(j,i)}) in[j], k = i(i-1)/2+j
 // (applySiteLoop, clover_term_qdp_w.h:1606-1634).  cl points at plane 0 of the block for this site.
-template <typename R>
+template <typename R, bool MR = false>
 __device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], const Cx<R>* __restrict__ cl, int stride, uint64_t strm) {
-  const Cx<R> d01 = ld_stream(cl, strm), d23 = ld_stream(cl + (size_t)stride, strm), d45 = ld_stream(cl + 2 * (size_t)stride, strm);
+  const Cx<R> d01 = MR ? ld_op(cl) : ld_stream(cl, strm);
+  const Cx<R> d23 = MR ? ld_op(cl + (size_t)stride) : ld_stream(cl + (size_t)stride, strm);
+  const Cx<R> d45 = MR ? ld_op(cl + 2 * (size_t)stride) : ld_stream(cl + 2 * (size_t)stride, strm);
   out[0] = mk<R>(d01.x * in[0].x, d01.x * in[0].y);
   out[1] = mk<R>(d01.y * in[1].x, d01.y * in[1].y);
   out[2] = mk<R>(d23.x * in[2].x, d23.x * in[2].y);
@@ -258,7 +264,7 @@ __device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], co
   for (int i = 1; i < 6; ++i) {
 #pragma unroll
     for (int j = 0; j < i; ++j) {
-      const Cx<R> o = ld_stream(cl + (size_t)(3 + k) * stride, strm);
+      const Cx<R> o = MR ? ld_op(cl + (size_t)(3 + k) * stride) : ld_stream(cl + (size_t)(3 + k) * stride, strm);
       cmac(out[i], o, in[j]);
       cmac_conj(out[j], o, in[i]);
       ++k;
@@ -332,6 +338,75 @@ struct FinBiOmega {
 #ifndef B200_DSLASH_MINBLOCKS_F
 #define B200_DSLASH_MINBLOCKS_F 4   // fp32: 64-bit loads need 4 CTAs/SM in flight (tuned on B200: 1 -> 80 %, 3 -> 96 %, 4 -> 100 % of HBM peak)
 #endif
+// ---- fused epilogues for one target site (shared by the single- and multi-RHS kernels) ------------------------
+template <typename R, int EPI, bool MR>
+__device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>& a, int idx, int stride, const L2Policy& pol, double red[3]) {
+  typedef Cx<R> C;
+  if (EPI == EPI_DSLASH) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, acc[k], pol.stream);
+  } else if (EPI == EPI_AINV) {
+    C o[12];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) clover_block<R, MR>(o + 6 * b, acc + 6 * b, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, o[k], pol.stream);
+  } else {
+    // all EPI_M* variants: m = A x - 1/4 D in.  Every load is issued before the first store (the stores are
+    // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
+    // and would cost one exposed DRAM round trip each.
+    C m[12], ex[12];
+    if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) ex[k] = ld_stream_rw(a.r + (size_t)k * stride + idx, pol.stream);
+    }
+    if (EPI == EPI_M_DOTR0) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) ex[k] = ld_stream(a.r0 + (size_t)k * stride + idx, pol.stream);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      C xi[6], o[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xi[k] = ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
+      clover_block<R, MR>(o, xi, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
+        if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
+          const C mm = m[6 * b + k];
+          red[0] += (double)mm.x * xi[k].x + (double)mm.y * xi[k].y;
+          red[1] += (double)mm.x * xi[k].y - (double)mm.y * xi[k].x;
+          red[2] += (double)mm.x * mm.x + (double)mm.y * mm.y;
+        }
+      }
+    }
+    if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
+      const R cg_a = (R)a.scal[S_A];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        C rv = ex[k];
+        rv.x -= cg_a * m[k].x; rv.y -= cg_a * m[k].y;
+        red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+        m[k] = rv;
+      }
+#pragma unroll
+      for (int k = 0; k < 12; ++k) st_stream(a.r + (size_t)k * stride + idx, m[k], pol.stream);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        if (EPI == EPI_M_NORM) red[0] += (double)m[k].x * m[k].x + (double)m[k].y * m[k].y;
+        if (EPI == EPI_M_DOTR0) {                             // <r0|m> = conj(r0) m
+          red[0] += (double)ex[k].x * m[k].x + (double)ex[k].y * m[k].y;
+          red[1] += (double)ex[k].x * m[k].y - (double)ex[k].y * m[k].x;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, m[k], pol.stream);
+    }
+  }
+}
+
 template <typename R, int EPI, bool RECON12, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS)) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
   typedef Cx<R> C;
@@ -346,71 +421,8 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
   if (active) {
     const L2Policy pol = make_l2_policy();
     C acc[12];
-    dslash_site<R, RECON12>(acc, a, ls, idx, pol);
-
-    if (EPI == EPI_DSLASH) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, acc[k], pol.stream);
-    } else if (EPI == EPI_AINV) {
-      C o[12];
-#pragma unroll
-      for (int b = 0; b < 2; ++b) clover_block<R>(o + 6 * b, acc + 6 * b, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
-#pragma unroll
-      for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, o[k], pol.stream);
-    } else {
-      // all EPI_M* variants: m = A x - 1/4 D in.  Every load is issued before the first store (the stores are
-      // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
-      // and would cost one exposed DRAM round trip each.
-      C m[12], ex[12];
-      if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) ex[k] = ld_stream_rw(a.r + (size_t)k * stride + idx, pol.stream);
-      }
-      if (EPI == EPI_M_DOTR0) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) ex[k] = ld_stream(a.r0 + (size_t)k * stride + idx, pol.stream);
-      }
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        C xi[6], o[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) xi[k] = ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
-        clover_block<R>(o, xi, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
-          if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
-            const C mm = m[6 * b + k];
-            red[0] += (double)mm.x * xi[k].x + (double)mm.y * xi[k].y;
-            red[1] += (double)mm.x * xi[k].y - (double)mm.y * xi[k].x;
-            red[2] += (double)mm.x * mm.x + (double)mm.y * mm.y;
-          }
-        }
-      }
-      if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
-        const R cg_a = (R)a.scal[S_A];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-          C rv = ex[k];
-          rv.x -= cg_a * m[k].x; rv.y -= cg_a * m[k].y;
-          red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
-          m[k] = rv;
-        }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) st_stream(a.r + (size_t)k * stride + idx, m[k], pol.stream);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) {
-          if (EPI == EPI_M_NORM) red[0] += (double)m[k].x * m[k].x + (double)m[k].y * m[k].y;
-          if (EPI == EPI_M_DOTR0) {                             // <r0|m> = conj(r0) m
-            red[0] += (double)ex[k].x * m[k].x + (double)ex[k].y * m[k].y;
-            red[1] += (double)ex[k].x * m[k].y - (double)ex[k].y * m[k].x;
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, m[k], pol.stream);
-      }
-    }
+    dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
+    site_epilogue<R, EPI, false>(acc, a, idx, stride, pol, red);
   }
 
   if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal});
@@ -418,6 +430,51 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
   if (EPI == EPI_M_CGREL) grid_reduce<1, BLOCK>(red, a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status});
   if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status});
+}
+
+// ---- multi-RHS variant ------------------------------------------------------------------------------------------
+// CTA = 32 consecutive target sites x NRB right-hand sides (threadIdx.y = right-hand side, one warp each).  All warps
+// of a CTA need the same 8 links and the same clover block per site: the first warp's load brings them into L1, the
+// others hit, so gauge + clover cross L2/HBM once per CTA instead of once per right-hand side -- per right-hand side
+// the operator moves (120 + (144+16G)/nrhs) reals per site instead of 264+16G.
+// Every right-hand side has its own scalar / status block and its own reduction (warp_grid_reduce), so the solves
+// advance in lockstep but converge independently.
+#ifndef B200_MRHS_NRB
+#define B200_MRHS_NRB 12
+#endif
+template <typename R, int EPI, bool RECON12, int NRB>
+__global__ void __launch_bounds__(32 * NRB, 1) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
+  typedef Cx<R> C;
+  const int grp = blockIdx.x % ngroups, site_block = blockIdx.x / ngroups;
+  const int rhs = grp * NRB + threadIdx.y;
+  if (rhs >= a0.nrhs) return;
+  DslashArgs<R> a = a0;
+  a.scal = a0.scal + rhs * S_COUNT; a.status = a0.status + rhs * ST_COUNT;
+  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  a.in = a0.in + rhs * a0.fstride;
+  if (a0.out) a.out = a0.out + rhs * a0.fstride;
+  if (a0.x) a.x = a0.x + rhs * a0.fstride;
+  if (a0.r) a.r = a0.r + rhs * a0.fstride;
+  if (a0.r0) a.r0 = a0.r0 + rhs * a0.fstride;
+  if (a0.ghost_fwd) { a.ghost_fwd = a0.ghost_fwd + rhs * a0.gstride; a.ghost_bwd = a0.ghost_bwd + rhs * a0.gstride; }
+  const int stride = a.g.Vh;
+  const int local = site_block * 32 + threadIdx.x;
+  const bool active = local < a.idx_count + a.idx_count2;
+  const int idx = !active ? a.idx_begin : (local < a.idx_count ? a.idx_begin + local : a.idx_begin2 + (local - a.idx_count));
+  double red[3] = {0.0, 0.0, 0.0};
+
+  if (active) {
+    const L2Policy pol = make_l2_policy();
+    C acc[12];
+    dslash_site<R, RECON12, true>(acc, a, ls, idx, pol);
+    site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red);
+  }
+
+  const int sb = site_block;   // block_offset of a split step is applied inside warp_grid_reduce
+  if (EPI == EPI_M_NORM) warp_grid_reduce<1>(red, a.red.template for_rhs<1>(rhs), sb, FinCgD{a.scal});
+  if (EPI == EPI_M_CG) warp_grid_reduce<1>(red, a.red.template for_rhs<1>(rhs), sb, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_DOTR0) warp_grid_reduce<2>(red, a.red.template for_rhs<2>(rhs), sb, FinBiAlpha{a.scal, a.status});
+  if (EPI == EPI_M_DOTX) warp_grid_reduce<3>(red, a.red.template for_rhs<3>(rhs), sb, FinBiOmega{a.scal, a.status});
 }
 
 }  // namespace b200

@@ -17,9 +17,10 @@
 #include "common.cuh"
 
 struct b200_field {
-  void* d;        // device planes C[12][Vh]
+  void* d;        // device planes C[nrhs][12][Vh]
   size_t bytes;
   int prec;
+  int nrhs;       // right-hand sides held (1 for an ordinary field)
 };
 
 namespace b200 {
@@ -53,18 +54,18 @@ class EngineBase {
   virtual int make_clover(double diag_mass, double cr, double ct, int aniso, int t_dir) = 0;
   virtual int get_clover(void* clov, void* invclov, int host_prec) = 0;
   virtual int clover_logdet(double* out) = 0;
-  virtual int field_alloc(b200_field** f) = 0;
+  virtual int field_alloc(b200_field** f, int nrhs = 1) = 0;
   virtual void field_free(b200_field* f) = 0;
-  virtual int field_upload(b200_field* f, const void* host, int host_prec) = 0;
-  virtual int field_download(const b200_field* f, void* host, int host_prec) = 0;
+  virtual int field_upload(b200_field* f, const void* host, int host_prec, int irhs = 0) = 0;
+  virtual int field_download(const b200_field* f, void* host, int host_prec, int irhs = 0) = 0;
   virtual int field_zero(b200_field* f) = 0;
   virtual int dslash(b200_field* out, const b200_field* in, int isign, int out_cb) = 0;
   virtual int clover_apply(b200_field* out, const b200_field* in, int cb, int inverse) = 0;
   virtual int matpc(b200_field* out, const b200_field* in, int isign) = 0;
   virtual int time_matpc(b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) = 0;
-  virtual int norm2(const b200_field* x, double* r) = 0;
-  virtual int inner(const b200_field* x, const b200_field* y, double r[2]) = 0;
-  virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, int mdagm, b200_solve_info* info) = 0;
+  virtual int norm2(const b200_field* x, double* r) = 0;                          // r[nrhs]
+  virtual int inner(const b200_field* x, const b200_field* y, double r[2]) = 0;   // r[nrhs][2]
+  virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, int mdagm, b200_solve_info* info) = 0;   // info[nrhs]
   virtual int iterate_begin(b200_field* psi, const b200_field* chi, int solver) = 0;
   virtual int iterate(int solver, int n_iter) = 0;
   virtual int qprop(void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter,

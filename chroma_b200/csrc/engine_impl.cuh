@@ -1,6 +1,7 @@
 // engine_impl.cuh -- Engine<R>: templated on the device precision (double / float).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstdarg>
 
 #include "engine.cuh"
@@ -24,9 +25,10 @@ constexpr size_t STAGING_BYTES = 256u << 20;
 
 template <typename R, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) clover_kernel(const Cx<R>* __restrict__ in, Cx<R>* __restrict__ out,
-                                                      const Cx<R>* __restrict__ clov, int Vh) {
+                                                      const Cx<R>* __restrict__ clov, int Vh, size_t fstride) {
   const int idx = blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= Vh) return;
+  in += blockIdx.y * fstride; out += blockIdx.y * fstride;
 #pragma unroll
   for (int b = 0; b < 2; ++b) {
     Cx<R> xi[6], o[6];
@@ -38,7 +40,7 @@ __global__ void __launch_bounds__(BLOCK) clover_kernel(const Cx<R>* __restrict__
   }
 }
 
-struct ScalarSet { int n; int slots[12]; double vals[12]; int reset_status; };
+struct ScalarSet { int n; int slots[12]; double vals[12]; int reset_status; int rhs; };
 __global__ void set_scalars_kernel(double* scal, int* status, ScalarSet s);
 __global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f);
 __global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f);
@@ -62,8 +64,8 @@ class Engine : public EngineBase {
   double* tr_log = nullptr; // [Vh] log|det A_ee| per even site (make_clover only)
   bool have_trlog = false;
   double* scal = nullptr; int* status = nullptr;
-  double* partial = nullptr; unsigned int* ticket = nullptr; int partial_cap = 0;
-  double* h_scal = nullptr; int* h_status = nullptr;   // pinned; h_status has 2 slots
+  double* partial = nullptr; unsigned int* ticket = nullptr; size_t partial_cap = 0;   // partial: doubles; ticket: [MAX_RHS]
+  double* h_scal = nullptr; int* h_status = nullptr;   // pinned; [MAX_RHS][S_COUNT] and 2 slots of [MAX_RHS][ST_COUNT]
   cudaEvent_t ev_poll[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
   void* staging = nullptr;
   b200_field* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -72,7 +74,7 @@ class Engine : public EngineBase {
   bool owns_stream = true, owns_scalars = true;   // false once a mixed-precision partner lent us its stream / scalar block
   long long operator_epoch = 0;                   // bumped whenever gauge or clover change (the fp32 twin re-syncs on it)
   // fixed-iteration (benchmark) state
-  C* it_psi = nullptr; const C* it_chi = nullptr; int it_k = 0;
+  C* it_psi = nullptr; const C* it_chi = nullptr; int it_k = 0, it_nb = 1;
 
   size_t nelem() const { return (size_t)12 * g.Vh; }
 
@@ -100,16 +102,15 @@ class Engine : public EngineBase {
     g.Vh = g.S3h * g.Lt;
     g.tsplit = cfg.pgrid[3] > 1 ? 1 : 0;
     B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    B200_CUDA(cudaMalloc(&scal, sizeof(double) * S_COUNT));
-    B200_CUDA(cudaMalloc(&status, sizeof(int) * ST_COUNT));
-    B200_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * S_COUNT, stream));
-    B200_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * ST_COUNT, stream));
-    partial_cap = std::max((g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK + 8, blas_grid);
-    B200_CUDA(cudaMalloc(&partial, sizeof(double) * 4 * (size_t)partial_cap));
-    B200_CUDA(cudaMalloc(&ticket, sizeof(unsigned int)));
-    B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream));
-    B200_CUDA(cudaHostAlloc(&h_scal, sizeof(double) * S_COUNT, cudaHostAllocDefault));
-    B200_CUDA(cudaHostAlloc(&h_status, sizeof(int) * ST_COUNT * 2, cudaHostAllocDefault));
+    B200_CUDA(cudaMalloc(&scal, sizeof(double) * S_COUNT * MAX_RHS));
+    B200_CUDA(cudaMalloc(&status, sizeof(int) * ST_COUNT * MAX_RHS));
+    B200_CUDA(cudaMemsetAsync(scal, 0, sizeof(double) * S_COUNT * MAX_RHS, stream));
+    B200_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * ST_COUNT * MAX_RHS, stream));
+    { int rc = ensure_partial(4 * (size_t)std::max((g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK + 8, blas_grid)); if (rc) return rc; }
+    B200_CUDA(cudaMalloc(&ticket, sizeof(unsigned int) * MAX_RHS));
+    B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int) * MAX_RHS, stream));
+    B200_CUDA(cudaHostAlloc(&h_scal, sizeof(double) * S_COUNT * MAX_RHS, cudaHostAllocDefault));
+    B200_CUDA(cudaHostAlloc(&h_status, sizeof(int) * ST_COUNT * MAX_RHS * 2, cudaHostAllocDefault));
     for (int i = 0; i < 2; ++i) B200_CUDA(cudaEventCreateWithFlags(&ev_poll[i], cudaEventDisableTiming));
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
@@ -134,6 +135,15 @@ class Engine : public EngineBase {
     if (ev_t1) cudaEventDestroy(ev_t1);
     if (owns_stream) cudaStreamDestroy(stream);
     stream = nullptr;
+  }
+
+  // reduction scratch: `doubles` partial sums (grown on demand by the batched kernels: N x nrhs x blocks)
+  int ensure_partial(size_t doubles) {
+    if (doubles <= partial_cap) return B200_OK;
+    if (partial) { B200_CUDA(cudaStreamSynchronize(stream)); cudaFree(partial); partial = nullptr; }
+    B200_CUDA(cudaMalloc(&partial, sizeof(double) * doubles));
+    partial_cap = doubles;
+    return B200_OK;
   }
 
   int sync() override { B200_CUDA(cudaSetDevice(cfg.device)); B200_CUDA(cudaStreamSynchronize(stream)); return B200_OK; }
@@ -307,72 +317,105 @@ class Engine : public EngineBase {
   }
 
   // ------------------------------------------------------------------ fields
-  int field_alloc(b200_field** f) override {
+  int field_alloc(b200_field** f, int nrhs = 1) override {
     B200_CUDA(cudaSetDevice(cfg.device));
+    if (nrhs < 1 || nrhs > MAX_RHS) { set_error("a batched field holds 1..%d right-hand sides", MAX_RHS); return B200_ERR_ARG; }
     b200_field* p = new b200_field;
-    p->bytes = sizeof(C) * nelem(); p->prec = sizeof(R); p->d = nullptr;
+    p->bytes = sizeof(C) * nelem() * nrhs; p->prec = sizeof(R); p->d = nullptr; p->nrhs = nrhs;
     cudaError_t e = cudaMalloc(&p->d, p->bytes);
-    if (e != cudaSuccess) { delete p; set_error("cudaMalloc(%zu) failed: %s", sizeof(C) * nelem(), cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    if (e != cudaSuccess) { delete p; set_error("cudaMalloc(%zu) failed: %s", sizeof(C) * nelem() * nrhs, cudaGetErrorString(e)); return B200_ERR_CUDA; }
     cudaMemsetAsync(p->d, 0, p->bytes, stream);
     *f = p;
     return B200_OK;
   }
   void field_free(b200_field* f) override { if (f) { cudaSetDevice(cfg.device); cudaStreamSynchronize(stream); cudaFree(f->d); delete f; } }
   int field_zero(b200_field* f) override { B200_CUDA(cudaSetDevice(cfg.device)); B200_CUDA(cudaMemsetAsync(f->d, 0, f->bytes, stream)); return B200_OK; }
-  int field_upload(b200_field* f, const void* host, int host_prec) override {
+  int field_upload(b200_field* f, const void* host, int host_prec, int irhs = 0) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (!f || !host) { set_error("null pointer"); return B200_ERR_ARG; }
-    if (host_prec == B200_DOUBLE) return upload_aos<double, 24, 12>((const double*)host, g.Vh, (C*)f->d, (size_t)g.Vh, MapIdentity(), 1.0);
-    if (host_prec == B200_SINGLE) return upload_aos<float, 24, 12>((const float*)host, g.Vh, (C*)f->d, (size_t)g.Vh, MapIdentity(), 1.0);
+    if (irhs < 0 || irhs >= f->nrhs) { set_error("right-hand side index %d out of range (field holds %d)", irhs, f->nrhs); return B200_ERR_ARG; }
+    C* d = (C*)f->d + (size_t)irhs * nelem();
+    if (host_prec == B200_DOUBLE) return upload_aos<double, 24, 12>((const double*)host, g.Vh, d, (size_t)g.Vh, MapIdentity(), 1.0);
+    if (host_prec == B200_SINGLE) return upload_aos<float, 24, 12>((const float*)host, g.Vh, d, (size_t)g.Vh, MapIdentity(), 1.0);
     set_error("host_prec must be 4 or 8"); return B200_ERR_ARG;
   }
-  int field_download(const b200_field* f, void* host, int host_prec) override {
+  int field_download(const b200_field* f, void* host, int host_prec, int irhs = 0) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (!f || !host) { set_error("null pointer"); return B200_ERR_ARG; }
-    if (host_prec == B200_DOUBLE) return download_aos<double, 24, 12>((double*)host, g.Vh, (const C*)f->d, (size_t)g.Vh, MapIdentity());
-    if (host_prec == B200_SINGLE) return download_aos<float, 24, 12>((float*)host, g.Vh, (const C*)f->d, (size_t)g.Vh, MapIdentity());
+    if (irhs < 0 || irhs >= f->nrhs) { set_error("right-hand side index %d out of range (field holds %d)", irhs, f->nrhs); return B200_ERR_ARG; }
+    const C* d = (const C*)f->d + (size_t)irhs * nelem();
+    if (host_prec == B200_DOUBLE) return download_aos<double, 24, 12>((double*)host, g.Vh, d, (size_t)g.Vh, MapIdentity());
+    if (host_prec == B200_SINGLE) return download_aos<float, 24, 12>((float*)host, g.Vh, d, (size_t)g.Vh, MapIdentity());
     set_error("host_prec must be 4 or 8"); return B200_ERR_ARG;
   }
 
-  int need_ws(int n) {
-    for (int i = 0; i < n; ++i) if (!ws[i]) { int rc = field_alloc(&ws[i]); if (rc) return rc; }
+  // workspace fields W(0..n-1), each able to hold `nrhs` right-hand sides
+  int need_ws(int n, int nrhs = 1) {
+    for (int i = 0; i < n; ++i) {
+      if (ws[i] && ws[i]->nrhs < nrhs) { field_free(ws[i]); ws[i] = nullptr; }
+      if (!ws[i]) { int rc = field_alloc(&ws[i], nrhs); if (rc) return rc; }
+    }
     return B200_OK;
+  }
+  int nb = 1;   // right-hand sides of the operation in flight (set by the public entry points; 1 = ordinary path)
+  // Select the batch size and make sure the reduction scratch holds <= 4 partial sums per right-hand side and block,
+  // for the BLAS grid as well as for the Dslash grids (32 sites per block when batched).
+  int set_batch(int n) {
+    nb = n;
+    const size_t dblocks = n > 1 ? (size_t)(g.Vh + 31) / 32 + 4 : (size_t)(g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK + 8;
+    return ensure_partial(4 * (size_t)n * std::max<size_t>((size_t)blas_grid, dblocks));
   }
   C* W(int i) { return (C*)ws[i]->d; }
 
   // ------------------------------------------------------------------ kernel launchers
+  static constexpr int NRB = B200_MRHS_NRB;
   template <int EPI>
   int launch_dslash(DslashArgs<R>& a) {
     a.gauge = gauge; a.scal = scal; a.status = status; a.g = g;
+    a.nrhs = nb; a.fstride = nelem(); a.gstride = (size_t)6 * g.S3h;
+    const int bs = nb > 1 ? 32 : DSLASH_BLOCK;          // target sites per CTA
     int rc;
     if (g.tsplit) {
       // pack + send both time faces over NVLink, run the interior while they fly, then both boundary slices
-      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, launches); if (rc) return rc;
+      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, nb, a.fstride, launches); if (rc) return rc;
       a.ghost_fwd = halo.ghost_fwd(); a.ghost_bwd = halo.ghost_bwd();
       const int n_int = g.Vh - 2 * g.S3h;
-      const int nb_int = (n_int + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
-      const int nb_face = (2 * g.S3h + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+      const int nb_int = (n_int + bs - 1) / bs;
+      const int nb_face = (2 * g.S3h + bs - 1) / bs;
       const int total = nb_int + nb_face;
       if (n_int > 0) {
         a.idx_begin = g.S3h; a.idx_count = n_int; a.idx_begin2 = 0; a.idx_count2 = 0; a.red = make_red(0, total);
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
-      rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, launches); if (rc) return rc;
+      rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, nb, launches); if (rc) return rc;
       a.idx_begin = 0; a.idx_count = g.S3h; a.idx_begin2 = g.Vh - g.S3h; a.idx_count2 = g.S3h; a.red = make_red(nb_int, total);
       return launch_one<EPI>(a, nb_face);
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr;
     a.idx_begin = 0; a.idx_count = g.Vh; a.idx_begin2 = 0; a.idx_count2 = 0;
-    const int blocks = (g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK;
+    const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
     return launch_one<EPI>(a, blocks);
   }
   template <int EPI>
   int launch_one(const DslashArgs<R>& a, int blocks) {
     if (blocks <= 0) return B200_OK;
+    if (nb > 1) return launch_mrhs<EPI>(a, blocks);
     if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
     else dslash_kernel<R, EPI, false, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
     return launched("dslash_kernel");
+  }
+  // batched launch: CTA = 32 sites x NRB right-hand sides; the groups of one site block are adjacent in the grid
+  template <int EPI>
+  int launch_mrhs(const DslashArgs<R>& a, int site_blocks) {
+    if (EPI == EPI_M_CGREL) { set_error("the reliable-update epilogue has no multi-RHS variant"); return B200_ERR_ARG; }
+    else {
+      const int ngroups = (nb + NRB - 1) / NRB;
+      const dim3 block(32, NRB);
+      if (recon == 12) dslash_mrhs_kernel<R, (EPI == EPI_M_CGREL ? EPI_M_CG : EPI), true, NRB><<<site_blocks * ngroups, block, 0, stream>>>(a, ls, ngroups);
+      else dslash_mrhs_kernel<R, (EPI == EPI_M_CGREL ? EPI_M_CG : EPI), false, NRB><<<site_blocks * ngroups, block, 0, stream>>>(a, ls, ngroups);
+      return launched("dslash_mrhs_kernel");
+    }
   }
 
   int ready() {
@@ -403,7 +446,8 @@ class Engine : public EngineBase {
   int dslash(b200_field* out, const b200_field* in, int isign, int out_cb) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (!gauge) { set_error("gauge field not loaded"); return B200_ERR_STATE; }
-    if ((isign != 1 && isign != -1) || (out_cb != 0 && out_cb != 1) || !out || !in || out == in) { set_error("b200_dslash: bad argument"); return B200_ERR_ARG; }
+    if ((isign != 1 && isign != -1) || (out_cb != 0 && out_cb != 1) || !out || !in || out == in || out->nrhs != in->nrhs) { set_error("b200_dslash: bad argument"); return B200_ERR_ARG; }
+    { int rcb = set_batch(in->nrhs); if (rcb) return rcb; }
     DslashArgs<R> a{};
     a.in = (const C*)in->d; a.out = (C*)out->d; a.parity = out_cb; a.isign = isign;
     return launch_dslash<EPI_DSLASH>(a);
@@ -412,27 +456,29 @@ class Engine : public EngineBase {
   int clover_apply(b200_field* out, const b200_field* in, int cb, int inverse) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (!clov) { set_error("clover term not loaded"); return B200_ERR_STATE; }
-    if ((cb != 0 && cb != 1) || !out || !in || out == in) { set_error("b200_clover_apply: bad argument"); return B200_ERR_ARG; }
+    if ((cb != 0 && cb != 1) || !out || !in || out == in || out->nrhs != in->nrhs) { set_error("b200_clover_apply: bad argument"); return B200_ERR_ARG; }
     if (inverse && cb != 0) { set_error("only the cb-0 inverse exists (invclov.choles(0), eoprec_clover_linop_w.cc:30)"); return B200_ERR_ARG; }
     const C* cl = inverse ? invclov : clov + (size_t)cb * 36 * g.Vh;
-    clover_kernel<R, 128><<<(g.Vh + 127) / 128, 128, 0, stream>>>((const C*)in->d, (C*)out->d, cl, g.Vh);
+    clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, in->nrhs), 128, 0, stream>>>((const C*)in->d, (C*)out->d, cl, g.Vh, nelem());
     return launched("clover_kernel");
   }
 
   int matpc(b200_field* out, const b200_field* in, int isign) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
-    if ((isign != 1 && isign != -1) || !out || !in || out == in) { set_error("b200_clover_matpc: bad argument"); return B200_ERR_ARG; }
-    rc = need_ws(1); if (rc) return rc;
+    if ((isign != 1 && isign != -1) || !out || !in || out == in || out->nrhs != in->nrhs) { set_error("b200_clover_matpc: bad argument"); return B200_ERR_ARG; }
+    { int rcb = set_batch(in->nrhs); if (rcb) return rcb; }
+    rc = need_ws(1, nb); if (rc) return rc;
     return apply_M((C*)out->d, (const C*)in->d, isign, EPI_M, nullptr, nullptr, 0, 0);
   }
 
   int time_matpc(b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
-    if ((isign != 1 && isign != -1) || !out || !in || out == in || reps < 1) { set_error("b200_dev_time_matpc: bad argument"); return B200_ERR_ARG; }
+    if ((isign != 1 && isign != -1) || !out || !in || out == in || reps < 1 || out->nrhs != in->nrhs) { set_error("b200_dev_time_matpc: bad argument"); return B200_ERR_ARG; }
     if (g.tsplit) { set_error("b200_dev_time_matpc: single-GPU measurement only"); return B200_ERR_ARG; }
-    rc = need_ws(1); if (rc) return rc;
+    { int rcb = set_batch(in->nrhs); if (rcb) return rcb; }
+    rc = need_ws(1, nb); if (rc) return rc;
     cudaEvent_t e[3];
     for (auto& x : e) B200_CUDA(cudaEventCreate(&x));
     double acc[2] = {0, 0};
@@ -458,47 +504,52 @@ class Engine : public EngineBase {
   }
 
   int fetch_scalars() {
-    B200_CUDA(cudaMemcpyAsync(h_scal, scal, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaMemcpyAsync(h_scal, scal, sizeof(double) * S_COUNT * MAX_RHS, cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
+  double hs(int rhs, int slot) const { return h_scal[rhs * S_COUNT + slot]; }
   int set_scalars(const ScalarSet& s) {
     set_scalars_kernel<<<1, 32, 0, stream>>>(scal, status, s);
     return launched("set_scalars");
   }
+  dim3 bgrid() const { return dim3(blas_grid, nb); }
 
   int norm2_dev(const C* x, int slot) {
-    norm2_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(x, nelem(), make_red(0, blas_grid), scal + slot);
+    norm2_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(x, nelem(), make_red(0, blas_grid), scal + slot, nelem());
     return launched("norm2");
   }
   int xmy_norm_dev(C* out, C* out2, const C* x, const C* y, int slot) {
-    xmy_norm_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(out, out2, x, y, nelem(), make_red(0, blas_grid), scal + slot);
+    xmy_norm_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(out, out2, x, y, nelem(), make_red(0, blas_grid), scal + slot, nelem());
     return launched("xmy_norm");
   }
   int axpby_dev(C* out, double a, const C* x, double b, const C* y) {
-    axpby_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(out, a, x, b, y, nelem());
+    axpby_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(out, a, x, b, y, nelem(), nelem());
     return launched("axpby");
   }
 
   int norm2(const b200_field* x, double* r) override {
     B200_CUDA(cudaSetDevice(cfg.device));
+    { int rcb = set_batch(x->nrhs); if (rcb) return rcb; }
     int rc = norm2_dev((const C*)x->d, S_TMP0); if (rc) return rc;
     rc = fetch_scalars(); if (rc) return rc;
-    *r = h_scal[S_TMP0];
+    for (int i = 0; i < nb; ++i) r[i] = hs(i, S_TMP0);
     return B200_OK;
   }
   int inner(const b200_field* x, const b200_field* y, double r[2]) override {
     B200_CUDA(cudaSetDevice(cfg.device));
-    inner_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>((const C*)x->d, (const C*)y->d, nelem(), make_red(0, blas_grid), scal + S_TMP0);
+    if (x->nrhs != y->nrhs) { set_error("b200_dev_inner: fields hold different numbers of right-hand sides"); return B200_ERR_ARG; }
+    { int rcb = set_batch(x->nrhs); if (rcb) return rcb; }
+    inner_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>((const C*)x->d, (const C*)y->d, nelem(), make_red(0, blas_grid), scal + S_TMP0, nelem());
     int rc = launched("inner"); if (rc) return rc;
     rc = fetch_scalars(); if (rc) return rc;
-    r[0] = h_scal[S_TMP0]; r[1] = h_scal[S_TMP1];
+    for (int i = 0; i < nb; ++i) { r[2 * i] = hs(i, S_TMP0); r[2 * i + 1] = hs(i, S_TMP1); }
     return B200_OK;
   }
 
   // ------------------------------------------------------------------ solver loops
   BlasCtl ctl(int iter, int check) {
-    BlasCtl c; c.scal = scal; c.status = status; c.red = make_red(0, blas_grid); c.iter = iter; c.check_stop = check;
+    BlasCtl c; c.scal = scal; c.status = status; c.red = make_red(0, blas_grid); c.iter = iter; c.check_stop = check; c.fstride = nelem();
     return c;
   }
 
@@ -506,18 +557,18 @@ class Engine : public EngineBase {
   int cg_iteration(C* psi, int k, int check) {
     int rc = apply_M(W(1), W(2), +1, EPI_M_NORM, nullptr, nullptr, k, check); if (rc) return rc;      // mp = M p, d, a
     rc = apply_M(nullptr, W(1), -1, EPI_M_CG, W(3), nullptr, k, check); if (rc) return rc;            // r -= a M^dag mp, cp, b
-    cg_update_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(psi, W(2), W(3), nelem(), ctl(k, check));
+    cg_update_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(psi, W(2), W(3), nelem(), ctl(k, check));
     return launched("cg_update");
   }
   // one BiCGStab iteration, invbicgstab.cc:74-170.  W(1)=r, W(2)=r0, W(3)=p, W(4)=v, W(5)=t
   int bicg_iteration(C* psi, int k, int check, int isign = +1) {
-    bicg_p_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(W(3), W(1), W(4), nelem(), ctl(k, check));
+    bicg_p_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(W(3), W(1), W(4), nelem(), ctl(k, check));
     int rc = launched("bicg_p"); if (rc) return rc;
     rc = apply_M(W(4), W(3), isign, EPI_M_DOTR0, nullptr, W(2), k, check); if (rc) return rc;         // v = M p, alpha
-    bicg_s_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(W(1), W(4), nelem(), ctl(k, check));
+    bicg_s_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(W(1), W(4), nelem(), ctl(k, check));
     rc = launched("bicg_s"); if (rc) return rc;
     rc = apply_M(W(5), W(1), isign, EPI_M_DOTX, nullptr, nullptr, k, check); if (rc) return rc;       // t = M r, omega
-    bicg_update_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(psi, W(1), W(3), W(5), W(2), nelem(), ctl(k, check));
+    bicg_update_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(psi, W(1), W(3), W(5), W(2), nelem(), ctl(k, check));
     return launched("bicg_update");
   }
 
@@ -534,72 +585,96 @@ class Engine : public EngineBase {
     int rc = norm2_dev(chi, S_TMP0); if (rc) return rc;
     rc = apply_M(W(2), psi, isign, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
     rc = xmy_norm_dev(W(1), W(2), chi, W(2), S_TMP1); if (rc) return rc;     // r = r0 = chi - M psi ; |r|^2 = <r0|r>
-    B200_CUDA(cudaMemsetAsync(W(3), 0, sizeof(C) * nelem(), stream));
-    B200_CUDA(cudaMemsetAsync(W(4), 0, sizeof(C) * nelem(), stream));
+    B200_CUDA(cudaMemsetAsync(W(3), 0, sizeof(C) * nelem() * nb, stream));
+    B200_CUDA(cudaMemsetAsync(W(4), 0, sizeof(C) * nelem() * nb, stream));
     return fetch_scalars();
   }
 
+  // Enqueue iterations in batches of ITER_BATCH and poll the status blocks with a pipelined async copy; stop when
+  // every right-hand side has either converged or broken down.  Outputs are arrays of nb entries.
   int poll_loop(C* psi, int solver, int max_iter, int* n_count, int* converged, int* breakdown, int isign = +1) {
     int k = 1, slot = 0, prev = -1;
     bool done = false;
-    *breakdown = 0;
+    const int SB = ST_COUNT * MAX_RHS;
     while (k <= max_iter && !done) {
       const int n = std::min(ITER_BATCH, max_iter - k + 1);
       for (int i = 0; i < n; ++i) {
         int rc = (solver == B200_SOLVER_CG) ? cg_iteration(psi, k + i, 1) : bicg_iteration(psi, k + i, 1, isign);
         if (rc) return rc;
       }
-      B200_CUDA(cudaMemcpyAsync(h_status + slot * ST_COUNT, status, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, stream));
+      B200_CUDA(cudaMemcpyAsync(h_status + slot * SB, status, sizeof(int) * SB, cudaMemcpyDeviceToHost, stream));
       B200_CUDA(cudaEventRecord(ev_poll[slot], stream));
       if (prev >= 0) {
         B200_CUDA(cudaEventSynchronize(ev_poll[prev]));
-        if (h_status[prev * ST_COUNT + ST_STOP] != 0 || h_status[prev * ST_COUNT + ST_BREAKDOWN] != 0) done = true;
+        done = true;
+        for (int r = 0; r < nb; ++r)
+          if (h_status[prev * SB + r * ST_COUNT + ST_STOP] == 0 && h_status[prev * SB + r * ST_COUNT + ST_BREAKDOWN] == 0) done = false;
       }
       prev = slot; slot ^= 1; k += n;
     }
     B200_CUDA(cudaStreamSynchronize(stream));
-    const int* st = h_status + prev * ST_COUNT;   // the last copy enqueued reflects the final state
-    *breakdown = st[ST_BREAKDOWN];
-    *converged = st[ST_STOP] != 0;
-    *n_count = st[ST_STOP] != 0 ? st[ST_STOP] : max_iter;
+    if (prev < 0) {   // max_iter == 0: nothing ran
+      for (int r = 0; r < nb; ++r) { breakdown[r] = 0; converged[r] = converged[r] ? 1 : 0; n_count[r] = 0; }
+      return B200_OK;
+    }
+    for (int r = 0; r < nb; ++r) {
+      const int* st = h_status + prev * SB + r * ST_COUNT;   // the last copy enqueued reflects the final state
+      breakdown[r] = st[ST_BREAKDOWN];
+      converged[r] = st[ST_STOP] != 0;
+      n_count[r] = st[ST_STOP] > 0 ? st[ST_STOP] : (st[ST_STOP] < 0 ? 0 : max_iter);   // -1 = converged before iterating
+    }
     return B200_OK;
   }
 
-  // InvCG2_a (invcg2.cc:70-232): solve M^dag M psi = rhs.  Uses W(0..4).
+  // InvCG2_a (invcg2.cc:70-232): solve M^dag M psi = rhs for nb right-hand sides in lockstep.  Uses W(0..4).
   int run_cg(C* psi, const C* rhs, double rsd, int max_iter, int* n_count, int* converged, double* rsd_sq_iter) {
     int rc = cg_begin(psi, rhs); if (rc) return rc;
-    const double chi_sq = h_scal[S_TMP0], cp = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
-    *rsd_sq_iter = cp; *n_count = 0; *converged = 0;
-    if (cp <= rsd_sq) { *converged = 1; return B200_OK; }          // invcg2.cc:136-146
-    ScalarSet s{}; s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = rsd_sq; s.slots[1] = S_C; s.vals[1] = cp; s.reset_status = 1;
-    rc = set_scalars(s); if (rc) return rc;
-    int breakdown = 0;
-    rc = poll_loop(psi, B200_SOLVER_CG, max_iter, n_count, converged, &breakdown); if (rc) return rc;
+    bool any = false;
+    for (int r = 0; r < nb; ++r) {
+      const double chi_sq = hs(r, S_TMP0), cp = hs(r, S_TMP1), rsd_sq = rsd * rsd * chi_sq;
+      rsd_sq_iter[r] = cp; n_count[r] = 0; converged[r] = cp <= rsd_sq;          // invcg2.cc:136-146
+      ScalarSet s{}; s.rhs = r; s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = rsd_sq; s.slots[1] = S_C; s.vals[1] = cp;
+      s.reset_status = converged[r] ? 2 : 1;                                      // 2: reset, then mark "stopped at iteration 0"
+      rc = set_scalars(s); if (rc) return rc;
+      any = any || !converged[r];
+    }
+    if (!any) return B200_OK;
+    int breakdown[MAX_RHS];
+    rc = poll_loop(psi, B200_SOLVER_CG, max_iter, n_count, converged, breakdown); if (rc) return rc;
     rc = fetch_scalars(); if (rc) return rc;
-    if (*n_count > 0) *rsd_sq_iter = h_scal[S_CP];
-    if (breakdown >= 90) return comm_timeout(breakdown);
+    for (int r = 0; r < nb; ++r) {
+      if (n_count[r] > 0) rsd_sq_iter[r] = hs(r, S_CP);
+      if (breakdown[r] >= 90) return comm_timeout(breakdown[r]);
+    }
     return B200_OK;
   }
   // InvBiCGStab_a (invbicgstab.cc:10-202): solve M psi = rhs (isign=+1) or M^dag psi = rhs (-1).  Uses W(0..5).
   int run_bicg(C* psi, const C* rhs, int isign, double rsd, int max_iter, int* n_count, int* converged, double* rsd_sq_iter) {
     int rc = bicg_begin(psi, rhs, isign); if (rc) return rc;
-    const double chi_sq = h_scal[S_TMP0], rr = h_scal[S_TMP1], rsd_sq = rsd * rsd * chi_sq;
-    *rsd_sq_iter = rr; *n_count = 0; *converged = 0;
-    ScalarSet s{}; s.reset_status = 1; s.n = 11;
-    const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
-    const double vl[11] = {rsd_sq, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};   // beta_1 = (rho_1/1)(1/1)
-    for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
-    int breakdown = 0;
-    if (rr == 0.0) breakdown = 1;                                // rho = <r0|r> = 0 (invbicgstab.cc:80-83)
-    else {
+    int breakdown[MAX_RHS];
+    bool any = false;
+    for (int r = 0; r < nb; ++r) {
+      const double chi_sq = hs(r, S_TMP0), rr = hs(r, S_TMP1), rsd_sq = rsd * rsd * chi_sq;
+      rsd_sq_iter[r] = rr; n_count[r] = 0; converged[r] = 0; breakdown[r] = 0;
+      ScalarSet s{}; s.rhs = r; s.reset_status = 1; s.n = 11;
+      const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
+      const double vl[11] = {rsd_sq, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};   // beta_1 = (rho_1/1)(1/1)
+      for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+      if (rr == 0.0) { breakdown[r] = 1; s.reset_status = 3; }                    // rho = <r0|r> = 0 (invbicgstab.cc:80-83)
       rc = set_scalars(s); if (rc) return rc;
-      rc = poll_loop(psi, B200_SOLVER_BICGSTAB, max_iter, n_count, converged, &breakdown, isign); if (rc) return rc;
-      rc = fetch_scalars(); if (rc) return rc;
-      if (*n_count > 0) *rsd_sq_iter = h_scal[S_RNORM];
+      any = any || rr != 0.0;
     }
-    if (breakdown >= 90) return comm_timeout(breakdown);
-    if (breakdown) { set_error("BiCGStab breakdown (code %d) at iteration <= %d", breakdown, *n_count); return B200_ERR_BREAKDOWN; }
-    return B200_OK;
+    if (any) {
+      rc = poll_loop(psi, B200_SOLVER_BICGSTAB, max_iter, n_count, converged, breakdown, isign); if (rc) return rc;
+      rc = fetch_scalars(); if (rc) return rc;
+    }
+    int bad = 0;
+    for (int r = 0; r < nb; ++r) {
+      if (n_count[r] > 0) rsd_sq_iter[r] = hs(r, S_RNORM);
+      if (breakdown[r] >= 90) return comm_timeout(breakdown[r]);
+      if (breakdown[r]) { bad = breakdown[r]; set_error("BiCGStab breakdown (code %d) on right-hand side %d at iteration <= %d", bad, r, n_count[r]); }
+    }
+    return bad ? B200_ERR_BREAKDOWN : B200_OK;
   }
   int comm_timeout(int code) {
     set_error("multi-GPU peer wait timed out (code %d: 90 = halo flag, 91 = reduction mailbox)", code);
@@ -614,22 +689,27 @@ class Engine : public EngineBase {
     rc = xmy_norm_dev(nullptr, nullptr, chi, mpsi, S_TMP2); if (rc) return rc;
     rc = norm2_dev(chi, S_TMP3); if (rc) return rc;
     rc = fetch_scalars(); if (rc) return rc;
-    info->resid = sqrt(h_scal[S_TMP2]);
-    info->rel_resid = h_scal[S_TMP3] > 0 ? info->resid / sqrt(h_scal[S_TMP3]) : 0.0;
+    for (int r = 0; r < nb; ++r) {
+      info[r].resid = sqrt(hs(r, S_TMP2));
+      info[r].rel_resid = hs(r, S_TMP3) > 0 ? info[r].resid / sqrt(hs(r, S_TMP3)) : 0.0;
+    }
     return B200_OK;
   }
 
+  // psi, chi may hold several right-hand sides (b200_mfield_alloc): they are then solved in lockstep by the batched
+  // kernels, each with its own scalars and stopping test; info is an array of psi->nrhs entries.
   int invert(b200_field* psi_f, const b200_field* chi_f, int solver, double rsd, int max_iter, int mdagm, b200_solve_info* info) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
-    if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0)) { set_error("b200_invert: bad argument"); return B200_ERR_ARG; }
+    if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0) || psi_f->nrhs != chi_f->nrhs) { set_error("b200_invert: bad argument"); return B200_ERR_ARG; }
     if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
-    rc = need_ws(7); if (rc) return rc;
+    { int rcb = set_batch(psi_f->nrhs); if (rcb) return rcb; }
+    rc = need_ws(7, nb); if (rc) return rc;
     C* psi = (C*)psi_f->d; const C* chi = (const C*)chi_f->d;
-    memset(info, 0, sizeof(*info));
+    memset(info, 0, sizeof(*info) * nb);
     B200_CUDA(cudaEventRecord(ev_t0, stream));
-    int n_count = 0, converged = 0;
-    double flops_iter, rsq = 0.0;
+    int n_count[MAX_RHS] = {0}, converged[MAX_RHS] = {0};
+    double flops_iter, rsq[MAX_RHS] = {0.0};
     if (solver == B200_SOLVER_CG) {
       flops_iter = 2.0 * 3792.0 + 240.0;
       const C* rhs = chi;
@@ -637,53 +717,61 @@ class Engine : public EngineBase {
         rc = apply_M(W(6), chi, -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
         rhs = W(6);
       }
-      rc = run_cg(psi, rhs, rsd, max_iter, &n_count, &converged, &rsq);
+      rc = run_cg(psi, rhs, rsd, max_iter, n_count, converged, rsq);
     } else if (!mdagm) {
       flops_iter = 2.0 * 3792.0 + 960.0;
-      rc = run_bicg(psi, chi, +1, rsd, max_iter, &n_count, &converged, &rsq);
+      rc = run_bicg(psi, chi, +1, rsd, max_iter, n_count, converged, rsq);
     } else {
       // two-step solve, syssolver_mdagm_bicgstab.h:62-110: Y = M psi; M^dag Y = chi; M psi = Y
       flops_iter = 2.0 * 3792.0 + 960.0;
-      int n1 = 0, c1 = 0;
+      int n1[MAX_RHS] = {0}, c1[MAX_RHS] = {0};
       rc = apply_M(W(6), psi, +1, EPI_M, nullptr, nullptr, 0, 0);
-      if (!rc) rc = run_bicg(W(6), chi, -1, rsd, max_iter, &n1, &c1, &rsq);
-      if (!rc) rc = run_bicg(psi, W(6), +1, rsd, max_iter, &n_count, &converged, &rsq);
-      n_count += n1; converged = converged && c1;
+      if (!rc) rc = run_bicg(W(6), chi, -1, rsd, max_iter, n1, c1, rsq);
+      if (!rc) rc = run_bicg(psi, W(6), +1, rsd, max_iter, n_count, converged, rsq);
+      for (int r = 0; r < nb; ++r) { n_count[r] += n1[r]; converged[r] = converged[r] && c1[r]; }
     }
-    info->n_count = n_count; info->converged = converged; info->rsd_sq_iter = rsq;
+    for (int r = 0; r < nb; ++r) { info[r].n_count = n_count[r]; info[r].converged = converged[r]; info[r].rsd_sq_iter = rsq[r]; }
     if (rc && rc != B200_ERR_BREAKDOWN) return rc;
     B200_CUDA(cudaEventRecord(ev_t1, stream));
     int rc2 = true_residual(psi, chi, mdagm, info); if (rc2) return rc2;
     float ms = 0.f;
     B200_CUDA(cudaEventElapsedTime(&ms, ev_t0, ev_t1));
-    info->secs = ms * 1e-3; info->secs_total = info->secs;
     const double gvol = (double)g.Vh * cfg.pgrid[3];
-    info->gflops = info->secs > 0 ? flops_iter * gvol * n_count / info->secs * 1e-9 : 0.0;
+    for (int r = 0; r < nb; ++r) {
+      info[r].secs = ms * 1e-3; info[r].secs_total = info[r].secs;       // the batch shares one wall clock
+      info[r].gflops = ms > 0 ? flops_iter * gvol * n_count[r] / (ms * 1e-3) * 1e-9 : 0.0;
+    }
     return rc;
   }
 
   int iterate_begin(b200_field* psi_f, const b200_field* chi_f, int solver) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
-    rc = need_ws(7); if (rc) return rc;
-    it_psi = (C*)psi_f->d; it_chi = (const C*)chi_f->d; it_k = 0;
-    ScalarSet s{}; s.reset_status = 1;
-    if (solver == B200_SOLVER_CG) {
-      rc = cg_begin(it_psi, it_chi); if (rc) return rc;
-      s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = 0.0; s.slots[1] = S_C; s.vals[1] = h_scal[S_TMP1];
-    } else {
-      rc = bicg_begin(it_psi, it_chi, +1); if (rc) return rc;
-      const double rr = h_scal[S_TMP1];
-      s.n = 11;
-      const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
-      const double vl[11] = {0.0, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};
-      for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+    if (psi_f->nrhs != chi_f->nrhs) { set_error("b200_dev_iterate_begin: fields hold different numbers of right-hand sides"); return B200_ERR_ARG; }
+    { int rcb = set_batch(psi_f->nrhs); if (rcb) return rcb; }
+    rc = need_ws(7, nb); if (rc) return rc;
+    it_psi = (C*)psi_f->d; it_chi = (const C*)chi_f->d; it_k = 0; it_nb = nb;
+    if (solver == B200_SOLVER_CG) { rc = cg_begin(it_psi, it_chi); if (rc) return rc; }
+    else { rc = bicg_begin(it_psi, it_chi, +1); if (rc) return rc; }
+    for (int r = 0; r < nb; ++r) {
+      ScalarSet s{}; s.reset_status = 1; s.rhs = r;
+      if (solver == B200_SOLVER_CG) {
+        s.n = 2; s.slots[0] = S_RSDSQ; s.vals[0] = 0.0; s.slots[1] = S_C; s.vals[1] = hs(r, S_TMP1);
+      } else {
+        const double rr = hs(r, S_TMP1);
+        s.n = 11;
+        const int sl[11] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM};
+        const double vl[11] = {0.0, rr, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, rr, 0.0};
+        for (int i = 0; i < 11; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+      }
+      rc = set_scalars(s); if (rc) return rc;
     }
-    return set_scalars(s);
+    return B200_OK;
   }
   int iterate(int solver, int n_iter) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (!it_psi) { set_error("b200_dev_iterate: call b200_dev_iterate_begin first"); return B200_ERR_STATE; }
+    { int rcb = set_batch(it_nb); if (rcb) return rcb; }
     for (int i = 0; i < n_iter; ++i) {
       ++it_k;
       int rc = (solver == B200_SOLVER_CG) ? cg_iteration(it_psi, it_k, 0) : bicg_iteration(it_psi, it_k, 0);
@@ -701,31 +789,57 @@ class Engine : public EngineBase {
     int rc = ready(); if (rc) return rc;
     if (!psi_h || !chi_h || !infos || nrhs < 1) { set_error("b200_qprop: bad argument"); return B200_ERR_ARG; }
     if (host_prec != B200_SINGLE && host_prec != B200_DOUBLE) { set_error("host_prec must be 4 or 8"); return B200_ERR_ARG; }
-    rc = need_ws(7); if (rc) return rc;
-    b200_field *chi_e = nullptr, *chi_o = nullptr, *psi_o = nullptr, *t1 = nullptr, *t2 = nullptr;
-    if ((rc = field_alloc(&chi_e)) || (rc = field_alloc(&chi_o)) || (rc = field_alloc(&psi_o)) || (rc = field_alloc(&t1)) || (rc = field_alloc(&t2))) return rc;
+    // How many right-hand sides go through the batched kernels at once: all of them (up to MAX_RHS) if the 12 batched
+    // vectors the solve needs (7 workspace + 5 here) fit in free HBM, else the largest batch that does.
+    size_t free_b = 0, total_b = 0;
+    B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    for (auto f : ws) if (f) free_b += f->bytes;
+    const size_t per_rhs = (size_t)12 * sizeof(C) * nelem() + (size_t)3 * sizeof(double) * (g.Vh / 32 + 8);
+    int cap = (int)std::min<size_t>((size_t)MAX_RHS, (size_t)(0.9 * (double)free_b) / per_rhs);
+    if (const char* e = getenv("B200_QPROP_BATCH")) cap = std::min(cap, std::max(1, atoi(e)));
+    if (cap < 1) { set_error("b200_qprop: not enough free device memory for even one right-hand side"); return B200_ERR_CUDA; }
+    cap = std::min(cap, nrhs);
     const size_t cbbytes = (size_t)g.Vh * 24 * host_prec;
-    for (int i = 0; i < nrhs && !rc; ++i) {
-      const char* ch = (const char*)chi_h + (size_t)i * 2 * cbbytes;
-      char* ph = (char*)psi_h + (size_t)i * 2 * cbbytes;
-      if ((rc = field_upload(chi_e, ch, host_prec))) break;
-      if ((rc = field_upload(chi_o, ch + cbbytes, host_prec))) break;
-      if ((rc = field_upload(psi_o, ph + cbbytes, host_prec))) break;
+    b200_field *chi_e = nullptr, *chi_o = nullptr, *psi_o = nullptr, *t1 = nullptr, *t2 = nullptr;
+    if ((rc = field_alloc(&chi_e, cap)) || (rc = field_alloc(&chi_o, cap)) || (rc = field_alloc(&psi_o, cap)) ||
+        (rc = field_alloc(&t1, cap)) || (rc = field_alloc(&t2, cap))) {
+      field_free(chi_e); field_free(chi_o); field_free(psi_o); field_free(t1); field_free(t2);
+      return rc;
+    }
+    int worst = B200_OK;
+    for (int i0 = 0; i0 < nrhs && !rc; i0 += cap) {
+      const int n = std::min(cap, nrhs - i0);
+      chi_e->nrhs = chi_o->nrhs = psi_o->nrhs = t1->nrhs = t2->nrhs = n;      // views of the first n right-hand sides
+      for (int j = 0; j < n && !rc; ++j) {
+        const char* ch = (const char*)chi_h + (size_t)(i0 + j) * 2 * cbbytes;
+        const char* ph = (const char*)psi_h + (size_t)(i0 + j) * 2 * cbbytes;
+        if ((rc = field_upload(chi_e, ch, host_prec, j))) break;
+        if ((rc = field_upload(chi_o, ch + cbbytes, host_prec, j))) break;
+        rc = field_upload(psi_o, ph + cbbytes, host_prec, j);
+      }
+      if (rc) break;
       // chi' = chi_o - D_oe A_ee^-1 chi_e = chi_o + 1/2 Dslash(A_ee^-1 chi_e)
       if ((rc = clover_apply(t1, chi_e, 0, 1))) break;
       if ((rc = dslash(t2, t1, +1, 1))) break;
+      if ((rc = set_batch(n))) break;
       if ((rc = axpby_dev((C*)t1->d, 1.0, (const C*)chi_o->d, 0.5, (const C*)t2->d))) break;
-      rc = invert(psi_o, t1, solver, rsd, max_iter, 0, &infos[i]);
+      rc = invert(psi_o, t1, solver, rsd, max_iter, 0, &infos[i0]);
+      if (rc == B200_ERR_BREAKDOWN) { worst = rc; rc = B200_OK; }
       if (rc) break;
       // psi_e = A_ee^-1 (chi_e - D_eo psi_o) = A_ee^-1 (chi_e + 1/2 Dslash psi_o)
       if ((rc = dslash(t1, psi_o, +1, 0))) break;
+      if ((rc = set_batch(n))) break;
       if ((rc = axpby_dev((C*)t2->d, 1.0, (const C*)chi_e->d, 0.5, (const C*)t1->d))) break;
       if ((rc = clover_apply(t1, t2, 0, 1))) break;
-      if ((rc = field_download(t1, ph, host_prec))) break;
-      if ((rc = field_download(psi_o, ph + cbbytes, host_prec))) break;
+      for (int j = 0; j < n && !rc; ++j) {
+        char* ph = (char*)psi_h + (size_t)(i0 + j) * 2 * cbbytes;
+        if ((rc = field_download(t1, ph, host_prec, j))) break;
+        rc = field_download(psi_o, ph + cbbytes, host_prec, j);
+      }
     }
+    chi_e->nrhs = chi_o->nrhs = psi_o->nrhs = t1->nrhs = t2->nrhs = cap;
     field_free(chi_e); field_free(chi_o); field_free(psi_o); field_free(t1); field_free(t2);
-    return rc;
+    return rc ? rc : worst;
   }
 };
 

@@ -149,6 +149,7 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   B200_CUDA(cudaSetDevice(hi.cfg.device));
   int rc = hi.ready(); if (rc) return rc;
   if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0) || !(delta > 0.0)) { set_error("b200_invert_reliable: bad argument"); return B200_ERR_ARG; }
+  if (psi_f->nrhs != 1 || chi_f->nrhs != 1) { set_error("b200_invert_reliable: one right-hand side at a time"); return B200_ERR_ARG; }
   if (!*lo_slot) {
     Config c = hi.cfg; c.prec = B200_SINGLE;
     EngineBase* e = make_engine_float(c);
@@ -158,6 +159,8 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   }
   Engine<float>& lo = *static_cast<Engine<float>*>(*lo_slot);
   if (lo.stream != hi.stream || lo.operator_epoch != hi.operator_epoch) { rc = adopt(lo, hi); if (rc) return rc; }
+  rc = hi.set_batch(1); if (rc) return rc;
+  rc = lo.set_batch(1); if (rc) return rc;
   rc = hi.need_ws(7); if (rc) return rc;
   rc = lo.need_ws(5); if (rc) return rc;
   typedef double2 CD; typedef float2 CF;

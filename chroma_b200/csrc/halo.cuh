@@ -48,30 +48,41 @@ struct PackArgs {
   Geom g;
   int src_par, isign, recon12;
   double scale_b;       // RECON12 only: aniso[3] * (bc_t if this rank owns the global last slice)
+  int nrhs;             // batched Dslash: gridDim.y right-hand sides, fields fstride apart, ghost faces gstride apart
+  size_t fstride, gstride;
 };
 
 template <typename R, bool RECON12>
 __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   typedef Cx<R> C;
-  if (a.status && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  // A converged right-hand side sends nothing.  With a single right-hand side the whole Dslash (wait kernel included)
+  // is skipped; in a batch the flags are still published so that the other right-hand sides can proceed.
+  const int rhs = blockIdx.y;
+  bool skip = false;
+  if (a.status) { const int* st = a.status + rhs * ST_COUNT; skip = st[ST_STOP] != 0 || st[ST_BREAKDOWN] != 0; }
+  if (a.nrhs == 1 && skip) return;
   if (a.pred && *a.pred == 0) return;
   const Geom& g = a.g;
   const int tid = blockIdx.x * 128 + threadIdx.x;
   const int stride = g.Vh, st = g.S3h;
   const R s = (R)a.isign;
   const L2Policy pol = make_l2_policy();
-  if (tid < st) {
+  const C* __restrict__ in = a.in + rhs * a.fstride;
+  C* __restrict__ to_bwd = a.to_bwd + rhs * a.gstride;
+  C* __restrict__ to_fwd = a.to_fwd + rhs * a.gstride;
+  if (skip) {
+  } else if (tid < st) {
     // face t = 0 -> forward-hop half spinor (1 - s g3) psi for the -t neighbour's slice Lt-1
     C h0[3], h1[3];
-    load_project<R, 3>(h0, h1, a.in + tid, stride, -s, pol.keep);
+    load_project<R, 3>(h0, h1, in + tid, stride, -s, pol.keep);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { a.to_bwd[(size_t)c * st + tid] = h0[c]; a.to_bwd[(size_t)(3 + c) * st + tid] = h1[c]; }
+    for (int c = 0; c < 3; ++c) { to_bwd[(size_t)c * st + tid] = h0[c]; to_bwd[(size_t)(3 + c) * st + tid] = h1[c]; }
   } else if (tid < 2 * st) {
     // face t = Lt-1 -> backward-hop half spinor U_t^dag (1 + s g3) psi for the +t neighbour's slice 0
     const int s3 = tid - st, idx = (g.Lt - 1) * st + s3;
     constexpr int NG = RECON12 ? 6 : 9;
     C h0[3], h1[3], U[9], r0[3], r1[3];
-    load_project<R, 3>(h0, h1, a.in + idx, stride, s, pol.keep);
+    load_project<R, 3>(h0, h1, in + idx, stride, s, pol.keep);
     load_link<R, RECON12>(U, a.gauge + ((size_t)(3 * 2 + a.src_par) * NG) * stride + idx, stride, pol.keep);
     if (RECON12) {
       const R sc = (R)a.scale_b;
@@ -80,7 +91,7 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
     }
     su3_mul<R, true>(r0, r1, U, h0, h1);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { a.to_fwd[(size_t)c * st + s3] = r0[c]; a.to_fwd[(size_t)(3 + c) * st + s3] = r1[c]; }
+    for (int c = 0; c < 3; ++c) { to_fwd[(size_t)c * st + s3] = r0[c]; to_fwd[(size_t)(3 + c) * st + s3] = r1[c]; }
   }
   // last block publishes the arrival flags
   __threadfence_system();
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(a.ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    is_last = (t == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
@@ -148,11 +159,11 @@ class Halo {
   static HaloLayout layout(const Geom& g) {
     HaloLayout l;
     l.flags_off = 0;                                  // [2 slots][2 dirs] u64
-    l.seq_off = 256;                                  // u64 reduction counter
-    l.mailbox_off = 512;                              // [2][8][8] doubles
-    l.ghost_off = 512 + 2 * 8 * 8 * sizeof(double);   // = 1536
-    l.ghost_face = (size_t)6 * g.S3h;
-    l.gauge_ghost_off = l.ghost_off + 4 * l.ghost_face * sizeof(C);
+    l.seq_off = 256;                                  // u64 reduction counters [MAX_RHS]
+    l.mailbox_off = 512;                              // [MAX_RHS][2][8][8] doubles
+    l.ghost_off = 512 + (size_t)MAX_RHS * MAILBOX_DOUBLES * sizeof(double);
+    l.ghost_face = (size_t)6 * g.S3h;                 // one right-hand side of one face; a face buffer holds MAX_RHS of them
+    l.gauge_ghost_off = l.ghost_off + 4 * l.ghost_face * MAX_RHS * sizeof(C);
     l.gauge_ghost_off = (l.gauge_ghost_off + 255) / 256 * 256;
     l.total = l.gauge_ghost_off + (size_t)2 * 4 * 2 * 9 * g.S3h * sizeof(C);
     return l;
@@ -199,7 +210,7 @@ class Halo {
     arena = nullptr;
   }
 
-  C* ghost_ptr(char* base, int slot, int dir) const { return (C*)(base + lay.ghost_off) + (size_t)(slot * 2 + dir) * lay.ghost_face; }
+  C* ghost_ptr(char* base, int slot, int dir) const { return (C*)(base + lay.ghost_off) + (size_t)(slot * 2 + dir) * lay.ghost_face * MAX_RHS; }
   unsigned long long* flag_ptr(char* base, int slot, int dir) const { return (unsigned long long*)(base + lay.flags_off) + slot * 2 + dir; }
   const C* ghost_fwd() const { return ghost_ptr(arena, (int)(seq & 1), 0); }
   const C* ghost_bwd() const { return ghost_ptr(arena, (int)(seq & 1), 1); }
@@ -219,7 +230,8 @@ class Halo {
   }
 
   // Pack + send both faces of `in` for the Dslash that targets `parity`.
-  int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, int run_if, long long& launches) {
+  int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, int run_if, int nrhs,
+            size_t fstride, long long& launches) {
     ++seq;
     const int slot = (int)(seq & 1);
     PackArgs<R> a;
@@ -231,7 +243,8 @@ class Halo {
     a.seq = seq; a.ticket = ticket; a.status = status; a.pred = run_if ? status_dev + run_if : nullptr; a.g = g;
     a.src_par = 1 - parity; a.isign = isign; a.recon12 = recon == 12;
     a.scale_b = ls.aniso[3] * (ls.t_is_last ? (double)ls.bc_t : 1.0);
-    const int blocks = (2 * g.S3h + 127) / 128;
+    a.nrhs = nrhs; a.fstride = fstride; a.gstride = lay.ghost_face;
+    const dim3 blocks((2 * g.S3h + 127) / 128, nrhs);
     if (recon == 12) pack_faces_kernel<R, true><<<blocks, 128, 0, stream>>>(a);
     else pack_faces_kernel<R, false><<<blocks, 128, 0, stream>>>(a);
     ++launches;
@@ -240,9 +253,10 @@ class Halo {
     return B200_OK;
   }
 
-  int wait(const int* status, int run_if, long long& launches) {
+  int wait(const int* status, int run_if, int nrhs, long long& launches) {
     const int slot = (int)(seq & 1);
-    wait_flags_kernel<<<1, 1, 0, stream>>>(flag_ptr(arena, slot, 0), flag_ptr(arena, slot, 1), seq, status_dev, status ? 1 : 0, run_if);
+    // a batch always waits: its flags are always published, and one right-hand side's stop flag says nothing about the others
+    wait_flags_kernel<<<1, 1, 0, stream>>>(flag_ptr(arena, slot, 0), flag_ptr(arena, slot, 1), seq, status_dev, (status && nrhs == 1) ? 1 : 0, run_if);
     ++launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("wait_flags launch failed: %s", cudaGetErrorString(e)); return B200_ERR_CUDA; }

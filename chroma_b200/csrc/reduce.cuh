@@ -9,11 +9,12 @@
 namespace b200 {
 
 // Cross-GPU reduction mailboxes (peer-mapped).  See comm.cuh for how they are wired up.
+constexpr int MAILBOX_DOUBLES = 2 * 8 * 8;   // per right-hand side: [slot 2][src rank 8][4 values + tag + pad]
 struct PeerReduce {
   int nranks;           // 1 => single GPU, nothing to do
   int rank;
-  unsigned long long* seq;  // device counter: number of cross-GPU reductions done so far on this rank
-  double* mailbox[8];       // mailbox[r] = rank r's mailbox base (peer pointer), layout [slot 2][src rank 8][4 values + seq]
+  unsigned long long* seq;  // device counters [MAX_RHS]: cross-GPU reductions done so far for each right-hand side
+  double* mailbox[8];       // mailbox[r] = rank r's mailbox base (peer pointer), layout [rhs][slot 2][src rank 8][4 values + seq]
   int* status;              // device status block (ST_BREAKDOWN = 91 on timeout)
 };
 
@@ -23,6 +24,19 @@ struct ReduceBuf {
   int block_offset;      // first partial slot of this launch (a step may be split into several launches)
   int total_blocks;      // blocks over all launches of the step
   PeerReduce peer;
+  // The view of right-hand side `rhs` of a batched step reducing N quantities: own partials, ticket, mailbox, status.
+  template <int N>
+  __device__ __forceinline__ ReduceBuf for_rhs(int rhs) const {
+    ReduceBuf r = *this;
+    r.partial += (size_t)rhs * N * total_blocks;
+    r.ticket += rhs;
+    if (r.peer.nranks > 1) {
+      r.peer.seq += rhs;
+      for (int i = 0; i < r.peer.nranks; ++i) r.peer.mailbox[i] += (size_t)rhs * MAILBOX_DOUBLES;
+    }
+    if (r.peer.status) r.peer.status += rhs * ST_COUNT;
+    return r;
+  }
 };
 
 template <int BLOCK>
@@ -106,6 +120,49 @@ __device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fi
       *rb.ticket = 0u;
       __threadfence();
     }
+  }
+}
+
+// Warp-synchronous variant for the multi-RHS Dslash kernels, where one WARP (32 consecutive sites of one right-hand
+// side) is the reduction unit: shuffle tree -> one partial per (rhs, site block) -> the warp that draws the last
+// ticket of its right-hand side sums that right-hand side's partials (lane-strided, then the same shuffle tree: a
+// fixed order) and lane 0 runs the finaliser.  rb must already be the for_rhs() view.  No __syncthreads: warps of
+// one CTA belong to different right-hand sides and may have returned early (converged).
+template <int N, typename Fin>
+__device__ __forceinline__ void warp_grid_reduce(double v[N], const ReduceBuf& rb, int site_block, Fin fin) {
+  const int lane = threadIdx.x & 31;
+  double s[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    s[k] = x;
+  }
+  unsigned int t = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + rb.block_offset + site_block] = s[k];
+    __threadfence();
+    t = atomicAdd(rb.ticket, 1u);
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != (unsigned int)rb.total_blocks - 1u) return;
+  __threadfence();
+  double tot[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double acc = 0.0;
+    for (int b = lane; b < rb.total_blocks; b += 32) acc += __ldcg(rb.partial + (size_t)k * rb.total_blocks + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    tot[k] = acc;
+  }
+  if (lane == 0) {
+    peer_allreduce<N>(rb.peer, tot);
+    fin(tot);
+    *rb.ticket = 0u;
+    __threadfence();
   }
 }
 

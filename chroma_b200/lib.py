@@ -70,6 +70,10 @@ SYMBOLS = {
     "b200_field_upload": (_i, [_vp, _vp, _vp, _i]),
     "b200_field_download": (_i, [_vp, _vp, _vp, _i]),
     "b200_field_zero": (_i, [_vp, _vp]),
+    "b200_mfield_alloc": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "b200_mfield_upload": (_i, [_vp, _vp, _i, _vp, _i]),
+    "b200_mfield_download": (_i, [_vp, _vp, _i, _vp, _i]),
+    "b200_field_nrhs": (_i, [_vp]),
     "b200_dev_dslash": (_i, [_vp, _vp, _vp, _i, _i]),
     "b200_dev_clover_apply": (_i, [_vp, _vp, _vp, _i, _i]),
     "b200_dev_clover_matpc": (_i, [_vp, _vp, _vp, _i]),

@@ -27,22 +27,34 @@ def _ptr(a):
 
 
 class Field:
-    """A device-resident checkerboard fermion (b200_field)."""
+    """A device-resident checkerboard fermion (b200_field), or a batch of nrhs of them (b200_mfield_alloc)."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, nrhs=1):
         self.ctx = ctx
+        self.nrhs = int(nrhs)
         self.h = C.c_void_p()
-        L.check(ctx.lib.b200_field_alloc(ctx.h, C.byref(self.h)))
+        if self.nrhs == 1:
+            L.check(ctx.lib.b200_field_alloc(ctx.h, C.byref(self.h)))
+        else:
+            L.check(ctx.lib.b200_mfield_alloc(ctx.h, self.nrhs, C.byref(self.h)))
 
-    def upload(self, host_cb):
+    def upload(self, host_cb, irhs=None):
+        """host_cb: one checkerboard [Vh,4,3,2] (into right-hand side irhs, default 0) or a stack [nrhs,Vh,4,3,2]."""
         host_cb = np.ascontiguousarray(host_cb)
+        if irhs is None and host_cb.size == self.nrhs * self.ctx.Vh * 24 and self.nrhs > 1:
+            for i in range(self.nrhs):
+                self.upload(host_cb.reshape(self.nrhs, -1)[i], i)
+            return self
         assert host_cb.size == self.ctx.Vh * 24, "expected one checkerboard [Vh,4,3,2]"
-        L.check(self.ctx.lib.b200_field_upload(self.ctx.h, self.h, _ptr(host_cb), _prec_of(host_cb)))
+        L.check(self.ctx.lib.b200_mfield_upload(self.ctx.h, self.h, int(irhs or 0), _ptr(host_cb), _prec_of(host_cb)))
         return self
 
-    def download(self, dtype=np.float64):
+    def download(self, dtype=np.float64, irhs=None):
+        """One checkerboard [Vh,4,3,2]; for a batch without irhs, the stack [nrhs,Vh,4,3,2]."""
+        if irhs is None and self.nrhs > 1:
+            return np.stack([self.download(dtype, i) for i in range(self.nrhs)])
         out = np.empty((self.ctx.Vh, 4, 3, 2), dtype=dtype)
-        L.check(self.ctx.lib.b200_field_download(self.ctx.h, self.h, _ptr(out), _prec_of(out)))
+        L.check(self.ctx.lib.b200_mfield_download(self.ctx.h, self.h, int(irhs or 0), _ptr(out), _prec_of(out)))
         return out
 
     def zero(self):
@@ -181,6 +193,13 @@ class Context:
             f.upload(host_cb)
         return f
 
+    def mfield(self, nrhs, host_stack=None):
+        """A batch of nrhs checkerboard fermions; host_stack: [nrhs,Vh,4,3,2]."""
+        f = Field(self, nrhs)
+        if host_stack is not None:
+            f.upload(host_stack)
+        return f
+
     def dev_dslash(self, out, inp, isign, out_cb):
         L.check(self.lib.b200_dev_dslash(self.h, out.h, inp.h, int(isign), int(out_cb)))
 
@@ -196,24 +215,27 @@ class Context:
         return ms[0], ms[1]
 
     def dev_norm2(self, x):
-        r = C.c_double()
-        L.check(self.lib.b200_dev_norm2(self.h, x.h, C.byref(r)))
-        return r.value
+        r = (C.c_double * x.nrhs)()
+        L.check(self.lib.b200_dev_norm2(self.h, x.h, r))
+        return r[0] if x.nrhs == 1 else list(r)
 
     def dev_inner(self, x, y):
-        r = (C.c_double * 2)()
+        r = (C.c_double * (2 * x.nrhs))()
         L.check(self.lib.b200_dev_inner(self.h, x.h, y.h, r))
-        return complex(r[0], r[1])
+        out = [complex(r[2 * i], r[2 * i + 1]) for i in range(x.nrhs)]
+        return out[0] if x.nrhs == 1 else out
 
     def dev_invert(self, psi, chi, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
-        info = L.SolveInfo()
-        L.check(self.lib.b200_dev_invert(self.h, psi.h, chi.h, int(solver), float(rsd), int(max_iter), C.byref(info)))
-        return info
+        """Batched fields: all right-hand sides in lockstep; returns a list of SolveInfo."""
+        infos = (L.SolveInfo * psi.nrhs)()
+        rc = self.lib.b200_dev_invert(self.h, psi.h, chi.h, int(solver), float(rsd), int(max_iter), infos)
+        L.check(rc)
+        return infos[0] if psi.nrhs == 1 else list(infos)
 
     def dev_invert_mdagm(self, psi, chi, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
-        info = L.SolveInfo()
-        L.check(self.lib.b200_dev_invert_mdagm(self.h, psi.h, chi.h, int(solver), float(rsd), int(max_iter), C.byref(info)))
-        return info
+        infos = (L.SolveInfo * psi.nrhs)()
+        L.check(self.lib.b200_dev_invert_mdagm(self.h, psi.h, chi.h, int(solver), float(rsd), int(max_iter), infos))
+        return infos[0] if psi.nrhs == 1 else list(infos)
 
     def dev_invert_reliable(self, psi, chi, rsd=1e-8, delta=0.1, max_iter=1000, mdagm=False):
         info = L.SolveInfo()

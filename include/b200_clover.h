@@ -164,7 +164,9 @@ int b200_invert_reliable(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_
 
 /* Full-lattice propagator solve for nrhs right-hand sides (the sequential 12 spin-colour loop of
  * quarkprop4_w.cc:70-117 with the even-odd source preparation and solution reconstruction of
- * eoprec_fermact_qprop.cc:41-80 done on the device).  chi/psi: REAL[nrhs][V][4][3][2]. */
+ * eoprec_fermact_qprop.cc:41-80 done on the device).  chi/psi: REAL[nrhs][V][4][3][2].  The right-hand sides are solved
+ * in batches of up to 12 by the multi-RHS kernels (as many as fit in free device memory; the environment variable
+ * B200_QPROP_BATCH caps the batch, 1 = the reference's one-at-a-time loop).  infos: nrhs entries. */
 int b200_qprop(b200_ctx* ctx, void* psi_full_host, const void* chi_full_host, int host_prec, int nrhs, int solver,
                double rsd_target, int max_iter, b200_solve_info* infos);
 
@@ -174,6 +176,16 @@ void b200_field_free(b200_ctx* ctx, b200_field* f);
 int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* cb_host, int host_prec);
 int b200_field_download(b200_ctx* ctx, const b200_field* f, void* cb_host, int host_prec);
 int b200_field_zero(b200_ctx* ctx, b200_field* f);
+/* Batched fields: nrhs (1..12) checkerboard fermions in one allocation, e.g. the 12 spin-colour sources of a propagator
+ * (quarkprop4_w.cc:70-117).  Every b200_dev_* operator accepts them in place of ordinary fields (all arguments of a call
+ * must hold the same number of right-hand sides) and then runs the multi-RHS kernels: one CTA serves all right-hand
+ * sides of its sites, so links and clover blocks are read from HBM once per batch instead of once per source.  Solvers
+ * advance the right-hand sides in lockstep with independent scalars and stopping tests.  Result arrays of
+ * b200_dev_norm2 / b200_dev_inner / b200_dev_invert* then hold nrhs entries (b200_dev_inner: nrhs pairs). */
+int b200_mfield_alloc(b200_ctx* ctx, int nrhs, b200_field** f);
+int b200_mfield_upload(b200_ctx* ctx, b200_field* f, int irhs, const void* cb_host, int host_prec);
+int b200_mfield_download(b200_ctx* ctx, const b200_field* f, int irhs, void* cb_host, int host_prec);
+int b200_field_nrhs(const b200_field* f);
 int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb);
 int b200_dev_clover_apply(b200_ctx* ctx, b200_field* out, const b200_field* in, int cb, int inverse);
 int b200_dev_clover_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign);

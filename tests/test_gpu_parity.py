@@ -292,6 +292,99 @@ def test_qprop_full_lattice(oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("nrhs", [12, 5])
+def test_multi_rhs_operator_parity(oracle, nrhs, prec):
+    """Batched fields through the multi-RHS kernels (one CTA = 32 sites x all right-hand sides, links shared through L1):
+    every right-hand side of Dslash, A^-1, M and M^dagger equals the oracle applied to that source alone."""
+    latt = (8, 4, 6, 6)        # Vh = 576 = 18 x 32; exercises wrap-around in every direction
+    u, op, ctx, cp = setup(oracle, latt, prec, gauge="random")
+    Vh = ctx.Vh
+    tol = 1e-13 if prec == "double" else 2e-6
+    srcs = np.stack([fields.gaussian_fermion(latt, seed=100 + i) for i in range(nrhs)])
+    for out_cb in (0, 1):
+        fin = ctx.mfield(nrhs, srcs[:, (1 - out_cb) * Vh:(2 - out_cb) * Vh].astype(NP[prec]))
+        fout = ctx.mfield(nrhs)
+        for isign in (+1, -1):
+            ctx.dev_dslash(fout, fin, isign, out_cb)
+            got = fout.download()
+            for i in range(nrhs):
+                want = op.dslash(srcs[i], isign, out_cb)[out_cb * Vh:(out_cb + 1) * Vh]
+                assert rel_site_err(got[i], want) < tol
+    fin = ctx.mfield(nrhs, srcs[:, Vh:].astype(NP[prec]))
+    fout = ctx.mfield(nrhs)
+    for isign in (+1, -1):
+        ctx.dev_matpc(fout, fin, isign)
+        got = fout.download()
+        for i in range(nrhs):
+            odd = srcs[i].copy()
+            odd[:Vh] = 0
+            assert rel_site_err(got[i], op.apply(odd, isign)[Vh:]) < 2 * tol
+    n2 = ctx.dev_norm2(fin)
+    for i in range(nrhs):
+        want = np.sum(srcs[i, Vh:].astype(NP[prec]).astype(np.float64) ** 2)
+        assert abs(n2[i] - want) < 1e-12 * want
+    ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["CG", "BICGSTAB"])
+def test_multi_rhs_solvers_lockstep(oracle, solver):
+    """12 different right-hand sides solved in lockstep converge independently: each needs the iteration count of its own
+    single-RHS solve (+-1: the batched reductions sum in a different, still fixed, order) and reaches the target residual.
+    Includes a zero source (converged before the first iteration) and sources of very different norms."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, "double", gauge="weak")
+    Vh = ctx.Vh
+    code = L.B200_SOLVER_CG if solver == "CG" else L.B200_SOLVER_BICGSTAB
+    rsd = 1e-9
+    srcs = []
+    for i in range(12):
+        f = fields.gaussian_fermion(latt, seed=200 + i, cb=1)[Vh:] if i % 3 else fields.point_source(latt, i % 4, i % 3)[:Vh].copy()
+        srcs.append(f * 10.0 ** (i - 6))
+    if solver == "CG":
+        srcs[7] = np.zeros_like(srcs[7])
+    srcs = np.stack(srcs)
+    chi = ctx.mfield(12, srcs)
+    psi = ctx.mfield(12)
+    infos = ctx.dev_invert(psi, chi, solver=code, rsd=rsd, max_iter=2000)
+    sol = psi.download()
+    for i in range(12):
+        if not srcs[i].any():
+            assert infos[i].converged == 1 and infos[i].n_count == 0 and not sol[i].any()
+            continue
+        one, info1 = ctx.invert(srcs[i], None, solver=code, rsd=rsd, max_iter=2000)
+        assert infos[i].converged == 1
+        assert abs(infos[i].n_count - info1.n_count) <= 1, (i, infos[i].n_count, info1.n_count)
+        full = np.zeros((2 * Vh, 4, 3, 2))
+        full[Vh:] = sol[i]
+        rhs = np.zeros_like(full)
+        rhs[Vh:] = srcs[i]
+        r = rhs - op.apply(full, +1)
+        rel = np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(srcs[i] ** 2))
+        assert rel < 20 * rsd, (i, rel)
+        assert abs(infos[i].rel_resid - rel) < 1e-2 * rel + 1e-14
+        assert rel_site_err(sol[i], one) < 1e-6
+    ctx.close()
+
+
+def test_qprop_batches(oracle, monkeypatch):
+    """b200_qprop in batches that do not divide the number of sources (12 = 5 + 5 + 2) gives the same propagator."""
+    latt = (4, 4, 4, 8)
+    u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
+    srcs = np.stack([fields.point_source(latt, s, c) for s in range(4) for c in range(3)])
+    sol12, _ = ctx.qprop(srcs, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-10, max_iter=500)
+    monkeypatch.setenv("B200_QPROP_BATCH", "5")
+    sol5, infos = ctx.qprop(srcs, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-10, max_iter=500)
+    monkeypatch.setenv("B200_QPROP_BATCH", "1")
+    sol1, _ = ctx.qprop(srcs, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-10, max_iter=500)
+    for i in range(12):
+        assert infos[i].converged == 1
+        r = op.unprec_apply(sol5[i], +1) - srcs[i]
+        assert np.linalg.norm(r) / np.linalg.norm(srcs[i]) < 1e-8
+        assert np.abs(sol5[i] - sol12[i]).max() < 1e-9 and np.abs(sol1[i] - sol12[i]).max() < 1e-9
+    ctx.close()
+
+
 def test_error_behaviour():
     """Bad arguments fail loudly with a code and a message (no exceptions cross the C ABI)."""
     lib = L.load()
