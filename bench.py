@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--prec", default="double", choices=["double", "single"])
     ap.add_argument("--recon", type=int, default=18, choices=[18, 12])
     ap.add_argument("--solver", default="CG", choices=["CG", "BICGSTAB"])
+    ap.add_argument("--nrhs", type=int, default=12, help="right-hand sides of the batched (propagator) leg; 1 = skip it")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--solve", action="store_true", help="also run a full solve to 1e-8 and report time-to-solution")
     return ap.parse_args()
@@ -361,6 +362,43 @@ def run_b200(args):
         ms_m = max_over_ranks(e2.elapsed_time(e3)) / args.steps
         dsl = {"gflops": FLOP_M * Vh_global / (ms_m * 1e-3) * 1e-9, "ms_per_apply": ms_m}
 
+    # ---------------- leg 2b: the same iteration for a batch of right-hand sides (the 12 spin-colour sources of a propagator,
+    # quarkprop4_w.cc:70-117) through the multi-RHS kernels: links and clover cross HBM once per batch
+    mrhs = None
+    if args.nrhs > 1:
+        try:
+            nr = args.nrhs
+            chi_b, psi_b, out_b = ctx.mfield(nr), ctx.mfield(nr), ctx.mfield(nr)
+            for i in range(nr):
+                chi_b.upload(np.roll(chi_np, 7 * i + 1, axis=0), i)
+            ctx.dev_iterate_begin(psi_b, chi_b, solver)
+            ctx.dev_iterate(solver, args.warmup)
+            barrier()
+            e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e6.record(stream)
+            ctx.dev_iterate(solver, args.steps)
+            e7.record(stream)
+            barrier()
+            ms_b = max_over_ranks(e6.elapsed_time(e7)) / args.steps
+            R = 8 if args.prec == "double" else 4
+            G = args.recon
+            mrhs = {"nrhs": nr, "ms_per_iteration": ms_b, "ms_per_iteration_per_rhs": ms_b / nr,
+                    "gflops": flop_iter * Vh_global * nr / (ms_b * 1e-3) * 1e-9,
+                    "speedup_per_rhs_vs_single": ms_step / (ms_b / nr)}
+            if world == 1:
+                ctx.dev_time_matpc(out_b, chi_b, +1, 2)
+                barrier()
+                mb_a, mb_b = ctx.dev_time_matpc(out_b, chi_b, +1, max(5, args.steps // 2))
+                bytes_m = ((120.0 + (144 + 16 * G) / nr) * R) * nr          # algorithmic bytes per site for the whole batch
+                peak, _ = peaks()
+                mrhs["clover_dslash"] = {"ms_per_apply": mb_a + mb_b, "gflops": FLOP_M * Vh * nr / ((mb_a + mb_b) * 1e-3) * 1e-9,
+                                         "algorithmic_bytes_per_site_per_rhs": bytes_m / nr,
+                                         "hbm_gbs": bytes_m * Vh / ((mb_a + mb_b) * 1e-3) * 1e-9,
+                                         "frac_of_peak": bytes_m * Vh / ((mb_a + mb_b) * 1e-3) * 1e-9 / peak}
+            del chi_b, psi_b, out_b
+        except Exception as e:  # noqa
+            mrhs = {"error": str(e)}
+
     # ---------------- leg 3: end to end through the host-pointer ABI call (what the Chroma adapter calls)
     # rsd = 0 never converges (cp <= 0 is false), so exactly `steps` iterations run.
     psi_np[...] = 0
@@ -424,7 +462,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.prec == "double" else "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": ck, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu, "clover_dslash": dsl, "solve": solve,
+            "roofline": roof, "cpu_baseline": cpu, "clover_dslash": dsl, "multi_rhs": mrhs, "solve": solve,
             "setup_s": t_setup, "timed_wall_s": wall1 - wall0,
         }
         print(json.dumps(line))

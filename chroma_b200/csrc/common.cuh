@@ -73,6 +73,18 @@ __device__ __forceinline__ float2 ld_keep_nol1(const float2* p, uint64_t pol) {
   asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
   return v;
 }
+// Asynchronous global -> shared copies of one complex number (the multi-RHS kernels stage links and clover blocks in
+// shared memory).  16-byte copies bypass L1 (.cg); 8-byte ones only exist as .ca.
+__device__ __forceinline__ void cp_async(double2* smem_dst, const double2* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async(float2* smem_dst, const float2* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // read-modify-write streams (the CG residual) must not use the non-coherent path
 __device__ __forceinline__ double2 ld_stream_rw(const double2* p, uint64_t pol) {
   double2 v;

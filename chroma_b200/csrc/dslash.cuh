@@ -57,6 +57,7 @@ struct DslashArgs {
   int nrhs;
   size_t fstride;   // elements between consecutive right-hand sides of a batched field (12*Vh)
   size_t gstride;   // same for the ghost faces (6*S3h)
+  int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice
 };
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
@@ -112,7 +113,7 @@ template <typename R, bool RECON12, bool MR = false>
 __device__ __forceinline__ void load_link(Cx<R> U[9], const Cx<R>* __restrict__ p, int stride, uint64_t strm) {
   constexpr int NG = RECON12 ? 6 : 9;
 #pragma unroll
-  for (int k = 0; k < NG; ++k) U[k] = MR ? ld_op(p + k * (size_t)stride) : ld_stream(p + k * (size_t)stride, strm);
+  for (int k = 0; k < NG; ++k) U[k] = MR ? p[k * stride] /* staged in shared memory */ : ld_stream(p + k * (size_t)stride, strm);
   if (RECON12) {
     // row2 = conj(row0 x row1): exact for SU(3); non-unit factors (anisotropy, -1 boundary phase)
     // are carried separately by the caller (see load_gauge in api.cu).
@@ -141,11 +142,11 @@ __device__ __forceinline__ void su3_mul(Cx<R> r0[3], Cx<R> r1[3], const Cx<R> U[
 
 // One hop: acc += recons( U(or U^dag) * project(psi_nbr) ).
 template <typename R, int MU, bool ADJ, bool RECON12, bool MR = false>
-__device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi_nbr, const Cx<R>* __restrict__ link,
-                                    int stride, R sg, R scale, const L2Policy& pol) {
+__device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi_nbr, const Cx<R>* link,
+                                    int stride, int lstride, R sg, R scale, const L2Policy& pol) {
   Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
   load_project<R, MU, MR>(h0, h1, psi_nbr, stride, sg, pol.keep);
-  load_link<R, RECON12, MR>(U, link, stride, pol.stream);
+  load_link<R, RECON12, MR>(U, link, lstride, pol.stream);
   if (RECON12) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
@@ -162,8 +163,11 @@ struct LinkScale {
 };
 
 // The Wilson hopping term for one target site.  (xh,y,z,t) are its checkerboard coordinates.
+// MR (multi-RHS kernels): the site's 8 links have been staged in shared memory, slot (2*mu + backward)*NG + k of lane
+// `sml` (slot stride 32); otherwise they stream from global memory.
 template <typename R, bool RECON12, bool MR = false>
-__device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol) {
+__device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol,
+                                            const Cx<R>* sml = nullptr) {
   typedef Cx<R> C;
   const Geom& g = a.g;
   const int stride = g.Vh;
@@ -181,6 +185,10 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
   const size_t gmu = 2 * gplane;
   const C* __restrict__ in = a.in;
   const R s = (R)a.isign;
+  const int ls_ = MR ? 32 : stride;                 // link plane stride
+  // link base pointers of the 8 hops
+#define B200_LF(mu) (MR ? sml + (2 * (mu)) * NG * 32 : Uf + (mu) * gmu)
+#define B200_LB(mu, nbr) (MR ? sml + (2 * (mu) + 1) * NG * 32 : Ub + (mu) * gmu + (nbr))
 
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = mk<R>(0, 0);
@@ -189,21 +197,21 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
   {
     const int xf = r ? (xh + 1 == g.Lxh ? idx - (g.Lxh - 1) : idx + 1) : idx;
     const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
-    hop<R, 0, false, RECON12, MR>(acc, in + xf, Uf + 0 * gmu, stride, -s, (R)ls.aniso[0], pol);
-    hop<R, 0, true, RECON12, MR>(acc, in + xb, Ub + 0 * gmu + xb, stride, s, (R)ls.aniso[0], pol);
+    hop<R, 0, false, RECON12, MR>(acc, in + xf, B200_LF(0), stride, ls_, -s, (R)ls.aniso[0], pol);
+    hop<R, 0, true, RECON12, MR>(acc, in + xb, B200_LB(0, xb), stride, ls_, s, (R)ls.aniso[0], pol);
   }
   {
     const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
     const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
-    hop<R, 1, false, RECON12, MR>(acc, in + yf, Uf + 1 * gmu, stride, -s, (R)ls.aniso[1], pol);
-    hop<R, 1, true, RECON12, MR>(acc, in + yb, Ub + 1 * gmu + yb, stride, s, (R)ls.aniso[1], pol);
+    hop<R, 1, false, RECON12, MR>(acc, in + yf, B200_LF(1), stride, ls_, -s, (R)ls.aniso[1], pol);
+    hop<R, 1, true, RECON12, MR>(acc, in + yb, B200_LB(1, yb), stride, ls_, s, (R)ls.aniso[1], pol);
   }
   {
     const int sz = g.Ly * g.Lxh;
     const int zf = (z + 1 == g.Lz) ? idx - (g.Lz - 1) * sz : idx + sz;
     const int zb = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
-    hop<R, 2, false, RECON12, MR>(acc, in + zf, Uf + 2 * gmu, stride, -s, (R)ls.aniso[2], pol);
-    hop<R, 2, true, RECON12, MR>(acc, in + zb, Ub + 2 * gmu + zb, stride, s, (R)ls.aniso[2], pol);
+    hop<R, 2, false, RECON12, MR>(acc, in + zf, B200_LF(2), stride, ls_, -s, (R)ls.aniso[2], pol);
+    hop<R, 2, true, RECON12, MR>(acc, in + zb, B200_LB(2, zb), stride, ls_, s, (R)ls.aniso[2], pol);
   }
   {
     const int st = g.S3h;
@@ -222,7 +230,7 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       const C* __restrict__ gp = a.ghost_fwd + (idx - (g.Lt - 1) * st);
 #pragma unroll
       for (int c = 0; c < 3; ++c) { h0[c] = ld_stream(gp + (size_t)c * st, pol.stream); h1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
-      load_link<R, RECON12, MR>(U, Uf + 3 * gmu, stride, pol.stream);
+      load_link<R, RECON12, MR>(U, B200_LF(3), ls_, pol.stream);
       if (RECON12) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { h0[c].x *= scf; h0[c].y *= scf; h1[c].x *= scf; h1[c].y *= scf; }
@@ -230,7 +238,7 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       su3_mul<R, false>(r0, r1, U, h0, h1);
       recons_acc<R, 3>(acc, r0, r1, -s);
     } else {
-      hop<R, 3, false, RECON12, MR>(acc, in + tf, Uf + 3 * gmu, stride, -s, scf, pol);
+      hop<R, 3, false, RECON12, MR>(acc, in + tf, B200_LF(3), stride, ls_, -s, scf, pol);
     }
     if (g.tsplit && first) {
       // U^dag (1 +/- g3) psi computed by the -t neighbour rank (it owns that link): just reconstruct
@@ -240,19 +248,37 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       for (int c = 0; c < 3; ++c) { r0[c] = ld_stream(gp + (size_t)c * st, pol.stream); r1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
       recons_acc<R, 3>(acc, r0, r1, s);
     } else {
-      hop<R, 3, true, RECON12, MR>(acc, in + tb, Ub + 3 * gmu + tb, stride, s, scb, pol);
+      hop<R, 3, true, RECON12, MR>(acc, in + tb, B200_LB(3, tb), stride, ls_, s, scb, pol);
     }
   }
+#undef B200_LF
+#undef B200_LB
+}
+
+// Indices (on the source checkerboard) of the four backward neighbours of target site idx -- where the backward links
+// live.  Same arithmetic as dslash_site; used by the multi-RHS kernels to stage the links.
+__device__ __forceinline__ void backward_neighbours(const Geom& g, int idx, int parity, int nbr[4]) {
+  int q = idx;
+  const int xh = q % g.Lxh; q /= g.Lxh;
+  const int y = q % g.Ly;   q /= g.Ly;
+  const int z = q % g.Lz;
+  const int t = q / g.Lz;
+  const int r = (y + z + t + parity) & 1;
+  nbr[0] = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
+  nbr[1] = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
+  const int sz = g.Ly * g.Lxh;
+  nbr[2] = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
+  nbr[3] = (t == 0) ? idx + (g.Lt - 1) * g.S3h : idx - g.S3h;
 }
 
 // ---- clover: one 6x6 Hermitian block times 6 complex --------------------------------------------
 // out[i] = d_i in[i] + sum_{j<i} o_{k(i,j)} in[j] + sum_{j>i} conj(o_{k(j,i)}) in[j], k = i(i-1)/2+j
 // (applySiteLoop, clover_term_qdp_w.h:1606-1634).  cl points at plane 0 of the block for this site.
 template <typename R, bool MR = false>
-__device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], const Cx<R>* __restrict__ cl, int stride, uint64_t strm) {
-  const Cx<R> d01 = MR ? ld_op(cl) : ld_stream(cl, strm);
-  const Cx<R> d23 = MR ? ld_op(cl + (size_t)stride) : ld_stream(cl + (size_t)stride, strm);
-  const Cx<R> d45 = MR ? ld_op(cl + 2 * (size_t)stride) : ld_stream(cl + 2 * (size_t)stride, strm);
+__device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], const Cx<R>* cl, int stride, uint64_t strm) {
+  const Cx<R> d01 = MR ? cl[0] : ld_stream(cl, strm);
+  const Cx<R> d23 = MR ? cl[stride] : ld_stream(cl + (size_t)stride, strm);
+  const Cx<R> d45 = MR ? cl[2 * stride] : ld_stream(cl + 2 * (size_t)stride, strm);
   out[0] = mk<R>(d01.x * in[0].x, d01.x * in[0].y);
   out[1] = mk<R>(d01.y * in[1].x, d01.y * in[1].y);
   out[2] = mk<R>(d23.x * in[2].x, d23.x * in[2].y);
@@ -264,7 +290,7 @@ __device__ __forceinline__ void clover_block(Cx<R> out[6], const Cx<R> in[6], co
   for (int i = 1; i < 6; ++i) {
 #pragma unroll
     for (int j = 0; j < i; ++j) {
-      const Cx<R> o = MR ? ld_op(cl + (size_t)(3 + k) * stride) : ld_stream(cl + (size_t)(3 + k) * stride, strm);
+      const Cx<R> o = MR ? cl[(3 + k) * stride] : ld_stream(cl + (size_t)(3 + k) * stride, strm);
       cmac(out[i], o, in[j]);
       cmac_conj(out[j], o, in[i]);
       ++k;
@@ -340,15 +366,19 @@ struct FinBiOmega {
 #endif
 // ---- fused epilogues for one target site (shared by the single- and multi-RHS kernels) ------------------------
 template <typename R, int EPI, bool MR>
-__device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>& a, int idx, int stride, const L2Policy& pol, double red[3]) {
+__device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>& a, int idx, int stride, const L2Policy& pol, double red[3],
+                                              const Cx<R>* smc = nullptr) {
   typedef Cx<R> C;
+  // clover block b of this site: staged in shared memory (multi-RHS) or streamed from global memory
+  const C* const cl0 = MR ? smc : a.clov + idx;
+  const int cs = MR ? 32 : stride;
   if (EPI == EPI_DSLASH) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, acc[k], pol.stream);
   } else if (EPI == EPI_AINV) {
     C o[12];
 #pragma unroll
-    for (int b = 0; b < 2; ++b) clover_block<R, MR>(o + 6 * b, acc + 6 * b, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
+    for (int b = 0; b < 2; ++b) clover_block<R, MR>(o + 6 * b, acc + 6 * b, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
 #pragma unroll
     for (int k = 0; k < 12; ++k) st_stream(a.out + (size_t)k * stride + idx, o[k], pol.stream);
   } else {
@@ -369,7 +399,7 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
       C xi[6], o[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) xi[k] = ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
-      clover_block<R, MR>(o, xi, a.clov + (size_t)(18 * b) * stride + idx, stride, pol.stream);
+      clover_block<R, MR>(o, xi, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
@@ -434,40 +464,107 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
 
 // ---- multi-RHS variant ------------------------------------------------------------------------------------------
 // CTA = 32 consecutive target sites x NRB right-hand sides (threadIdx.y = right-hand side, one warp each).  All warps
-// of a CTA need the same 8 links and the same clover block per site: the first warp's load brings them into L1, the
-// others hit, so gauge + clover cross L2/HBM once per CTA instead of once per right-hand side -- per right-hand side
-// the operator moves (120 + (144+16G)/nrhs) reals per site instead of 264+16G.
+// of a CTA need the same 8 links and the same clover block per site: the CTA stages them in shared memory once
+// (cp.async), so gauge + clover cross L2/HBM once per CTA instead of once per right-hand side, occupy no registers
+// while in flight, and the per-thread global loads are the spinors only -- per right-hand side the operator moves
+// (120 + (144+16G)/nrhs) reals per site instead of 264+16G.
 // Every right-hand side has its own scalar / status block and its own reduction (warp_grid_reduce), so the solves
 // advance in lockstep but converge independently.
+// Tuned on B200 at 48^3x48 with 12 sources (scripts/tune_mrhs.sh, profiles/r01_tune_mrhs.txt): the kernel is bound by
+// latency x occupancy, so the best shapes are the ones that put the most warps on an SM without spilling --
+// fp64: 6 sources/CTA x 2 CTAs/SM (12 warps, 170 registers) 1.71x per source over the single-RHS kernel
+//       (4x2 at 255 registers: 1.34x; 4x4 at 128: 1.47x; 12x1: 1.69x);
+// fp32: 12 sources/CTA x 2 CTAs/SM (24 warps, 85 registers) 1.53x (6x4: 1.45x; 4x4: 1.30x).
 #ifndef B200_MRHS_NRB
-#define B200_MRHS_NRB 12
+#define B200_MRHS_NRB 6       // right-hand sides per CTA, fp64
 #endif
+#ifndef B200_MRHS_MINB
+#define B200_MRHS_MINB 2      // min CTAs/SM for the register allocator, fp64
+#endif
+#ifndef B200_MRHS_NRB_F
+#define B200_MRHS_NRB_F 12    // fp32
+#endif
+#ifndef B200_MRHS_MINB_F
+#define B200_MRHS_MINB_F 2
+#endif
+template <typename R, int EPI, bool RECON12> struct MrhsSmem {
+  static constexpr int NG = RECON12 ? 6 : 9;
+  static constexpr int NL = 8 * NG;                                 // link slots
+  static constexpr int NS = NL + (EPI == EPI_DSLASH ? 0 : 36);      // + clover slots
+  static constexpr size_t bytes = (size_t)NS * 32 * sizeof(Cx<R>);
+};
 template <typename R, int EPI, bool RECON12, int NRB>
-__global__ void __launch_bounds__(32 * NRB, 1) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
+__global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
   typedef Cx<R> C;
+  typedef MrhsSmem<R, EPI, RECON12> SM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* const sm = reinterpret_cast<C*>(smem_raw);
   const int grp = blockIdx.x % ngroups, site_block = blockIdx.x / ngroups;
   const int rhs = grp * NRB + threadIdx.y;
-  if (rhs >= a0.nrhs) return;
-  DslashArgs<R> a = a0;
-  a.scal = a0.scal + rhs * S_COUNT; a.status = a0.status + rhs * ST_COUNT;
-  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
-  a.in = a0.in + rhs * a0.fstride;
-  if (a0.out) a.out = a0.out + rhs * a0.fstride;
-  if (a0.x) a.x = a0.x + rhs * a0.fstride;
-  if (a0.r) a.r = a0.r + rhs * a0.fstride;
-  if (a0.r0) a.r0 = a0.r0 + rhs * a0.fstride;
-  if (a0.ghost_fwd) { a.ghost_fwd = a0.ghost_fwd + rhs * a0.gstride; a.ghost_bwd = a0.ghost_bwd + rhs * a0.gstride; }
-  const int stride = a.g.Vh;
+  const int stride = a0.g.Vh;
   const int local = site_block * 32 + threadIdx.x;
-  const bool active = local < a.idx_count + a.idx_count2;
-  const int idx = !active ? a.idx_begin : (local < a.idx_count ? a.idx_begin + local : a.idx_begin2 + (local - a.idx_count));
+  const bool active = local < a0.idx_count + a0.idx_count2;
+  int idx = !active ? a0.idx_begin : (local < a0.idx_count ? a0.idx_begin + local : a0.idx_begin2 + (local - a0.idx_count));
+  if (a0.zc_sites && local < a0.idx_count) {
+    // Traversal order of a batch: the t+-1 neighbours of a site are re-read one time slice later, and one slice of
+    // nrhs spinors (127 MB for 12 at 48^3, fp64) does not survive in the 126 MB L2.  So the launch sweeps t inside
+    // z-chunks small enough that three slices of a chunk stay L2-resident (memory layout unchanged: only WHICH site a
+    // thread takes changes).  idx_begin / idx_count are whole time slices here.
+    const int nt = a0.idx_count / a0.g.S3h, t0 = a0.idx_begin / a0.g.S3h;
+    const int per = a0.zc_sites * nt;
+    const int zc = local / per, rem = local - zc * per;
+    const int t = rem / a0.zc_sites, w = rem - t * a0.zc_sites;
+    idx = (t0 + t) * a0.g.S3h + zc * a0.zc_sites + w;
+  }
+
+  // ---- stage this CTA's operator data: the 8 links (and the clover block) of its 32 sites go to shared memory ONCE,
+  // with asynchronous copies issued by all NRB warps; every right-hand side then reads them from there.
+  if (active) {
+    int nbr[4];
+    backward_neighbours(a0.g, idx, a0.parity, nbr);
+    const size_t gplane = (size_t)SM::NG * stride, gmu = 2 * gplane;
+    const C* const Uf = a0.gauge + (size_t)a0.parity * gplane + idx;
+    const C* const Ub = a0.gauge + (size_t)(1 - a0.parity) * gplane;
+#pragma unroll
+    for (int i = 0; i < (SM::NS + NRB - 1) / NRB; ++i) {
+      const int e = threadIdx.y + i * NRB;
+      if (e < SM::NS) {
+        const C* src;
+        if (e < SM::NL) {
+          const int d = e / SM::NG, k = e - d * SM::NG, mu = d >> 1;
+          src = (d & 1) ? Ub + mu * gmu + nbr[mu] + (size_t)k * stride : Uf + mu * gmu + (size_t)k * stride;
+        } else {
+          src = a0.clov + (size_t)(e - SM::NL) * stride + idx;
+        }
+        cp_async(sm + e * 32 + threadIdx.x, src);
+      }
+    }
+  }
+  cp_async_commit();
+
+  DslashArgs<R> a = a0;
+  const bool have_rhs = rhs < a0.nrhs;
+  if (have_rhs) {
+    a.scal = a0.scal + rhs * S_COUNT; a.status = a0.status + rhs * ST_COUNT;
+    a.in = a0.in + rhs * a0.fstride;
+    if (a0.out) a.out = a0.out + rhs * a0.fstride;
+    if (a0.x) a.x = a0.x + rhs * a0.fstride;
+    if (a0.r) a.r = a0.r + rhs * a0.fstride;
+    if (a0.r0) a.r0 = a0.r0 + rhs * a0.fstride;
+    if (a0.ghost_fwd) { a.ghost_fwd = a0.ghost_fwd + rhs * a0.gstride; a.ghost_bwd = a0.ghost_bwd + rhs * a0.gstride; }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // a converged right-hand side (or an empty slot of the last group) leaves only now: its warp helped staging
+  if (!have_rhs) return;
+  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {
     const L2Policy pol = make_l2_policy();
     C acc[12];
-    dslash_site<R, RECON12, true>(acc, a, ls, idx, pol);
-    site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red);
+    dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x);
+    site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
   }
 
   const int sb = site_block;   // block_offset of a split step is applied inside warp_grid_reduce

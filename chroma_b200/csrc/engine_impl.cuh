@@ -97,6 +97,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
     if (prop.major < 10) { set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); return B200_ERR_CUDA; }
     blas_grid = prop.multiProcessorCount * 8;
+    if (const char* e = getenv("B200_MRHS_L2_KB")) l2_budget = atol(e) << 10;
     g.Lxh = cfg.ldims[0] / 2; g.Ly = cfg.ldims[1]; g.Lz = cfg.ldims[2]; g.Lt = cfg.ldims[3];
     g.S3h = g.Lxh * g.Ly * g.Lz;
     g.Vh = g.S3h * g.Lt;
@@ -357,6 +358,7 @@ class Engine : public EngineBase {
     }
     return B200_OK;
   }
+  long l2_budget = 40l << 20;   // bytes of L2 the batched traversal may assume for its three live time slices (B200_MRHS_L2_KB overrides)
   int nb = 1;   // right-hand sides of the operation in flight (set by the public entry points; 1 = ordinary path)
   // Select the batch size and make sure the reduction scratch holds <= 4 partial sums per right-hand side and block,
   // for the BLAS grid as well as for the Dslash grids (32 sites per block when batched).
@@ -368,11 +370,12 @@ class Engine : public EngineBase {
   C* W(int i) { return (C*)ws[i]->d; }
 
   // ------------------------------------------------------------------ kernel launchers
-  static constexpr int NRB = B200_MRHS_NRB;
+  static constexpr int NRB = sizeof(R) == 4 ? B200_MRHS_NRB_F : B200_MRHS_NRB;   // right-hand sides per CTA (tuned per precision)
   template <int EPI>
   int launch_dslash(DslashArgs<R>& a) {
     a.gauge = gauge; a.scal = scal; a.status = status; a.g = g;
     a.nrhs = nb; a.fstride = nelem(); a.gstride = (size_t)6 * g.S3h;
+    a.zc_sites = nb > 1 ? zchunk_sites() : 0;
     const int bs = nb > 1 ? 32 : DSLASH_BLOCK;          // target sites per CTA
     int rc;
     if (g.tsplit) {
@@ -405,6 +408,16 @@ class Engine : public EngineBase {
     else dslash_kernel<R, EPI, false, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
     return launched("dslash_kernel");
   }
+  // z-chunk (in sites per time slice) of the batched traversal order: the largest divisor of Lz for which three time
+  // slices of the batch's source spinors fit in ~1/3 of the L2 (B200: 126 MB); 0 = natural order
+  int zchunk_sites() const {
+    const long budget = l2_budget;
+    const long plane = (long)g.Lxh * g.Ly * 12 * (long)sizeof(C) * nb;      // one z-plane of one time slice, all right-hand sides
+    if (3 * plane * g.Lz <= budget || budget <= 0) return 0;
+    int zc = 1;
+    for (int d = 1; d <= g.Lz; ++d) if (g.Lz % d == 0 && 3 * plane * d <= budget) zc = d;
+    return zc * g.Lxh * g.Ly;
+  }
   // batched launch: CTA = 32 sites x NRB right-hand sides; the groups of one site block are adjacent in the grid
   template <int EPI>
   int launch_mrhs(const DslashArgs<R>& a, int site_blocks) {
@@ -412,8 +425,16 @@ class Engine : public EngineBase {
     else {
       const int ngroups = (nb + NRB - 1) / NRB;
       const dim3 block(32, NRB);
-      if (recon == 12) dslash_mrhs_kernel<R, (EPI == EPI_M_CGREL ? EPI_M_CG : EPI), true, NRB><<<site_blocks * ngroups, block, 0, stream>>>(a, ls, ngroups);
-      else dslash_mrhs_kernel<R, (EPI == EPI_M_CGREL ? EPI_M_CG : EPI), false, NRB><<<site_blocks * ngroups, block, 0, stream>>>(a, ls, ngroups);
+      constexpr int E = (EPI == EPI_M_CGREL ? EPI_M_CG : EPI);
+      if (recon == 12) {
+        auto k = dslash_mrhs_kernel<R, E, true, NRB>;
+        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, true>::bytes));
+        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::bytes, stream>>>(a, ls, ngroups);
+      } else {
+        auto k = dslash_mrhs_kernel<R, E, false, NRB>;
+        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, false>::bytes));
+        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::bytes, stream>>>(a, ls, ngroups);
+      }
       return launched("dslash_mrhs_kernel");
     }
   }

@@ -293,10 +293,13 @@ def test_qprop_full_lattice(oracle):
 
 
 @pytest.mark.parametrize("prec", ["double", "single"])
-@pytest.mark.parametrize("nrhs", [12, 5])
-def test_multi_rhs_operator_parity(oracle, nrhs, prec):
-    """Batched fields through the multi-RHS kernels (one CTA = 32 sites x all right-hand sides, links shared through L1):
-    every right-hand side of Dslash, A^-1, M and M^dagger equals the oracle applied to that source alone."""
+@pytest.mark.parametrize("nrhs,l2_kb", [(12, None), (5, None), (12, 250), (7, 40)])
+def test_multi_rhs_operator_parity(oracle, nrhs, l2_kb, prec, monkeypatch):
+    """Batched fields through the multi-RHS kernels (one CTA = 32 sites x a group of right-hand sides, links shared through
+    L1): every right-hand side of Dslash, A^-1, M and M^dagger equals the oracle applied to that source alone.  l2_kb
+    shrinks the L2 budget so that the z-chunked traversal order (used on big lattices) is exercised on a small one."""
+    if l2_kb is not None:
+        monkeypatch.setenv("B200_MRHS_L2_KB", str(l2_kb))
     latt = (8, 4, 6, 6)        # Vh = 576 = 18 x 32; exercises wrap-around in every direction
     u, op, ctx, cp = setup(oracle, latt, prec, gauge="random")
     Vh = ctx.Vh
