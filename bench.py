@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--nrhs", type=int, default=12, help="right-hand sides of the batched (propagator) leg; 1 = skip it")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--solve", action="store_true", help="also run a full solve to 1e-8 and report time-to-solution")
+    ap.add_argument("--grid", type=int, nargs=2, default=None, metavar=("PZ", "PT"),
+                    help="process grid in Z x T (PZ*PT = --gpus); default: T split only (1 x N)")
     return ap.parse_args()
 
 
@@ -106,7 +108,8 @@ def run_reference(args):
 def workload_config(args, n):
     return {"workload": "%dx%dx%dx%d EO-prec Wilson-clover %s, %s, recon-%d, Mass=0.1 clovCoeff=1.0 antiperiodic-T, weak-field gauge"
             % (tuple(args.lattice) + (args.solver, "fp64" if args.prec == "double" else "fp32", args.recon)),
-            "lattice": list(args.lattice), "partition": "T-split x%d" % n,
+            "lattice": list(args.lattice),
+            "partition": ("T-split x%d" % n) if not args.grid or args.grid[0] == 1 else "Z x T grid %d x %d" % tuple(args.grid),
             "l2_policy": "working set per step (gauge+clover+vectors, >10 GB) exceeds the 126 MB L2; no flush needed"}
 
 
@@ -155,14 +158,17 @@ class Clocks:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def torch_weak_gauge(latt_local, t0_global, latt_global, seed, eps, device):
+def torch_weak_gauge(latt_local, t0_global, latt_global, seed, eps, device, z0_global=0):
     """Smooth SU(3) field, generated on the GPU (same recipe as fields.weak_gauge: Gram-Schmidt of 1+eps*G).  The random
-    stream is keyed by (seed, mu, GLOBAL time slice, checkerboard), so every rank count sees the same global field."""
+    stream is keyed by (seed, mu, GLOBAL time slice, checkerboard), so every rank count / process grid sees the same
+    global field (a rank of a Z-split grid draws the whole slice and keeps its z range, which is contiguous in cb2 order)."""
     import torch
     V = int(np.prod(latt_local))
     Vh = V // 2
     lt = latt_local[3]
     s3h = Vh // lt
+    row = (latt_local[0] // 2) * latt_local[1]
+    s3h_g = row * latt_global[2]
     out = np.empty((4, V, 3, 3, 2), dtype=np.float64)
     eye = torch.eye(3, dtype=torch.complex128, device=device)
     gen = torch.Generator(device=device)
@@ -172,7 +178,7 @@ def torch_weak_gauge(latt_local, t0_global, latt_global, seed, eps, device):
             for t in range(lt):
                 gen.manual_seed(((seed * 4 + mu) * 2 + cb) * 100003 + (t0_global + t))
                 lo = cb * Vh + t * s3h
-                g[lo:lo + s3h] = torch.randn((s3h, 3, 3, 2), generator=gen, device=device, dtype=torch.float64)
+                g[lo:lo + s3h] = torch.randn((s3h_g, 3, 3, 2), generator=gen, device=device, dtype=torch.float64)[z0_global * row:z0_global * row + s3h]
         m = eye + eps * torch.view_as_complex(g)
         r0 = m[:, 0, :]
         r0 = r0 / torch.linalg.norm(r0, dim=-1, keepdim=True)
@@ -187,17 +193,19 @@ def torch_weak_gauge(latt_local, t0_global, latt_global, seed, eps, device):
     return out
 
 
-def torch_gaussian_source(latt_local, t0_global, seed, device, dtype):
-    """Gaussian odd-checkerboard source keyed by (seed, GLOBAL time slice): identical for every rank count."""
+def torch_gaussian_source(latt_local, t0_global, seed, device, dtype, z0_global=0, lz_global=None):
+    """Gaussian odd-checkerboard source keyed by (seed, GLOBAL time slice): identical for every rank count / grid."""
     import torch
     Vh = int(np.prod(latt_local)) // 2
     lt = latt_local[3]
     s3h = Vh // lt
+    row = (latt_local[0] // 2) * latt_local[1]
+    s3h_g = row * (lz_global or latt_local[2])
     gen = torch.Generator(device=device)
     out = torch.empty((Vh, 4, 3, 2), device=device, dtype=torch.float64)
     for t in range(lt):
         gen.manual_seed(seed * 100003 + 7 + (t0_global + t))
-        out[t * s3h:(t + 1) * s3h] = torch.randn((s3h, 4, 3, 2), generator=gen, device=device, dtype=torch.float64)
+        out[t * s3h:(t + 1) * s3h] = torch.randn((s3h_g, 4, 3, 2), generator=gen, device=device, dtype=torch.float64)[z0_global * row:z0_global * row + s3h]
     return out.to(dtype).cpu().pin_memory()
 
 
@@ -265,23 +273,28 @@ def run_b200(args):
         comm = make_comm(dist, rank, world)
 
     latt = tuple(args.lattice)
-    assert latt[3] % world == 0 and (latt[3] // world) % 2 == 0, "T extent must split into even slabs"
-    lt = latt[3] // world
-    latt_local = (latt[0], latt[1], latt[2], lt)
+    pz, pt = tuple(args.grid) if args.grid else (1, world)
+    assert pz * pt == world, "--grid PZ PT must multiply to the number of ranks"
+    cz, ct = rank % pz, rank // pz                      # rank = pt_coord * PZ + pz_coord (include/b200_clover.h)
+    assert latt[3] % pt == 0 and (latt[3] // pt) % 2 == 0, "T extent must split into even slabs"
+    assert latt[2] % pz == 0 and (latt[2] // pz) % 2 == 0, "Z extent must split into even slabs"
+    lt, lz = latt[3] // pt, latt[2] // pz
+    latt_local = (latt[0], latt[1], lz, lt)
     solver = L.B200_SOLVER_CG if args.solver == "CG" else L.B200_SOLVER_BICGSTAB
     flop_iter = FLOP_CG if args.solver == "CG" else 2 * FLOP_M + 960.0
 
     t_setup = time.time()
-    ctx = Context(latt, prec=args.prec, device=local_rank, proc_grid=(1, 1, 1, world), proc_coord=(0, 0, 0, rank), comm=comm)
-    u = torch_weak_gauge(latt_local, rank * lt, latt, 11, 0.2, dev)
-    apply_bc_local(u, latt_local, rank == world - 1)
+    ctx = Context(latt, prec=args.prec, device=local_rank, proc_grid=(1, 1, pz, pt), proc_coord=(0, 0, cz, ct), comm=comm)
+    u = torch_weak_gauge(latt_local, ct * lt, latt, 11, 0.2, dev, z0_global=cz * lz)
+    apply_bc_local(u, latt_local, ct == pt - 1)
     ctx.load_gauge(u if args.prec == "double" else u.astype(np.float32), t_boundary=-1, reconstruct=args.recon)
     del u
     ctx.make_clover(1.0 + 3.0 + 0.1, 0.5, 0.5)
     Vh = ctx.Vh
     Vh_global = Vh * world
     npdt = np.float64 if args.prec == "double" else np.float32
-    chi_host = torch_gaussian_source(latt_local, rank * lt, 12, dev, torch.float64 if args.prec == "double" else torch.float32)
+    chi_host = torch_gaussian_source(latt_local, ct * lt, 12, dev, torch.float64 if args.prec == "double" else torch.float32,
+                                     z0_global=cz * lz, lz_global=latt[2])
     psi_host = torch.zeros_like(chi_host).pin_memory()
     chi_np, psi_np = chi_host.numpy(), psi_host.numpy()
     t_setup = time.time() - t_setup

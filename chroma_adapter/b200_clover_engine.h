@@ -23,9 +23,11 @@ namespace Chroma
   namespace B200Glue
   {
     //! b200_comm callbacks on top of QDP++'s global sums (used ONCE, to swap CUDA IPC handles between the ranks)
-    inline int allgather(void*, const void* send, void* recv, size_t bytes)
+    //! user -> int[2] = {rank, size} in the ENGINE's rank order (pt*Pz + pz), which need not be Layout::nodeNumber()
+    inline int allgather(void* user, const void* send, void* recv, size_t bytes)
     {
-      const int nodes = Layout::numNodes(), me = Layout::nodeNumber();
+      const int* rs = static_cast<const int*>(user);
+      const int me = rs[0], nodes = rs[1];
       std::vector<int> buf(static_cast<size_t>(nodes) * bytes, 0);
       const unsigned char* s = static_cast<const unsigned char*>(send);
       for (size_t i = 0; i < bytes; ++i) buf[static_cast<size_t>(me) * bytes + i] = s[i];
@@ -63,7 +65,7 @@ namespace Chroma
         QDP_abort(1);
       }
 
-      // geometry: the engine splits T only (one rank per GPU inside one NVSwitch box)
+      // geometry: the engine splits T, or T and Z (1 x 1 x Pz x Pt; one rank per GPU inside one NVSwitch box)
       int gdims[4], grid[4], coord[4];
       const multi1d<int>& machsize = Layout::logicalSize();
       const multi1d<int>& mycoord = Layout::nodeCoord();
@@ -73,8 +75,9 @@ namespace Chroma
         coord[mu] = mycoord[mu];
       }
       b200_comm comm;
-      comm.rank = coord[3]; comm.size = grid[3];
-      comm.allgather = B200Glue::allgather; comm.barrier = B200Glue::barrier; comm.user = 0;
+      comm_rs[0] = coord[3] * grid[2] + coord[2]; comm_rs[1] = grid[2] * grid[3];
+      comm.rank = comm_rs[0]; comm.size = comm_rs[1];
+      comm.allgather = B200Glue::allgather; comm.barrier = B200Glue::barrier; comm.user = comm_rs;
       int device = p.device;
       if (device < 0) {
         const int ndev = b200_device_count();
@@ -148,6 +151,7 @@ namespace Chroma
     }
 
     b200_ctx* ctx;
+    int comm_rs[2];   // {rank, size} handed to the b200_comm callbacks
     const SysSolverB200CloverParams invParam;
     int host_prec;
     bool mixed;

@@ -39,14 +39,16 @@ __device__ void scale_planes_body(C2* p, int nplanes, size_t stride, size_t off,
 __global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
 __global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
 
-__global__ void wait_flags_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long seq, int* status, int check_stop, int run_if) {
+__global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* status, int check_stop, int run_if) {
   if (check_stop && status && (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0)) return;
   if (run_if && status && status[run_if] == 0) return;
-  const volatile unsigned long long* v0 = f0;
-  const volatile unsigned long long* v1 = f1;
   const long long t0 = clock64();
-  while (*v0 < seq || *v1 < seq) {
-    if (clock64() - t0 > PEER_SPIN_CYCLES) { if (status) status[ST_BREAKDOWN] = 90; break; }
+  for (int f = 0; f < 4; ++f) {
+    if (!w.f[f]) continue;
+    const volatile unsigned long long* v = w.f[f];
+    while (*v < seq) {
+      if (clock64() - t0 > PEER_SPIN_CYCLES) { if (status) status[ST_BREAKDOWN] = 90; break; }
+    }
   }
   __threadfence_system();
 }

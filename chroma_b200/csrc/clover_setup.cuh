@@ -16,6 +16,7 @@ template <typename R>
 struct CloverSetupArgs {
   const Cx<R>* gauge;       // engine gauge planes [4][2][NG][Vh]
   const Cx<R>* ghost_links; // T-split only: [2 faces (t=-1, t=Lt)][4][2][9][S3h], original links incl. phases
+  const Cx<R>* ghost_links_z; // Z-split only: [2 faces (z=-1, z=Lz)][4][2][9][(Lt+2)*Ly*Lxh], rows t = -1 .. Lt (corners included)
   Cx<R>* clov_out;          // [36][Vh] of this parity
   double inv_aniso[4];      // undo the anisotropy factor folded into uncompressed links
   int recon12, bc_t, t_is_last;
@@ -57,20 +58,29 @@ __device__ __forceinline__ void adj_mm(Z* r, const Z* a, const Z* b) {
   }
 }
 
-// The link U_mu at local coordinates c (c[3] may be -1 or Lt on a T-split lattice; everything else wraps),
-// as Chroma's state->getLinks() holds it: boundary phase included, anisotropy NOT included.
+// The link U_mu at local coordinates c (on a split lattice c[3] may be -1 or Lt and c[2] may be -1 or Lz, both at once
+// for the corner links; everything else wraps), as Chroma's state->getLinks() holds it: boundary phase included,
+// anisotropy NOT included.
 template <typename R>
 __device__ void fetch_link(Z U[9], const CloverSetupArgs<R>& a, int mu, int cx, int cy, int cz, int ct) {
   const Geom& g = a.g;
   const int Lx = 2 * g.Lxh;
-  cx = (cx + Lx) % Lx; cy = (cy + g.Ly) % g.Ly; cz = (cz + g.Lz) % g.Lz;
-  int face = -1;
-  if (g.tsplit) { if (ct < 0) face = 0; else if (ct >= g.Lt) face = 1; }
-  else ct = (ct + g.Lt) % g.Lt;
-  // parity of the site: with a T split the ghost slices keep the parity of their global coordinate;
-  // local extents are even, so (t = -1) and (t = Lt) have the parity of an odd / even t respectively.
-  const int par = (cx + cy + cz + ct + 2) & 1;
-  if (face >= 0) {
+  cx = (cx + Lx) % Lx; cy = (cy + g.Ly) % g.Ly;
+  if (!g.zsplit) cz = (cz + g.Lz) % g.Lz;
+  if (!g.tsplit) ct = (ct + g.Lt) % g.Lt;
+  // parity of the site: ghost slices keep the parity of their global coordinate; local extents are even, so
+  // (t = -1) and (t = Lt) have the parity of an odd / even t respectively (same for z).
+  const int par = (cx + cy + cz + ct + 4) & 1;
+  if (g.zsplit && (cz < 0 || cz >= g.Lz)) {
+    const int face = cz < 0 ? 0 : 1;
+    const size_t sze = (size_t)g.Lxh * g.Ly * (g.Lt + 2);
+    const int f = ((ct + 1) * g.Ly + cy) * g.Lxh + cx / 2;
+    const Cx<R>* p = a.ghost_links_z + ((size_t)((face * 4 + mu) * 2 + par) * 9) * sze + f;
+    for (int k = 0; k < 9; ++k) { const Cx<R> v = p[(size_t)k * sze]; U[k] = make_double2((double)v.x, (double)v.y); }
+    return;
+  }
+  if (g.tsplit && (ct < 0 || ct >= g.Lt)) {
+    const int face = ct < 0 ? 0 : 1;
     const int s3 = (cz * g.Ly + cy) * g.Lxh + cx / 2;
     const Cx<R>* p = a.ghost_links + ((size_t)((face * 4 + mu) * 2 + par) * 9) * g.S3h + s3;
     for (int k = 0; k < 9; ++k) { const Cx<R> v = p[(size_t)k * g.S3h]; U[k] = make_double2((double)v.x, (double)v.y); }

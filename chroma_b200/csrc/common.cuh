@@ -121,7 +121,22 @@ struct Geom {
   int Vh;               // local checkerboard volume = plane stride
   int S3h;              // sites per time slice per checkerboard = Lxh*Ly*Lz
   int tsplit;           // 1 if T is split across ranks (ghost faces instead of wrap-around in t)
+  int zsplit;           // 1 if Z is split across ranks as well (T x Z process grid)
+  int SZh;              // sites per z-plane per checkerboard = Lxh*Ly*Lt (one Z face)
 };
+
+// A box of target sites of one launch: t in [t0, t0+nt), z in [z0, z0+nz), every x and y.  A Dslash launch covers up
+// to four boxes (the whole lattice; the interior of a split lattice; its boundary slices / planes).
+struct SiteBox { int t0, nt, z0, nz; };
+__host__ __device__ __forceinline__ int box_count(const Geom& g, const SiteBox& b) { return g.Lxh * g.Ly * b.nz * b.nt; }
+// cb2 index of the `local`-th site of a box (local < box_count)
+__host__ __device__ __forceinline__ int box_site(const Geom& g, const SiteBox& b, int local) {
+  if (b.nz == g.Lz) return b.t0 * g.S3h + local;                 // whole time slices are contiguous in cb2 order
+  const int row = g.Lxh * g.Ly;
+  const int w = local % row, q = local / row;
+  const int zz = q % b.nz, tt = q / b.nz;
+  return ((b.t0 + tt) * g.Lz + b.z0 + zz) * row + w;
+}
 
 // Right-hand sides solved in lockstep by the batched (multi-RHS) kernels: the 12 spin-colour sources of a propagator
 // (quarkprop4_w.cc:70-117).  Every right-hand side owns one ScalarSlot block and one StatusSlot block.

@@ -40,25 +40,59 @@ struct DslashArgs {
   // T-split ghost faces (half spinors, C[6][S3h]); only read when g.tsplit
   const C* ghost_fwd;   // (1 -/+ g3) psi(x+t) projected by the +t neighbour rank, for sites at t = Lt-1
   const C* ghost_bwd;   // U_t^dag (1 +/- g3) psi(x-t) projected AND multiplied by the -t rank, for sites at t = 0
+  // Z-split ghost faces (C[6][SZh], face index (t*Ly+y)*Lxh+xh); only read when g.zsplit
+  const C* ghost_zfwd;  // (1 -/+ g2) psi(x+z) from the +z neighbour rank, for sites at z = Lz-1
+  const C* ghost_zbwd;  // U_z^dag (1 +/- g2) psi(x-z) from the -z neighbour rank, for sites at z = 0
   double* scal;     // device scalars (ScalarSlot)
   int* status;      // device status (StatusSlot)
   ReduceBuf red;
   Geom g;
   int parity;       // target parity
   int isign;        // +1: D, -1: D^dagger
-  int idx_begin;    // first target site of this launch
-  int idx_count;    // number of target sites of this launch
-  int idx_begin2;   // optional second range (both boundary time slices in one launch) ...
-  int idx_count2;   // ... of this many sites
+  SiteBox box[4];   // target sites of this launch: the union of nbox boxes (whole lattice / interior / boundary pieces)
+  int nbox;
+  int nsites;       // total number of target sites of this launch
   int iter;         // solver iteration this launch belongs to (for the stop flag)
   int check_stop;   // 1: return immediately if status[ST_STOP] != 0
   int run_if;       // != 0: status slot that must be non-zero for this launch to do anything (predicated launch)
   // multi-RHS launches (dslash_mrhs_kernel): in/out/x/r/r0 point at right-hand side 0 of `nrhs` consecutive fields
   int nrhs;
   size_t fstride;   // elements between consecutive right-hand sides of a batched field (12*Vh)
-  size_t gstride;   // same for the ghost faces (6*S3h)
-  int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice
+  size_t gstride;   // same for the T ghost faces (6*S3h)
+  size_t gstride_z; // ... and the Z ghost faces (6*SZh)
+  int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice (box 0)
 };
+
+// The `local`-th target site of a launch (local < a.nsites).  ZC: the batched kernels sweep box 0 in z-chunks.
+template <typename R, bool ZC>
+__device__ __forceinline__ int launch_site(const DslashArgs<R>& a, int local) {
+  const Geom& g = a.g;
+  const int n0 = box_count(g, a.box[0]);
+  if (local < n0) {
+    if (ZC && a.zc_sites) {
+      // Traversal order of a batch: the t+-1 neighbours of a site are re-read one time slice later, and one slice of
+      // nrhs spinors (127 MB for 12 at 48^3, fp64) does not survive in the 126 MB L2.  So the launch sweeps t inside
+      // z-chunks small enough that three slices of a chunk stay L2-resident (memory layout unchanged: only WHICH site a
+      // thread takes changes).
+      const int slice = g.Lxh * g.Ly * a.box[0].nz, nt = a.box[0].nt;
+      const int per = a.zc_sites * nt;
+      const int zc = local / per, rem = local - zc * per;
+      const int t = rem / a.zc_sites, w = rem - t * a.zc_sites;
+      local = t * slice + zc * a.zc_sites + w;
+    }
+    return box_site(g, a.box[0], local);
+  }
+  local -= n0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    if (k < a.nbox) {
+      const int n = box_count(g, a.box[k]);
+      if (local < n) return box_site(g, a.box[k], local);
+      local -= n;
+    }
+  }
+  return 0;
+}
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
 template <typename R, int MU, bool MR = false>
@@ -155,6 +189,31 @@ __device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi
   recons_acc<R, MU>(acc, r0, r1, sg);
 }
 
+// Hops across a rank boundary (split direction MU).  Forward: the half spinor was already projected by the +mu
+// neighbour rank, only the link multiply is left.  Backward: U^dag (1 +/- g_mu) psi was computed by the -mu neighbour
+// rank (it owns that link): just reconstruct.  gp points at this site's entry of the ghost face, fs = face stride.
+template <typename R, int MU, bool RECON12, bool MR>
+__device__ __forceinline__ void ghost_hop_fwd(Cx<R> acc[12], const Cx<R>* __restrict__ gp, int fs, const Cx<R>* link, int lstride,
+                                              R sg, R scale, const L2Policy& pol) {
+  Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { h0[c] = ld_stream(gp + (size_t)c * fs, pol.stream); h1[c] = ld_stream(gp + (size_t)(3 + c) * fs, pol.stream); }
+  load_link<R, RECON12, MR>(U, link, lstride, pol.stream);
+  if (RECON12) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
+  }
+  su3_mul<R, false>(r0, r1, U, h0, h1);
+  recons_acc<R, MU>(acc, r0, r1, sg);
+}
+template <typename R, int MU>
+__device__ __forceinline__ void ghost_hop_bwd(Cx<R> acc[12], const Cx<R>* __restrict__ gp, int fs, R sg, const L2Policy& pol) {
+  Cx<R> r0[3], r1[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { r0[c] = ld_stream(gp + (size_t)c * fs, pol.stream); r1[c] = ld_stream(gp + (size_t)(3 + c) * fs, pol.stream); }
+  recons_acc<R, MU>(acc, r0, r1, sg);
+}
+
 // Per-direction scale factors used only with RECON12 (anisotropy * boundary sign), see api.cu.
 struct LinkScale {
   double aniso[4];    // aniso_coeff[mu]
@@ -208,10 +267,14 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
   }
   {
     const int sz = g.Ly * g.Lxh;
-    const int zf = (z + 1 == g.Lz) ? idx - (g.Lz - 1) * sz : idx + sz;
-    const int zb = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
-    hop<R, 2, false, RECON12, MR>(acc, in + zf, B200_LF(2), stride, ls_, -s, (R)ls.aniso[2], pol);
-    hop<R, 2, true, RECON12, MR>(acc, in + zb, B200_LB(2, zb), stride, ls_, s, (R)ls.aniso[2], pol);
+    const bool last = (z + 1 == g.Lz), first = (z == 0);
+    const int zf = last ? idx - (g.Lz - 1) * sz : idx + sz;
+    const int zb = first ? idx + (g.Lz - 1) * sz : idx - sz;
+    const int fz = (t * g.Ly + y) * g.Lxh + xh;     // index of this site on a Z face
+    if (g.zsplit && last) ghost_hop_fwd<R, 2, RECON12, MR>(acc, a.ghost_zfwd + fz, g.SZh, B200_LF(2), ls_, -s, (R)ls.aniso[2], pol);
+    else hop<R, 2, false, RECON12, MR>(acc, in + zf, B200_LF(2), stride, ls_, -s, (R)ls.aniso[2], pol);
+    if (g.zsplit && first) ghost_hop_bwd<R, 2>(acc, a.ghost_zbwd + fz, g.SZh, s, pol);
+    else hop<R, 2, true, RECON12, MR>(acc, in + zb, B200_LB(2, zb), stride, ls_, s, (R)ls.aniso[2], pol);
   }
   {
     const int st = g.S3h;
@@ -224,32 +287,10 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
       if (ls.t_is_last && last) scf *= (R)ls.bc_t;
       if (ls.t_is_last && first && !g.tsplit) scb *= (R)ls.bc_t;
     }
-    if (g.tsplit && last) {
-      // half spinor already projected by the +t neighbour rank: only the link multiply is left
-      C h0[3], h1[3], U[9], r0[3], r1[3];
-      const C* __restrict__ gp = a.ghost_fwd + (idx - (g.Lt - 1) * st);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { h0[c] = ld_stream(gp + (size_t)c * st, pol.stream); h1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
-      load_link<R, RECON12, MR>(U, B200_LF(3), ls_, pol.stream);
-      if (RECON12) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { h0[c].x *= scf; h0[c].y *= scf; h1[c].x *= scf; h1[c].y *= scf; }
-      }
-      su3_mul<R, false>(r0, r1, U, h0, h1);
-      recons_acc<R, 3>(acc, r0, r1, -s);
-    } else {
-      hop<R, 3, false, RECON12, MR>(acc, in + tf, B200_LF(3), stride, ls_, -s, scf, pol);
-    }
-    if (g.tsplit && first) {
-      // U^dag (1 +/- g3) psi computed by the -t neighbour rank (it owns that link): just reconstruct
-      C r0[3], r1[3];
-      const C* __restrict__ gp = a.ghost_bwd + idx;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { r0[c] = ld_stream(gp + (size_t)c * st, pol.stream); r1[c] = ld_stream(gp + (size_t)(3 + c) * st, pol.stream); }
-      recons_acc<R, 3>(acc, r0, r1, s);
-    } else {
-      hop<R, 3, true, RECON12, MR>(acc, in + tb, B200_LB(3, tb), stride, ls_, s, scb, pol);
-    }
+    if (g.tsplit && last) ghost_hop_fwd<R, 3, RECON12, MR>(acc, a.ghost_fwd + (idx - (g.Lt - 1) * st), st, B200_LF(3), ls_, -s, scf, pol);
+    else hop<R, 3, false, RECON12, MR>(acc, in + tf, B200_LF(3), stride, ls_, -s, scf, pol);
+    if (g.tsplit && first) ghost_hop_bwd<R, 3>(acc, a.ghost_bwd + idx, st, s, pol);
+    else hop<R, 3, true, RECON12, MR>(acc, in + tb, B200_LB(3, tb), stride, ls_, s, scb, pol);
   }
 #undef B200_LF
 #undef B200_LB
@@ -444,11 +485,11 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
   if (a.run_if && a.status[a.run_if] == 0) return;
   const int stride = a.g.Vh;
   const int local = blockIdx.x * BLOCK + threadIdx.x;
-  const bool active = local < a.idx_count + a.idx_count2;
-  const int idx = !active ? a.idx_begin : (local < a.idx_count ? a.idx_begin + local : a.idx_begin2 + (local - a.idx_count));
+  const bool active = local < a.nsites;
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {
+    const int idx = launch_site<R, false>(a, local);
     const L2Policy pol = make_l2_policy();
     C acc[12];
     dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
@@ -503,19 +544,8 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   const int rhs = grp * NRB + threadIdx.y;
   const int stride = a0.g.Vh;
   const int local = site_block * 32 + threadIdx.x;
-  const bool active = local < a0.idx_count + a0.idx_count2;
-  int idx = !active ? a0.idx_begin : (local < a0.idx_count ? a0.idx_begin + local : a0.idx_begin2 + (local - a0.idx_count));
-  if (a0.zc_sites && local < a0.idx_count) {
-    // Traversal order of a batch: the t+-1 neighbours of a site are re-read one time slice later, and one slice of
-    // nrhs spinors (127 MB for 12 at 48^3, fp64) does not survive in the 126 MB L2.  So the launch sweeps t inside
-    // z-chunks small enough that three slices of a chunk stay L2-resident (memory layout unchanged: only WHICH site a
-    // thread takes changes).  idx_begin / idx_count are whole time slices here.
-    const int nt = a0.idx_count / a0.g.S3h, t0 = a0.idx_begin / a0.g.S3h;
-    const int per = a0.zc_sites * nt;
-    const int zc = local / per, rem = local - zc * per;
-    const int t = rem / a0.zc_sites, w = rem - t * a0.zc_sites;
-    idx = (t0 + t) * a0.g.S3h + zc * a0.zc_sites + w;
-  }
+  const bool active = local < a0.nsites;
+  const int idx = active ? launch_site<R, true>(a0, local) : 0;
 
   // ---- stage this CTA's operator data: the 8 links (and the clover block) of its 32 sites go to shared memory ONCE,
   // with asynchronous copies issued by all NRB warps; every right-hand side then reads them from there.
@@ -552,6 +582,7 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
     if (a0.r) a.r = a0.r + rhs * a0.fstride;
     if (a0.r0) a.r0 = a0.r0 + rhs * a0.fstride;
     if (a0.ghost_fwd) { a.ghost_fwd = a0.ghost_fwd + rhs * a0.gstride; a.ghost_bwd = a0.ghost_bwd + rhs * a0.gstride; }
+    if (a0.ghost_zfwd) { a.ghost_zfwd = a0.ghost_zfwd + rhs * a0.gstride_z; a.ghost_zbwd = a0.ghost_zbwd + rhs * a0.gstride_z; }
   }
   cp_async_wait_all();
   __syncthreads();

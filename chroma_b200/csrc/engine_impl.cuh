@@ -77,6 +77,8 @@ class Engine : public EngineBase {
   C* it_psi = nullptr; const C* it_chi = nullptr; int it_k = 0, it_nb = 1;
 
   size_t nelem() const { return (size_t)12 * g.Vh; }
+  bool split() const { return g.tsplit || g.zsplit; }
+  double nranks() const { return (double)cfg.pgrid[2] * cfg.pgrid[3]; }
 
   // ------------------------------------------------------------------ lifecycle
   int init() override {
@@ -87,9 +89,9 @@ class Engine : public EngineBase {
       // that local parity == global parity on every rank (cf. cpp_dslash_parscalar_64bit.cc:187-212)
       if (cfg.ldims[i] % 2 != 0 || cfg.ldims[i] < 2) { set_error("local lattice extent %d (dim %d) must be even and >= 2", cfg.ldims[i], i); return B200_ERR_ARG; }
     }
-    if (cfg.pgrid[0] != 1 || cfg.pgrid[1] != 1 || cfg.pgrid[2] != 1) { set_error("only a T split of the process grid is supported"); return B200_ERR_ARG; }
-    if (cfg.pgrid[3] > 8) { set_error("at most 8 ranks in T"); return B200_ERR_ARG; }
-    if (cfg.pgrid[3] > 1 && !cfg.have_comm) { set_error("a b200_comm is required for a split lattice"); return B200_ERR_COMM; }
+    if (cfg.pgrid[0] != 1 || cfg.pgrid[1] != 1) { set_error("the process grid may split T and Z only (1 x 1 x Pz x Pt)"); return B200_ERR_ARG; }
+    if (cfg.pgrid[2] * cfg.pgrid[3] > 8) { set_error("at most 8 ranks (one NVSwitch node)"); return B200_ERR_ARG; }
+    if (cfg.pgrid[2] * cfg.pgrid[3] > 1 && !cfg.have_comm) { set_error("a b200_comm is required for a split lattice"); return B200_ERR_COMM; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: this engine has no CPU fallback"); return B200_ERR_CUDA; }
     B200_CUDA(cudaSetDevice(cfg.device));
@@ -102,6 +104,8 @@ class Engine : public EngineBase {
     g.S3h = g.Lxh * g.Ly * g.Lz;
     g.Vh = g.S3h * g.Lt;
     g.tsplit = cfg.pgrid[3] > 1 ? 1 : 0;
+    g.zsplit = cfg.pgrid[2] > 1 ? 1 : 0;
+    g.SZh = g.Lxh * g.Ly * g.Lt;
     B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     B200_CUDA(cudaMalloc(&scal, sizeof(double) * S_COUNT * MAX_RHS));
     B200_CUDA(cudaMalloc(&status, sizeof(int) * ST_COUNT * MAX_RHS));
@@ -116,7 +120,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
     B200_CUDA(cudaMalloc(&staging, STAGING_BYTES));
-    if (g.tsplit) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
+    if (split()) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
@@ -274,9 +278,10 @@ class Engine : public EngineBase {
     for (int mu = 0; mu < 4; ++mu) a.inv_aniso[mu] = (recon == 18) ? 1.0 / aniso_[mu] : 1.0;
     a.bc_t = (recon == 12) ? t_boundary_ : 1; a.t_is_last = ls.t_is_last;
     a.diag_mass = diag_mass; a.cr = cr; a.ct = ct; a.aniso = aniso; a.t_dir = t_dir;
-    a.ghost_links = g.tsplit ? halo.gauge_ghost() : nullptr;
+    a.ghost_links = split() ? halo.gauge_ghost() : nullptr;
+    a.ghost_links_z = split() ? halo.gauge_ghost_z() : nullptr;
     a.parity = 0; a.clov_out = nullptr;
-    if (g.tsplit) { rc = halo.exchange_gauge_ghost(a, launches); if (rc) return rc; }
+    if (split()) { rc = halo.exchange_gauge_ghost(a, launches); if (rc) return rc; }
     for (int par = 0; par < 2; ++par) {
       a.parity = par; a.clov_out = clov + (size_t)par * 36 * g.Vh;
       make_clover_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(a);
@@ -374,28 +379,38 @@ class Engine : public EngineBase {
   template <int EPI>
   int launch_dslash(DslashArgs<R>& a) {
     a.gauge = gauge; a.scal = scal; a.status = status; a.g = g;
-    a.nrhs = nb; a.fstride = nelem(); a.gstride = (size_t)6 * g.S3h;
-    a.zc_sites = nb > 1 ? zchunk_sites() : 0;
+    a.nrhs = nb; a.fstride = nelem(); a.gstride = (size_t)6 * g.S3h; a.gstride_z = (size_t)6 * g.SZh;
     const int bs = nb > 1 ? 32 : DSLASH_BLOCK;          // target sites per CTA
     int rc;
-    if (g.tsplit) {
-      // pack + send both time faces over NVLink, run the interior while they fly, then both boundary slices
+    for (auto& b : a.box) b = SiteBox{0, 0, 0, 0};
+    if (split()) {
+      // pack + send the faces over NVLink, run the interior while they fly, then the boundary slices / planes
       rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, nb, a.fstride, launches); if (rc) return rc;
-      a.ghost_fwd = halo.ghost_fwd(); a.ghost_bwd = halo.ghost_bwd();
-      const int n_int = g.Vh - 2 * g.S3h;
+      a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
+      const SiteBox inner{g.tsplit ? 1 : 0, g.tsplit ? g.Lt - 2 : g.Lt, g.zsplit ? 1 : 0, g.zsplit ? g.Lz - 2 : g.Lz};
+      const int n_int = box_count(g, inner);
+      const int n_face = g.Vh - n_int;
       const int nb_int = (n_int + bs - 1) / bs;
-      const int nb_face = (2 * g.S3h + bs - 1) / bs;
+      const int nb_face = (n_face + bs - 1) / bs;
       const int total = nb_int + nb_face;
       if (n_int > 0) {
-        a.idx_begin = g.S3h; a.idx_count = n_int; a.idx_begin2 = 0; a.idx_count2 = 0; a.red = make_red(0, total);
+        a.box[0] = inner; a.nbox = 1; a.nsites = n_int; a.red = make_red(0, total);
+        a.zc_sites = nb > 1 ? zchunk_sites(inner.nz) : 0;
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
       rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, nb, launches); if (rc) return rc;
-      a.idx_begin = 0; a.idx_count = g.S3h; a.idx_begin2 = g.Vh - g.S3h; a.idx_count2 = g.S3h; a.red = make_red(nb_int, total);
+      int k = 0;
+      if (g.tsplit) { a.box[k++] = SiteBox{0, 1, 0, g.Lz}; a.box[k++] = SiteBox{g.Lt - 1, 1, 0, g.Lz}; }
+      if (g.zsplit && inner.nt > 0) {
+        a.box[k++] = SiteBox{inner.t0, inner.nt, 0, 1};
+        a.box[k++] = SiteBox{inner.t0, inner.nt, g.Lz - 1, 1};
+      }
+      a.nbox = k; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total);
       return launch_one<EPI>(a, nb_face);
     }
-    a.ghost_fwd = nullptr; a.ghost_bwd = nullptr;
-    a.idx_begin = 0; a.idx_count = g.Vh; a.idx_begin2 = 0; a.idx_count2 = 0;
+    a.ghost_fwd = nullptr; a.ghost_bwd = nullptr; a.ghost_zfwd = nullptr; a.ghost_zbwd = nullptr;
+    a.box[0] = SiteBox{0, g.Lt, 0, g.Lz}; a.nbox = 1; a.nsites = g.Vh;
+    a.zc_sites = nb > 1 ? zchunk_sites(g.Lz) : 0;
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
     return launch_one<EPI>(a, blocks);
@@ -408,14 +423,14 @@ class Engine : public EngineBase {
     else dslash_kernel<R, EPI, false, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
     return launched("dslash_kernel");
   }
-  // z-chunk (in sites per time slice) of the batched traversal order: the largest divisor of Lz for which three time
-  // slices of the batch's source spinors fit in ~1/3 of the L2 (B200: 126 MB); 0 = natural order
-  int zchunk_sites() const {
+  // z-chunk (in sites per time slice) of the batched traversal order of a box nz planes thick: the largest divisor of
+  // nz for which three time slices of the batch's source spinors fit in ~1/3 of the L2 (B200: 126 MB); 0 = natural order
+  int zchunk_sites(int nz) const {
     const long budget = l2_budget;
     const long plane = (long)g.Lxh * g.Ly * 12 * (long)sizeof(C) * nb;      // one z-plane of one time slice, all right-hand sides
-    if (3 * plane * g.Lz <= budget || budget <= 0) return 0;
+    if (nz <= 0 || 3 * plane * nz <= budget || budget <= 0) return 0;
     int zc = 1;
-    for (int d = 1; d <= g.Lz; ++d) if (g.Lz % d == 0 && 3 * plane * d <= budget) zc = d;
+    for (int d = 1; d <= nz; ++d) if (nz % d == 0 && 3 * plane * d <= budget) zc = d;
     return zc * g.Lxh * g.Ly;
   }
   // batched launch: CTA = 32 sites x NRB right-hand sides; the groups of one site block are adjacent in the grid
@@ -497,7 +512,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
     if ((isign != 1 && isign != -1) || !out || !in || out == in || reps < 1 || out->nrhs != in->nrhs) { set_error("b200_dev_time_matpc: bad argument"); return B200_ERR_ARG; }
-    if (g.tsplit) { set_error("b200_dev_time_matpc: single-GPU measurement only"); return B200_ERR_ARG; }
+    if (split()) { set_error("b200_dev_time_matpc: single-GPU measurement only"); return B200_ERR_ARG; }
     { int rcb = set_batch(in->nrhs); if (rcb) return rcb; }
     rc = need_ws(1, nb); if (rc) return rc;
     cudaEvent_t e[3];
@@ -757,7 +772,7 @@ class Engine : public EngineBase {
     int rc2 = true_residual(psi, chi, mdagm, info); if (rc2) return rc2;
     float ms = 0.f;
     B200_CUDA(cudaEventElapsedTime(&ms, ev_t0, ev_t1));
-    const double gvol = (double)g.Vh * cfg.pgrid[3];
+    const double gvol = (double)g.Vh * nranks();
     for (int r = 0; r < nb; ++r) {
       info[r].secs = ms * 1e-3; info[r].secs_total = info[r].secs;       // the batch shares one wall clock
       info[r].gflops = ms > 0 ? flops_iter * gvol * n_count[r] / (ms * 1e-3) * 1e-9 : 0.0;

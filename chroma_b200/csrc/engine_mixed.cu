@@ -239,7 +239,7 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   float ms = 0.f;
   B200_CUDA(cudaEventElapsedTime(&ms, hi.ev_t0, hi.ev_t1));
   info->secs = ms * 1e-3; info->secs_total = info->secs;
-  const double gvol = (double)hi.g.Vh * hi.cfg.pgrid[3];
+  const double gvol = (double)hi.g.Vh * hi.nranks();
   // flop count as RelInvCG_a books it: per iteration 2 M + 20*Nc*Ns, per replacement 2 M + 6*Nc*Ns (reliable_cg.cc:87,108-110,138-139)
   const double flops = (2.0 * 3792.0 + 240.0) * n_count + (2.0 * 3792.0 + 72.0) * n_upd;
   info->gflops = info->secs > 0 ? flops * gvol / info->secs * 1e-9 : 0.0;

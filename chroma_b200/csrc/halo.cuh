@@ -1,4 +1,4 @@
-// halo.cuh -- T-split multi-GPU support: half-spinor face exchange and cross-GPU reductions over NVLink
+// halo.cuh -- multi-GPU support (T split, then T x Z): half-spinor face exchange and cross-GPU reductions over NVLink
 // peer memory (CUDA IPC), no host round trip and no library call inside the solver loop.
 //
 // Replaces the QMP face exchange of the reference's multi-node Dslash (tables_parscalar.h:35-113, 296-319;
@@ -8,12 +8,12 @@
 // so the hopping term needs no gauge ghost.
 //
 // Protocol per Dslash number n (all ranks issue the same sequence of Dslashes):
-//   pack kernel   projects both time faces of the source field and STORES them straight into the neighbours'
-//                 ghost buffers (slot n&1) through peer-mapped pointers; its last block then writes n into the
-//                 neighbours' arrival flags (threadfence_system before the flag).
-//   interior      dslash kernel on time slices 1 .. Lt-2 runs while the faces are in flight.
-//   wait kernel   one thread spins on the two local arrival flags until both equal n.
-//   boundary      dslash kernel on slices 0 and Lt-1, reading the ghost half spinors.
+//   pack kernel   projects the faces of the source field (t = 0, Lt-1; on a T x Z grid also z = 0, Lz-1) and STORES
+//                 them straight into the neighbours' ghost buffers (slot n&1) through peer-mapped pointers; its last
+//                 block then writes n into the neighbours' arrival flags (threadfence_system before the flag).
+//   interior      dslash kernel on the sites with no ghost dependence runs while the faces are in flight.
+//   wait kernel   one thread spins on the local arrival flags (2 or 4) until all equal n.
+//   boundary      dslash kernel on the boundary slices / planes, reading the ghost half spinors.
 // Two slots are enough: a rank can only start packing Dslash n+2 after it finished the boundary of n+1, which
 // needed the neighbour's pack n+1, which the neighbour issued after ITS boundary kernel of n had read slot n&1.
 // Predicated Dslashes (run_if, used by the reliable-update solver) are skipped by ALL ranks or by none (the flag is
@@ -28,29 +28,57 @@
 namespace b200 {
 
 struct HaloLayout {
-  size_t flags_off, seq_off, mailbox_off, ghost_off, gauge_ghost_off, total;
-  size_t ghost_face;   // elements (complex) of one ghost face buffer: 6*S3h
+  size_t flags_off, seq_off, mailbox_off, ghost_off, gauge_ghost_off, gauge_ghost_z_off, total;
+  size_t face_t, face_z;   // elements (complex) of one right-hand side of one ghost face: 6*S3h (T), 6*SZh (Z)
+  size_t slot_elems;       // elements of one slot = both T faces + both Z faces, MAX_RHS right-hand sides each
 };
 
+// Faces of the pack kernel / ghost buffers of the receiver, in this order everywhere:
+//   0: my t=0 plane     -> (1 - s g3) psi               -> the -t neighbour's "T forward" ghost  (its sites at t = Lt-1)
+//   1: my t=Lt-1 plane  -> U_t^dag (1 + s g3) psi        -> the +t neighbour's "T backward" ghost (its sites at t = 0)
+//   2: my z=0 plane     -> (1 - s g2) psi               -> the -z neighbour's "Z forward" ghost
+//   3: my z=Lz-1 plane  -> U_z^dag (1 + s g2) psi        -> the +z neighbour's "Z backward" ghost
 template <typename R>
 struct PackArgs {
   typedef Cx<R> C;
   const C* in;          // source field (parity src_par)
   const C* gauge;
-  C* to_bwd;            // -t neighbour's ghost_fwd buffer of this slot (peer pointer)
-  C* to_fwd;            // +t neighbour's ghost_bwd buffer of this slot (peer pointer)
-  unsigned long long* flag_bwd;   // -t neighbour's arrival flag [slot][0]
-  unsigned long long* flag_fwd;   // +t neighbour's arrival flag [slot][1]
+  C* to[4];             // destination ghost buffer of each face in the neighbour's arena (peer pointer), null if not split
+  unsigned long long* flag[4];   // that neighbour's arrival flag for the face
   unsigned long long seq;
   unsigned int* ticket;
   const int* status;    // may be null
   const int* pred;      // may be null: status word that must be non-zero for this launch to run (predicated Dslash)
   Geom g;
   int src_par, isign, recon12;
-  double scale_b;       // RECON12 only: aniso[3] * (bc_t if this rank owns the global last slice)
+  double scale_b[2];    // RECON12 only: factor of the backward faces: aniso[3] * (bc_t if this rank owns the global last slice); aniso[2]
   int nrhs;             // batched Dslash: gridDim.y right-hand sides, fields fstride apart, ghost faces gstride apart
-  size_t fstride, gstride;
+  size_t fstride, gstride[2];   // gstride: T faces, Z faces
 };
+
+// forward-hop face: project only
+template <typename R, int MU>
+__device__ __forceinline__ void pack_project(Cx<R>* __restrict__ dst, int f, int fs, const Cx<R>* __restrict__ src, int stride, R sg, const L2Policy& pol) {
+  Cx<R> h0[3], h1[3];
+  load_project<R, MU>(h0, h1, src, stride, sg, pol.keep);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { dst[(size_t)c * fs + f] = h0[c]; dst[(size_t)(3 + c) * fs + f] = h1[c]; }
+}
+// backward-hop face: project and multiply by U^dagger (the sender owns the link)
+template <typename R, int MU, bool RECON12>
+__device__ __forceinline__ void pack_project_mul(Cx<R>* __restrict__ dst, int f, int fs, const Cx<R>* __restrict__ src, const Cx<R>* __restrict__ link,
+                                                 int stride, R sg, R scale, const L2Policy& pol) {
+  Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
+  load_project<R, MU>(h0, h1, src, stride, sg, pol.keep);
+  load_link<R, RECON12>(U, link, stride, pol.keep);
+  if (RECON12) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
+  }
+  su3_mul<R, true>(r0, r1, U, h0, h1);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { dst[(size_t)c * fs + f] = r0[c]; dst[(size_t)(3 + c) * fs + f] = r1[c]; }
+}
 
 template <typename R, bool RECON12>
 __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
@@ -63,35 +91,31 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   if (a.nrhs == 1 && skip) return;
   if (a.pred && *a.pred == 0) return;
   const Geom& g = a.g;
-  const int tid = blockIdx.x * 128 + threadIdx.x;
-  const int stride = g.Vh, st = g.S3h;
+  int tid = blockIdx.x * 128 + threadIdx.x;
+  const int stride = g.Vh, st = g.S3h, sz = g.SZh, row = g.Lxh * g.Ly;
   const R s = (R)a.isign;
   const L2Policy pol = make_l2_policy();
+  constexpr int NG = RECON12 ? 6 : 9;
   const C* __restrict__ in = a.in + rhs * a.fstride;
-  C* __restrict__ to_bwd = a.to_bwd + rhs * a.gstride;
-  C* __restrict__ to_fwd = a.to_fwd + rhs * a.gstride;
+  const int nT = g.tsplit ? 2 * st : 0, nZ = g.zsplit ? 2 * sz : 0;
   if (skip) {
-  } else if (tid < st) {
-    // face t = 0 -> forward-hop half spinor (1 - s g3) psi for the -t neighbour's slice Lt-1
-    C h0[3], h1[3];
-    load_project<R, 3>(h0, h1, in + tid, stride, -s, pol.keep);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { to_bwd[(size_t)c * st + tid] = h0[c]; to_bwd[(size_t)(3 + c) * st + tid] = h1[c]; }
-  } else if (tid < 2 * st) {
-    // face t = Lt-1 -> backward-hop half spinor U_t^dag (1 + s g3) psi for the +t neighbour's slice 0
-    const int s3 = tid - st, idx = (g.Lt - 1) * st + s3;
-    constexpr int NG = RECON12 ? 6 : 9;
-    C h0[3], h1[3], U[9], r0[3], r1[3];
-    load_project<R, 3>(h0, h1, in + idx, stride, s, pol.keep);
-    load_link<R, RECON12>(U, a.gauge + ((size_t)(3 * 2 + a.src_par) * NG) * stride + idx, stride, pol.keep);
-    if (RECON12) {
-      const R sc = (R)a.scale_b;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { h0[c].x *= sc; h0[c].y *= sc; h1[c].x *= sc; h1[c].y *= sc; }
+  } else if (tid < nT) {
+    if (tid < st) {
+      pack_project<R, 3>(a.to[0] + rhs * a.gstride[0], tid, st, in + tid, stride, -s, pol);
+    } else {
+      const int f = tid - st, idx = (g.Lt - 1) * st + f;
+      pack_project_mul<R, 3, RECON12>(a.to[1] + rhs * a.gstride[0], f, st, in + idx, a.gauge + ((size_t)(3 * 2 + a.src_par) * NG) * stride + idx,
+                                      stride, s, (R)a.scale_b[0], pol);
     }
-    su3_mul<R, true>(r0, r1, U, h0, h1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { to_fwd[(size_t)c * st + s3] = r0[c]; to_fwd[(size_t)(3 + c) * st + s3] = r1[c]; }
+  } else if (tid < nT + nZ) {
+    tid -= nT;
+    const bool back = tid >= sz;
+    const int f = back ? tid - sz : tid;                 // face index (t*Ly + y)*Lxh + xh
+    const int t = f / row, w = f - t * row;
+    const int idx = t * st + (back ? (g.Lz - 1) * row : 0) + w;
+    if (!back) pack_project<R, 2>(a.to[2] + rhs * a.gstride[1], f, sz, in + idx, stride, -s, pol);
+    else pack_project_mul<R, 2, RECON12>(a.to[3] + rhs * a.gstride[1], f, sz, in + idx, a.gauge + ((size_t)(2 * 2 + a.src_par) * NG) * stride + idx,
+                                         stride, s, (R)a.scale_b[1], pol);
   }
   // last block publishes the arrival flags
   __threadfence_system();
@@ -104,22 +128,25 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
     __threadfence_system();
-    *(volatile unsigned long long*)a.flag_bwd = a.seq;
-    *(volatile unsigned long long*)a.flag_fwd = a.seq;
+#pragma unroll
+    for (int f = 0; f < 4; ++f) if (a.flag[f]) *(volatile unsigned long long*)a.flag[f] = a.seq;
     *a.ticket = 0u;
     __threadfence_system();
   }
 }
 
-__global__ void wait_flags_kernel(const unsigned long long* f0, const unsigned long long* f1, unsigned long long seq, int* status, int check_stop, int run_if);
+struct WaitFlags { const unsigned long long* f[4]; };   // local arrival flags of the faces in use (null = not split)
+__global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* status, int check_stop, int run_if);
 
-// One-time push of the boundary link slices needed by the field-strength (clover leaves reach x +/- t):
-// face 0 of the receiver = slice t=-1 (sender's last slice), face 1 = slice t=Lt (sender's first slice).
+// One-time push of the boundary links the field strength needs (clover leaves reach x +/- mu +/- nu).
+// T faces: face 0 of the receiver = slice t=-1 (sender's last slice), face 1 = slice t=Lt (sender's first slice).
+// Z faces (T x Z grids) are EXTENDED in t to t = -1 .. Lt, so that they carry the corner links x -/+ t -/+ z: they are
+// pushed AFTER the T faces have arrived, and the rows t = -1 / Lt are read from the sender's own T ghost.
 template <typename R>
 struct GaugePushArgs {
   CloverSetupArgs<R> cs;        // for fetch_link (original links incl. phases, no anisotropy)
-  Cx<R>* to_fwd_face0;          // +t neighbour's gauge ghost, face 0
-  Cx<R>* to_bwd_face1;          // -t neighbour's gauge ghost, face 1
+  Cx<R>* to_fwd_face0;          // +mu neighbour's gauge ghost, face 0
+  Cx<R>* to_bwd_face1;          // -mu neighbour's gauge ghost, face 1
 };
 template <typename R>
 __global__ void __launch_bounds__(128) push_gauge_kernel(const GaugePushArgs<R> a) {
@@ -141,12 +168,33 @@ __global__ void __launch_bounds__(128) push_gauge_kernel(const GaugePushArgs<R> 
     for (int k = 0; k < 9; ++k) p[(size_t)k * st] = mk<R>((R)U[k].x, (R)U[k].y);
   }
 }
+template <typename R>
+__global__ void __launch_bounds__(128) push_gauge_z_kernel(const GaugePushArgs<R> a) {
+  const Geom& g = a.cs.g;
+  const int tid = blockIdx.x * 128 + threadIdx.x;
+  const int sze = g.Lxh * g.Ly * (g.Lt + 2);         // one extended Z face of one parity
+  if (tid >= 2 * 2 * sze) return;
+  const int face = tid / (2 * sze), rem = tid % (2 * sze), par = rem / sze, f = rem % sze;
+  const int z = face == 0 ? g.Lz - 1 : 0;            // my plane that goes out
+  int q = f;
+  const int xh = q % g.Lxh; q /= g.Lxh;
+  const int y = q % g.Ly; const int t = q / g.Ly - 1;   // -1 .. Lt
+  const int x = 2 * xh + ((y + z + t + par + 2) & 1);
+  Cx<R>* dst = face == 0 ? a.to_fwd_face0 : a.to_bwd_face1;
+  for (int mu = 0; mu < 4; ++mu) {
+    Z U[9];
+    fetch_link<R>(U, a.cs, mu, x, y, z, t);
+    Cx<R>* p = dst + ((size_t)(mu * 2 + par) * 9) * sze + f;
+    for (int k = 0; k < 9; ++k) p[(size_t)k * sze] = mk<R>((R)U[k].x, (R)U[k].y);
+  }
+}
 
 template <typename R>
 class Halo {
  public:
   typedef Cx<R> C;
-  int nranks = 1, rank = 0, fwd = 0, bwd = 0, device = 0;
+  int nranks = 1, rank = 0, device = 0;
+  int nbr[4] = {0, 0, 0, 0};             // rank that receives face f of the pack kernel: -t, +t, -z, +z neighbour
   Geom g{};
   cudaStream_t stream = nullptr;
   char* arena = nullptr;                 // local
@@ -158,26 +206,37 @@ class Halo {
 
   static HaloLayout layout(const Geom& g) {
     HaloLayout l;
-    l.flags_off = 0;                                  // [2 slots][2 dirs] u64
+    l.flags_off = 0;                                  // [2 slots][4 faces] u64
     l.seq_off = 256;                                  // u64 reduction counters [MAX_RHS]
     l.mailbox_off = 512;                              // [MAX_RHS][2][8][8] doubles
     l.ghost_off = 512 + (size_t)MAX_RHS * MAILBOX_DOUBLES * sizeof(double);
-    l.ghost_face = (size_t)6 * g.S3h;                 // one right-hand side of one face; a face buffer holds MAX_RHS of them
-    l.gauge_ghost_off = l.ghost_off + 4 * l.ghost_face * MAX_RHS * sizeof(C);
+    l.face_t = g.tsplit ? (size_t)6 * g.S3h : 0;      // one right-hand side of one face; a face buffer holds MAX_RHS of them
+    l.face_z = g.zsplit ? (size_t)6 * g.SZh : 0;
+    l.slot_elems = 2 * (l.face_t + l.face_z) * MAX_RHS;
+    l.gauge_ghost_off = l.ghost_off + 2 * l.slot_elems * sizeof(C);
     l.gauge_ghost_off = (l.gauge_ghost_off + 255) / 256 * 256;
-    l.total = l.gauge_ghost_off + (size_t)2 * 4 * 2 * 9 * g.S3h * sizeof(C);
+    l.gauge_ghost_z_off = l.gauge_ghost_off + (g.tsplit ? (size_t)2 * 4 * 2 * 9 * g.S3h * sizeof(C) : 0);
+    l.gauge_ghost_z_off = (l.gauge_ghost_z_off + 255) / 256 * 256;
+    l.total = l.gauge_ghost_z_off + (g.zsplit ? (size_t)2 * 4 * 2 * 9 * g.Lxh * g.Ly * (g.Lt + 2) * sizeof(C) : 0) + 256;
     return l;
+  }
+
+  // Rank of grid coordinate (pz, pt): x fastest, like QMP's logical topology (here px = py = 0).
+  static int rank_of(const Config& cfg, int pz, int pt) {
+    const int Pz = cfg.pgrid[2], Pt = cfg.pgrid[3];
+    return ((pt + Pt) % Pt) * Pz + (pz + Pz) % Pz;
   }
 
   int init(const Config& cfg, const Geom& g_, cudaStream_t s) {
     g = g_; stream = s; device = cfg.device;
-    nranks = cfg.pgrid[3]; rank = cfg.pcoord[3];
+    nranks = cfg.pgrid[2] * cfg.pgrid[3]; rank = rank_of(cfg, cfg.pcoord[2], cfg.pcoord[3]);
     comm = cfg.comm;
     if (comm.size != nranks || comm.rank != rank || !comm.allgather || !comm.barrier) {
-      set_error("b200_comm (rank %d/%d) does not match the T process grid (coord %d of %d)", comm.rank, comm.size, rank, nranks);
+      set_error("b200_comm (rank %d/%d) does not match the process grid: expected rank pt*Pz+pz = %d of %d", comm.rank, comm.size, rank, nranks);
       return B200_ERR_COMM;
     }
-    fwd = (rank + 1) % nranks; bwd = (rank + nranks - 1) % nranks;
+    nbr[0] = rank_of(cfg, cfg.pcoord[2], cfg.pcoord[3] - 1); nbr[1] = rank_of(cfg, cfg.pcoord[2], cfg.pcoord[3] + 1);
+    nbr[2] = rank_of(cfg, cfg.pcoord[2] - 1, cfg.pcoord[3]); nbr[3] = rank_of(cfg, cfg.pcoord[2] + 1, cfg.pcoord[3]);
     lay = layout(g);
     B200_CUDA(cudaMalloc(&arena, lay.total));
     B200_CUDA(cudaMemset(arena, 0, lay.total));
@@ -210,12 +269,19 @@ class Halo {
     arena = nullptr;
   }
 
-  C* ghost_ptr(char* base, int slot, int dir) const { return (C*)(base + lay.ghost_off) + (size_t)(slot * 2 + dir) * lay.ghost_face * MAX_RHS; }
-  unsigned long long* flag_ptr(char* base, int slot, int dir) const { return (unsigned long long*)(base + lay.flags_off) + slot * 2 + dir; }
-  const C* ghost_fwd() const { return ghost_ptr(arena, (int)(seq & 1), 0); }
-  const C* ghost_bwd() const { return ghost_ptr(arena, (int)(seq & 1), 1); }
+  // Ghost buffer that RECEIVES face f (see PackArgs) in slot `slot` of the arena at `base`.  Within a slot: the two T
+  // faces, then the two Z faces.  The receiver reads face 0 as its "T forward" ghost, face 1 as "T backward", etc.
+  C* ghost_ptr(char* base, int slot, int f) const {
+    C* p = (C*)(base + lay.ghost_off) + (size_t)slot * lay.slot_elems;
+    return f < 2 ? p + (size_t)f * lay.face_t * MAX_RHS : p + 2 * lay.face_t * MAX_RHS + (size_t)(f - 2) * lay.face_z * MAX_RHS;
+  }
+  unsigned long long* flag_ptr(char* base, int slot, int f) const { return (unsigned long long*)(base + lay.flags_off) + slot * 4 + f; }
+  bool face_on(int f) const { return f < 2 ? g.tsplit != 0 : g.zsplit != 0; }
+  const C* ghost(int f) const { return face_on(f) ? ghost_ptr(arena, (int)(seq & 1), f) : nullptr; }
   C* gauge_ghost_of(char* base) const { return (C*)(base + lay.gauge_ghost_off); }
-  const C* gauge_ghost() const { return gauge_ghost_of(arena); }
+  C* gauge_ghost_z_of(char* base) const { return (C*)(base + lay.gauge_ghost_z_off); }
+  const C* gauge_ghost() const { return g.tsplit ? gauge_ghost_of(arena) : nullptr; }
+  const C* gauge_ghost_z() const { return g.zsplit ? gauge_ghost_z_of(arena) : nullptr; }
 
   int* status_dev = nullptr;             // engine status block, for timeouts
   PeerReduce peer_reduce() const {
@@ -229,22 +295,24 @@ class Halo {
     return p;
   }
 
-  // Pack + send both faces of `in` for the Dslash that targets `parity`.
+  // Pack + send all faces of `in` for the Dslash that targets `parity`.
   int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, int run_if, int nrhs,
             size_t fstride, long long& launches) {
     ++seq;
     const int slot = (int)(seq & 1);
     PackArgs<R> a;
     a.in = in; a.gauge = gauge;
-    a.to_bwd = ghost_ptr(peer[bwd], slot, 0);
-    a.to_fwd = ghost_ptr(peer[fwd], slot, 1);
-    a.flag_bwd = flag_ptr(peer[bwd], slot, 0);
-    a.flag_fwd = flag_ptr(peer[fwd], slot, 1);
+    for (int f = 0; f < 4; ++f) {
+      a.to[f] = face_on(f) ? ghost_ptr(peer[nbr[f]], slot, f) : nullptr;
+      a.flag[f] = face_on(f) ? flag_ptr(peer[nbr[f]], slot, f) : nullptr;
+    }
     a.seq = seq; a.ticket = ticket; a.status = status; a.pred = run_if ? status_dev + run_if : nullptr; a.g = g;
     a.src_par = 1 - parity; a.isign = isign; a.recon12 = recon == 12;
-    a.scale_b = ls.aniso[3] * (ls.t_is_last ? (double)ls.bc_t : 1.0);
-    a.nrhs = nrhs; a.fstride = fstride; a.gstride = lay.ghost_face;
-    const dim3 blocks((2 * g.S3h + 127) / 128, nrhs);
+    a.scale_b[0] = ls.aniso[3] * (ls.t_is_last ? (double)ls.bc_t : 1.0);
+    a.scale_b[1] = ls.aniso[2];
+    a.nrhs = nrhs; a.fstride = fstride; a.gstride[0] = lay.face_t; a.gstride[1] = lay.face_z;
+    const int nthreads = (g.tsplit ? 2 * g.S3h : 0) + (g.zsplit ? 2 * g.SZh : 0);
+    const dim3 blocks((nthreads + 127) / 128, nrhs);
     if (recon == 12) pack_faces_kernel<R, true><<<blocks, 128, 0, stream>>>(a);
     else pack_faces_kernel<R, false><<<blocks, 128, 0, stream>>>(a);
     ++launches;
@@ -255,24 +323,39 @@ class Halo {
 
   int wait(const int* status, int run_if, int nrhs, long long& launches) {
     const int slot = (int)(seq & 1);
+    WaitFlags w;
+    for (int f = 0; f < 4; ++f) w.f[f] = face_on(f) ? flag_ptr(arena, slot, f) : nullptr;
     // a batch always waits: its flags are always published, and one right-hand side's stop flag says nothing about the others
-    wait_flags_kernel<<<1, 1, 0, stream>>>(flag_ptr(arena, slot, 0), flag_ptr(arena, slot, 1), seq, status_dev, (status && nrhs == 1) ? 1 : 0, run_if);
+    wait_flags_kernel<<<1, 1, 0, stream>>>(w, seq, status_dev, (status && nrhs == 1) ? 1 : 0, run_if);
     ++launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("wait_flags launch failed: %s", cudaGetErrorString(e)); return B200_ERR_CUDA; }
     return B200_OK;
   }
 
+  // cs.ghost_links / cs.ghost_links_z must already point at this rank's gauge ghosts.
   int exchange_gauge_ghost(const CloverSetupArgs<R>& cs, long long& launches) {
     GaugePushArgs<R> a;
     a.cs = cs;
-    a.to_fwd_face0 = gauge_ghost_of(peer[fwd]);
-    a.to_bwd_face1 = gauge_ghost_of(peer[bwd]) + (size_t)4 * 2 * 9 * g.S3h;
-    push_gauge_kernel<R><<<(4 * g.S3h + 127) / 128, 128, 0, stream>>>(a);
-    ++launches;
-    B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaStreamSynchronize(stream));
-    if (comm.barrier(comm.user) != 0) { set_error("barrier failed"); return B200_ERR_COMM; }
+    if (g.tsplit) {
+      a.to_fwd_face0 = gauge_ghost_of(peer[nbr[1]]);
+      a.to_bwd_face1 = gauge_ghost_of(peer[nbr[0]]) + (size_t)4 * 2 * 9 * g.S3h;
+      push_gauge_kernel<R><<<(4 * g.S3h + 127) / 128, 128, 0, stream>>>(a);
+      ++launches;
+      B200_CUDA(cudaGetLastError());
+      B200_CUDA(cudaStreamSynchronize(stream));
+      if (comm.barrier(comm.user) != 0) { set_error("barrier failed"); return B200_ERR_COMM; }
+    }
+    if (g.zsplit) {
+      const size_t sze = (size_t)g.Lxh * g.Ly * (g.Lt + 2);
+      a.to_fwd_face0 = gauge_ghost_z_of(peer[nbr[3]]);
+      a.to_bwd_face1 = gauge_ghost_z_of(peer[nbr[2]]) + (size_t)4 * 2 * 9 * sze;
+      push_gauge_z_kernel<R><<<(int)((4 * sze + 127) / 128), 128, 0, stream>>>(a);
+      ++launches;
+      B200_CUDA(cudaGetLastError());
+      B200_CUDA(cudaStreamSynchronize(stream));
+      if (comm.barrier(comm.user) != 0) { set_error("barrier failed"); return B200_ERR_COMM; }
+    }
     return B200_OK;
   }
 };

@@ -108,3 +108,22 @@ def t_slab(full, L, t0, t1):
     Vh = V // 2
     s3h = Vh // L[3]
     return np.concatenate([full[cb * Vh + t0 * s3h: cb * Vh + t1 * s3h] for cb in range(2)], axis=0)
+
+
+def sub_lattice(full, L, lo, hi):
+    """Rows of a full-lattice cb2-ordered array [V, ...] that belong to the box lo[mu] <= x_mu < hi[mu], in the LOCAL cb2
+    order of a rank that owns that box (box extents even and lo even in every direction, so local parity == global
+    parity).  Generalises t_slab to the T x Z process grids."""
+    from .geometry import site_coords, site_index
+    lo = np.asarray(lo)
+    ext = tuple(int(h - l) for l, h in zip(lo, hi))
+    assert all(e % 2 == 0 and e >= 2 for e in ext) and all(int(l) % 2 == 0 for l in lo)
+    c = site_coords(ext) + lo[None, :]
+    return full[site_index(L, c)]
+
+
+def grid_box(L, proc_grid, proc_coord):
+    """(lo, hi) of the sub-lattice of rank proc_coord in a proc_grid decomposition of L."""
+    ext = [L[m] // proc_grid[m] for m in range(4)]
+    lo = [proc_coord[m] * ext[m] for m in range(4)]
+    return lo, [lo[m] + ext[m] for m in range(4)]

@@ -90,7 +90,9 @@ int b200_device_count(void);   /* CUDA devices visible to this process (<= 0: no
 
 /* Create an engine context on CUDA device `device` for a local lattice.  global_dims/proc_grid/
  * proc_coord describe the 4-D domain decomposition the way Layout::lattSize()/logicalSize()/
- * nodeCoord do; comm may be NULL when the grid is 1x1x1x1.  This round splits T only.
+ * nodeCoord do; comm may be NULL when the grid is 1x1x1x1.  The grid may split T and Z (1 x 1 x Pz x Pt, at most 8
+ * ranks: T slabs first, then T x Z as for BASELINE config 5); local extents must be even.  comm->rank must be
+ * pt*Pz + pz for grid coordinate (pz, pt) and comm->size = Pz*Pt.
  * prec = B200_DOUBLE or B200_SINGLE chooses the device storage + arithmetic precision (reductions
  * are always accumulated in double).  Replaces initQuda (lib/init/chroma_init.cc:250). */
 int b200_create(b200_ctx** ctx, int device, const int global_dims[4], const int proc_grid[4],

@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """Multi-GPU parity check, one rank per GPU (launch with torchrun --nproc-per-node N).
 
-Every rank builds the same seeded GLOBAL fields, keeps its T slab, runs the engine with NVLink halo exchange /
-cross-GPU reductions, and compares its slab of the result with the CPU oracle applied to the global lattice:
+Every rank builds the same seeded GLOBAL fields, keeps its sub-lattice (T slabs, or a Pz x Pt grid of T x Z boxes with
+MGPU_GRID=pz,pt), runs the engine with NVLink halo exchange / cross-GPU reductions, and compares its part of the result
+with the CPU oracle applied to the global lattice:
 Dslash, M, M^dagger to 1e-13 per site; GPU-built clover term (needs the gauge ghost slices); CG and BiCGStab
 iteration counts against the CPU restatement.  Exit code 0 = all ranks passed.
+MGPU_ONE_DEVICE=1 puts every rank on cuda:0 (time-sliced contexts, peer memory through CUDA IPC on one device): slow,
+but it exercises the whole multi-rank protocol on a single-GPU box.
 """
 import os
 import sys
@@ -34,28 +37,42 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    if os.environ.get("MGPU_ONE_DEVICE"):
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     latt = tuple(int(x) for x in os.environ.get("MGPU_LATT", "8,8,8,%d" % (4 * world)).split(","))
     prec = os.environ.get("MGPU_PREC", "double")
     recon = int(os.environ.get("MGPU_RECON", "18"))
     tol = 1e-13 if prec == "double" else 2e-6
     npdt = np.float64 if prec == "double" else np.float32
-    lt = latt[3] // world
-    t0, t1 = rank * lt, (rank + 1) * lt
+    pz, pt = (int(x) for x in os.environ.get("MGPU_GRID", "1,%d" % world).split(","))
+    assert pz * pt == world
+    grid, coord = (1, 1, pz, pt), (0, 0, rank % pz, rank // pz)       # rank = pt_coord * Pz + pz_coord
+    lo, hi = fields.grid_box(latt, grid, coord)
     V = int(np.prod(latt))
     Vh = V // 2
-    s3h = Vh // latt[3]
+    Vh_loc = Vh // world
+    my_sites = fields.sub_lattice(np.arange(V), latt, lo, hi)          # global cb2 index of every local site, local cb2 order
 
     u = fields.apply_bc(latt, fields.weak_gauge(latt, seed=11), (1, 1, 1, -1))
     op = orc.Op(latt, u, 0.1, 1.0)
     comm = make_comm(dist, rank, world)
-    ctx = Context(latt, prec=prec, device=local_rank, proc_grid=(1, 1, 1, world), proc_coord=(0, 0, 0, rank), comm=comm)
-    u_loc = np.stack([fields.t_slab(u[mu], latt, t0, t1) for mu in range(4)])
+    ctx = Context(latt, prec=prec, device=local_rank, proc_grid=grid, proc_coord=coord, comm=comm)
+    u_loc = np.stack([u[mu][my_sites] for mu in range(4)])
     ctx.load_gauge(u_loc.astype(npdt), t_boundary=-1, reconstruct=recon)
     ok = True
 
-    def slab_cb(full, cb):   # rows of checkerboard cb of a full-lattice array that live in my slab
-        return full[cb * Vh + t0 * s3h: cb * Vh + t1 * s3h]
+    def slab_cb(full, cb):   # rows of checkerboard cb of a full-lattice array that live in my sub-lattice
+        return full[my_sites[cb * Vh_loc:(cb + 1) * Vh_loc]]
+
+    def gather_odd(sol):     # assemble the global odd-checkerboard field from every rank's local solution
+        parts, where = [None] * world, [None] * world
+        dist.all_gather_object(parts, sol.astype(np.float64))
+        dist.all_gather_object(where, my_sites[Vh_loc:])
+        full = np.zeros((V, 4, 3, 2))
+        for r in range(world):
+            full[where[r]] = parts[r]
+        return full
 
     def report(name, err, bound):
         nonlocal ok
@@ -66,7 +83,7 @@ def main():
     # ---- GPU-built clover (uses ghost link slices) vs restated build
     ctx.make_clover(4.1, 0.5, 0.5)
     clov, inv = ctx.get_clover()
-    want_clov = fields.t_slab(op.clov, latt, t0, t1)
+    want_clov = op.clov[my_sites]
     report("make_clover vs restated", float(np.abs(clov - want_clov).max()), 1e-12 if prec == "double" else 1e-5)
     report("ldagdlinv vs restated", float(np.abs(inv - slab_cb(op.invclov, 0)).max()), 1e-11 if prec == "double" else 1e-5)
 
@@ -93,12 +110,7 @@ def main():
     for name, code, ref in (("CG", L.B200_SOLVER_CG, op.solve_cg), ("BICGSTAB", L.B200_SOLVER_BICGSTAB, op.solve_bicgstab)):
         _, n_ref, _, _ = ref(podd, np.zeros_like(podd), rsd, 2000)
         sol, info = ctx.invert(slab_cb(podd, 1).astype(npdt), None, solver=code, rsd=rsd, max_iter=2000)
-        full = np.zeros_like(podd)
-        # gather the solution slabs to check the true residual with the CPU operator
-        parts = [None] * world
-        dist.all_gather_object(parts, sol.astype(np.float64))
-        for r in range(world):
-            full[Vh + r * lt * s3h: Vh + (r + 1) * lt * s3h] = parts[r]
+        full = gather_odd(sol)   # gather the solution pieces to check the true residual with the CPU operator
         res = podd - op.apply(full, +1)
         rel = np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(podd[Vh:] ** 2))
         good = info.converged == 1 and abs(info.n_count - n_ref) <= max(2, 0.05 * n_ref) and rel < 20 * rsd
@@ -107,13 +119,7 @@ def main():
               (rank, name, info.n_count, n_ref, rel, info.rel_resid, "ok" if good else "FAIL"), flush=True)
 
     # ---- HMC-side normal-equation solve and mixed-precision reliable-update CG (predicated fp64 launches across ranks)
-    def gather_full(sol):
-        full = np.zeros_like(podd)
-        parts = [None] * world
-        dist.all_gather_object(parts, sol.astype(np.float64))
-        for r in range(world):
-            full[Vh + r * lt * s3h: Vh + (r + 1) * lt * s3h] = parts[r]
-        return full
+    gather_full = gather_odd
 
     _, n_ref, _ = op.solve_mdagm_cg(podd, np.zeros_like(podd), rsd, 2000)
     sol, info = ctx.invert_mdagm(slab_cb(podd, 1).astype(npdt), None, solver=L.B200_SOLVER_CG, rsd=rsd, max_iter=2000)
@@ -149,11 +155,7 @@ def main():
     sol_b = psi_b.download()
     for i in range(nr):
         _, n_ref, _, _ = op.solve_bicgstab(srcs[i], np.zeros_like(srcs[i]), rsd, 2000)
-        parts = [None] * world
-        dist.all_gather_object(parts, sol_b[i].astype(np.float64))
-        full = np.zeros_like(podd)
-        for r in range(world):
-            full[Vh + r * lt * s3h: Vh + (r + 1) * lt * s3h] = parts[r]
+        full = gather_odd(sol_b[i])
         res = srcs[i] - op.apply(full, +1)
         rel = np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(srcs[i][Vh:] ** 2))
         good = infos[i].converged == 1 and abs(infos[i].n_count - n_ref) <= max(2, 0.08 * n_ref) and rel < 20 * rsd
@@ -166,7 +168,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if rank == 0:
-        print("MGPU_CHECK %s (world %d, lattice %s, %s, recon %d)" % ("PASSED" if flag.item() else "FAILED", world, latt, prec, recon), flush=True)
+        print("MGPU_CHECK %s (world %d = %d x %d in Z x T, lattice %s, %s, recon %d)" % ("PASSED" if flag.item() else "FAILED", world, pz, pt, latt, prec, recon), flush=True)
     sys.exit(0 if flag.item() else 1)
 
 

@@ -1,5 +1,8 @@
-"""Multi-GPU parity (T-split, NVLink peer-memory halos and reductions): spawns scripts/mgpu_check.py under torchrun.
-Needs >= 2 GPUs on the box; skipped otherwise (the driver's 1-GPU tier skips it, `gpurun --gpus N` runs it)."""
+"""Multi-GPU parity (T and T x Z process grids, NVLink peer-memory halos and reductions): spawns scripts/mgpu_check.py
+under torchrun.  The N-GPU cases need >= N GPUs on the box and are skipped otherwise (`gpurun --gpus N` runs them); the
+`one_device` cases put every rank on cuda:0 (time-sliced contexts sharing memory through CUDA IPC), so the whole
+multi-rank protocol -- face packing, arrival flags, ghost reads, corner links of the clover build, in-kernel cross-rank
+reductions -- is also exercised on a single-GPU box."""
 import os
 import subprocess
 import sys
@@ -47,3 +50,31 @@ def test_eight_gpu_parity():
     if ngpu() < 8:
         pytest.skip("needs 8 GPUs")
     run_check(8, {"MGPU_LATT": "8,4,4,32"}, 29524)
+
+
+@pytest.mark.parametrize("grid,latt", [("2,1", "8,8,8,8"), ("2,2", "8,4,8,8")])
+def test_txz_grid_parity(grid, latt):
+    """Z-only and T x Z process grids, one rank per GPU."""
+    world = int(grid.split(",")[0]) * int(grid.split(",")[1])
+    if ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    run_check(world, {"MGPU_LATT": latt, "MGPU_GRID": grid}, 29525)
+
+
+def test_eight_gpu_txz_grid():
+    if ngpu() < 8:
+        pytest.skip("needs 8 GPUs")
+    run_check(8, {"MGPU_LATT": "8,4,8,16", "MGPU_GRID": "2,4"}, 29526)
+
+
+@pytest.mark.parametrize("grid,latt,prec,recon", [("1,2", "4,4,4,8", "double", "18"), ("2,1", "4,4,8,4", "double", "18"),
+                                                  ("2,2", "4,4,8,8", "double", "18"), ("2,2", "4,4,4,4", "double", "12"),
+                                                  ("2,2", "4,4,8,8", "single", "18")])
+def test_one_device_grid_parity(grid, latt, prec, recon):
+    """Every rank on cuda:0.  (2,2) on 4^4 has local extent 2 in both split directions: no interior site at all."""
+    if ngpu() < 1:
+        pytest.skip("needs a GPU")
+    if os.environ.get("B200_SKIP_ONE_DEVICE_TESTS"):
+        pytest.skip("disabled by B200_SKIP_ONE_DEVICE_TESTS")
+    world = int(grid.split(",")[0]) * int(grid.split(",")[1])
+    run_check(world, {"MGPU_LATT": latt, "MGPU_GRID": grid, "MGPU_PREC": prec, "MGPU_RECON": recon, "MGPU_ONE_DEVICE": "1"}, 29527)

@@ -104,3 +104,79 @@ def test_halo_protocol_on_cpu(oracle):
                     assert (~owned[f]).sum() == (c[mine, 3] == t1 - 1).sum() and (~owned[b]).sum() == (c[mine, 3] == t0).sum()
                 got += np.einsum("xab,xsb->xsa", U[mu][mine], hf) + hb           # receiver multiplies the forward hop by ITS link
             assert np.abs(got - want[mine]).max() < 1e-13
+
+
+@pytest.mark.parametrize("latt,grid", [((4, 4, 8, 8), (1, 1, 2, 2)), ((4, 6, 4, 8), (1, 1, 2, 4)), ((4, 4, 8, 4), (1, 1, 4, 1))])
+def test_sub_lattice_is_local_cb2_order(latt, grid):
+    """T x Z boxes cut out of a global cb2-ordered field are in the LOCAL cb2 order of their rank, and tile the lattice."""
+    from chroma_b200 import fields, geometry
+    V = int(np.prod(latt))
+    c = geometry.site_coords(latt)
+    seen = np.zeros(V, dtype=int)
+    for pt in range(grid[3]):
+        for pz in range(grid[2]):
+            lo, hi = fields.grid_box(latt, grid, (0, 0, pz, pt))
+            loc = fields.sub_lattice(c, latt, lo, hi)
+            want = geometry.site_coords(tuple(h - l for l, h in zip(lo, hi))) + np.asarray(lo)[None, :]
+            assert np.array_equal(loc, want)
+            seen[geometry.site_index(latt, loc)] += 1
+    assert (seen == 1).all()
+
+
+def test_z_face_index_matches_on_both_sides():
+    """halo.cuh addresses a Z face by f = (t*Ly + y)*Lxh + xh on BOTH sides of the cut: the sender packs its z = 0 (or
+    Lz-1) site of the source parity into slot f, and the receiver's target site at z = Lz-1 (or 0) reads slot f computed
+    from its own (xh, y, t).  Check with the cb2 index arithmetic that the two are the same physical neighbour pair."""
+    from chroma_b200 import geometry
+    ll = (6, 4, 4, 2)                                     # local extents of every rank (even)
+    Lxh, Ly, Lz, Lt = ll[0] // 2, ll[1], ll[2], ll[3]
+    Vh = int(np.prod(ll)) // 2
+    c = geometry.site_coords(ll)
+    row = Lxh * Ly
+    for par in (0, 1):                                    # target parity
+        tgt = c[par * Vh:(par + 1) * Vh]
+        idx = np.arange(Vh)
+        xh = idx % Lxh
+        for zface, znbr in ((Lz - 1, 0), (0, Lz - 1)):    # forward hop from z = Lz-1 reads the +z rank's z = 0 plane, and v.v.
+            m = tgt[:, 2] == zface
+            f_recv = (tgt[m, 3] * Ly + tgt[m, 1]) * Lxh + xh[m]
+            # the neighbour site as the OTHER rank indexes it: same (x, y, t), z = znbr, parity 1 - par
+            nb = tgt[m].copy()
+            nb[:, 2] = znbr
+            assert ((nb.sum(axis=1) & 1) == 1 - par).all()
+            nidx = geometry.site_index(ll, nb) - (1 - par) * Vh
+            t_s, w_s = nidx // (row * Lz), nidx % row
+            assert np.array_equal(nidx, t_s * row * Lz + znbr * row + w_s)      # the sender's idx formula in pack_faces_kernel
+            assert np.array_equal(t_s * row + w_s, f_recv)
+
+
+def test_site_boxes_tile_the_local_lattice():
+    """Engine::launch_dslash splits a T x Z-split local lattice into an interior box and up to four boundary boxes;
+    restate box_site (common.cuh) and check that the boxes tile one checkerboard exactly once, in every split mode."""
+    def box_site(g, b, local):
+        Lxh, Ly, Lz, Lt = g
+        t0, nt, z0, nz = b
+        row = Lxh * Ly
+        if nz == Lz:
+            return t0 * row * Lz + local
+        w, q = local % row, local // row
+        return ((t0 + q // nz) * Lz + z0 + q % nz) * row + w
+
+    for g in ((2, 4, 6, 8), (2, 2, 2, 4), (3, 2, 4, 2), (2, 2, 2, 2)):
+        Lxh, Ly, Lz, Lt = g
+        Vh = Lxh * Ly * Lz * Lt
+        for tsplit in (0, 1):
+            for zsplit in (0, 1):
+                if not (tsplit or zsplit):
+                    continue
+                inner = (1 if tsplit else 0, Lt - 2 if tsplit else Lt, 1 if zsplit else 0, Lz - 2 if zsplit else Lz)
+                boxes = [inner] if inner[1] * inner[3] > 0 else []
+                if tsplit:
+                    boxes += [(0, 1, 0, Lz), (Lt - 1, 1, 0, Lz)]
+                if zsplit and inner[1] > 0:
+                    boxes += [(inner[0], inner[1], 0, 1), (inner[0], inner[1], Lz - 1, 1)]
+                seen = np.zeros(Vh, dtype=int)
+                for b in boxes:
+                    for local in range(Lxh * Ly * b[3] * b[1]):
+                        seen[box_site(g, b, local)] += 1
+                assert (seen == 1).all(), (g, tsplit, zsplit)
