@@ -433,6 +433,24 @@ def run_b200(args):
            "d2h_bytes_per_step": cb_bytes * world / args.steps, "ms_per_call": ms_e2e,
            "call": "b200_invert(host psi, host chi, max_iter=steps): H2D chi+psi0, M^dag chi, preamble, %d iterations, "
                    "true residual, D2H psi" % args.steps}
+    # where the end-to-end time goes (untimed diagnostics, after the headline call): each stage between two events
+    try:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        psi_d = ctx.field()
+        barrier()
+        ev[0].record(stream)
+        chi_f.upload(chi_np); psi_d.upload(psi_np)
+        ev[1].record(stream)
+        ctx.dev_invert(psi_d, chi_f, solver=solver, rsd=0.0, max_iter=args.steps)
+        ev[2].record(stream)
+        L.check(ctx.lib.b200_mfield_download(ctx.h, psi_d.h, 0, C.c_void_p(psi_np.ctypes.data), ctx.prec))
+        ev[3].record(stream)
+        barrier()
+        e2e["breakdown_ms"] = {"h2d_chi_psi0": ev[0].elapsed_time(ev[1]), "device_solve": ev[1].elapsed_time(ev[2]),
+                               "d2h_psi": ev[2].elapsed_time(ev[3]), "iterations_only": ms_step * args.steps}
+        del psi_d
+    except Exception as e:  # noqa
+        e2e["breakdown_ms"] = {"error": str(e)}
     t_clock_end = time.time()
 
     # ---------------- optional: a real solve to 1e-8 (time to solution)

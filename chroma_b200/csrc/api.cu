@@ -70,11 +70,11 @@ using namespace b200;
 
 // ---- host-pointer entry points: upload -> device op -> download -------------------------------------------
 namespace {
+// Device twins of host operands.  They live in the context (b200_ctx::host_tmp) and are reused by every later call.
 struct TmpFields {
-  b200_ctx* ctx; b200_field* f[3] = {nullptr, nullptr, nullptr};
-  explicit TmpFields(b200_ctx* c) : ctx(c) {}
-  int get(int n) { for (int i = 0; i < n; ++i) { int rc = ctx->eng->field_alloc(&f[i]); if (rc) return rc; } return 0; }
-  ~TmpFields() { for (auto p : f) if (p) ctx->eng->field_free(p); }
+  b200_ctx* ctx; b200_field** f;
+  explicit TmpFields(b200_ctx* c) : ctx(c), f(c->host_tmp) {}
+  int get(int n) { for (int i = 0; i < n; ++i) if (!f[i]) { int rc = ctx->eng->field_alloc(&f[i]); if (rc) return rc; } return 0; }
 };
 }  // namespace
 
@@ -130,12 +130,14 @@ int b200_create(b200_ctx** out, int device, const int global_dims[4], const int 
   b200_ctx* ctx = new b200_ctx;
   ctx->eng = e;
   ctx->sloppy = nullptr;
+  for (auto& f : ctx->host_tmp) f = nullptr;
   *out = ctx;
   return B200_OK;
 }
 
 void b200_destroy(b200_ctx* ctx) {
   if (!ctx) return;
+  for (auto f : ctx->host_tmp) if (f && ctx->eng) ctx->eng->field_free(f);
   delete ctx->sloppy;   // first: it borrows the main engine's stream and scalar block
   delete ctx->eng;
   delete ctx;

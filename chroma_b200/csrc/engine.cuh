@@ -90,4 +90,8 @@ EngineBase* make_engine_float(const Config& c);
 struct b200_ctx {
   b200::EngineBase* eng;
   b200::EngineBase* sloppy;   // fp32 twin of an fp64 engine, made on demand by b200_invert_reliable
+  // device twins of the host psi / chi of the host-pointer entry points: allocated on the first solve and kept for the
+  // life of the context (Chroma calls operator() 12 times per propagator, quarkprop4_w.cc:70-117; a cudaMalloc/cudaFree
+  // pair of 1 GB per call costs more than the transfers)
+  b200_field* host_tmp[3];
 };
