@@ -109,6 +109,8 @@ namespace Chroma
       const double clov_r = 0.5 * ff * toDouble(p.CloverParams.clovCoeffR);
       const double clov_t = 0.5 * toDouble(p.CloverParams.clovCoeffT);
       check(b200_make_clover(ctx, diag_mass, clov_r, clov_t, aniso.anisoP ? 1 : 0, aniso.t_dir), "b200_make_clover");
+      // SymEvenOddPrecCloverLinOp::create also inverts the odd block (seoprec_clover_linop_w.cc:31-33): done on the GPU
+      if (p.SymmetricLinopP) check(b200_set_preconditioning(ctx, B200_PRECOND_SYMMETRIC), "b200_set_preconditioning");
     }
 
     ~B200CloverEngine() { if (ctx) b200_destroy(ctx); }
@@ -133,6 +135,30 @@ namespace Chroma
       if (invParam.verboseP)
         QDPIO::cout << "B200_CLOVER_SOLVER: time=" << info.secs << " s\tPerformance=" << info.gflops
                     << " GFLOPS\tTotal Time (incl. copies)=" << info.secs_total << " s" << std::endl;
+      return info;
+    }
+
+    //! (M^dag M + shifts[s]) psi[s] = chi on rb[1]; psi[s] are zeroed by the engine like MInvCG2_a does (minvcg2.cc:118-122)
+    std::vector<b200_solve_info> solveMulti(multi1d<T>& psi, const multi1d<Real>& shifts, const T& chi) const
+    {
+      const int n = shifts.size();
+      if (n < 1 || n > B200_MAX_SHIFTS) fail("multi-shift solve: number of shifts out of range");
+      if (psi.size() < n) psi.resize(n);
+      std::vector<void*> out(n);
+      std::vector<double> sh(n), rsd(n, toDouble(invParam.RsdTarget));
+      for (int s = 0; s < n; ++s) {
+        psi[s][rb[1]] = zero;     // touch the field so that QDP++ has allocated it before we take its address
+        out[s] = (void*)&(psi[s].elem(rb[1].start()).elem(0).elem(0).real());
+        sh[s] = toDouble(shifts[s]);
+      }
+      const void* in = (const void*)&(chi.elem(rb[1].start()).elem(0).elem(0).real());
+      std::vector<b200_solve_info> info(n);
+      std::memset(info.data(), 0, sizeof(b200_solve_info) * n);
+      check(b200_invert_multishift(ctx, out.data(), in, host_prec, n, sh.data(), rsd.data(), invParam.MaxIter, info.data()),
+            "b200_invert_multishift");
+      if (invParam.verboseP)
+        QDPIO::cout << "B200_CLOVER_SOLVER (multi-shift): time=" << info[0].secs << " s\tPerformance=" << info[0].gflops
+                    << " GFLOPS\tTotal Time (incl. copies)=" << info[0].secs_total << " s" << std::endl;
       return info;
     }
 

@@ -40,7 +40,7 @@ namespace Chroma
   SysSolverB200CloverParams::SysSolverB200CloverParams()
     : AntiPeriodicT(true), MaxIter(5000), RsdTarget(Real(1.0e-8)), Delta(Real(0.1)), solverType(B200_CG_SOLVER),
       precision(B200_PREC_DEFAULT), sloppyPrecision(B200_PREC_DEFAULT), reconstruct(B200_RECONS_NONE_T),
-      SilentFailP(false), RsdToleranceFactor(Real(10)), verboseP(false), device(-1)
+      SilentFailP(false), RsdToleranceFactor(Real(10)), verboseP(false), device(-1), SymmetricLinopP(false)
   {}
 
   SysSolverB200CloverParams::SysSolverB200CloverParams(XMLReader& xml, const std::string& path)
@@ -62,6 +62,7 @@ namespace Chroma
     if (paramtop.count("RsdToleranceFactor") > 0) read(paramtop, "RsdToleranceFactor", RsdToleranceFactor);
     if (paramtop.count("Verbose") > 0) read(paramtop, "Verbose", verboseP);
     if (paramtop.count("Device") > 0) read(paramtop, "Device", device);
+    if (paramtop.count("SymmetricLinop") > 0) read(paramtop, "SymmetricLinop", SymmetricLinopP);
   }
 
   void read(XMLReader& xml, const std::string& path, SysSolverB200CloverParams& p)
@@ -87,6 +88,7 @@ namespace Chroma
     write(xml, "RsdToleranceFactor", p.RsdToleranceFactor);
     write(xml, "Verbose", p.verboseP);
     write(xml, "Device", p.device);
+    write(xml, "SymmetricLinop", p.SymmetricLinopP);
     pop(xml);
   }
 }

@@ -7,7 +7,8 @@
  *  meaning for this engine, under the same tag names where one exists, so that an existing QUDA XML group works after
  *  changing <invType>: MaxIter, RsdTarget, CloverParams, AntiPeriodicT, SolverType, Delta, CudaPrecision,
  *  CudaSloppyPrecision, CudaReconstruct, RsdToleranceFactor, SilentFail, Verbose.  Tags this engine ignores
- *  (AsymmetricLinop -- we always solve Chroma's asymmetric operator --, AxialGaugeFix, AutotuneDslash, Pipeline,
+ *  (AsymmetricLinop -- QUDA's internal choice; here the operator solved is always the caller's own A, see
+ *  SymmetricLinop --, AxialGaugeFix, AutotuneDslash, Pipeline,
  *  GCRInnerParams, BackupSolverParam, DumpOnFail) are accepted and skipped.
  */
 #ifndef __SYSSOLVER_B200_CLOVER_PARAMS_H__
@@ -41,6 +42,10 @@ namespace Chroma
     Real RsdToleranceFactor;
     bool verboseP;
     int device;                        //!< CUDA device; -1 = node number modulo visible devices
+    //! false (default): the fermion action hands the plugin an EvenOddPrecCloverLinOp (CLOVER, clover_fermact_w.cc);
+    //! true: a SymEvenOddPrecCloverLinOp (SEOPREC_CLOVER, seoprec_clover_fermact_w.cc).  The engine must solve the
+    //! caller's own A for the plugin's residual check with A to pass.
+    bool SymmetricLinopP;
   };
 
   void read(XMLReader& xml, const std::string& path, SysSolverB200CloverParams& p);

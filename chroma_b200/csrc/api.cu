@@ -53,6 +53,48 @@ __global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* stat
   __threadfence_system();
 }
 
+// iter = 0: the set-up before the loop (minvcg2.cc:211-240); iter >= 1: end of loop iteration `iter` (:268-340).
+// On entry scal[S_A] = -b (new), scal[S_B] = a of the next iteration, scal[S_CP] = c = |r|^2 (new).
+__global__ void ms_scalars_kernel(MsState* __restrict__ ms, const double* __restrict__ scal, int* __restrict__ status, int iter, int check) {
+  if (check && (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0)) return;
+  const int s = threadIdx.x;
+  const int n = ms->n_shift;
+  const double b = -scal[S_A], a_next = scal[S_B], c = scal[S_CP];
+  const double a = ms->a, bp = ms->b;
+  int conv = 1;
+  if (s < n) {
+    const double sh = ms->shift[s];
+    if (iter == 0) {
+      const double z1 = 1.0 / (1.0 - sh * b);
+      ms->zprev[s] = 1.0; ms->zcur[s] = z1; ms->bs[s] = b * z1;
+      ms->conv[s] = 0; ms->conv_prev[s] = 0; ms->css[s] = c * z1 * z1;
+      conv = 0;
+      ms->as[s] = a_next * z1 * (b * z1) / (1.0 * b);
+    } else {
+      conv = ms->conv[s];
+      ms->conv_prev[s] = conv;
+      if (!conv) {
+        const double z0 = ms->zcur[s], z1 = ms->zprev[s];        // after the iz flip: z0 = z[1-iz], z1 = z[iz]
+        double zn = z0 * z1 * bp;
+        zn /= b * a * (z1 - z0) + z1 * bp * (1.0 - sh * b);
+        const double bs = b * zn / z0;
+        ms->zprev[s] = z0; ms->zcur[s] = zn; ms->bs[s] = bs;
+        const double css = c * zn * zn;
+        ms->css[s] = css;
+        conv = css < ms->rsd_sq[s];
+        ms->conv[s] = conv;
+        ms->as[s] = a_next * zn * bs / (z0 * b);
+      }
+    }
+  }
+  const bool all = __all_sync(0xffffffffu, conv != 0);
+  __syncwarp();
+  if (s == 0) {
+    ms->a = a_next; ms->b = b;
+    if (iter > 0 && all && check && status[ST_STOP] == 0) status[ST_STOP] = iter;
+  }
+}
+
 __global__ void __launch_bounds__(BLAS_BLOCK) sum_double_kernel(const double* x, size_t n, ReduceBuf red, double* dst) {
   double s[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) s[0] += x[i];
@@ -152,7 +194,12 @@ int b200_load_gauge(b200_ctx* ctx, const void* const u[4], int host_prec, const 
 int b200_load_clover(b200_ctx* ctx, const void* clov, const void* invclov, int host_prec) { CHECK_CTX(ctx); return ctx->eng->load_clover(clov, invclov, host_prec); }
 int b200_make_clover(b200_ctx* ctx, double diag_mass, double clov_r, double clov_t, int aniso, int t_dir) { CHECK_CTX(ctx); return ctx->eng->make_clover(diag_mass, clov_r, clov_t, aniso, t_dir); }
 int b200_get_clover(b200_ctx* ctx, void* clov, void* invclov, int host_prec) { CHECK_CTX(ctx); return ctx->eng->get_clover(clov, invclov, host_prec); }
-int b200_clover_logdet(b200_ctx* ctx, double* out) { CHECK_CTX(ctx); if (!out) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->clover_logdet(out); }
+int b200_clover_logdet(b200_ctx* ctx, double* out) { CHECK_CTX(ctx); if (!out) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->clover_logdet(out, 0); }
+int b200_clover_logdet_oo(b200_ctx* ctx, double* out) { CHECK_CTX(ctx); if (!out) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->clover_logdet(out, 1); }
+int b200_set_preconditioning(b200_ctx* ctx, int mode) {
+  CHECK_CTX(ctx);
+  return ctx->eng->set_preconditioning(mode);   // the fp32 twin of b200_invert_reliable re-syncs through operator_epoch
+}
 
 int b200_field_alloc(b200_ctx* ctx, b200_field** f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_alloc(f); }
 void b200_field_free(b200_ctx* ctx, b200_field* f) { if (ctx && ctx->eng) ctx->eng->field_free(f); }
@@ -182,6 +229,34 @@ int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* c
                              b200_solve_info* info) {
   CHECK_CTX(ctx);
   return reliable_solve(ctx->eng, &ctx->sloppy, psi, chi, rsd, delta, max_iter, mdagm, info);
+}
+int b200_dev_invert_multishift(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int n_shift, const double* shifts, const double* rsd,
+                               int max_iter, b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return ctx->eng->invert_multishift(psi, chi, n_shift, shifts, rsd, max_iter, info);
+}
+int b200_invert_multishift(b200_ctx* ctx, void* const psi[], const void* chi, int host_prec, int n_shift, const double* shifts,
+                           const double* rsd, int max_iter, b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  if (!psi || !chi || !shifts || !rsd || !info) { set_error("b200_invert_multishift: null pointer"); return B200_ERR_ARG; }
+  if (n_shift < 1 || n_shift > B200_MAX_SHIFTS) { set_error("b200_invert_multishift: 1..%d shifts (got %d)", (int)B200_MAX_SHIFTS, n_shift); return B200_ERR_ARG; }
+  for (int s = 0; s < n_shift; ++s) if (!psi[s]) { set_error("b200_invert_multishift: null psi[%d]", s); return B200_ERR_ARG; }
+  B200_CUDA(cudaSetDevice(ctx->eng->cfg.device));
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
+  B200_CUDA(cudaEventRecord(e0, ctx->eng->stream));
+  TmpFields t(ctx); int rc = t.get(1);
+  b200_field* sol = nullptr;
+  if (!rc) rc = ctx->eng->field_alloc(&sol, n_shift);
+  if (!rc) rc = ctx->eng->field_upload(t.f[0], chi, host_prec);
+  if (!rc) rc = ctx->eng->invert_multishift(sol, t.f[0], n_shift, shifts, rsd, max_iter, info);
+  for (int s = 0; s < n_shift && !rc; ++s) rc = ctx->eng->field_download(sol, psi[s], host_prec, s);
+  cudaEventRecord(e1, ctx->eng->stream); cudaEventSynchronize(e1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  if (!rc) for (int s = 0; s < n_shift; ++s) info[s].secs_total = ms * 1e-3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (sol) ctx->eng->field_free(sol);
+  return rc;
 }
 int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver) {
   CHECK_CTX(ctx);

@@ -17,6 +17,11 @@
 //   EPI_M_DOTX   EPI_M and <out|x>, |out|^2           -> BiCGStab omega   (invbicgstab.cc:126-140)
 //   EPI_M_CGREL  EPI_M_CG whose finaliser also takes the reliable-update decisions (reliable_cg.cc:113-121)
 //
+// The EPI_M* epilogues come in three operator modes (template parameter MODE, DslashArgs::mmode):
+//   MODE_ASYM       m = A x - 1/4 D in            EvenOddPrecCloverLinOp, eoprec_clover_linop_w.cc:142-187
+//   MODE_SYM_PLUS   m = x - 1/4 A^-1 (D in)       SymEvenOddPrecCloverLinOp PLUS,  seoprec_clover_linop_w.cc:160-166, 175
+//   MODE_SYM_MINUS  m = x - 1/4 D in              ... MINUS (A_oo^-1 was applied to the source first), :168-175
+//
 // Neighbour indices come from coordinate arithmetic (no shift table in HBM; replaces ShiftTable,
 // shift_table_scalar.h:10-147).  The arithmetic is HBM-bound: 1320 flop per (48+8G) reals moved.
 #pragma once
@@ -26,6 +31,7 @@
 namespace b200 {
 
 enum Epilogue { EPI_DSLASH = 0, EPI_AINV, EPI_M, EPI_M_NORM, EPI_M_CG, EPI_M_DOTR0, EPI_M_DOTX, EPI_M_CGREL };
+enum OperatorMode { MODE_ASYM = 0, MODE_SYM_PLUS = 1, MODE_SYM_MINUS = 2 };
 
 template <typename R>
 struct DslashArgs {
@@ -61,6 +67,7 @@ struct DslashArgs {
   size_t gstride;   // same for the T ghost faces (6*S3h)
   size_t gstride_z; // ... and the Z ghost faces (6*SZh)
   int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice (box 0)
+  int mmode;        // OperatorMode of the EPI_M* epilogues (selects the kernel instantiation; single-RHS kernels only)
 };
 
 // The `local`-th target site of a launch (local < a.nsites).  ZC: the batched kernels sweep box 0 in z-chunks.
@@ -406,7 +413,7 @@ struct FinBiOmega {
 #define B200_DSLASH_MINBLOCKS_F 4   // fp32: 64-bit loads need 4 CTAs/SM in flight (tuned on B200: 1 -> 80 %, 3 -> 96 %, 4 -> 100 % of HBM peak)
 #endif
 // ---- fused epilogues for one target site (shared by the single- and multi-RHS kernels) ------------------------
-template <typename R, int EPI, bool MR>
+template <typename R, int EPI, bool MR, int MODE = MODE_ASYM>
 __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>& a, int idx, int stride, const L2Policy& pol, double red[3],
                                               const Cx<R>* smc = nullptr) {
   typedef Cx<R> C;
@@ -440,10 +447,13 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
       C xi[6], o[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) xi[k] = ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
-      clover_block<R, MR>(o, xi, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
+      if (MODE == MODE_ASYM) clover_block<R, MR>(o, xi, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
+      if (MODE == MODE_SYM_PLUS) clover_block<R, MR>(o, acc + 6 * b, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
+        if (MODE == MODE_ASYM) m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
+        if (MODE == MODE_SYM_PLUS) m[6 * b + k] = mk<R>(xi[k].x - (R)0.25 * o[k].x, xi[k].y - (R)0.25 * o[k].y);
+        if (MODE == MODE_SYM_MINUS) m[6 * b + k] = mk<R>(xi[k].x - (R)0.25 * acc[6 * b + k].x, xi[k].y - (R)0.25 * acc[6 * b + k].y);
         if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
           const C mm = m[6 * b + k];
           red[0] += (double)mm.x * xi[k].x + (double)mm.y * xi[k].y;
@@ -478,7 +488,7 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
   }
 }
 
-template <typename R, int EPI, bool RECON12, int BLOCK>
+template <typename R, int EPI, bool RECON12, int BLOCK, int MODE = MODE_ASYM>
 __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS)) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
   typedef Cx<R> C;
   if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
@@ -493,7 +503,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
     const L2Policy pol = make_l2_policy();
     C acc[12];
     dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
-    site_epilogue<R, EPI, false>(acc, a, idx, stride, pol, red);
+    site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
   }
 
   if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal});

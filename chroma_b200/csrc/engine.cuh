@@ -53,7 +53,10 @@ class EngineBase {
   virtual int load_clover(const void* clov, const void* invclov, int host_prec) = 0;
   virtual int make_clover(double diag_mass, double cr, double ct, int aniso, int t_dir) = 0;
   virtual int get_clover(void* clov, void* invclov, int host_prec) = 0;
-  virtual int clover_logdet(double* out) = 0;
+  virtual int clover_logdet(double* out, int cb) = 0;
+  virtual int set_preconditioning(int mode) = 0;
+  virtual int invert_multishift(b200_field* psi, const b200_field* chi, int n_shift, const double* shifts, const double* rsd,
+                                int max_iter, b200_solve_info* info) = 0;   // info[n_shift]
   virtual int field_alloc(b200_field** f, int nrhs = 1) = 0;
   virtual void field_free(b200_field* f) = 0;
   virtual int field_upload(b200_field* f, const void* host, int host_prec, int irhs = 0) = 0;

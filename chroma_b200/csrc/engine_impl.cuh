@@ -10,6 +10,7 @@
 #include "pack.cuh"
 #include "clover_setup.cuh"
 #include "halo.cuh"
+#include "multishift.cuh"
 
 namespace b200 {
 
@@ -23,9 +24,13 @@ constexpr int DSLASH_BLOCK_MAX = B200_DSLASH_BLOCK > B200_DSLASH_BLOCK_F ? B200_
 constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
 constexpr size_t STAGING_BYTES = 256u << 20;
 
+// status != nullptr: a solver launch -- return at once when the solve has stopped / when slot run_if is clear
 template <typename R, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) clover_kernel(const Cx<R>* __restrict__ in, Cx<R>* __restrict__ out,
-                                                      const Cx<R>* __restrict__ clov, int Vh, size_t fstride) {
+                                                      const Cx<R>* __restrict__ clov, int Vh, size_t fstride,
+                                                      const int* __restrict__ status = nullptr, int run_if = 0) {
+  if (status && (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0)) return;
+  if (status && run_if && status[run_if] == 0) return;
   const int idx = blockIdx.x * BLOCK + threadIdx.x;
   if (idx >= Vh) return;
   in += blockIdx.y * fstride; out += blockIdx.y * fstride;
@@ -63,12 +68,18 @@ class Engine : public EngineBase {
   C* invclov = nullptr;     // [36][Vh]  (cb 0)
   double* tr_log = nullptr; // [Vh] log|det A_ee| per even site (make_clover only)
   bool have_trlog = false;
+  // symmetric preconditioning (SymEvenOddPrecCloverLinOp, seoprec_clover_linop_w.cc:16-41): needs A_oo^-1 as well
+  int sym = 0;              // 0: M = A_oo - 1/4 D A_ee^-1 D ; 1: M = 1 - 1/4 A_oo^-1 D A_ee^-1 D
+  C* invclov_oo = nullptr;  // [36][Vh] (cb 1), derived on the device from clov whenever sym is on
+  double* tr_log_oo = nullptr;
+  // multi-shift CG (MInvCG2_a)
+  MsState* ms_dev = nullptr; b200_field* ms_p = nullptr; C* ms_psi = nullptr;
   double* scal = nullptr; int* status = nullptr;
   double* partial = nullptr; unsigned int* ticket = nullptr; size_t partial_cap = 0;   // partial: doubles; ticket: [MAX_RHS]
   double* h_scal = nullptr; int* h_status = nullptr;   // pinned; [MAX_RHS][S_COUNT] and 2 slots of [MAX_RHS][ST_COUNT]
   cudaEvent_t ev_poll[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
   void* staging = nullptr;
-  b200_field* ws[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  b200_field* ws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Halo<R> halo;
   int blas_grid = 148 * 8;
   bool owns_stream = true, owns_scalars = true;   // false once a mixed-precision partner lent us its stream / scalar block
@@ -131,7 +142,8 @@ class Engine : public EngineBase {
     cudaStreamSynchronize(stream);
     halo.destroy();
     for (auto& f : ws) if (f) { field_free(f); f = nullptr; }
-    cudaFree(gauge); cudaFree(clov); cudaFree(invclov); cudaFree(tr_log);
+    if (ms_p) { field_free(ms_p); ms_p = nullptr; }
+    cudaFree(gauge); cudaFree(clov); cudaFree(invclov); cudaFree(tr_log); cudaFree(invclov_oo); cudaFree(tr_log_oo); cudaFree(ms_dev);
     if (owns_scalars) { cudaFree(scal); cudaFree(status); }
     cudaFree(partial); cudaFree(ticket); cudaFree(staging);
     cudaFreeHost(h_scal); cudaFreeHost(h_status);
@@ -256,7 +268,29 @@ class Engine : public EngineBase {
     else rc = upload_aos<float, 72, 36>((const float*)invclov_h, g.Vh, invclov, (size_t)g.Vh, MapClover(), 1.0);
     if (rc) return rc;
     have_trlog = false;
+    rc = refresh_sym(); if (rc) return rc;
     ++operator_epoch;
+    B200_CUDA(cudaStreamSynchronize(stream));
+    return B200_OK;
+  }
+
+  // A_oo^-1 (and log|det A_oo|) from the odd half of clov: invclov.choles(1), seoprec_clover_linop_w.cc:31-33
+  int refresh_sym() {
+    if (!sym || !clov) return B200_OK;
+    if (!invclov_oo) B200_CUDA(cudaMalloc(&invclov_oo, sizeof(C) * 36 * (size_t)g.Vh));
+    if (!tr_log_oo) B200_CUDA(cudaMalloc(&tr_log_oo, sizeof(double) * (size_t)g.Vh));
+    B200_CUDA(cudaMemcpyAsync(invclov_oo, clov + (size_t)36 * g.Vh, sizeof(C) * 36 * (size_t)g.Vh, cudaMemcpyDeviceToDevice, stream));
+    ldagdlinv_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov_oo, tr_log_oo, g.Vh);
+    return launched("ldagdlinv(oo)");
+  }
+  int set_preconditioning(int mode) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (mode != B200_PRECOND_ASYMMETRIC && mode != B200_PRECOND_SYMMETRIC) { set_error("preconditioning must be B200_PRECOND_ASYMMETRIC or B200_PRECOND_SYMMETRIC"); return B200_ERR_ARG; }
+    if (mode == sym) return B200_OK;
+    sym = mode;
+    int rc = refresh_sym(); if (rc) return rc;
+    ++operator_epoch;
+    it_psi = nullptr;
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
   }
@@ -291,6 +325,7 @@ class Engine : public EngineBase {
     ldagdlinv_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov, tr_log, g.Vh);
     rc = launched("ldagdlinv"); if (rc) return rc;
     have_trlog = true;
+    rc = refresh_sym(); if (rc) return rc;
     ++operator_epoch;
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
@@ -312,10 +347,13 @@ class Engine : public EngineBase {
     return rc;
   }
 
-  int clover_logdet(double* out) override {
+  int clover_logdet(double* out, int cb) override {
     B200_CUDA(cudaSetDevice(cfg.device));
-    if (!have_trlog) { set_error("tr log is only available after b200_make_clover"); return B200_ERR_STATE; }
-    sum_double_kernel<<<blas_grid, BLAS_BLOCK, 0, stream>>>(tr_log, (size_t)g.Vh, make_red(0, blas_grid), scal + S_TMP0);
+    if (cb != 0 && cb != 1) { set_error("cb must be 0 or 1"); return B200_ERR_ARG; }
+    if (cb == 0 && !have_trlog) { set_error("tr log is only available after b200_make_clover"); return B200_ERR_STATE; }
+    if (cb == 1 && (!sym || !tr_log_oo)) { set_error("log det A_oo needs symmetric preconditioning and a clover term"); return B200_ERR_STATE; }
+    { int rcb = set_batch(1); if (rcb) return rcb; }
+    sum_double_kernel<<<blas_grid, BLAS_BLOCK, 0, stream>>>(cb ? tr_log_oo : tr_log, (size_t)g.Vh, make_red(0, blas_grid), scal + S_TMP0);
     int rc = launched("sum_double"); if (rc) return rc;
     rc = fetch_scalars(); if (rc) return rc;
     *out = h_scal[S_TMP0];
@@ -325,7 +363,7 @@ class Engine : public EngineBase {
   // ------------------------------------------------------------------ fields
   int field_alloc(b200_field** f, int nrhs = 1) override {
     B200_CUDA(cudaSetDevice(cfg.device));
-    if (nrhs < 1 || nrhs > MAX_RHS) { set_error("a batched field holds 1..%d right-hand sides", MAX_RHS); return B200_ERR_ARG; }
+    if (nrhs < 1 || nrhs > MAX_SHIFT) { set_error("a batched field holds 1..%d vectors", MAX_SHIFT); return B200_ERR_ARG; }
     b200_field* p = new b200_field;
     p->bytes = sizeof(C) * nelem() * nrhs; p->prec = sizeof(R); p->d = nullptr; p->nrhs = nrhs;
     cudaError_t e = cudaMalloc(&p->d, p->bytes);
@@ -368,6 +406,8 @@ class Engine : public EngineBase {
   // Select the batch size and make sure the reduction scratch holds <= 4 partial sums per right-hand side and block,
   // for the BLAS grid as well as for the Dslash grids (32 sites per block when batched).
   int set_batch(int n) {
+    if (n < 1 || n > MAX_RHS) { set_error("the batched kernels take 1..%d right-hand sides (field holds %d)", MAX_RHS, n); return B200_ERR_ARG; }
+    if (n > 1 && sym) { set_error("batched right-hand sides are not available with symmetric preconditioning"); return B200_ERR_ARG; }
     nb = n;
     const size_t dblocks = n > 1 ? (size_t)(g.Vh + 31) / 32 + 4 : (size_t)(g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK + 8;
     return ensure_partial(4 * (size_t)n * std::max<size_t>((size_t)blas_grid, dblocks));
@@ -419,9 +459,15 @@ class Engine : public EngineBase {
   int launch_one(const DslashArgs<R>& a, int blocks) {
     if (blocks <= 0) return B200_OK;
     if (nb > 1) return launch_mrhs<EPI>(a, blocks);
-    if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
-    else dslash_kernel<R, EPI, false, DSLASH_BLOCK><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
+    if (EPI >= EPI_M && a.mmode == MODE_SYM_PLUS) launch_mode<EPI, (EPI >= EPI_M ? MODE_SYM_PLUS : MODE_ASYM)>(a, blocks);
+    else if (EPI >= EPI_M && a.mmode == MODE_SYM_MINUS) launch_mode<EPI, (EPI >= EPI_M ? MODE_SYM_MINUS : MODE_ASYM)>(a, blocks);
+    else launch_mode<EPI, MODE_ASYM>(a, blocks);
     return launched("dslash_kernel");
+  }
+  template <int EPI, int MODE>
+  void launch_mode(const DslashArgs<R>& a, int blocks) {
+    if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
+    else dslash_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
   }
   // z-chunk (in sites per time slice) of the batched traversal order of a box nz planes thick: the largest divisor of
   // nz for which three time slices of the batch's source spinors fit in ~1/3 of the L2 (B200: 126 MB); 0 = natural order
@@ -457,16 +503,29 @@ class Engine : public EngineBase {
   int ready() {
     if (!gauge) { set_error("gauge field not loaded"); return B200_ERR_STATE; }
     if (!clov || !invclov) { set_error("clover term not loaded"); return B200_ERR_STATE; }
+    if (sym && !invclov_oo) { set_error("symmetric preconditioning: A_oo^-1 not built"); return B200_ERR_STATE; }
     return B200_OK;
   }
+  // workspace fields an entry point needs: the symmetric M^dag keeps A_oo^-1 x in W(8)
+  int nws(int n) const { return sym ? 9 : n; }
 
   // out = M in (isign=+1) / M^dag in (-1) with one of the EPI_M* epilogues; te is the even temporary
+  // Symmetric preconditioning (seoprec_clover_linop_w.cc:147-193):
+  //   PLUS : t = A_ee^-1 D x ; out = x - 1/4 A_oo^-1 D t                (MODE_SYM_PLUS epilogue)
+  //   MINUS: w = A_oo^-1 x ; t = A_ee^-1 D^dag w ; out = x - 1/4 D^dag t  (clover pass + MODE_SYM_MINUS epilogue)
   int apply_M(C* out, const C* in, int isign, int epi, C* r, const C* r0, int iter, int check, int run_if = 0) {
+    const C* src = in;
+    if (sym && isign < 0) {
+      clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, 1), 128, 0, stream>>>(in, W(8), invclov_oo, g.Vh, nelem(), (check || run_if) ? status : nullptr, run_if);
+      int rc0 = launched("clover_kernel"); if (rc0) return rc0;
+      src = W(8);
+    }
     DslashArgs<R> a{};
-    a.in = in; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign; a.iter = iter; a.check_stop = check; a.run_if = run_if;
+    a.in = src; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign; a.iter = iter; a.check_stop = check; a.run_if = run_if;
     int rc = launch_dslash<EPI_AINV>(a); if (rc) return rc;
     DslashArgs<R> b{};
     b.in = W(0); b.out = out; b.clov = clov + (size_t)36 * g.Vh; b.x = in; b.r = r; b.r0 = r0;
+    if (sym) { b.clov = invclov_oo; b.mmode = isign > 0 ? MODE_SYM_PLUS : MODE_SYM_MINUS; }
     b.parity = 1; b.isign = isign; b.iter = iter; b.check_stop = check; b.run_if = run_if;
     switch (epi) {
       case EPI_M_CGREL: return launch_dslash<EPI_M_CGREL>(b);
@@ -493,8 +552,9 @@ class Engine : public EngineBase {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (!clov) { set_error("clover term not loaded"); return B200_ERR_STATE; }
     if ((cb != 0 && cb != 1) || !out || !in || out == in || out->nrhs != in->nrhs) { set_error("b200_clover_apply: bad argument"); return B200_ERR_ARG; }
-    if (inverse && cb != 0) { set_error("only the cb-0 inverse exists (invclov.choles(0), eoprec_clover_linop_w.cc:30)"); return B200_ERR_ARG; }
-    const C* cl = inverse ? invclov : clov + (size_t)cb * 36 * g.Vh;
+    if (inverse && cb != 0 && !(sym && invclov_oo)) { set_error("without symmetric preconditioning only the cb-0 inverse exists (invclov.choles(0), eoprec_clover_linop_w.cc:30)"); return B200_ERR_ARG; }
+    if (in->nrhs > MAX_RHS) { set_error("b200_clover_apply: at most %d right-hand sides", MAX_RHS); return B200_ERR_ARG; }
+    const C* cl = inverse ? (cb ? invclov_oo : invclov) : clov + (size_t)cb * 36 * g.Vh;
     clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, in->nrhs), 128, 0, stream>>>((const C*)in->d, (C*)out->d, cl, g.Vh, nelem());
     return launched("clover_kernel");
   }
@@ -504,7 +564,7 @@ class Engine : public EngineBase {
     int rc = ready(); if (rc) return rc;
     if ((isign != 1 && isign != -1) || !out || !in || out == in || out->nrhs != in->nrhs) { set_error("b200_clover_matpc: bad argument"); return B200_ERR_ARG; }
     { int rcb = set_batch(in->nrhs); if (rcb) return rcb; }
-    rc = need_ws(1, nb); if (rc) return rc;
+    rc = need_ws(nws(1), nb); if (rc) return rc;
     return apply_M((C*)out->d, (const C*)in->d, isign, EPI_M, nullptr, nullptr, 0, 0);
   }
 
@@ -514,7 +574,7 @@ class Engine : public EngineBase {
     if ((isign != 1 && isign != -1) || !out || !in || out == in || reps < 1 || out->nrhs != in->nrhs) { set_error("b200_dev_time_matpc: bad argument"); return B200_ERR_ARG; }
     if (split()) { set_error("b200_dev_time_matpc: single-GPU measurement only"); return B200_ERR_ARG; }
     { int rcb = set_batch(in->nrhs); if (rcb) return rcb; }
-    rc = need_ws(1, nb); if (rc) return rc;
+    rc = need_ws(nws(1), nb); if (rc) return rc;
     cudaEvent_t e[3];
     for (auto& x : e) B200_CUDA(cudaEventCreate(&x));
     double acc[2] = {0, 0};
@@ -523,7 +583,13 @@ class Engine : public EngineBase {
       a.in = (const C*)in->d; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign;
       DslashArgs<R> b{};
       b.in = W(0); b.out = (C*)out->d; b.clov = clov + (size_t)36 * g.Vh; b.x = (const C*)in->d; b.parity = 1; b.isign = isign;
+      if (sym) { b.clov = invclov_oo; b.mmode = isign > 0 ? MODE_SYM_PLUS : MODE_SYM_MINUS; }
       B200_CUDA(cudaEventRecord(e[0], stream));
+      if (sym && isign < 0) {   // the A_oo^-1 pass of the symmetric M^dag is booked with the first kernel
+        clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, 1), 128, 0, stream>>>((const C*)in->d, W(8), invclov_oo, g.Vh, nelem());
+        rc = launched("clover_kernel"); if (rc) return rc;
+        a.in = W(8);
+      }
       rc = launch_dslash<EPI_AINV>(a); if (rc) return rc;
       B200_CUDA(cudaEventRecord(e[1], stream));
       rc = launch_dslash<EPI_M>(b); if (rc) return rc;
@@ -608,6 +674,18 @@ class Engine : public EngineBase {
     return launched("bicg_update");
   }
 
+  // one multi-shift CG iteration, minvcg2.cc:243-342 (the p updates of :246-262 were done by the previous ms_update).
+  // W(1)=Mp, W(2)=p0, W(3)=r; ms_p = p[s]; ms_psi = psi[s]
+  static constexpr int SOLVER_MULTISHIFT = 100;
+  int ms_iteration(int k, int check) {
+    int rc = apply_M(W(1), W(2), +1, EPI_M_NORM, nullptr, nullptr, k, check); if (rc) return rc;      // d ; S_A = cp/d = -b
+    rc = apply_M(nullptr, W(1), -1, EPI_M_CG, W(3), nullptr, k, check); if (rc) return rc;            // r += b M^dag M p0 ; c ; S_B = c/cp
+    ms_scalars_kernel<<<1, 32, 0, stream>>>(ms_dev, scal, status, k, check);
+    rc = launched("ms_scalars"); if (rc) return rc;
+    ms_update_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(ms_psi, (C*)ms_p->d, W(2), W(3), nelem(), nelem(), ms_dev, status, k, check);
+    return launched("ms_update");
+  }
+
   // InvCG2_a set-up (invcg2.cc:100-150): returns chi_sq, cp in h_scal[S_TMP0], h_scal[S_TMP1]
   int cg_begin(C* psi, const C* chi) {
     int rc = norm2_dev(chi, S_TMP0); if (rc) return rc;
@@ -635,7 +713,8 @@ class Engine : public EngineBase {
     while (k <= max_iter && !done) {
       const int n = std::min(ITER_BATCH, max_iter - k + 1);
       for (int i = 0; i < n; ++i) {
-        int rc = (solver == B200_SOLVER_CG) ? cg_iteration(psi, k + i, 1) : bicg_iteration(psi, k + i, 1, isign);
+        int rc = (solver == B200_SOLVER_CG) ? cg_iteration(psi, k + i, 1)
+               : (solver == SOLVER_MULTISHIFT) ? ms_iteration(k + i, 1) : bicg_iteration(psi, k + i, 1, isign);
         if (rc) return rc;
       }
       B200_CUDA(cudaMemcpyAsync(h_status + slot * SB, status, sizeof(int) * SB, cudaMemcpyDeviceToHost, stream));
@@ -740,7 +819,7 @@ class Engine : public EngineBase {
     if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0) || psi_f->nrhs != chi_f->nrhs) { set_error("b200_invert: bad argument"); return B200_ERR_ARG; }
     if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
     { int rcb = set_batch(psi_f->nrhs); if (rcb) return rcb; }
-    rc = need_ws(7, nb); if (rc) return rc;
+    rc = need_ws(nws(7), nb); if (rc) return rc;
     C* psi = (C*)psi_f->d; const C* chi = (const C*)chi_f->d;
     memset(info, 0, sizeof(*info) * nb);
     B200_CUDA(cudaEventRecord(ev_t0, stream));
@@ -780,12 +859,97 @@ class Engine : public EngineBase {
     return rc;
   }
 
+  // MInvCG2_a (minvcg2.cc:74-373) behind MdagMMultiSysSolverCG::operator() (multi_syssolver_mdagm_cg.h:58-105):
+  // (M^dag M + shifts[s]) psi[s] = chi.  psi_f is a batched field with at least n_shift vectors (zeroed here, as the
+  // reference does); info[s] gets the common iteration count and the TRUE relative residual of shift s.
+  int invert_multishift(b200_field* psi_f, const b200_field* chi_f, int n_shift, const double* shifts, const double* rsd,
+                        int max_iter, b200_solve_info* info) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    int rc = ready(); if (rc) return rc;
+    if (!psi_f || !chi_f || !shifts || !rsd || !info || psi_f == chi_f || max_iter < 0) { set_error("b200_invert_multishift: bad argument"); return B200_ERR_ARG; }
+    if (n_shift < 1 || n_shift > MAX_SHIFT) { set_error("b200_invert_multishift: 1..%d shifts (got %d)", MAX_SHIFT, n_shift); return B200_ERR_ARG; }
+    if (psi_f->nrhs < n_shift || chi_f->nrhs != 1) { set_error("b200_invert_multishift: psi must hold n_shift vectors, chi one"); return B200_ERR_ARG; }
+    for (int s = 0; s < n_shift; ++s) if (!(rsd[s] >= 0.0)) { set_error("b200_invert_multishift: negative residual target"); return B200_ERR_ARG; }
+    { int rcb = set_batch(1); if (rcb) return rcb; }
+    rc = need_ws(nws(5), 1); if (rc) return rc;
+    if (ms_p && ms_p->nrhs < n_shift) { field_free(ms_p); ms_p = nullptr; }
+    if (!ms_p) { rc = field_alloc(&ms_p, n_shift); if (rc) return rc; }
+    if (!ms_dev) B200_CUDA(cudaMalloc(&ms_dev, sizeof(MsState)));
+    C* psi = (C*)psi_f->d; const C* chi = (const C*)chi_f->d;
+    ms_psi = psi;
+    const size_t vbytes = sizeof(C) * nelem();
+    memset(info, 0, sizeof(*info) * n_shift);
+    B200_CUDA(cudaEventRecord(ev_t0, stream));
+    B200_CUDA(cudaMemsetAsync(psi, 0, vbytes * n_shift, stream));                    // minvcg2.cc:118-122
+    rc = norm2_dev(chi, S_TMP0); if (rc) return rc;
+    rc = fetch_scalars(); if (rc) return rc;
+    const double chi_norm_sq = hs(0, S_TMP0);
+    int n_count = 0, converged = 1;
+    if (!(sqrt(chi_norm_sq) < 1.0e-5)) {                                             // fuzz, minvcg2.cc:135-148
+      MsState h;
+      memset(&h, 0, sizeof(h));
+      h.n_shift = n_shift; h.isz = 0;
+      for (int s = 0; s < n_shift; ++s) {
+        h.shift[s] = shifts[s]; h.rsd_sq[s] = chi_norm_sq * rsd[s] * rsd[s];
+        if (shifts[s] < shifts[h.isz]) h.isz = s;
+      }
+      B200_CUDA(cudaMemcpyAsync(ms_dev, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+      B200_CUDA(cudaStreamSynchronize(stream));                                      // h lives on this stack frame
+      B200_CUDA(cudaMemcpyAsync(W(3), chi, vbytes, cudaMemcpyDeviceToDevice, stream));   // r = p0 = p[s] = chi (:166-179)
+      B200_CUDA(cudaMemcpyAsync(W(2), chi, vbytes, cudaMemcpyDeviceToDevice, stream));
+      for (int s = 0; s < n_shift; ++s)
+        B200_CUDA(cudaMemcpyAsync((C*)ms_p->d + (size_t)s * nelem(), chi, vbytes, cudaMemcpyDeviceToDevice, stream));
+      ScalarSet sc{}; sc.rhs = 0; sc.reset_status = 1; sc.n = 2;
+      sc.slots[0] = S_RSDSQ; sc.vals[0] = -1.0;                                      // the fused |r|^2 finaliser must never stop the solve
+      sc.slots[1] = S_C; sc.vals[1] = chi_norm_sq;                                   // cp = |chi|^2
+      rc = set_scalars(sc); if (rc) return rc;
+      // b = -cp/d ; r += b M^dag M p0 ; z, bs ; psi[s] = -bs chi ; c = |r|^2       (:186-232) -- iteration "0"
+      rc = ms_iteration(0, 0); if (rc) return rc;
+      rc = fetch_scalars(); if (rc) return rc;
+      const double c0 = hs(0, S_CP);
+      converged = c0 < h.rsd_sq[h.isz];                                              // :240
+      if (!converged) {
+        int nc[MAX_RHS] = {0}, cv[MAX_RHS] = {0}, bd[MAX_RHS] = {0};
+        rc = poll_loop(psi, SOLVER_MULTISHIFT, max_iter, nc, cv, bd); if (rc) return rc;
+        if (bd[0] >= 90) return comm_timeout(bd[0]);
+        n_count = nc[0]; converged = cv[0];
+      }
+    }
+    B200_CUDA(cudaEventRecord(ev_t1, stream));
+    // per-shift true residuals, multi_syssolver_mdagm_cg.h:84-99
+    MsState hfin;
+    memset(&hfin, 0, sizeof(hfin));
+    if (n_count > 0) { B200_CUDA(cudaMemcpyAsync(&hfin, ms_dev, sizeof(hfin), cudaMemcpyDeviceToHost, stream)); B200_CUDA(cudaStreamSynchronize(stream)); }
+    for (int s = 0; s < n_shift; ++s) {
+      const C* ps = psi + (size_t)s * nelem();
+      rc = apply_M(W(1), ps, +1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+      rc = apply_M(W(4), W(1), -1, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+      shifted_resid_kernel<R><<<blas_grid, BLAS_BLOCK, 0, stream>>>(chi, W(4), ps, shifts[s], nelem(), make_red(0, blas_grid), scal + S_TMP2);
+      rc = launched("shifted_resid"); if (rc) return rc;
+      rc = fetch_scalars(); if (rc) return rc;
+      info[s].resid = sqrt(hs(0, S_TMP2));
+      info[s].rel_resid = chi_norm_sq > 0 ? info[s].resid / sqrt(chi_norm_sq) : 0.0;
+      info[s].n_count = n_count; info[s].converged = converged;
+      info[s].rsd_sq_iter = n_count > 0 ? hfin.css[s] : 0.0;
+    }
+    float ms_t = 0.f;
+    B200_CUDA(cudaEventElapsedTime(&ms_t, ev_t0, ev_t1));
+    const double gvol = (double)g.Vh * nranks();
+    // flops as MInvCG2_a books them: 2 M + 4*(4*Nc*Ns) for p0, r and the two norms + (6+2)*Nc*Ns per shift (minvcg2.cc:250-305)
+    const double flops_iter = 2.0 * 3792.0 + 4.0 * 48.0 + n_shift * 96.0;
+    for (int s = 0; s < n_shift; ++s) {
+      info[s].secs = ms_t * 1e-3; info[s].secs_total = info[s].secs;
+      info[s].gflops = ms_t > 0 ? flops_iter * gvol * n_count / (ms_t * 1e-3) * 1e-9 : 0.0;
+    }
+    return B200_OK;
+  }
+
   int iterate_begin(b200_field* psi_f, const b200_field* chi_f, int solver) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     int rc = ready(); if (rc) return rc;
     if (psi_f->nrhs != chi_f->nrhs) { set_error("b200_dev_iterate_begin: fields hold different numbers of right-hand sides"); return B200_ERR_ARG; }
     { int rcb = set_batch(psi_f->nrhs); if (rcb) return rcb; }
-    rc = need_ws(7, nb); if (rc) return rc;
+    rc = need_ws(nws(7), nb); if (rc) return rc;
     it_psi = (C*)psi_f->d; it_chi = (const C*)chi_f->d; it_k = 0; it_nb = nb;
     if (solver == B200_SOLVER_CG) { rc = cg_begin(it_psi, it_chi); if (rc) return rc; }
     else { rc = bicg_begin(it_psi, it_chi, +1); if (rc) return rc; }
@@ -835,6 +999,7 @@ class Engine : public EngineBase {
     if (const char* e = getenv("B200_QPROP_BATCH")) cap = std::min(cap, std::max(1, atoi(e)));
     if (cap < 1) { set_error("b200_qprop: not enough free device memory for even one right-hand side"); return B200_ERR_CUDA; }
     cap = std::min(cap, nrhs);
+    if (sym) cap = 1;     // the symmetric operator has no batched kernels: one right-hand side at a time
     const size_t cbbytes = (size_t)g.Vh * 24 * host_prec;
     b200_field *chi_e = nullptr, *chi_o = nullptr, *psi_o = nullptr, *t1 = nullptr, *t2 = nullptr;
     if ((rc = field_alloc(&chi_e, cap)) || (rc = field_alloc(&chi_o, cap)) || (rc = field_alloc(&psi_o, cap)) ||
@@ -854,6 +1019,26 @@ class Engine : public EngineBase {
         rc = field_upload(psi_o, ph + cbbytes, host_prec, j);
       }
       if (rc) break;
+      if (sym) {
+        // SymEvenOddPrecActQprop::operator(), seoprec_fermact_qprop.cc:45-89 with M_oe = A_oo^-1 (-1/2 Dslash),
+        // M_eo = A_ee^-1 (-1/2 Dslash) (lib/seoprec_linop.h:170-204):
+        //   chi'_e = A_ee^-1 chi_e ; chi'_o = A_oo^-1 (chi_o + 1/2 Dslash chi'_e) ; S psi_o = chi'_o ;
+        //   psi_e = chi'_e + 1/2 A_ee^-1 Dslash psi_o
+        if ((rc = clover_apply(t1, chi_e, 0, 1))) break;
+        if ((rc = dslash(t2, t1, +1, 1))) break;
+        if ((rc = axpby_dev((C*)chi_o->d, 1.0, (const C*)chi_o->d, 0.5, (const C*)t2->d))) break;
+        if ((rc = clover_apply(t2, chi_o, 1, 1))) break;
+        rc = invert(psi_o, t2, solver, rsd, max_iter, 0, &infos[i0]);
+        if (rc == B200_ERR_BREAKDOWN) { worst = rc; rc = B200_OK; }
+        if (rc) break;
+        if ((rc = dslash(chi_o, psi_o, +1, 0))) break;
+        if ((rc = clover_apply(t2, chi_o, 0, 1))) break;
+        if ((rc = axpby_dev((C*)chi_e->d, 1.0, (const C*)t1->d, 0.5, (const C*)t2->d))) break;
+        char* ph = (char*)psi_h + (size_t)i0 * 2 * cbbytes;
+        if ((rc = field_download(chi_e, ph, host_prec, 0))) break;
+        rc = field_download(psi_o, ph + cbbytes, host_prec, 0);
+        continue;
+      }
       // chi' = chi_o - D_oe A_ee^-1 chi_e = chi_o + 1/2 Dslash(A_ee^-1 chi_e)
       if ((rc = clover_apply(t1, chi_e, 0, 1))) break;
       if ((rc = dslash(t2, t1, +1, 1))) break;

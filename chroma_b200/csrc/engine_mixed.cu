@@ -138,6 +138,14 @@ static int adopt(Engine<float>& lo, Engine<double>& hi) {
   hi.launches += 3;
   B200_CUDA(cudaGetLastError());
   lo.have_trlog = false;
+  // symmetric preconditioning: the fp32 twin takes an fp32 copy of A_oo^-1 as well
+  lo.sym = hi.sym;
+  if (hi.sym) {
+    if (!lo.invclov_oo) B200_CUDA(cudaMalloc(&lo.invclov_oo, sizeof(float2) * 36 * Vh));
+    planes_d2f_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, hi.stream>>>(lo.invclov_oo, hi.invclov_oo, 36 * Vh);
+    hi.launches += 1;
+    B200_CUDA(cudaGetLastError());
+  }
   lo.operator_epoch = hi.operator_epoch;
   return B200_OK;
 }
@@ -161,8 +169,8 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   if (lo.stream != hi.stream || lo.operator_epoch != hi.operator_epoch) { rc = adopt(lo, hi); if (rc) return rc; }
   rc = hi.set_batch(1); if (rc) return rc;
   rc = lo.set_batch(1); if (rc) return rc;
-  rc = hi.need_ws(7); if (rc) return rc;
-  rc = lo.need_ws(5); if (rc) return rc;
+  rc = hi.need_ws(hi.nws(7)); if (rc) return rc;
+  rc = lo.need_ws(lo.nws(5)); if (rc) return rc;
   typedef double2 CD; typedef float2 CF;
   CD* psi = (CD*)psi_f->d; const CD* chi = (const CD*)chi_f->d;
   CD *tmp1 = hi.W(1), *tmp2 = hi.W(2), *bvec = hi.W(3), *xd = hi.W(4);

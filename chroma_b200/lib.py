@@ -13,6 +13,8 @@ B200_SINGLE, B200_DOUBLE = 4, 8
 B200_RECONS_NONE, B200_RECONS_12 = 18, 12
 B200_SOLVER_CG, B200_SOLVER_BICGSTAB = 0, 1
 B200_PLUS, B200_MINUS = 1, -1
+B200_PRECOND_ASYMMETRIC, B200_PRECOND_SYMMETRIC = 0, 1
+B200_MAX_SHIFTS = 32
 B200_OK, B200_ERR_ARG, B200_ERR_CUDA, B200_ERR_STATE, B200_ERR_BREAKDOWN, B200_ERR_COMM = 0, 1, 2, 3, 4, 5
 
 
@@ -58,12 +60,15 @@ SYMBOLS = {
     "b200_make_clover": (_i, [_vp, _d, _d, _d, _i, _i]),
     "b200_get_clover": (_i, [_vp, _vp, _vp, _i]),
     "b200_clover_logdet": (_i, [_vp, C.POINTER(_d)]),
+    "b200_clover_logdet_oo": (_i, [_vp, C.POINTER(_d)]),
+    "b200_set_preconditioning": (_i, [_vp, _i]),
     "b200_dslash": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "b200_clover_apply": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "b200_clover_matpc": (_i, [_vp, _vp, _vp, _i, _i]),
     "b200_invert": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_invert_mdagm": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_invert_reliable": (_i, [_vp, _vp, _vp, _i, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
+    "b200_invert_multishift": (_i, [_vp, C.POINTER(_vp), _vp, _i, _i, C.POINTER(_d), C.POINTER(_d), _i, C.POINTER(SolveInfo)]),
     "b200_qprop": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_field_alloc": (_i, [_vp, C.POINTER(_vp)]),
     "b200_field_free": (None, [_vp, _vp]),
@@ -83,6 +88,7 @@ SYMBOLS = {
     "b200_dev_invert": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_dev_invert_mdagm": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_dev_invert_reliable": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
+    "b200_dev_invert_multishift": (_i, [_vp, _vp, _vp, _i, C.POINTER(_d), C.POINTER(_d), _i, C.POINTER(SolveInfo)]),
     "b200_dev_iterate_begin": (_i, [_vp, _vp, _vp, _i]),
     "b200_dev_iterate": (_i, [_vp, _i, _i]),
     "b200_stream": (_vp, [_vp]),

@@ -125,10 +125,15 @@ class Context:
         L.check(self.lib.b200_get_clover(self.h, _ptr(clov), _ptr(inv), _prec_of(clov)))
         return clov, inv
 
-    def clover_logdet(self):
+    def clover_logdet(self, cb=0):
         out = C.c_double()
-        L.check(self.lib.b200_clover_logdet(self.h, C.byref(out)))
+        fn = self.lib.b200_clover_logdet_oo if cb else self.lib.b200_clover_logdet
+        L.check(fn(self.h, C.byref(out)))
         return out.value
+
+    def set_preconditioning(self, symmetric):
+        """False: EvenOddPrecCloverLinOp (default); True: SymEvenOddPrecCloverLinOp (seoprec_clover_linop_w.cc:147-193)."""
+        L.check(self.lib.b200_set_preconditioning(self.h, L.B200_PRECOND_SYMMETRIC if symmetric else L.B200_PRECOND_ASYMMETRIC))
 
     # -- host-buffer operators (what the adapter calls)
     def _cb_out(self, like):
@@ -176,6 +181,21 @@ class Context:
         L.check(self.lib.b200_invert_reliable(self.h, _ptr(psi), _ptr(chi_odd), _prec_of(chi_odd), float(rsd), float(delta), int(max_iter),
                                               int(bool(mdagm)), C.byref(info)))
         return psi.reshape(self.Vh, 4, 3, 2), info
+
+    def invert_multishift(self, chi_odd, shifts, rsd, max_iter=1000):
+        """(M^dag M + shifts[s]) psi[s] = chi (MInvCG2_a behind MdagMMultiSysSolverCG).  rsd: scalar or one per shift.
+        Returns (psi [n_shift,Vh,4,3,2], [SolveInfo per shift])."""
+        chi_odd = np.ascontiguousarray(chi_odd)
+        shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+        n = len(shifts)
+        rsd = np.ascontiguousarray(np.broadcast_to(np.asarray(rsd, dtype=np.float64), (n,)))
+        psi = np.zeros((n, self.Vh, 4, 3, 2), dtype=chi_odd.dtype)
+        ptrs = (C.c_void_p * n)(*[psi[s].ctypes.data for s in range(n)])
+        infos = (L.SolveInfo * n)()
+        L.check(self.lib.b200_invert_multishift(self.h, ptrs, _ptr(chi_odd), _prec_of(chi_odd), n,
+                                                shifts.ctypes.data_as(C.POINTER(C.c_double)), rsd.ctypes.data_as(C.POINTER(C.c_double)),
+                                                int(max_iter), infos))
+        return psi, list(infos)
 
     def qprop(self, chi_full, psi0_full=None, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=1000):
         """chi_full: [nrhs, V, 4, 3, 2] full-lattice sources -> full-lattice solutions of the UNPRECONDITIONED operator."""
@@ -241,6 +261,16 @@ class Context:
         info = L.SolveInfo()
         L.check(self.lib.b200_dev_invert_reliable(self.h, psi.h, chi.h, float(rsd), float(delta), int(max_iter), int(bool(mdagm)), C.byref(info)))
         return info
+
+    def dev_invert_multishift(self, psi, chi, shifts, rsd, max_iter=1000):
+        """psi: a batched field with >= len(shifts) vectors; chi: an ordinary field."""
+        shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+        n = len(shifts)
+        rsd = np.ascontiguousarray(np.broadcast_to(np.asarray(rsd, dtype=np.float64), (n,)))
+        infos = (L.SolveInfo * n)()
+        L.check(self.lib.b200_dev_invert_multishift(self.h, psi.h, chi.h, n, shifts.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    rsd.ctypes.data_as(C.POINTER(C.c_double)), int(max_iter), infos))
+        return list(infos)
 
     def dev_iterate_begin(self, psi, chi, solver):
         L.check(self.lib.b200_dev_iterate_begin(self.h, psi.h, chi.h, int(solver)))
@@ -309,6 +339,10 @@ class SysSolverB200CloverParams:
     RsdToleranceFactor: float = 10.0
     SilentFail: bool = False
     Verbose: bool = False
+    # False: the plugin was handed an EvenOddPrecCloverLinOp (clover_fermact_w.cc); True: a SymEvenOddPrecCloverLinOp
+    # (seoprec_clover_fermact_w.cc) -- the operator solved must be the caller's A so that its residual check passes
+    # (cf. AsymmetricLinop of the QUDA plugin, syssolver_linop_clover_quda_w.h:318-325)
+    SymmetricLinop: bool = False
 
 
 @dataclass
@@ -348,6 +382,8 @@ class LinOpSysSolverB200Clover:
         else:
             dm, cr, ct = cp.derived()
             self.ctx.make_clover(dm, cr, ct, aniso=cp.anisoParam.anisoP, t_dir=cp.anisoParam.t_dir)
+        if params.SymmetricLinop:
+            self.ctx.set_preconditioning(True)
         self.solver = L.B200_SOLVER_CG if params.SolverType == "CG" else L.B200_SOLVER_BICGSTAB
         self.last_info = None
 
@@ -371,3 +407,20 @@ class LinOpSysSolverB200Clover:
 
     def close(self):
         self.ctx.close()
+
+
+class MdagMMultiSysSolverB200Clover(LinOpSysSolverB200Clover):
+    """Mirror of the multi-shift plugin: MdagMMultiSysSolverCG::operator()(psi[], shifts, chi)
+    (lib/actions/ferm/invert/multi_syssolver_mdagm_cg.h:58-105), registered in TheMdagMFermMultiSystemSolverFactory
+    (multi_syssolver_mdagm_factory.h) under the same `B200_CLOVER_INVERTER` name.  RsdTarget applies to every shift
+    (multi_syssolver_mdagm_cg.h:62-70 broadcasts a single RsdCG)."""
+
+    def __call__(self, shifts, chi_odd):
+        psi, infos = self.ctx.invert_multishift(chi_odd, shifts, self.p.RsdTarget, self.p.MaxIter)
+        self.last_info = infos
+        if not infos[0].converged and not self.p.SilentFail:
+            raise SolverFailure("B200 multi-shift CG: too many iterations (%d)" % infos[0].n_count)   # minvcg2.cc:365-367
+        worst = max(i.rel_resid for i in infos)
+        if worst > self.p.RsdToleranceFactor * self.p.RsdTarget and not self.p.SilentFail:
+            raise SolverFailure("B200 multi-shift CG: rel resid %g > %g * %g" % (worst, self.p.RsdToleranceFactor, self.p.RsdTarget))
+        return psi, SystemSolverResults(n_count=infos[0].n_count, resid=max(i.resid for i in infos))

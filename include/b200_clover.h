@@ -29,9 +29,11 @@
  *  - "dev" entry points work on device-resident checkerboard fields (b200_field) in the engine's
  *    site-major SoA layout; they exist so a caller can keep vectors on the GPU between calls
  *    (the way QUDA's BUILD_QUDA_DEVIFACE_SPINOR path does, syssolver_linop_clover_quda_w.cc:78-92).
- *  - The operator is Chroma's ASYMMETRIC even-odd preconditioned clover operator on the odd
+ *  - By default the operator is Chroma's ASYMMETRIC even-odd preconditioned clover operator on the odd
  *    checkerboard, M = A_oo - 1/4 D_oe A_ee^-1 D_eo (eoprec_clover_linop_w.cc:142-187), so that
- *    the adapter's residual check with Chroma's own linop passes.
+ *    the adapter's residual check with Chroma's own linop passes.  b200_set_preconditioning switches every
+ *    entry point to the SYMMETRIC one, M = 1 - 1/4 A_oo^-1 D_oe A_ee^-1 D_eo (seoprec_clover_linop_w.cc:147-193),
+ *    for plugins created with a SymEvenOddPrecCloverLinOp.
  *  - There is no CPU fallback: every entry point fails with B200_ERR_CUDA if no sm_100 device.
  */
 #ifndef B200_CLOVER_H
@@ -50,6 +52,8 @@ enum { B200_SINGLE = 4, B200_DOUBLE = 8 };            /* bytes per real */
 enum { B200_RECONS_NONE = 18, B200_RECONS_12 = 12 };   /* reals stored per link; enum_quda_io.h:77-80 */
 enum { B200_SOLVER_CG = 0, B200_SOLVER_BICGSTAB = 1 }; /* enum_quda_io.h:21-26 */
 enum { B200_PLUS = 1, B200_MINUS = -1 };               /* enum PlusMinus */
+enum { B200_PRECOND_ASYMMETRIC = 0, B200_PRECOND_SYMMETRIC = 1 }; /* EvenOddPrecCloverLinOp / SymEvenOddPrecCloverLinOp */
+enum { B200_MAX_SHIFTS = 32 };                         /* most shifts one b200_invert_multishift call takes */
 
 enum {
   B200_OK = 0,
@@ -123,6 +127,20 @@ int b200_make_clover(b200_ctx* ctx, double diag_mass, double clov_r, double clov
 int b200_get_clover(b200_ctx* ctx, void* clov_tri, void* invclov_tri, int host_prec);
 /* sum over cb-0 sites of log|det A_ee| from the LDL^dagger pass (tr_log_diag, clover_term_qdp_w.h:737) */
 int b200_clover_logdet(b200_ctx* ctx, double* tr_log_ee);
+/* ... and of log|det A_oo| over the cb-1 sites (symmetric preconditioning only: invclov.choles(1),
+ * seoprec_clover_linop_w.cc:31-33; logDetOddOddLinOp of the symmetric log-det operator) */
+int b200_clover_logdet_oo(b200_ctx* ctx, double* tr_log_oo);
+
+/* Choose the even-odd preconditioning every later call uses (default B200_PRECOND_ASYMMETRIC):
+ *   B200_PRECOND_ASYMMETRIC  M = A_oo - 1/4 D_oe A_ee^-1 D_eo        EvenOddPrecCloverLinOp (eoprec_clover_linop_w.cc:142-187)
+ *   B200_PRECOND_SYMMETRIC   M = 1 - 1/4 A_oo^-1 D_oe A_ee^-1 D_eo   SymEvenOddPrecCloverLinOp::operator()
+ *                         (seoprec_clover_linop_w.cc:147-193; M^dag = 1 - 1/4 D^dag A_ee^-1 D^dag A_oo^-1)
+ * A_oo^-1 is derived on the device from the clover term that is (or later gets) loaded or built -- the LDL^dagger
+ * inverse of clover_term_qdp_w.h:619-846 on cb 1, i.e. SymEvenOddPrecCloverLinOp::create's invclov.choles(1)
+ * (seoprec_clover_linop_w.cc:31-33).  With the symmetric operator b200_clover_apply accepts inverse = 1 on cb 1,
+ * b200_qprop follows SymEvenOddPrecActQprop (seoprec_fermact_qprop.cc:41-100), and batched (multi-RHS) fields are
+ * refused (B200_ERR_ARG): right-hand sides are then solved one at a time. */
+int b200_set_preconditioning(b200_ctx* ctx, int preconditioning);
 
 /* Wilson hopping term on one checkerboard: out (parity out_cb) = D in (parity 1-out_cb).
  * Replaces Dslash<REAL>::operator() (cpp_dslash_scalar.h:20-105; cpp_dslash_scalar_64bit.cc:35-65)
@@ -164,6 +182,17 @@ int b200_invert_mdagm(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_hos
 int b200_invert_reliable(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec, double rsd_target,
                          double delta, int max_iter, int mdagm, b200_solve_info* info);
 
+/* Multi-shift CG: (M^dag M + shifts[s]) psi[s] = chi for s = 0..n_shift-1 from one Krylov sequence -- MInvCG2_a
+ * (lib/actions/ferm/invert/minvcg2.cc:74-373) behind MdagMMultiSysSolverCG::operator()
+ * (multi_syssolver_mdagm_cg.h:58-105; factory TheMdagMFermMultiSystemSolverFactory, used by the rational monomials of RHMC).
+ * psi_odd_host: n_shift host pointers, every psi[s] is zeroed first like the reference (:118-122); rsd_target: one
+ * relative target per shift; the solve stops when every shift's recurrence residual c z_s^2 < rsd_s^2 |chi|^2 (:326-340).
+ * info: n_shift entries -- common n_count, and the TRUE residual |chi - (M^dag M + shift_s) psi_s| of each shift
+ * (the check the shell logs, multi_syssolver_mdagm_cg.h:84-99).  Not converging within max_iter is reported as
+ * info->converged = 0 (the reference aborts, minvcg2.cc:365-367).  1 <= n_shift <= B200_MAX_SHIFTS. */
+int b200_invert_multishift(b200_ctx* ctx, void* const psi_odd_host[], const void* chi_odd_host, int host_prec, int n_shift,
+                           const double* shifts, const double* rsd_target, int max_iter, b200_solve_info* info);
+
 /* Full-lattice propagator solve for nrhs right-hand sides (the sequential 12 spin-colour loop of
  * quarkprop4_w.cc:70-117 with the even-odd source preparation and solution reconstruction of
  * eoprec_fermact_qprop.cc:41-80 done on the device).  chi/psi: REAL[nrhs][V][4][3][2].  The right-hand sides are solved
@@ -199,6 +228,10 @@ int b200_dev_invert_mdagm(b200_ctx* ctx, b200_field* psi, const b200_field* chi,
                           int max_iter, b200_solve_info* info);
 int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd_target, double delta,
                              int max_iter, int mdagm, b200_solve_info* info);
+/* psi: a batched field (b200_mfield_alloc) holding at least n_shift vectors -- up to B200_MAX_SHIFTS; fields with more
+ * than 12 vectors are storage only, the batched operators refuse them -- chi: an ordinary field */
+int b200_dev_invert_multishift(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int n_shift, const double* shifts,
+                               const double* rsd_target, int max_iter, b200_solve_info* info);
 /* Benchmark leg: set up the solver recurrences (r, p, ... as the solver's own preamble does), then run exactly
  * n_iter iterations of the loop body per call with the convergence test disabled. */
 int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver);

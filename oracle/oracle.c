@@ -486,6 +486,7 @@ typedef struct {
   double* invclov;    /* copy of A with cb 0 inverted (A_ee^-1) */
   double* tmp1; double* tmp2;
   double* tr_log_diag;
+  int sym;            /* 0: EvenOddPrecCloverLinOp, 1: SymEvenOddPrecCloverLinOp (invclov cb 1 inverted too) */
 } orc_op;
 
 /* EvenOddPrecCloverLinOp::create, eoprec_clover_linop_w.cc:19-39: clov.create (mesField +
@@ -534,8 +535,10 @@ void orc_op_dslash(const orc_op* op, double* chi, const double* psi, int isign, 
 /* EvenOddPrecCloverLinOp::operator(), eoprec_clover_linop_w.cc:142-187 (no twisted mass):
  * tmp1 = D_eo psi; tmp2 = A_ee^-1 tmp1; tmp1 = D_oe tmp2; chi = A_oo psi; chi -= 1/4 tmp1.
  * Fields are full-lattice arrays; only the odd half of chi is written. */
+static void orc_sym_apply(orc_op* op, double* chi, const double* psi, int isign);
 void orc_op_apply(orc_op* op, double* chi, const double* psi, int isign) {
   int Vh = op->g->Vh;
+  if (op->sym) { orc_sym_apply(op, chi, psi, isign); return; }
   orc_op_dslash(op, op->tmp1, psi, isign, 0);
   orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 0);
   orc_op_dslash(op, op->tmp1, op->tmp2, isign, 1);
@@ -544,6 +547,49 @@ void orc_op_apply(orc_op* op, double* chi, const double* psi, int isign) {
   size_t n = (size_t)Vh*SPINOR;
 #pragma omp parallel for
   for (size_t i = 0; i < n; ++i) c[i] += -0.25*t[i];
+}
+
+/* ------------------------------------------------------------------------- */
+/* SymEvenOddPrecCloverLinOp  (section 8 f4)                                   */
+/* ------------------------------------------------------------------------- */
+/* SymEvenOddPrecCloverLinOp::create, seoprec_clover_linop_w.cc:16-41: as the asymmetric create plus
+ * invclov.choles(1).  Switching it on inverts the cb-1 half of invclov in place (once); tr_log_diag then holds
+ * log|det| on both checkerboards (logDetEvenEvenLinOp + logDetOddOddLinOp of the symmetric log-det operator). */
+void orc_op_set_symmetric(orc_op* op, int sym) {
+  if (sym && !op->sym) orc_ldagdlinv(op->g, op->invclov, 1, op->tr_log_diag);
+  if (!sym && op->sym) {   /* restore A_oo in invclov so that a later switch inverts it again */
+    size_t n = (size_t)op->g->Vh*CLOV;
+    memcpy(op->invclov + n, op->clov + n, n*sizeof(double));
+  }
+  op->sym = sym ? 1 : 0;
+}
+int orc_op_is_symmetric(const orc_op* op) { return op->sym; }
+double orc_op_tr_log(const orc_op* op, int cb) {
+  double s = 0; int Vh = op->g->Vh;
+  for (int i = 0; i < Vh; ++i) s += op->tr_log_diag[cb*Vh + i];
+  return s;
+}
+
+/* SymEvenOddPrecCloverLinOp::operator(), seoprec_clover_linop_w.cc:147-193 (no twisted mass):
+ * PLUS : tmp1 = D_eo psi; tmp2 = A_ee^-1 tmp1; tmp1 = D_oe tmp2; tmp2 = A_oo^-1 tmp1
+ * MINUS: tmp1 = A_oo^-1 psi; tmp2 = D_eo^dag tmp1; tmp1 = A_ee^-1 tmp2; tmp2 = D_oe^dag tmp1
+ * chi = psi - 1/4 tmp2 on rb[1]. */
+static void orc_sym_apply(orc_op* op, double* chi, const double* psi, int isign) {
+  int Vh = op->g->Vh; size_t n = (size_t)Vh*SPINOR;
+  if (isign > 0) {
+    orc_op_dslash(op, op->tmp1, psi, isign, 0);
+    orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 0);
+    orc_op_dslash(op, op->tmp1, op->tmp2, isign, 1);
+    orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 1);
+  } else {
+    orc_clover_apply(op->g, op->tmp1, psi, op->invclov, 1);
+    orc_op_dslash(op, op->tmp2, op->tmp1, isign, 0);
+    orc_clover_apply(op->g, op->tmp1, op->tmp2, op->invclov, 0);
+    orc_op_dslash(op, op->tmp2, op->tmp1, isign, 1);
+  }
+  const double* t = op->tmp2 + n; const double* x = psi + n; double* c = chi + n;
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) c[i] = x[i] + -0.25*t[i];
 }
 
 /* ------------------------------------------------------------------------- */
@@ -643,6 +689,98 @@ int orc_solve_cg(orc_op* op, const double* chi, double* psi, double RsdCG, int M
 }
 
 /* ------------------------------------------------------------------------- */
+/* MInvCG2_a, lib/actions/ferm/invert/minvcg2.cc:74-373  (section 8 f4)       */
+/* ------------------------------------------------------------------------- */
+/* Multi-shift CG: (M^dag M + shifts[s]) psi[s] = chi on rb[1] for all s at once.  psi = n_shift full-lattice
+ * arrays back to back (all zeroed on entry, as the reference does).  Returns n_count. */
+int orc_minvcg2(orc_op* op, const double* chi, double* psi, const double* shifts, const double* RsdCG,
+                int n_shift, int MaxCG) {
+  const orc_geom* g = op->g;
+  size_t V = (size_t)g->V, n = (size_t)g->Vh*SPINOR, off = n, FS = V*SPINOR;
+  int isz = 0, n_count = 0, s, k;
+  for (s = 1; s < n_shift; ++s) if (shifts[s] < shifts[isz]) isz = s;
+  memset(psi, 0, sizeof(double)*FS*n_shift);
+  double chi_norm_sq = norm2_odd(g, chi);
+  if (sqrt(chi_norm_sq) < 1.0e-5) return 0;                               /* fuzz, minvcg2.cc:135-148 */
+  double* rsd_sq = (double*)malloc(sizeof(double)*n_shift);
+  double cp = chi_norm_sq;
+  for (s = 0; s < n_shift; ++s) rsd_sq[s] = cp*RsdCG[s]*RsdCG[s];
+  double* r = (double*)calloc(FS, sizeof(double));
+  double* p0 = (double*)calloc(FS, sizeof(double));
+  double* p = (double*)calloc(FS*n_shift, sizeof(double));
+  double* Mp = (double*)calloc(FS, sizeof(double));
+  double* MMp = (double*)calloc(FS, sizeof(double));
+  memcpy(r + off, chi + off, n*sizeof(double));
+  memcpy(p0 + off, chi + off, n*sizeof(double));
+  for (s = 0; s < n_shift; ++s) memcpy(p + s*FS + off, chi + off, n*sizeof(double));
+  orc_op_apply(op, Mp, p0, +1);
+  double d = norm2_odd(g, Mp);
+  orc_op_apply(op, MMp, Mp, -1);
+  double b = -cp/d;
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) r[off+i] += b*MMp[off+i];
+  double* bs = (double*)malloc(sizeof(double)*n_shift);
+  double* z[2]; z[0] = (double*)malloc(sizeof(double)*n_shift); z[1] = (double*)malloc(sizeof(double)*n_shift);
+  int* convsP = (int*)calloc(n_shift, sizeof(int));
+  int iz = 1;
+  for (s = 0; s < n_shift; ++s) {
+    z[1-iz][s] = 1.0;
+    z[iz][s] = 1.0/(1.0 - shifts[s]*b);
+    bs[s] = b*z[iz][s];
+  }
+  for (s = 0; s < n_shift; ++s) {
+    double* ps = psi + s*FS; double f = bs[s];
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) ps[off+i] = -f*chi[off+i];
+  }
+  double c = norm2_odd(g, r);
+  int convP = c < rsd_sq[isz];
+  for (k = 1; k <= MaxCG && !convP; ++k) {
+    double a = c/cp;
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) p0[off+i] = r[off+i] + a*p0[off+i];
+    for (s = 0; s < n_shift; ++s) if (!convsP[s]) {
+      double as = a*z[iz][s]*bs[s]/(z[1-iz][s]*b), zz = z[iz][s];
+      double* pp = p + s*FS;
+#pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) pp[off+i] = zz*r[off+i] + as*pp[off+i];
+    }
+    cp = c;
+    orc_op_apply(op, Mp, p0, +1);
+    d = norm2_odd(g, Mp);
+    orc_op_apply(op, MMp, Mp, -1);
+    double bp = b;
+    b = -cp/d;
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) r[off+i] += b*MMp[off+i];
+    c = norm2_odd(g, r);
+    iz = 1 - iz;
+    for (s = 0; s < n_shift; ++s) if (!convsP[s]) {
+      double z0 = z[1-iz][s], z1 = z[iz][s];
+      z[iz][s] = z0*z1*bp;
+      z[iz][s] /= b*a*(z1 - z0) + z1*bp*(1.0 - shifts[s]*b);
+      bs[s] = b*z[iz][s]/z0;
+    }
+    for (s = 0; s < n_shift; ++s) if (!convsP[s]) {
+      double f = bs[s]; double* ps = psi + s*FS; const double* pp = p + s*FS;
+#pragma omp parallel for
+      for (size_t i = 0; i < n; ++i) ps[off+i] -= f*pp[off+i];
+    }
+    convP = 1;
+    for (s = 0; s < n_shift; ++s) {
+      if (!convsP[s]) {
+        double css = c*z[iz][s]*z[iz][s];
+        convsP[s] = css < rsd_sq[s];
+      }
+      convP &= convsP[s];
+    }
+    n_count = k;
+  }
+  free(rsd_sq); free(r); free(p0); free(p); free(Mp); free(MMp); free(bs); free(z[0]); free(z[1]); free(convsP);
+  return n_count;
+}
+
+/* ------------------------------------------------------------------------- */
 /* InvBiCGStab_a, lib/actions/ferm/invert/invbicgstab.cc:10-202                */
 /* ------------------------------------------------------------------------- */
 /* Returns n_count (MaxBiCGStab if not converged), -1 on breakdown (the reference aborts). */
@@ -721,6 +859,20 @@ int orc_solve_bicgstab(orc_op* op, const double* chi, double* psi, double Rsd, i
  * evenOddLinOp = -1/2 D_eo, eoprec_clover_linop_w.cc:98-133) */
 void orc_qprop_prepare(orc_op* op, double* chi_prime, const double* chi) {
   int Vh = op->g->Vh; size_t n = (size_t)Vh*SPINOR;
+  if (op->sym) {
+    /* SymEvenOddPrecActQprop::operator() step (i), seoprec_fermact_qprop.cc:45-62:
+     * chi' = L^-1 M_diag^-1 chi:  chi'_e = A_ee^-1 chi_e;  chi'_o = A_oo^-1 chi_o - M_oe chi'_e with
+     * M_oe = A_oo^-1 (-1/2 Dslash)  (lib/seoprec_linop.h:188-204).  Both halves of chi_prime are written. */
+    orc_clover_apply(op->g, chi_prime, chi, op->invclov, 0);
+    orc_clover_apply(op->g, chi_prime, chi, op->invclov, 1);
+    orc_op_dslash(op, op->tmp1, chi_prime, +1, 1);
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) op->tmp1[n+i] *= -0.5;
+    orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 1);
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) chi_prime[n+i] -= op->tmp2[n+i];
+    return;
+  }
   orc_clover_apply(op->g, op->tmp1, chi, op->invclov, 0);
   orc_op_dslash(op, op->tmp2, op->tmp1, +1, 1);
 #pragma omp parallel for
@@ -729,6 +881,17 @@ void orc_qprop_prepare(orc_op* op, double* chi_prime, const double* chi) {
 /* psi_e = A_ee^-1 (chi_e - D_eo psi_o), with D_eo = -1/2 Dslash */
 void orc_qprop_reconstruct(orc_op* op, double* psi, const double* chi) {
   int Vh = op->g->Vh; size_t n = (size_t)Vh*SPINOR;
+  if (op->sym) {
+    /* step (ii), seoprec_fermact_qprop.cc:72-89; here chi is the PREPARED source chi' (its even half is the trivial
+     * solution): psi_e = chi'_e - M_eo psi_o with M_eo = A_ee^-1 (-1/2 Dslash)  (lib/seoprec_linop.h:170-186) */
+    orc_op_dslash(op, op->tmp1, psi, +1, 0);
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) op->tmp1[i] *= -0.5;
+    orc_clover_apply(op->g, op->tmp2, op->tmp1, op->invclov, 0);
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) psi[i] = chi[i] - op->tmp2[i];
+    return;
+  }
   orc_op_dslash(op, op->tmp1, psi, +1, 0);
 #pragma omp parallel for
   for (size_t i = 0; i < n; ++i) op->tmp2[i] = chi[i] + 0.5*op->tmp1[i];

@@ -47,6 +47,7 @@ def lib():
         L.orc_op_invclov.restype = c_dbl_p
         L.orc_op_packed_gauge.restype = c_dbl_p
         L.orc_norm2_odd.restype = C.c_double
+        L.orc_op_tr_log.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -194,6 +195,40 @@ class Op:
 
     def _arr(self, ptr, shape):
         return np.ctypeslib.as_array(ptr, shape=shape)
+
+    def set_symmetric(self, sym=True):
+        """Switch to SymEvenOddPrecCloverLinOp (seoprec_clover_linop_w.cc:16-41, 147-193): 1 - 1/4 A_oo^-1 D A_ee^-1 D.
+        apply(), the solvers and the qprop prepare / reconstruct steps all follow the switch."""
+        lib().orc_op_set_symmetric(self.h, C.c_int(int(bool(sym))))
+
+    @property
+    def symmetric(self):
+        return bool(lib().orc_op_is_symmetric(self.h))
+
+    def tr_log(self, cb):
+        """sum over checkerboard cb of log|det A| (cb 1 only after set_symmetric)."""
+        return float(lib().orc_op_tr_log(self.h, C.c_int(cb)))
+
+    def minvcg2(self, chi, shifts, rsd, maxit):
+        """MInvCG2_a (minvcg2.cc:74-373): (M^dag M + shifts[s]) psi[s] = chi.  Returns (psi[n_shift], n_count)."""
+        shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+        rsd = np.ascontiguousarray(np.broadcast_to(np.asarray(rsd, dtype=np.float64), shifts.shape))
+        chi = np.ascontiguousarray(chi, dtype=np.float64)
+        psi = np.zeros((len(shifts),) + chi.shape)
+        n = lib().orc_minvcg2(self.h, _p(chi), _p(psi), _p(shifts), _p(rsd), C.c_int(len(shifts)), C.c_int(maxit))
+        return psi, n
+
+    def solve_multishift(self, chi, shifts, rsd, maxit):
+        """MdagMMultiSysSolverCG::operator() (multi_syssolver_mdagm_cg.h:58-105): MInvCG2 and the per-shift relative
+        residuals |chi - (M^dag M + shift) psi| / |chi| it logs."""
+        psi, n = self.minvcg2(chi, shifts, rsd, maxit)
+        Vh = self.Vh
+        cn = np.sqrt(np.sum(np.asarray(chi)[Vh:] ** 2))
+        rel = []
+        for s, sh in enumerate(shifts):
+            r = chi - self.apply(self.apply(psi[s], +1), -1) - sh * psi[s]
+            rel.append(float(np.sqrt(np.sum(r[Vh:] ** 2)) / cn))
+        return psi, n, rel
 
     @property
     def clov(self):

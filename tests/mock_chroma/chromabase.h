@@ -21,6 +21,7 @@ inline Real operator*(const Real& a, const Real& b) { return Real(a.v * b.v); }
 inline Real operator/(const Real& a, const Real& b) { return Real(a.v / b.v); }
 struct Boolean { bool b; };
 inline Boolean operator>(const Real& a, const Real& b) { Boolean r = {a.v > b.v}; return r; }
+inline Real operator+(const Real& a, const Real& b) { return Real(a.v + b.v); }
 inline double toDouble(const Real& r) { return r.v; }
 inline bool toBool(const Boolean& b) { return b.b; }
 inline Real sqrt(const Real& r) { return Real(std::sqrt(r.v)); }
@@ -31,6 +32,7 @@ template <typename T> class multi1d {
   multi1d() {}
   explicit multi1d(int n) : d(n) {}
   int size() const { return (int)d.size(); }
+  void resize(int n) { d.resize(n); }
   T& operator[](int i) { return d[i]; }
   const T& operator[](int i) const { return d[i]; }
  private:
@@ -53,6 +55,7 @@ template <typename L> struct SubsetProxy {
   L& l;
   SubsetProxy& operator=(const L&) { return *this; }
   SubsetProxy& operator-=(const L&) { return *this; }
+  SubsetProxy& operator*=(const Real&) { return *this; }   // chi[rb[0]] *= mhalf, seoprec_clover_linop_w.cc:113
   SubsetProxy& operator=(const Zero&) { return *this; }
 };
 class LatticeFermion {

@@ -10,7 +10,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ADAPTER = os.path.join(ROOT, "chroma_adapter")
-SOURCES = ["syssolver_b200_clover_params.cc", "syssolver_linop_clover_b200_w.cc", "syssolver_mdagm_clover_b200_w.cc"]
+SOURCES = ["syssolver_b200_clover_params.cc", "syssolver_linop_clover_b200_w.cc", "syssolver_mdagm_clover_b200_w.cc",
+           "multi_syssolver_mdagm_clover_b200_w.cc"]
 
 
 @pytest.fixture(scope="module")

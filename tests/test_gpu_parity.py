@@ -11,8 +11,8 @@ import pytest
 
 from chroma_b200 import fields
 from chroma_b200 import lib as L
-from chroma_b200.solver import (CloverFermActParams, AnisoParam, Context, LinOpSysSolverB200Clover, SolverFailure,
-                                SysSolverB200CloverParams)
+from chroma_b200.solver import (CloverFermActParams, AnisoParam, Context, LinOpSysSolverB200Clover,
+                                MdagMMultiSysSolverB200Clover, SolverFailure, SysSolverB200CloverParams)
 
 pytestmark = pytest.mark.gpu
 
@@ -386,6 +386,184 @@ def test_qprop_batches(oracle, monkeypatch):
         assert np.linalg.norm(r) / np.linalg.norm(srcs[i]) < 1e-8
         assert np.abs(sol5[i] - sol12[i]).max() < 1e-9 and np.abs(sol1[i] - sol12[i]).max() < 1e-9
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------- SURVEY section 8 (f4)
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("recon,aniso,gpu_clover", [(L.B200_RECONS_NONE, False, False), (L.B200_RECONS_12, True, True)])
+def test_symmetric_operator_parity(oracle, prec, recon, aniso, gpu_clover):
+    """SymEvenOddPrecCloverLinOp::operator() (seoprec_clover_linop_w.cc:147-193) PLUS and MINUS against the restatement,
+    A_oo^-1 built on the device (invclov.choles(1)) against the restated ldagdlinv, log det A_oo, and the switch back."""
+    latt = (6, 4, 4, 8)
+    u, op, ctx, cp = setup(oracle, latt, prec, recon=recon, aniso=aniso, gpu_clover=gpu_clover)
+    Vh = ctx.Vh
+    psi = fields.gaussian_fermion(latt, seed=21, cb=1)
+    x = psi[Vh:].astype(NP[prec])
+    asym_plus = ctx.matpc(x, +1)
+    ctx.set_preconditioning(True)
+    op.set_symmetric(True)
+    tol = TOL[prec] * (10 if recon == L.B200_RECONS_12 else 1)
+    for isign in (+1, -1):
+        got = ctx.matpc(x, isign)
+        want = op.apply(psi, isign)[Vh:]
+        assert rel_site_err(got, want) < tol, (isign, rel_site_err(got, want))
+    g = oracle.Geom(latt)
+    got = ctx.clover_apply(x, 1, inverse=True)
+    want = oracle.clover_apply(g, psi, op.invclov, 1)[Vh:]
+    assert rel_site_err(got, want) < (1e-12 if prec == "double" else 2e-6)
+    if prec == "double":
+        assert ctx.clover_logdet(1) == pytest.approx(op.tr_log(1), rel=1e-12)
+    # device-resident path + gamma5-hermiticity <chi, S psi> = <S^dag chi, psi>
+    chi = fields.gaussian_fermion(latt, seed=22, cb=1)
+    fx, fc, fo, fo2 = ctx.field(x), ctx.field(chi[Vh:].astype(NP[prec])), ctx.field(), ctx.field()
+    ctx.dev_matpc(fo, fx, +1)
+    ctx.dev_matpc(fo2, fc, -1)
+    a, b = ctx.dev_inner(fc, fo), ctx.dev_inner(fo2, fx)
+    assert abs(a - b) < (1e-11 if prec == "double" else 1e-4) * abs(a)
+    # batched fields are refused, the asymmetric operator comes back bit-identical
+    with pytest.raises(L.B200Error) as e:
+        ctx.dev_matpc(ctx.mfield(2), ctx.mfield(2), +1)
+    assert e.value.code == L.B200_ERR_ARG
+    ctx.set_preconditioning(False)
+    assert np.array_equal(ctx.matpc(x, +1), asym_plus)
+    with pytest.raises(L.B200Error):
+        ctx.clover_apply(x, 1, inverse=True)
+    ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["CG", "BICGSTAB", "MDAGM_CG", "RELIABLE"])
+def test_symmetric_solvers(oracle, solver):
+    """Every solver shell on the symmetric operator: iteration counts against the restated loops run on the restated
+    SymEvenOddPrecCloverLinOp, true residual recomputed on the CPU (symm_prec_tests.cc:210-249 is the reference's check)."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, "double", gauge="weak")
+    ctx.set_preconditioning(True)
+    op.set_symmetric(True)
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    z = np.zeros_like(chi)
+    rsd = 1e-8
+    mdagm = solver == "MDAGM_CG"
+    if solver == "CG":
+        ref, n_ref, _, _ = op.solve_cg(chi, z, rsd, 2000)
+        psi, info = ctx.invert(chi[Vh:], None, solver=L.B200_SOLVER_CG, rsd=rsd, max_iter=2000)
+    elif solver == "BICGSTAB":
+        ref, n_ref, _, _ = op.solve_bicgstab(chi, z, rsd, 2000)
+        psi, info = ctx.invert(chi[Vh:], None, solver=L.B200_SOLVER_BICGSTAB, rsd=rsd, max_iter=2000)
+    elif solver == "MDAGM_CG":
+        ref, n_ref, _ = op.solve_mdagm_cg(chi, z, rsd, 2000)
+        psi, info = ctx.invert_mdagm(chi[Vh:], None, solver=L.B200_SOLVER_CG, rsd=rsd, max_iter=2000)
+    else:
+        ref, n_ref, _, _ = op.solve_reliable_cg(chi, z, rsd, 0.1, 2000)
+        psi, info = ctx.invert_reliable(chi[Vh:], None, rsd=rsd, delta=0.1, max_iter=2000)
+    assert info.converged == 1
+    assert abs(info.n_count - n_ref) <= max(3, 0.08 * n_ref), (info.n_count, n_ref)
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - (op.apply(op.apply(full, +1), -1) if mdagm else op.apply(full, +1))
+    rel = np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(chi[Vh:] ** 2))
+    assert rel < 50 * rsd
+    assert abs(info.rel_resid - rel) < 1e-2 * rel + 1e-14
+    assert rel_site_err(psi, ref[Vh:]) < 1e-5
+    ctx.close()
+
+
+def test_symmetric_qprop_and_plugin(oracle):
+    """SymEvenOddPrecActQprop (seoprec_fermact_qprop.cc:41-100) on the device solves the same unpreconditioned system;
+    the plugin mirror with SymmetricLinop solves the caller's symmetric A."""
+    latt = (4, 4, 4, 8)
+    u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
+    ctx.set_preconditioning(True)
+    srcs = np.stack([fields.point_source(latt, s, c) for s, c in ((0, 0), (3, 2))] + [fields.gaussian_fermion(latt, seed=31)])
+    sol, infos = ctx.qprop(srcs, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-10, max_iter=500)
+    for i in range(len(srcs)):
+        r = op.unprec_apply(sol[i], +1) - srcs[i]
+        assert np.linalg.norm(r) / np.linalg.norm(srcs[i]) < 1e-8
+        assert infos[i].converged == 1
+    ctx.close()
+    op.set_symmetric(True)
+    chi = fields.gaussian_fermion(latt, seed=32, cb=1)
+    Vh = chi.shape[0] // 2
+    p = SysSolverB200CloverParams(CloverParams=CloverFermActParams(Mass=0.1, clovCoeffR=1.0, clovCoeffT=1.0),
+                                  RsdTarget=1e-9, MaxIter=1000, SolverType="CG", SymmetricLinop=True)
+    S = LinOpSysSolverB200Clover(latt, u, p)
+    psi = np.zeros((Vh, 4, 3, 2))
+    res = S(psi, chi[Vh:])
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - op.apply(full, +1)
+    assert np.sqrt(np.sum(r[Vh:] ** 2)) == pytest.approx(res.resid, rel=1e-3)
+    assert res.resid / np.sqrt(np.sum(chi[Vh:] ** 2)) < 1e-8
+    S.close()
+
+
+@pytest.mark.parametrize("prec,symmetric", [("double", False), ("double", True), ("single", False)])
+def test_multishift_cg(oracle, prec, symmetric):
+    """MInvCG2_a (minvcg2.cc:74-373): same iteration count as the CPU restatement, every shift's TRUE residual below its
+    own target, solutions equal to the restatement's, shifts converge (and freeze) independently."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, prec, gauge="weak")
+    ctx.set_preconditioning(symmetric)
+    op.set_symmetric(symmetric)
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    shifts = [0.0005, 0.01, 0.08, 0.6, 3.0]
+    rsd = [1e-8, 1e-8, 1e-7, 1e-6, 1e-5] if prec == "double" else [1e-5, 1e-5, 1e-5, 1e-4, 1e-4]
+    ref, n_ref, rel_ref = op.solve_multishift(chi, shifts, rsd, 2000)
+    psi, infos = ctx.invert_multishift(chi[Vh:].astype(NP[prec]), shifts, rsd, max_iter=2000)
+    assert all(i.converged == 1 for i in infos)
+    assert len({i.n_count for i in infos}) == 1
+    assert abs(infos[0].n_count - n_ref) <= max(2, 0.05 * n_ref), (infos[0].n_count, n_ref)
+    for s, sh in enumerate(shifts):
+        full = np.zeros_like(chi)
+        full[Vh:] = psi[s]
+        r = chi - op.apply(op.apply(full, +1), -1) - sh * full
+        rel = np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(chi[Vh:] ** 2))
+        assert rel < (10 if prec == "double" else 100) * rsd[s], (s, rel)
+        assert abs(infos[s].rel_resid - rel) < 2e-2 * rel + (1e-14 if prec == "double" else 1e-7)
+        assert rel_site_err(psi[s], ref[s][Vh:]) < (1e-5 if prec == "double" else 5e-3)
+    # one shift == ordinary CG on M^dag M + sigma; zero source returns zero in zero iterations (minvcg2.cc:135-148)
+    one, inf1 = ctx.invert_multishift(chi[Vh:].astype(NP[prec]), [0.08], rsd[2], max_iter=2000)
+    assert rel_site_err(one[0], psi[2]) < (1e-6 if prec == "double" else 5e-3) and inf1[0].n_count <= infos[0].n_count
+    zero, inf0 = ctx.invert_multishift(np.zeros((Vh, 4, 3, 2), dtype=NP[prec]), shifts, rsd, max_iter=50)
+    assert inf0[0].n_count == 0 and not zero.any()
+    # not converging is reported, not fatal; too many shifts are refused
+    _, infx = ctx.invert_multishift(chi[Vh:].astype(NP[prec]), shifts, 1e-12, max_iter=3)
+    assert infx[0].converged == 0 and infx[0].n_count == 3
+    with pytest.raises(L.B200Error) as e:
+        ctx.invert_multishift(chi[Vh:].astype(NP[prec]), np.linspace(0.1, 1, L.B200_MAX_SHIFTS + 1), 1e-6, max_iter=3)
+    assert e.value.code == L.B200_ERR_ARG
+    ctx.close()
+
+
+def test_multishift_plugin_mirror_and_device_fields(oracle):
+    """MdagMMultiSysSolverCG::operator()(psi[], shifts, chi) mirror, and the device-resident entry with 16 shifts
+    (more vectors than the batched operators take: storage-only batched field)."""
+    latt = (4, 4, 4, 8)
+    u = fields.apply_bc(latt, fields.weak_gauge(latt, seed=11))
+    op = oracle.Op(latt, u, 0.1, 1.0)
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = chi.shape[0] // 2
+    p = SysSolverB200CloverParams(CloverParams=CloverFermActParams(Mass=0.1, clovCoeffR=1.0, clovCoeffT=1.0),
+                                  RsdTarget=1e-9, MaxIter=1000)
+    S = MdagMMultiSysSolverB200Clover(latt, u, p)
+    shifts = list(np.geomspace(1e-3, 5.0, 16))
+    psi, res = S(shifts, chi[Vh:])
+    ref, n_ref, _ = op.solve_multishift(chi, shifts, 1e-9, 1000)
+    assert abs(res.n_count - n_ref) <= 2
+    for s in range(16):
+        assert rel_site_err(psi[s], ref[s][Vh:]) < 1e-6
+    ctx = S.ctx
+    fpsi, fchi = ctx.mfield(16), ctx.field(chi[Vh:])
+    infos = ctx.dev_invert_multishift(fpsi, fchi, shifts, 1e-9, max_iter=1000)
+    assert infos[0].n_count == res.n_count
+    assert np.array_equal(fpsi.download(irhs=7), psi[7])
+    with pytest.raises(L.B200Error):                      # 16 vectors: storage only
+        ctx.dev_matpc(ctx.mfield(16), fpsi, +1)
+    p.MaxIter = 2
+    with pytest.raises(SolverFailure):
+        S(shifts, chi[Vh:])
+    S.close()
 
 
 def test_error_behaviour():

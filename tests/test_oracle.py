@@ -406,3 +406,65 @@ def test_mdagm_and_reliable_restatements(oracle):
         psi3, n_rel, n_upd, res3 = op.solve_reliable_cg(chi, z, 1e-10, delta, 500)
         assert n_upd >= 1 and res3 / nchi < 2e-9
         assert abs(n_rel - n64) <= 0.15 * n64 + 3, (n_rel, n64)
+
+
+# ---------------------------------------------------------------------------------------- section 8 (f4)
+def test_symmetric_operator_restatement(oracle):
+    """SymEvenOddPrecCloverLinOp (seoprec_clover_linop_w.cc:147-193): S = A_oo^-1 M_asym, <chi, S psi> = <S^dag chi, psi>
+    (the checks of mainprogs/tests/symm_prec_tests.cc:107-157), and the symmetric qprop
+    (seoprec_fermact_qprop.cc:41-100) solves the same full-lattice system as the asymmetric one."""
+    L = (4, 4, 4, 8)
+    u = fields.apply_bc(L, fields.weak_gauge(L, seed=71))
+    asym = oracle.Op(L, u, 0.1, 1.0)
+    sym = oracle.Op(L, u, 0.1, 1.0)
+    sym.set_symmetric(True)
+    assert sym.symmetric and not asym.symmetric
+    g = oracle.Geom(L)
+    Vh = g.Vh
+    psi = fields.gaussian_fermion(L, seed=72, cb=1)
+    chi = fields.gaussian_fermion(L, seed=73, cb=1)
+    s_psi = sym.apply(psi, +1)
+    want = oracle.clover_apply(g, asym.apply(psi, +1), sym.invclov, 1)
+    assert rel_site_err(s_psi[Vh:], want[Vh:]) < 1e-13
+    # A_oo^-1 A_oo = 1 on cb 1
+    one = oracle.clover_apply(g, oracle.clover_apply(g, psi, sym.clov, 1), sym.invclov, 1)
+    assert rel_site_err(one[Vh:], psi[Vh:]) < 1e-12
+    a = np.vdot(cplx(chi), cplx(s_psi))
+    b = np.vdot(cplx(sym.apply(chi, -1)), cplx(psi))
+    assert abs(a - b) < 1e-11 * abs(a)
+    # switching back restores the asymmetric operator exactly
+    sym.set_symmetric(False)
+    assert np.array_equal(sym.apply(psi, +1), asym.apply(psi, +1))
+    sym.set_symmetric(True)
+    assert np.array_equal(sym.apply(psi, +1), s_psi)
+    # full-lattice propagator through the symmetric decomposition
+    full = fields.gaussian_fermion(L, seed=74)
+    chip = sym.qprop_prepare(full)
+    psi_o, n, _, rel = sym.solve_cg(chip, np.zeros_like(full), 1e-10, 500)
+    sol = sym.qprop_reconstruct(psi_o, chip)
+    r = sym.unprec_apply(sol, +1) - full
+    assert np.linalg.norm(r) / np.linalg.norm(full) < 1e-8
+    assert 0 < n < 500
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_multishift_cg_restatement(oracle, symmetric):
+    """MInvCG2_a (minvcg2.cc:74-373): every shifted system reaches its own target, the unshifted-limit solution agrees
+    with InvCG2_a on the same operator, and the iteration count is that of the smallest shift."""
+    L = (4, 4, 4, 8)
+    u = fields.apply_bc(L, fields.weak_gauge(L, seed=11))
+    op = oracle.Op(L, u, 0.1, 1.0)
+    op.set_symmetric(symmetric)
+    chi = fields.gaussian_fermion(L, seed=12, cb=1)
+    Vh = chi.shape[0] // 2
+    shifts = [0.0, 0.02, 0.3, 1.5]
+    psi, n, rel = op.solve_multishift(chi, shifts, [1e-9, 1e-9, 1e-8, 1e-7], 500)
+    assert 0 < n < 500
+    assert rel[0] < 5e-9 and rel[1] < 5e-9 and rel[2] < 5e-8 and rel[3] < 5e-7
+    ref, n_cg, _ = op.invcg2(chi, np.zeros_like(chi), 1e-9, 500)
+    assert abs(n - n_cg) <= 2
+    assert np.abs(psi[0] - ref)[Vh:].max() < 1e-7 * np.abs(ref[Vh:]).max()
+    # a single shift reproduces the shifted solution of the batch
+    one, n1, _ = op.solve_multishift(chi, [0.3], 1e-8, 500)
+    assert n1 <= n
+    assert np.abs(one[0] - psi[2])[Vh:].max() < 1e-6 * np.abs(psi[2][Vh:]).max()
