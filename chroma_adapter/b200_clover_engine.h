@@ -58,10 +58,10 @@ namespace Chroma
       int dev_prec = host_prec;
       if (p.precision == B200_PREC_SINGLE) dev_prec = B200_SINGLE;
       if (p.precision == B200_PREC_DOUBLE) dev_prec = B200_DOUBLE;
-      mixed = (dev_prec == B200_DOUBLE) &&
-              (p.sloppyPrecision == B200_PREC_SINGLE || p.solverType == B200_RELIABLE_CG_SOLVER);
-      if (p.solverType == B200_RELIABLE_CG_SOLVER && dev_prec != B200_DOUBLE) {
-        QDPIO::cerr << "B200_CLOVER_INVERTER: RELIABLE_CG needs CudaPrecision DOUBLE" << std::endl;
+      const bool reliable = p.solverType == B200_RELIABLE_CG_SOLVER || p.solverType == B200_RELIABLE_BICGSTAB_SOLVER;
+      mixed = (dev_prec == B200_DOUBLE) && (p.sloppyPrecision == B200_PREC_SINGLE || reliable);
+      if (reliable && dev_prec != B200_DOUBLE) {
+        QDPIO::cerr << "B200_CLOVER_INVERTER: RELIABLE_CG / RELIABLE_BICGSTAB need CudaPrecision DOUBLE" << std::endl;
         QDP_abort(1);
       }
 
@@ -124,10 +124,13 @@ namespace Chroma
       std::memset(&info, 0, sizeof(info));
       const double rsd = toDouble(invParam.RsdTarget);
       int rc;
-      if (mixed && invParam.solverType != B200_BICGSTAB_SOLVER)
+      const bool bicg = invParam.solverType == B200_BICGSTAB_SOLVER || invParam.solverType == B200_RELIABLE_BICGSTAB_SOLVER;
+      if (mixed && !bicg)
         rc = b200_invert_reliable(ctx, out, in, host_prec, rsd, toDouble(invParam.Delta), invParam.MaxIter, mdagm ? 1 : 0, &info);
+      else if (mixed)
+        rc = b200_invert_reliable_bicgstab(ctx, out, in, host_prec, rsd, toDouble(invParam.Delta), invParam.MaxIter, mdagm ? 1 : 0, &info);
       else {
-        const int solver = invParam.solverType == B200_BICGSTAB_SOLVER ? B200_SOLVER_BICGSTAB : B200_SOLVER_CG;
+        const int solver = bicg ? B200_SOLVER_BICGSTAB : B200_SOLVER_CG;
         rc = mdagm ? b200_invert_mdagm(ctx, out, in, host_prec, solver, rsd, invParam.MaxIter, &info)
                    : b200_invert(ctx, out, in, host_prec, solver, rsd, invParam.MaxIter, &info);
       }

@@ -16,7 +16,7 @@ namespace Chroma
         if (s == names[i]) { out = static_cast<E>(i); return true; }
       return false;
     }
-    const char* const solverNames[] = {"CG", "BICGSTAB", "RELIABLE_CG"};
+    const char* const solverNames[] = {"CG", "BICGSTAB", "RELIABLE_CG", "RELIABLE_BICGSTAB"};
     const char* const precNames[] = {"DEFAULT", "SINGLE", "DOUBLE"};
     const char* const reconsNames[] = {"RECONS_NONE", "RECONS_12"};
 
@@ -52,7 +52,7 @@ namespace Chroma
     read(paramtop, "RsdTarget", RsdTarget);
     read(paramtop, "CloverParams", CloverParams);
     read(paramtop, "AntiPeriodicT", AntiPeriodicT);
-    readEnum(paramtop, "SolverType", solverNames, 3, solverType, B200_CG_SOLVER, true);
+    readEnum(paramtop, "SolverType", solverNames, 4, solverType, B200_CG_SOLVER, true);
 
     if (paramtop.count("Delta") > 0) read(paramtop, "Delta", Delta);
     readEnum(paramtop, "CudaPrecision", precNames, 3, precision, B200_PREC_DEFAULT, false);

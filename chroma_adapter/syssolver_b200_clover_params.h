@@ -20,7 +20,7 @@
 
 namespace Chroma
 {
-  enum B200SolverType { B200_CG_SOLVER, B200_BICGSTAB_SOLVER, B200_RELIABLE_CG_SOLVER };
+  enum B200SolverType { B200_CG_SOLVER, B200_BICGSTAB_SOLVER, B200_RELIABLE_CG_SOLVER, B200_RELIABLE_BICGSTAB_SOLVER };
   enum B200PrecisionType { B200_PREC_DEFAULT, B200_PREC_SINGLE, B200_PREC_DOUBLE };
   enum B200ReconsType { B200_RECONS_NONE_T, B200_RECONS_12_T };
 
@@ -33,7 +33,7 @@ namespace Chroma
     bool AntiPeriodicT;
     int MaxIter;
     Real RsdTarget;
-    Real Delta;                        //!< reliable-update threshold (RELIABLE_CG, or CG with a sloppy precision)
+    Real Delta;                        //!< reliable-update threshold (RELIABLE_CG / RELIABLE_BICGSTAB, or CG / BICGSTAB with a sloppy precision)
     B200SolverType solverType;
     B200PrecisionType precision;       //!< device precision (DEFAULT = precision of the Chroma build)
     B200PrecisionType sloppyPrecision; //!< SINGLE below a DOUBLE precision selects the mixed-precision solver

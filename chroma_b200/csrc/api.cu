@@ -230,6 +230,17 @@ int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* c
   CHECK_CTX(ctx);
   return reliable_solve(ctx->eng, &ctx->sloppy, psi, chi, rsd, delta, max_iter, mdagm, info);
 }
+int b200_dev_invert_reliable_bicgstab(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd, double delta, int max_iter, int mdagm,
+                                      b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return reliable_bicgstab_solve(ctx->eng, &ctx->sloppy, psi, chi, rsd, delta, max_iter, mdagm, info);
+}
+int b200_invert_reliable_bicgstab(b200_ctx* ctx, void* psi, const void* chi, int host_prec, double rsd, double delta, int max_iter, int mdagm,
+                                  b200_solve_info* info) {
+  CHECK_CTX(ctx);
+  return host_solve(ctx, psi, chi, host_prec, info,
+                    [&](b200_field* p, b200_field* c) { return reliable_bicgstab_solve(ctx->eng, &ctx->sloppy, p, c, rsd, delta, max_iter, mdagm, info); });
+}
 int b200_dev_invert_multishift(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int n_shift, const double* shifts, const double* rsd,
                                int max_iter, b200_solve_info* info) {
   CHECK_CTX(ctx);

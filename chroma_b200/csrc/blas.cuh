@@ -23,6 +23,7 @@ struct BlasCtl {
   double* scal; int* status; ReduceBuf red;
   int iter; int check_stop;
   size_t fstride;
+  int rel;        // bicg_update_kernel: also take the reliable-update decisions (reliable_bicgstab.cc:198-205)
   template <int N>
   __device__ __forceinline__ BlasCtl for_rhs(int rhs) const {
     BlasCtl c = *this;
@@ -86,12 +87,26 @@ __global__ void __launch_bounds__(BLAS_BLOCK) bicg_s_kernel(Cx<R>* __restrict__ 
 // ---------------------------------------------------------------- BiCGStab: psi += omega r + alpha p ; r -= omega t ;
 // |r|^2 and rho_next = <r0|r> in the same pass (invbicgstab.cc:149-160 and :77 of the next iteration)
 struct FinBiUpdate {
-  double* scal; int* status; int iter; int check;
+  double* scal; int* status; int iter; int check; int rel;
   __device__ void operator()(const double* t) const {
     const double rnorm = t[0], nr = t[1], ni = t[2];
     scal[S_RNORM] = rnorm;
-    bool conv = false;
-    if (check && status[ST_STOP] == 0 && rnorm < scal[S_RSDSQ]) { status[ST_STOP] = iter; conv = true; }
+    bool conv = false, upd_r = false;
+    if (rel) {
+      // reliable updates (reliable_bicgstab.cc:193-205): decide here, on the device, whether the fp64 side replaces the
+      // residual (updateR) and folds the fp32 partial solution into psi (updateX); if so the convergence test moves to
+      // the finaliser of the replacement kernel (FinRelReplace), which sees the TRUE residual
+      const double rn = sqrt(rnorm);
+      double maxrx = scal[S_MAXRX], maxrr = scal[S_MAXRR];
+      const double r0 = scal[S_R0NORM], delta = scal[S_DELTA];
+      if (rn > maxrx) maxrx = rn;
+      if (rn > maxrr) maxrr = rn;
+      scal[S_MAXRX] = maxrx; scal[S_MAXRR] = maxrr;
+      const bool upd_x = (rn < delta * r0) && (r0 <= maxrx);
+      upd_r = ((rn < delta * maxrr) && (r0 <= maxrr)) || upd_x;
+      status[ST_UPD_R] = upd_r ? 1 : 0; status[ST_UPD_X] = upd_x ? 1 : 0;
+    }
+    if (!upd_r && check && status[ST_STOP] == 0 && rnorm < scal[S_RSDSQ]) { status[ST_STOP] = iter; conv = true; }
     const double pr = scal[S_RHO_RE], pi = scal[S_RHO_IM];
     scal[S_RHOP_RE] = pr; scal[S_RHOP_IM] = pi;
     scal[S_RHO_RE] = nr; scal[S_RHO_IM] = ni;
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(BLAS_BLOCK) bicg_update_kernel(Cx<R>* __restri
     red[1] += (double)q.x * rv.x + (double)q.y * rv.y;
     red[2] += (double)q.x * rv.y - (double)q.y * rv.x;
   }
-  grid_reduce<3, BLAS_BLOCK>(red, c.red, FinBiUpdate{c.scal, c.status, c.iter, c.check_stop});
+  grid_reduce<3, BLAS_BLOCK>(red, c.red, FinBiUpdate{c.scal, c.status, c.iter, c.check_stop, c.rel});
 }
 
 // ---------------------------------------------------------------- generic helpers (setup / verification, not the hot loop)

@@ -85,6 +85,10 @@ class EngineBase {
 int reliable_solve(EngineBase* hi, EngineBase** lo_slot, b200_field* psi, const b200_field* chi, double rsd, double delta,
                    int max_iter, int mdagm, b200_solve_info* info);
 
+// Mixed-precision reliable-update BiCGStab (engine_mixed.cu): RelInvBiCGStab_a, reliable_bicgstab.cc:13-290
+int reliable_bicgstab_solve(EngineBase* hi, EngineBase** lo_slot, b200_field* psi, const b200_field* chi, double rsd, double delta,
+                            int max_iter, int mdagm, b200_solve_info* info);
+
 EngineBase* make_engine_double(const Config& c);
 EngineBase* make_engine_float(const Config& c);
 

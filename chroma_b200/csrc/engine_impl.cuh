@@ -650,8 +650,10 @@ class Engine : public EngineBase {
   }
 
   // ------------------------------------------------------------------ solver loops
+  int ctl_rel = 0;   // set by the mixed-precision BiCGStab driver: bicg_update also takes the reliable-update decisions
   BlasCtl ctl(int iter, int check) {
     BlasCtl c; c.scal = scal; c.status = status; c.red = make_red(0, blas_grid); c.iter = iter; c.check_stop = check; c.fstride = nelem();
+    c.rel = ctl_rel;
     return c;
   }
 

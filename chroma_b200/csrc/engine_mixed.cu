@@ -71,6 +71,7 @@ struct FinRelReplace {
     if (status[ST_UPD_X]) { scal[S_R0NORM] = rnorm; scal[S_MAXRX] = rnorm; }
     const double c = scal[S_C];
     scal[S_CP] = r_sq; scal[S_B] = r_sq / c; scal[S_C] = r_sq;
+    scal[S_RNORM] = r_sq;                           // BiCGStab keeps |r|^2 here (rho is NOT recomputed, reliable_bicgstab.cc:205-216)
     status[ST_NUPD] += 1;
     if (status[ST_STOP] == 0 && r_sq < scal[S_RSDSQ]) status[ST_STOP] = iter;
   }
@@ -150,6 +151,20 @@ static int adopt(Engine<float>& lo, Engine<double>& hi) {
   return B200_OK;
 }
 
+// the fp32 twin of an fp64 engine: created on first use, re-synchronised whenever the operator changed
+static int sloppy_twin(Engine<double>& hi, EngineBase** lo_slot) {
+  if (!*lo_slot) {
+    Config c = hi.cfg; c.prec = B200_SINGLE;
+    EngineBase* e = make_engine_float(c);
+    int rc = e->init();
+    if (rc) { delete e; return rc; }
+    *lo_slot = e;
+  }
+  Engine<float>& lo = *static_cast<Engine<float>*>(*lo_slot);
+  if (lo.stream != hi.stream || lo.operator_epoch != hi.operator_epoch) return adopt(lo, hi);
+  return B200_OK;
+}
+
 int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, const b200_field* chi_f, double rsd, double delta,
                    int max_iter, int mdagm, b200_solve_info* info) {
   if (!hi_b || hi_b->cfg.prec != B200_DOUBLE) { set_error("b200_invert_reliable needs a context created with B200_DOUBLE"); return B200_ERR_ARG; }
@@ -158,15 +173,8 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   int rc = hi.ready(); if (rc) return rc;
   if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0) || !(delta > 0.0)) { set_error("b200_invert_reliable: bad argument"); return B200_ERR_ARG; }
   if (psi_f->nrhs != 1 || chi_f->nrhs != 1) { set_error("b200_invert_reliable: one right-hand side at a time"); return B200_ERR_ARG; }
-  if (!*lo_slot) {
-    Config c = hi.cfg; c.prec = B200_SINGLE;
-    EngineBase* e = make_engine_float(c);
-    rc = e->init();
-    if (rc) { delete e; return rc; }
-    *lo_slot = e;
-  }
+  rc = sloppy_twin(hi, lo_slot); if (rc) return rc;
   Engine<float>& lo = *static_cast<Engine<float>*>(*lo_slot);
-  if (lo.stream != hi.stream || lo.operator_epoch != hi.operator_epoch) { rc = adopt(lo, hi); if (rc) return rc; }
   rc = hi.set_batch(1); if (rc) return rc;
   rc = lo.set_batch(1); if (rc) return rc;
   rc = hi.need_ws(hi.nws(7)); if (rc) return rc;
@@ -253,6 +261,143 @@ int reliable_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, co
   info->gflops = info->secs > 0 ? flops * gvol / info->secs * 1e-9 : 0.0;
   if (breakdown >= 90) return hi.comm_timeout(breakdown);
   return B200_OK;
+}
+
+// ================================================================================================ reliable BiCGStab
+// RelInvBiCGStab_a (lib/actions/ferm/invert/reliable_bicgstab.cc:13-290): the BiCGStab recurrences run in fp32 on the
+// sloppy engine (the same five fused launches per iteration as the fp64 solver, engine_impl.cuh::bicg_iteration); the
+// finaliser of the fused |r|^2 / <r0|r> reduction (FinBiUpdate with rel = 1) takes the updateR / updateX decisions on
+// the device; the fp64 residual replacement r = b - A x (one operator apply + rel_replace_kernel) is enqueued every
+// iteration as PREDICATED launches.  rho is not recomputed after a replacement, exactly as in the reference (:205-216).
+__global__ void __launch_bounds__(BLAS_BLOCK) planes_f2d_pred_kernel(double2* __restrict__ dst, const float2* __restrict__ src, size_t n,
+                                                                    const int* __restrict__ status) {
+  if (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0 || status[ST_UPD_R] == 0) return;
+  for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
+    const float2 v = src[i];
+    dst[i] = make_double2((double)v.x, (double)v.y);
+  }
+}
+
+// One A psi = rhs solve (A = M for isign = +1, M^dag for -1).  hi: W(0) even temporary, W(1) tmp, W(3) b, W(4) x_dble;
+// lo: W(1) r, W(2) r0, W(3) p, W(4) v, W(5) t, W(6) x (bicg_iteration's layout).
+static int rel_bicg_run(Engine<double>& hi, Engine<float>& lo, double2* psi, const double2* rhs, int isign, double rsd, double delta,
+                        int max_iter, int* n_count, int* converged, int* n_upd, double* rsq_iter) {
+  typedef double2 CD; typedef float2 CF;
+  CD *tmp = hi.W(1), *bvec = hi.W(3), *xd = hi.W(4);
+  CF *r = lo.W(1), *r0 = lo.W(2), *p = lo.W(3), *v = lo.W(4), *x = lo.W(6);
+  const size_t n = hi.nelem();
+  cudaStream_t st = hi.stream;
+  // set-up, reliable_bicgstab.cc:56-104
+  int rc = hi.norm2_dev(rhs, S_TMP0); if (rc) return rc;
+  rc = hi.apply_M(tmp, psi, isign, EPI_M, nullptr, nullptr, 0, 0); if (rc) return rc;
+  rc = hi.xmy_norm_dev(bvec, nullptr, rhs, tmp, S_TMP1); if (rc) return rc;              // b = rhs - A psi ; b_sq
+  planes_d2f_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, st>>>(r, bvec, n);
+  planes_d2f_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, st>>>(r0, bvec, n);
+  hi.launches += 2;
+  B200_CUDA(cudaMemsetAsync(x, 0, sizeof(CF) * n, st));
+  B200_CUDA(cudaMemsetAsync(p, 0, sizeof(CF) * n, st));
+  B200_CUDA(cudaMemsetAsync(v, 0, sizeof(CF) * n, st));
+  rc = hi.fetch_scalars(); if (rc) return rc;
+  const double rhs_sq = hi.h_scal[S_TMP0], r_sq0 = hi.h_scal[S_TMP1], rsd_sq = rsd * rsd * rhs_sq;
+  *rsq_iter = r_sq0; *n_count = 0; *converged = 0; *n_upd = 0;
+  if (r_sq0 < rsd_sq || r_sq0 == 0.0) { *converged = 1; return B200_OK; }             // nothing to do (rho would be 0)
+  {
+    ScalarSet s{}; s.reset_status = 1; s.n = 12;
+    const double rn = sqrt(r_sq0);
+    // rho_1 = |r|^2 (r0 = r), rho_0 = alpha = omega = 1 => beta_1 = rho_1, p_1 = r  (:96-114)
+    const int sl[12] = {S_RSDSQ, S_RHO_RE, S_RHO_IM, S_RHOP_RE, S_RHOP_IM, S_ALPHA_RE, S_ALPHA_IM, S_OMEGA_RE, S_OMEGA_IM, S_BETA_RE, S_BETA_IM, S_C};
+    const double vl[12] = {rsd_sq, r_sq0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.0, r_sq0, 0.0, 1.0};
+    for (int i = 0; i < 12; ++i) { s.slots[i] = sl[i]; s.vals[i] = vl[i]; }
+    rc = hi.set_scalars(s); if (rc) return rc;
+    ScalarSet s2{}; s2.reset_status = 0; s2.n = 4;
+    const int sl2[4] = {S_R0NORM, S_MAXRX, S_MAXRR, S_DELTA};
+    const double vl2[4] = {rn, rn, rn, delta};
+    for (int i = 0; i < 4; ++i) { s2.slots[i] = sl2[i]; s2.vals[i] = vl2[i]; }
+    rc = hi.set_scalars(s2); if (rc) return rc;
+  }
+  lo.ctl_rel = 1;
+  int k = 1, slot = 0, prev = -1;
+  bool done = false;
+  while (k <= max_iter && !done) {
+    const int nbat = std::min(ITER_BATCH, max_iter - k + 1);
+    for (int i = 0; i < nbat; ++i) {
+      const int it = k + i;
+      rc = lo.bicg_iteration(x, it, 1, isign); if (rc) { lo.ctl_rel = 0; return rc; }
+      planes_f2d_pred_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, st>>>(xd, x, n, hi.status);
+      rc = hi.launched("planes_f2d_pred"); if (rc) { lo.ctl_rel = 0; return rc; }
+      rc = hi.apply_M(tmp, xd, isign, EPI_M, nullptr, nullptr, it, 1, ST_UPD_R); if (rc) { lo.ctl_rel = 0; return rc; }
+      rel_replace_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, st>>>(bvec, tmp, r, psi, xd, x, n, hi.ctl(it, 1));
+      rc = hi.launched("rel_replace"); if (rc) { lo.ctl_rel = 0; return rc; }
+    }
+    B200_CUDA(cudaMemcpyAsync(hi.h_status + slot * ST_COUNT, hi.status, sizeof(int) * ST_COUNT, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaEventRecord(hi.ev_poll[slot], st));
+    if (prev >= 0) {
+      B200_CUDA(cudaEventSynchronize(hi.ev_poll[prev]));
+      if (hi.h_status[prev * ST_COUNT + ST_STOP] != 0 || hi.h_status[prev * ST_COUNT + ST_BREAKDOWN] != 0) done = true;
+    }
+    prev = slot; slot ^= 1; k += nbat;
+  }
+  lo.ctl_rel = 0;
+  B200_CUDA(cudaStreamSynchronize(st));
+  int breakdown = 0;
+  if (prev >= 0) {
+    const int* stt = hi.h_status + prev * ST_COUNT;
+    breakdown = stt[ST_BREAKDOWN];
+    *converged = stt[ST_STOP] != 0;
+    *n_count = *converged ? stt[ST_STOP] : max_iter;
+    *n_upd = stt[ST_NUPD];
+  }
+  // psi += x (reliable_bicgstab.cc:247-252); x is zero if the last iteration was a group update
+  planes_add_f2d_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, st>>>(psi, x, n);
+  rc = hi.launched("planes_add_f2d"); if (rc) return rc;
+  rc = hi.fetch_scalars(); if (rc) return rc;
+  if (*n_count > 0) *rsq_iter = hi.h_scal[S_RNORM];
+  if (breakdown >= 90) return hi.comm_timeout(breakdown);
+  if (breakdown) { set_error("reliable BiCGStab breakdown (code %d) at iteration <= %d", breakdown, *n_count); return B200_ERR_BREAKDOWN; }
+  return B200_OK;
+}
+
+// Shells: LinOpSysSolverReliableBiCGStabClover::operator() (syssolver_linop_rel_bicgstab_clover.h:105-146): M psi = chi;
+// MdagMSysSolverReliableBiCGStabClover::operator() (syssolver_mdagm_rel_bicgstab_clover.h:104-170): Y = M psi,
+// M^dag Y = chi, M psi = Y.
+int reliable_bicgstab_solve(EngineBase* hi_b, EngineBase** lo_slot, b200_field* psi_f, const b200_field* chi_f, double rsd, double delta,
+                            int max_iter, int mdagm, b200_solve_info* info) {
+  if (!hi_b || hi_b->cfg.prec != B200_DOUBLE) { set_error("b200_invert_reliable_bicgstab needs a context created with B200_DOUBLE"); return B200_ERR_ARG; }
+  Engine<double>& hi = *static_cast<Engine<double>*>(hi_b);
+  B200_CUDA(cudaSetDevice(hi.cfg.device));
+  int rc = hi.ready(); if (rc) return rc;
+  if (!psi_f || !chi_f || !info || psi_f == chi_f || max_iter < 0 || !(rsd >= 0.0) || !(delta > 0.0)) { set_error("b200_invert_reliable_bicgstab: bad argument"); return B200_ERR_ARG; }
+  if (psi_f->nrhs != 1 || chi_f->nrhs != 1) { set_error("b200_invert_reliable_bicgstab: one right-hand side at a time"); return B200_ERR_ARG; }
+  rc = sloppy_twin(hi, lo_slot); if (rc) return rc;
+  Engine<float>& lo = *static_cast<Engine<float>*>(*lo_slot);
+  rc = hi.set_batch(1); if (rc) return rc;
+  rc = lo.set_batch(1); if (rc) return rc;
+  rc = hi.need_ws(hi.nws(7)); if (rc) return rc;
+  rc = lo.need_ws(lo.nws(7)); if (rc) return rc;
+  double2* psi = (double2*)psi_f->d; const double2* chi = (const double2*)chi_f->d;
+  memset(info, 0, sizeof(*info));
+  B200_CUDA(cudaEventRecord(hi.ev_t0, hi.stream));
+  int n1 = 0, c1 = 1, u1 = 0, n2 = 0, c2 = 0, u2 = 0;
+  double rsq = 0.0;
+  if (!mdagm) {
+    rc = rel_bicg_run(hi, lo, psi, chi, +1, rsd, delta, max_iter, &n2, &c2, &u2, &rsq);
+  } else {
+    rc = hi.apply_M(hi.W(6), psi, +1, EPI_M, nullptr, nullptr, 0, 0);
+    if (!rc) rc = rel_bicg_run(hi, lo, hi.W(6), chi, -1, rsd, delta, max_iter, &n1, &c1, &u1, &rsq);
+    if (!rc) rc = rel_bicg_run(hi, lo, psi, hi.W(6), +1, rsd, delta, max_iter, &n2, &c2, &u2, &rsq);
+  }
+  info->n_count = n1 + n2; info->converged = c1 && c2; info->n_updates = u1 + u2; info->rsd_sq_iter = rsq;
+  if (rc && rc != B200_ERR_BREAKDOWN) return rc;
+  B200_CUDA(cudaEventRecord(hi.ev_t1, hi.stream));
+  int rc2 = hi.true_residual(psi, chi, mdagm, info); if (rc2) return rc2;
+  float ms = 0.f;
+  B200_CUDA(cudaEventElapsedTime(&ms, hi.ev_t0, hi.ev_t1));
+  info->secs = ms * 1e-3; info->secs_total = info->secs;
+  const double gvol = (double)hi.g.Vh * hi.nranks();
+  // flops as RelInvBiCGStab_a books them: 2 A + 80*Nc*Ns per iteration, A + 6*Nc*Ns per replacement (:188-190, :222-223)
+  const double flops = (2.0 * 3792.0 + 960.0) * info->n_count + (3792.0 + 72.0) * info->n_updates;
+  info->gflops = info->secs > 0 ? flops * gvol / info->secs * 1e-9 : 0.0;
+  return rc;
 }
 
 }  // namespace b200

@@ -68,6 +68,7 @@ SYMBOLS = {
     "b200_invert": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_invert_mdagm": (_i, [_vp, _vp, _vp, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_invert_reliable": (_i, [_vp, _vp, _vp, _i, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
+    "b200_invert_reliable_bicgstab": (_i, [_vp, _vp, _vp, _i, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
     "b200_invert_multishift": (_i, [_vp, C.POINTER(_vp), _vp, _i, _i, C.POINTER(_d), C.POINTER(_d), _i, C.POINTER(SolveInfo)]),
     "b200_qprop": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_field_alloc": (_i, [_vp, C.POINTER(_vp)]),
@@ -88,6 +89,7 @@ SYMBOLS = {
     "b200_dev_invert": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_dev_invert_mdagm": (_i, [_vp, _vp, _vp, _i, _d, _i, C.POINTER(SolveInfo)]),
     "b200_dev_invert_reliable": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
+    "b200_dev_invert_reliable_bicgstab": (_i, [_vp, _vp, _vp, _d, _d, _i, _i, C.POINTER(SolveInfo)]),
     "b200_dev_invert_multishift": (_i, [_vp, _vp, _vp, _i, C.POINTER(_d), C.POINTER(_d), _i, C.POINTER(SolveInfo)]),
     "b200_dev_iterate_begin": (_i, [_vp, _vp, _vp, _i]),
     "b200_dev_iterate": (_i, [_vp, _i, _i]),

@@ -182,6 +182,15 @@ class Context:
                                               int(bool(mdagm)), C.byref(info)))
         return psi.reshape(self.Vh, 4, 3, 2), info
 
+    def invert_reliable_bicgstab(self, chi_odd, psi0_odd=None, rsd=1e-8, delta=0.1, max_iter=1000, mdagm=False):
+        """Mixed-precision reliable-update BiCGStab (RelInvBiCGStab_a); the context must be double precision."""
+        chi_odd = np.ascontiguousarray(chi_odd)
+        psi = np.zeros_like(chi_odd) if psi0_odd is None else np.ascontiguousarray(psi0_odd, dtype=chi_odd.dtype).copy()
+        info = L.SolveInfo()
+        L.check(self.lib.b200_invert_reliable_bicgstab(self.h, _ptr(psi), _ptr(chi_odd), _prec_of(chi_odd), float(rsd), float(delta),
+                                                       int(max_iter), int(bool(mdagm)), C.byref(info)))
+        return psi.reshape(self.Vh, 4, 3, 2), info
+
     def invert_multishift(self, chi_odd, shifts, rsd, max_iter=1000):
         """(M^dag M + shifts[s]) psi[s] = chi (MInvCG2_a behind MdagMMultiSysSolverCG).  rsd: scalar or one per shift.
         Returns (psi [n_shift,Vh,4,3,2], [SolveInfo per shift])."""
@@ -260,6 +269,12 @@ class Context:
     def dev_invert_reliable(self, psi, chi, rsd=1e-8, delta=0.1, max_iter=1000, mdagm=False):
         info = L.SolveInfo()
         L.check(self.lib.b200_dev_invert_reliable(self.h, psi.h, chi.h, float(rsd), float(delta), int(max_iter), int(bool(mdagm)), C.byref(info)))
+        return info
+
+    def dev_invert_reliable_bicgstab(self, psi, chi, rsd=1e-8, delta=0.1, max_iter=1000, mdagm=False):
+        info = L.SolveInfo()
+        L.check(self.lib.b200_dev_invert_reliable_bicgstab(self.h, psi.h, chi.h, float(rsd), float(delta), int(max_iter),
+                                                           int(bool(mdagm)), C.byref(info)))
         return info
 
     def dev_invert_multishift(self, psi, chi, shifts, rsd, max_iter=1000):

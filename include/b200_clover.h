@@ -182,6 +182,15 @@ int b200_invert_mdagm(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_hos
 int b200_invert_reliable(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec, double rsd_target,
                          double delta, int max_iter, int mdagm, b200_solve_info* info);
 
+/* Mixed-precision reliable-update BiCGStab for M psi = chi: fp32 BiCGStab recurrences, fp64 residual replacement
+ * r = b - M x and group-wise solution updates -- RelInvBiCGStab_a (lib/actions/ferm/invert/reliable_bicgstab.cc:13-290)
+ * behind LinOpSysSolverReliableBiCGStabClover::operator() (syssolver_linop_rel_bicgstab_clover.h:105-146; XML: RsdTarget,
+ * Delta, MaxIter, syssolver_rel_bicgstab_clover_params.cc:15-18).  mdagm != 0: the two-step M^dag M psi = chi solve of
+ * MdagMSysSolverReliableBiCGStabClover (syssolver_mdagm_rel_bicgstab_clover.h:104-170): Y = M psi, M^dag Y = chi,
+ * M psi = Y; n_count and n_updates are the sums over both solves.  Needs a B200_DOUBLE context. */
+int b200_invert_reliable_bicgstab(b200_ctx* ctx, void* psi_odd_host, const void* chi_odd_host, int host_prec,
+                                  double rsd_target, double delta, int max_iter, int mdagm, b200_solve_info* info);
+
 /* Multi-shift CG: (M^dag M + shifts[s]) psi[s] = chi for s = 0..n_shift-1 from one Krylov sequence -- MInvCG2_a
  * (lib/actions/ferm/invert/minvcg2.cc:74-373) behind MdagMMultiSysSolverCG::operator()
  * (multi_syssolver_mdagm_cg.h:58-105; factory TheMdagMFermMultiSystemSolverFactory, used by the rational monomials of RHMC).
@@ -228,6 +237,8 @@ int b200_dev_invert_mdagm(b200_ctx* ctx, b200_field* psi, const b200_field* chi,
                           int max_iter, b200_solve_info* info);
 int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd_target, double delta,
                              int max_iter, int mdagm, b200_solve_info* info);
+int b200_dev_invert_reliable_bicgstab(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd_target, double delta,
+                                      int max_iter, int mdagm, b200_solve_info* info);
 /* psi: a batched field (b200_mfield_alloc) holding at least n_shift vectors -- up to B200_MAX_SHIFTS; fields with more
  * than 12 vectors are storage only, the batched operators refuse them -- chi: an ordinary field */
 int b200_dev_invert_multishift(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int n_shift, const double* shifts,

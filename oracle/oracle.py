@@ -378,6 +378,95 @@ class Op:
         return psi, iters, n_upd, resid
 
 
+    def solve_reliable_bicgstab(self, chi, psi0, rsd, delta, maxit, isign=+1):
+        """RelInvBiCGStab_a<double, float> (lib/actions/ferm/invert/reliable_bicgstab.cc:13-290) behind the shell of
+        LinOpSysSolverReliableBiCGStabClover (syssolver_linop_rel_bicgstab_clover.h:105-146): A psi = chi with A = M
+        (isign=+1) or M^dag (-1).  fp32 vectors emulated by rounding, as in solve_reliable_cg.  Note that, like the
+        reference, rho is NOT recomputed after a residual replacement (:186, :205-216).
+        Returns (psi, iterations [1-based], n_r_updates, |chi - A psi|)."""
+        Vh = self.Vh
+        c64 = lambda a: (a[..., 0] + 1j * a[..., 1])                                     # noqa: E731
+        f32 = lambda z: z.astype(np.complex64).astype(np.complex128)                     # noqa: E731
+
+        def A(z):          # complex odd-cb vector -> complex odd-cb vector, evaluated in double
+            full = np.zeros((self.V, 4, 3, 2))
+            full[Vh:, ..., 0] = z.real
+            full[Vh:, ..., 1] = z.imag
+            return c64(self.apply(full, isign)[Vh:])
+
+        chi_c = c64(np.asarray(chi, dtype=np.float64)[Vh:])
+        psi = c64(np.ascontiguousarray(psi0, dtype=np.float64)[Vh:]).copy()
+        rsd_sq = rsd * rsd * float(np.vdot(chi_c, chi_c).real)
+        b = chi_c - A(psi)
+        r_sq = float(np.vdot(b, b).real)
+        r = f32(b)
+        r0 = r.copy()
+        x = np.zeros_like(r)
+        p = np.zeros_like(r)
+        v = np.zeros_like(r)
+        rNorm = np.sqrt(r_sq)
+        r0Norm = maxrx = maxrr = rNorm
+        rho = rho_prev = alpha = omega = 1.0 + 0j
+        n_upd = 0
+        iters = maxit
+        for k in range(maxit):
+            if k == 0:
+                rho = r_sq + 0j
+                p = r.copy()
+            else:
+                beta = np.complex64((rho / rho_prev) * (alpha / omega))
+                p = f32(r + complex(beta) * f32(p - complex(np.complex64(omega)) * v))
+            v = f32(A(p))
+            ctmp = np.vdot(r0, v)
+            if ctmp == 0:
+                raise ArithmeticError("BiCGStab breakdown: <r_0|v> = 0")
+            alpha = rho / ctmp
+            rho_prev = rho
+            r = f32(r - complex(np.complex64(alpha)) * v)
+            t = f32(A(r))
+            omega = np.vdot(t, r) / float(np.vdot(t, t).real)
+            x = f32(f32(x + complex(np.complex64(omega)) * r) + complex(np.complex64(alpha)) * p)
+            r = f32(r - complex(np.complex64(omega)) * t)
+            r_sq = float(np.vdot(r, r).real)
+            rho = np.vdot(r0, r)
+            rNorm = np.sqrt(r_sq)
+            maxrx = max(maxrx, rNorm)
+            maxrr = max(maxrr, rNorm)
+            updateX = rNorm < delta * r0Norm and r0Norm <= maxrx
+            updateR = (rNorm < delta * maxrr and r0Norm <= maxrr) or updateX
+            if updateR:
+                n_upd += 1
+                r_d = b - A(x)
+                r_sq = float(np.vdot(r_d, r_d).real)
+                r = f32(r_d)
+                rNorm = np.sqrt(r_sq)
+                maxrr = rNorm
+                if updateX:
+                    psi = psi + x
+                    x = np.zeros_like(x)
+                    b = r_d
+                    r0Norm = maxrx = rNorm
+            if r_sq < rsd_sq:
+                psi = psi + x
+                iters = k + 1
+                break
+        else:
+            psi = psi + x
+        out = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+        out[Vh:, ..., 0] = psi.real
+        out[Vh:, ..., 1] = psi.imag
+        res = chi_c - A(psi)
+        return out, iters, n_upd, float(np.sqrt(np.vdot(res, res).real))
+
+    def solve_mdagm_reliable_bicgstab(self, chi, psi0, rsd, delta, maxit):
+        """MdagMSysSolverReliableBiCGStabClover::operator() (syssolver_mdagm_rel_bicgstab_clover.h:104-170): Y = M psi;
+        M^dag Y = chi (MINUS); M psi = Y (PLUS); n_count = sum; resid = |chi - M^dag M psi|."""
+        Y = self.apply(psi0, +1)
+        Y, n1, u1, _ = self.solve_reliable_bicgstab(chi, Y, rsd, delta, maxit, -1)
+        psi, n2, u2, _ = self.solve_reliable_bicgstab(Y, psi0, rsd, delta, maxit, +1)
+        return psi, n1 + n2, u1 + u2, self._mdagm_resid(chi, psi)
+
+
 # --------------------------------------------------------------------------- reference build
 class RefDslash:
     """Reference CPlusPlusWilsonDslash::Dslash<double|float> (cpp_dslash_scalar.h:20-105)."""

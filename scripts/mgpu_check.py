@@ -163,6 +163,45 @@ def main():
         print("[rank %d] batched BiCGStab rhs %d iters %d (cpu %d) true rel resid %.3e %s" %
               (rank, i, infos[i].n_count, n_ref, rel, "ok" if good else "FAIL"), flush=True)
 
+    # ---- section 8 (f3/f4) across the cut: reliable BiCGStab, multi-shift CG, symmetric preconditioning
+    del fin, fout, psi_b
+    if prec == "double":
+        _, n_ref, nupd, _ = op.solve_reliable_bicgstab(podd, np.zeros_like(podd), 1e-10, 0.1, 2000)
+        sol, info = ctx.invert_reliable_bicgstab(slab_cb(podd, 1), None, rsd=1e-10, delta=0.1, max_iter=2000)
+        full = gather_full(sol)
+        res = podd - op.apply(full, +1)
+        rel = np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(podd[Vh:] ** 2))
+        good = info.converged == 1 and abs(info.n_count - n_ref) <= max(4, 0.15 * n_ref) and rel < 2e-9
+        ok &= good
+        print("[rank %d] reliable BiCGStab iters %d (cpu %d, %d/%d updates) true rel resid %.3e %s" %
+              (rank, info.n_count, n_ref, info.n_updates, nupd, rel, "ok" if good else "FAIL"), flush=True)
+    shifts = [0.001, 0.05, 0.7]
+    ref_ms, n_ref, _ = op.solve_multishift(podd, shifts, rsd, 2000)
+    sol_ms, infos = ctx.invert_multishift(slab_cb(podd, 1).astype(npdt), shifts, rsd, max_iter=2000)
+    good = all(i.converged == 1 for i in infos) and abs(infos[0].n_count - n_ref) <= max(2, 0.05 * n_ref)
+    worst = 0.0
+    for s_, sh in enumerate(shifts):
+        full = gather_odd(sol_ms[s_])
+        res = podd - op.apply(op.apply(full, +1), -1) - sh * full
+        worst = max(worst, np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(podd[Vh:] ** 2)))
+    good = good and worst < 50 * rsd
+    ok &= good
+    print("[rank %d] multi-shift CG iters %d (cpu %d) worst true rel resid %.3e %s" % (rank, infos[0].n_count, n_ref, worst, "ok" if good else "FAIL"), flush=True)
+    ctx.set_preconditioning(True)
+    op.set_symmetric(True)
+    for isign in (+1, -1):
+        want = slab_cb(op.apply(podd, isign), 1)
+        got = ctx.matpc(slab_cb(podd, 1).astype(npdt), isign)
+        report("symmetric M isign=%+d" % isign, rel_site_err(got.astype(np.float64), want), 2 * tol)
+    _, n_ref, _, _ = op.solve_bicgstab(podd, np.zeros_like(podd), rsd, 2000)
+    sol, info = ctx.invert(slab_cb(podd, 1).astype(npdt), None, solver=L.B200_SOLVER_BICGSTAB, rsd=rsd, max_iter=2000)
+    full = gather_odd(sol)
+    res = podd - op.apply(full, +1)
+    rel = np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(podd[Vh:] ** 2))
+    good = info.converged == 1 and abs(info.n_count - n_ref) <= max(2, 0.08 * n_ref) and rel < 20 * rsd
+    ok &= good
+    print("[rank %d] symmetric BiCGStab iters %d (cpu %d) true rel resid %.3e %s" % (rank, info.n_count, n_ref, rel, "ok" if good else "FAIL"), flush=True)
+
     ctx.close()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

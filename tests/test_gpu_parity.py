@@ -251,6 +251,49 @@ def test_reliable_cg_mixed_precision(oracle, delta, mdagm):
     ctxf.close()
 
 
+@pytest.mark.parametrize("mdagm", [False, True])
+@pytest.mark.parametrize("delta", [0.1, 0.01])
+def test_reliable_bicgstab_mixed_precision(oracle, delta, mdagm):
+    """RelInvBiCGStab_a (reliable_bicgstab.cc:13-290), fp32 recurrences / fp64 residual replacement: reaches an fp64
+    target residual fp32 alone cannot, iteration and replacement counts close to the CPU restatement of the same
+    algorithm (fp32 BiCGStab is more erratic than CG, hence the wider band), two-step M^dag M variant included."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, cp = setup(oracle, latt, "double", gauge="weak")
+    chi = fields.gaussian_fermion(latt, seed=12, cb=1)
+    Vh = ctx.Vh
+    rsd = 1e-10
+    z = np.zeros_like(chi)
+    if mdagm:
+        psi_ref, n_ref, nupd_ref, _ = op.solve_mdagm_reliable_bicgstab(chi, z, rsd, delta, 2000)
+        _, n64, _ = op.solve_mdagm_bicgstab(chi, z, rsd, 2000)
+    else:
+        psi_ref, n_ref, nupd_ref, _ = op.solve_reliable_bicgstab(chi, z, rsd, delta, 2000)
+        _, n64, _, _ = op.solve_bicgstab(chi, z, rsd, 2000)
+    psi, info = ctx.invert_reliable_bicgstab(chi[Vh:], None, rsd=rsd, delta=delta, max_iter=2000, mdagm=mdagm)
+    assert info.converged == 1
+    assert abs(info.n_count - n_ref) <= max(4, 0.15 * n_ref), (info.n_count, n_ref)
+    assert info.n_count <= 1.25 * n64 + 4, (info.n_count, n64)
+    assert info.n_updates >= 1 and abs(info.n_updates - nupd_ref) <= max(3, 0.3 * nupd_ref), (info.n_updates, nupd_ref)
+    full = np.zeros_like(chi)
+    full[Vh:] = psi
+    r = chi - (op.apply(op.apply(full, +1), -1) if mdagm else op.apply(full, +1))
+    rel = np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(chi[Vh:] ** 2))
+    assert rel < (200 if mdagm else 20) * rsd, rel              # far below what fp32 alone can reach (~1e-6)
+    assert abs(info.rel_resid - rel) < 1e-2 * rel + 1e-14
+    assert rel_site_err(psi, psi_ref[Vh:]) < 1e-6
+    # deterministic; an exact initial guess returns at once; a float context must refuse
+    psi2, info2 = ctx.invert_reliable_bicgstab(chi[Vh:], None, rsd=rsd, delta=delta, max_iter=2000, mdagm=mdagm)
+    assert info2.n_count == info.n_count and np.array_equal(psi2, psi)
+    psi3, info3 = ctx.invert_reliable_bicgstab(chi[Vh:], psi, rsd=1e-8, delta=delta, max_iter=2000, mdagm=mdagm)
+    assert info3.n_count == 0 and info3.converged == 1 and np.array_equal(psi3, psi)
+    ctx.close()
+    u, op, ctxf, cp = setup(oracle, latt, "single", gauge="weak")
+    with pytest.raises(L.B200Error) as e:
+        ctxf.invert_reliable_bicgstab(chi[Vh:].astype(np.float32), None, rsd=1e-6, delta=0.1, max_iter=10)
+    assert e.value.code == L.B200_ERR_ARG
+    ctxf.close()
+
+
 def test_plugin_mirror_drop_in(oracle):
     """LinOpSysSolverB200Clover used the way quarkprop4_w.cc:86-109 uses a LinOpSystemSolver: XML-like params in,
     (psi, chi) -> {n_count, resid}; GPU-built clover; non-convergence raises unless SilentFail (.h:634-644)."""

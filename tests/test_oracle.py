@@ -468,3 +468,24 @@ def test_multishift_cg_restatement(oracle, symmetric):
     one, n1, _ = op.solve_multishift(chi, [0.3], 1e-8, 500)
     assert n1 <= n
     assert np.abs(one[0] - psi[2])[Vh:].max() < 1e-6 * np.abs(psi[2][Vh:]).max()
+
+
+def test_reliable_bicgstab_restatement(oracle):
+    """RelInvBiCGStab_a restated with emulated fp32 vectors: reaches an fp64-level true residual, needs at least one
+    residual replacement, and takes about as many iterations as plain fp64 BiCGStab (both M and the two-step M^dag M)."""
+    L = (4, 4, 4, 8)
+    u = fields.apply_bc(L, fields.weak_gauge(L, seed=11))
+    op = oracle.Op(L, u, 0.1, 1.0)
+    chi = fields.gaussian_fermion(L, seed=12, cb=1)
+    Vh = chi.shape[0] // 2
+    z = np.zeros_like(chi)
+    nchi = np.sqrt(np.sum(chi[Vh:] ** 2))
+    _, n64, _, _ = op.solve_bicgstab(chi, z, 1e-10, 500)
+    for delta in (0.1, 0.01):
+        psi, n, n_upd, res = op.solve_reliable_bicgstab(chi, z, 1e-10, delta, 500)
+        assert n_upd >= 1 and res / nchi < 2e-9
+        assert abs(n - n64) <= 0.25 * n64 + 4, (n, n64)
+    psi, n, n_upd, res = op.solve_mdagm_reliable_bicgstab(chi, z, 1e-10, 0.1, 500)
+    assert n_upd >= 2 and res / nchi < 5e-8
+    ref, _, _ = op.solve_mdagm_cg(chi, z, 1e-11, 500)
+    assert np.abs(psi - ref)[Vh:].max() < 1e-6 * np.abs(ref[Vh:]).max()
