@@ -9,8 +9,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libb200clover.so")
-OBJDIR = os.path.join(HERE, "_obj")
+# B200_BUILD_TAG=<tag> builds a tuning variant next to the product library (libb200clover_<tag>.so, own object dir);
+# chroma_b200/lib.py loads it when B200_LIB_TAG=<tag> is set.  Variants are built HERE (nvcc cross-compiles without a GPU)
+# so that GPU time is spent measuring, not compiling.
+_TAG = os.environ.get("B200_BUILD_TAG", "")
+OUT = os.path.join(HERE, "libb200clover%s.so" % ("_" + _TAG if _TAG else ""))
+OBJDIR = os.path.join(HERE, "_obj" + ("_" + _TAG if _TAG else ""))
 SOURCES = ["api.cu", "engine_d.cu", "engine_f.cu", "engine_mixed.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -19,7 +23,7 @@ FLAGS = [
 ]
 # tuning knobs (defaults live in the sources): B200_DSLASH_BLOCK, B200_DSLASH_MINBLOCKS
 for _k in ("B200_DSLASH_BLOCK", "B200_DSLASH_MINBLOCKS", "B200_DSLASH_BLOCK_F", "B200_DSLASH_MINBLOCKS_F",
-           "B200_MRHS_NRB", "B200_MRHS_MINB", "B200_MRHS_NRB_F", "B200_MRHS_MINB_F"):
+           "B200_MRHS_NRB", "B200_MRHS_MINB", "B200_MRHS_NRB_F", "B200_MRHS_MINB_F", "B200_MRHS_PREFETCH"):
     if os.environ.get(_k):
         FLAGS += ["-D%s=%s" % (_k, os.environ[_k])]
 

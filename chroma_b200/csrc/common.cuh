@@ -83,6 +83,15 @@ __device__ __forceinline__ void cp_async(float2* smem_dst, const float2* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// ... with an L2 residency hint (the batched kernels prefetch the next hop's neighbour spinor into shared memory)
+__device__ __forceinline__ void cp_async_hint(double2* smem_dst, const double2* gsrc, uint64_t pol) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_hint(float2* smem_dst, const float2* gsrc, uint64_t pol) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // read-modify-write streams (the CG residual) must not use the non-coherent path

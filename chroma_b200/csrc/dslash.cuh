@@ -102,14 +102,15 @@ __device__ __forceinline__ int launch_site(const DslashArgs<R>& a, int local) {
 }
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
-template <typename R, int MU, bool MR = false>
+// SM: the spinor was prefetched into shared memory (plane stride = `stride` = 32), see dslash_site_pf.
+template <typename R, int MU, bool MR = false, bool SM = false>
 __device__ __forceinline__ void load_project(Cx<R> h0[3], Cx<R> h1[3], const Cx<R>* __restrict__ p, int stride, R sg, uint64_t keep) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const Cx<R> a0 = MR ? ld_keep_nol1(p + (0 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a1 = MR ? ld_keep_nol1(p + (1 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a2 = MR ? ld_keep_nol1(p + (2 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a3 = MR ? ld_keep_nol1(p + (3 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a0 = SM ? p[(0 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (0 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a1 = SM ? p[(1 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (1 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a2 = SM ? p[(2 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (2 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a3 = SM ? p[(3 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (3 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
     if (MU == 0) {          // h0 = a0 + sg*i*a3, h1 = a1 + sg*i*a2
       h0[c] = mk<R>(a0.x - sg * a3.y, a0.y + sg * a3.x);
       h1[c] = mk<R>(a1.x - sg * a2.y, a1.y + sg * a2.x);
@@ -303,6 +304,99 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
 #undef B200_LB
 }
 
+// ---- batched kernels: the hopping term with the neighbour spinors software-pipelined through shared memory ----------
+// The batched kernel is bound by latency x occupancy: a warp walks 8 dependent "load 12 complex numbers,
+// wait, multiply" rounds, and the registers that would hold a second hop's loads in flight are the ones that limit the
+// warps per SM.  So the NEXT hop's neighbour spinor is fetched with cp.async into a per-warp shared-memory buffer
+// (12 planes x 32 lanes) while the current hop is multiplied: twice the bytes in flight per warp, and no register is
+// tied up while they fly.  Every lane reads back only what it copied itself, so cp.async.wait_group is all the
+// synchronisation needed.  `sp` = this lane's column of the warp's buffer; after the last hop the buffer receives
+// `after` (the x operand of the EPI_M* epilogues) if given.  Same arithmetic, same order as dslash_site.
+template <typename R>
+__device__ __forceinline__ void prefetch_spinor(Cx<R>* sp, const Cx<R>* __restrict__ p, int stride, uint64_t pol) {
+#pragma unroll
+  for (int k = 0; k < 12; ++k) cp_async_hint(sp + k * 32, p + (size_t)k * stride, pol);
+  cp_async_commit();
+}
+template <typename R, int MU, bool ADJ, bool RECON12>
+__device__ __forceinline__ void hop_pf(Cx<R> acc[12], Cx<R>* sp, const Cx<R>* link, R sg, R scale, const L2Policy& pol,
+                                       const Cx<R>* __restrict__ next, int stride, uint64_t next_pol) {
+  Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
+  cp_async_wait_all();
+  load_project<R, MU, true, true>(h0, h1, sp, 32, sg, 0);
+  if (next) prefetch_spinor<R>(sp, next, stride, next_pol);      // the buffer is free again: start the next hop's fetch
+  load_link<R, RECON12, true>(U, link, 32, pol.stream);
+  if (RECON12) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { h0[c].x *= scale; h0[c].y *= scale; h1[c].x *= scale; h1[c].y *= scale; }
+  }
+  su3_mul<R, ADJ>(r0, r1, U, h0, h1);
+  recons_acc<R, MU>(acc, r0, r1, sg);
+}
+template <typename R, bool RECON12>
+__device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol,
+                                               const Cx<R>* sml, Cx<R>* sp, const Cx<R>* after) {
+  typedef Cx<R> C;
+  const Geom& g = a.g;
+  const int stride = g.Vh;
+  int q = idx;
+  const int xh = q % g.Lxh; q /= g.Lxh;
+  const int y = q % g.Ly;   q /= g.Ly;
+  const int z = q % g.Lz;
+  const int t = q / g.Lz;
+  const int r = (y + z + t + a.parity) & 1;
+  constexpr int NG = RECON12 ? 6 : 9;
+  const C* __restrict__ in = a.in;
+  const R s = (R)a.isign;
+#define B200_LF(mu) (sml + (2 * (mu)) * NG * 32)
+#define B200_LB(mu) (sml + (2 * (mu) + 1) * NG * 32)
+  const int xf = r ? (xh + 1 == g.Lxh ? idx - (g.Lxh - 1) : idx + 1) : idx;
+  const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
+  const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
+  const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
+  const int sz = g.Ly * g.Lxh, st = g.S3h;
+  const bool zl = (z + 1 == g.Lz), z0 = (z == 0), tl = (t + 1 == g.Lt), t0 = (t == 0);
+  const int zf = zl ? idx - (g.Lz - 1) * sz : idx + sz;
+  const int zb = z0 ? idx + (g.Lz - 1) * sz : idx - sz;
+  const int tf = tl ? idx - (g.Lt - 1) * st : idx + st;
+  const int tb = t0 ? idx + (g.Lt - 1) * st : idx - st;
+  const bool gzf = g.zsplit && zl, gzb = g.zsplit && z0, gtf = g.tsplit && tl, gtb = g.tsplit && t0;   // hops served by ghost faces
+  const int fz = (t * g.Ly + y) * g.Lxh + xh;
+  R scf = (R)ls.aniso[3], scb = (R)ls.aniso[3];
+  if (RECON12) {
+    if (ls.t_is_last && tl) scf *= (R)ls.bc_t;
+    if (ls.t_is_last && t0 && !g.tsplit) scb *= (R)ls.bc_t;
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = mk<R>(0, 0);
+
+  prefetch_spinor<R>(sp, in + xf, stride, pol.keep);
+  hop_pf<R, 0, false, RECON12>(acc, sp, B200_LF(0), -s, (R)ls.aniso[0], pol, in + xb, stride, pol.keep);
+  hop_pf<R, 0, true, RECON12>(acc, sp, B200_LB(0), s, (R)ls.aniso[0], pol, in + yf, stride, pol.keep);
+  hop_pf<R, 1, false, RECON12>(acc, sp, B200_LF(1), -s, (R)ls.aniso[1], pol, in + yb, stride, pol.keep);
+  hop_pf<R, 1, true, RECON12>(acc, sp, B200_LB(1), s, (R)ls.aniso[1], pol, gzf ? nullptr : in + zf, stride, pol.keep);
+  // a hop across a rank boundary reads its (already projected) half spinor from the ghost face: nothing was prefetched
+  // for it, so the buffer is free and the fetch for the hop after it starts first
+  if (gzf) {
+    if (!gzb) prefetch_spinor<R>(sp, in + zb, stride, pol.keep);
+    ghost_hop_fwd<R, 2, RECON12, true>(acc, a.ghost_zfwd + fz, g.SZh, B200_LF(2), 32, -s, (R)ls.aniso[2], pol);
+  } else hop_pf<R, 2, false, RECON12>(acc, sp, B200_LF(2), -s, (R)ls.aniso[2], pol, gzb ? nullptr : in + zb, stride, pol.keep);
+  if (gzb) {
+    if (!gtf) prefetch_spinor<R>(sp, in + tf, stride, pol.keep);
+    ghost_hop_bwd<R, 2>(acc, a.ghost_zbwd + fz, g.SZh, s, pol);
+  } else hop_pf<R, 2, true, RECON12>(acc, sp, B200_LB(2), s, (R)ls.aniso[2], pol, gtf ? nullptr : in + tf, stride, pol.keep);
+  if (gtf) {
+    if (!gtb) prefetch_spinor<R>(sp, in + tb, stride, pol.keep);
+    ghost_hop_fwd<R, 3, RECON12, true>(acc, a.ghost_fwd + (idx - (g.Lt - 1) * st), st, B200_LF(3), 32, -s, scf, pol);
+  } else hop_pf<R, 3, false, RECON12>(acc, sp, B200_LF(3), -s, scf, pol, gtb ? nullptr : in + tb, stride, pol.keep);
+  if (gtb) {
+    if (after) prefetch_spinor<R>(sp, after, stride, pol.stream);
+    ghost_hop_bwd<R, 3>(acc, a.ghost_bwd + idx, st, s, pol);
+  } else hop_pf<R, 3, true, RECON12>(acc, sp, B200_LB(3), s, scb, pol, after, stride, pol.stream);
+#undef B200_LF
+#undef B200_LB
+}
+
 // Indices (on the source checkerboard) of the four backward neighbours of target site idx -- where the backward links
 // live.  Same arithmetic as dslash_site; used by the multi-RHS kernels to stage the links.
 __device__ __forceinline__ void backward_neighbours(const Geom& g, int idx, int parity, int nbr[4]) {
@@ -413,9 +507,11 @@ struct FinBiOmega {
 #define B200_DSLASH_MINBLOCKS_F 4   // fp32: 64-bit loads need 4 CTAs/SM in flight (tuned on B200: 1 -> 80 %, 3 -> 96 %, 4 -> 100 % of HBM peak)
 #endif
 // ---- fused epilogues for one target site (shared by the single- and multi-RHS kernels) ------------------------
-template <typename R, int EPI, bool MR, int MODE = MODE_ASYM>
+// spx != nullptr (batched kernels with prefetch): the x operand of the EPI_M* epilogues was copied to shared memory
+// (this lane's column, plane stride 32) behind the last hop.
+template <typename R, int EPI, bool MR, int MODE = MODE_ASYM, bool XS = false>
 __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>& a, int idx, int stride, const L2Policy& pol, double red[3],
-                                              const Cx<R>* smc = nullptr) {
+                                              const Cx<R>* smc = nullptr, const Cx<R>* spx = nullptr) {
   typedef Cx<R> C;
   // clover block b of this site: staged in shared memory (multi-RHS) or streamed from global memory
   const C* const cl0 = MR ? smc : a.clov + idx;
@@ -434,6 +530,7 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
     // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
     // and would cost one exposed DRAM round trip each.
     C m[12], ex[12];
+    if (XS) cp_async_wait_all();
     if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) ex[k] = ld_stream_rw(a.r + (size_t)k * stride + idx, pol.stream);
@@ -446,7 +543,7 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
     for (int b = 0; b < 2; ++b) {
       C xi[6], o[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) xi[k] = ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
+      for (int k = 0; k < 6; ++k) xi[k] = XS ? spx[(6 * b + k) * 32] : ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
       if (MODE == MODE_ASYM) clover_block<R, MR>(o, xi, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
       if (MODE == MODE_SYM_PLUS) clover_block<R, MR>(o, acc + 6 * b, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
 #pragma unroll
@@ -538,11 +635,16 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
 #ifndef B200_MRHS_MINB_F
 #define B200_MRHS_MINB_F 2
 #endif
+#ifndef B200_MRHS_PREFETCH
+#define B200_MRHS_PREFETCH 1  // 1: neighbour spinors software-pipelined through shared memory (dslash_site_pf); 0: direct loads
+#endif
 template <typename R, int EPI, bool RECON12> struct MrhsSmem {
   static constexpr int NG = RECON12 ? 6 : 9;
   static constexpr int NL = 8 * NG;                                 // link slots
   static constexpr int NS = NL + (EPI == EPI_DSLASH ? 0 : 36);      // + clover slots
   static constexpr size_t bytes = (size_t)NS * 32 * sizeof(Cx<R>);
+  // + one 12-plane spinor buffer per right-hand side (warp) of the CTA
+  static constexpr size_t total(int nrb) { return bytes + (B200_MRHS_PREFETCH ? (size_t)nrb * 12 * 32 * sizeof(Cx<R>) : 0); }
 };
 template <typename R, int EPI, bool RECON12, int NRB>
 __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
@@ -604,8 +706,15 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   if (active) {
     const L2Policy pol = make_l2_policy();
     C acc[12];
+#if B200_MRHS_PREFETCH
+    C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;
+    constexpr bool XS = (EPI >= EPI_M);
+    dslash_site_pf<R, RECON12>(acc, a, ls, idx, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
+    site_epilogue<R, EPI, true, MODE_ASYM, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
+#else
     dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x);
     site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
+#endif
   }
 
   const int sb = site_block;   // block_offset of a split step is applied inside warp_grid_reduce

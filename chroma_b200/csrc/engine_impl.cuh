@@ -489,12 +489,12 @@ class Engine : public EngineBase {
       constexpr int E = (EPI == EPI_M_CGREL ? EPI_M_CG : EPI);
       if (recon == 12) {
         auto k = dslash_mrhs_kernel<R, E, true, NRB>;
-        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, true>::bytes));
-        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::bytes, stream>>>(a, ls, ngroups);
+        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, true>::total(NRB)));
+        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::total(NRB), stream>>>(a, ls, ngroups);
       } else {
         auto k = dslash_mrhs_kernel<R, E, false, NRB>;
-        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, false>::bytes));
-        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::bytes, stream>>>(a, ls, ngroups);
+        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, false>::total(NRB)));
+        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::total(NRB), stream>>>(a, ls, ngroups);
       }
       return launched("dslash_mrhs_kernel");
     }

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200clover.so")
+# B200_LIB_TAG selects a tuning variant built with B200_BUILD_TAG (chroma_b200/build.py); default: the product library
+LIB_PATH = os.path.join(_HERE, "libb200clover%s.so" % ("_" + os.environ["B200_LIB_TAG"] if os.environ.get("B200_LIB_TAG") else ""))
 
 B200_SINGLE, B200_DOUBLE = 4, 8
 B200_RECONS_NONE, B200_RECONS_12 = 18, 12

@@ -42,6 +42,13 @@ def main():
     m_times("asymmetric")
     info = ctx.dev_invert(psi_f.zero(), chi_f, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=2000)
     out["asymmetric"]["cg_solve"] = {"iterations": info.n_count, "secs": info.secs, "rel_resid": info.rel_resid}
+    info = ctx.dev_invert(psi_f.zero(), chi_f, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-8, max_iter=2000)
+    out["asymmetric"]["bicgstab_solve"] = {"iterations": info.n_count, "secs": info.secs, "rel_resid": info.rel_resid}
+    # mixed-precision reliable updates (fp32 recurrences, fp64 residual replacement), same target
+    for name, fn in (("reliable_cg_solve", ctx.dev_invert_reliable), ("reliable_bicgstab_solve", ctx.dev_invert_reliable_bicgstab)):
+        fn(psi_f.zero(), chi_f, rsd=1e-8, delta=0.1, max_iter=2000)          # first call builds the fp32 twin
+        info = fn(psi_f.zero(), chi_f, rsd=1e-8, delta=0.1, max_iter=2000)
+        out["asymmetric"][name] = {"iterations": info.n_count, "secs": info.secs, "rel_resid": info.rel_resid, "n_updates": info.n_updates}
     # multi-shift on the asymmetric operator
     shifts = list(np.geomspace(1e-4, 2.0, n_shift))
     mp = ctx.mfield(n_shift)
