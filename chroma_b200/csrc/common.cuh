@@ -83,11 +83,15 @@ __device__ __forceinline__ void cp_async(float2* smem_dst, const float2* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
-// ... with an L2 residency hint (the batched kernels prefetch the next hop's neighbour spinor into shared memory)
+// ... with an L2 residency hint (the batched kernels prefetch the next hop's neighbour spinor into shared memory).
+// L1 = true allocates the line in L1 as well (.ca); 16-byte copies may bypass it (.cg), 8-byte ones cannot.
+template <bool L1>
 __device__ __forceinline__ void cp_async_hint(double2* smem_dst, const double2* gsrc, uint64_t pol) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+  if (L1) asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+  else asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
 }
+template <bool L1>
 __device__ __forceinline__ void cp_async_hint(float2* smem_dst, const float2* gsrc, uint64_t pol) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");

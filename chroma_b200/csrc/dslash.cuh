@@ -101,16 +101,28 @@ __device__ __forceinline__ int launch_site(const DslashArgs<R>& a, int local) {
   return 0;
 }
 
+// Batched-kernel knobs (tuned on B200, profiles/r01_tune_mrhs_prefetch.txt):
+#ifndef B200_MRHS_PREFETCH
+#define B200_MRHS_PREFETCH 1    // fp64: neighbour spinors software-pipelined through shared memory (dslash_site_pf); 0: direct loads
+#endif
+#ifndef B200_MRHS_PREFETCH_F
+#define B200_MRHS_PREFETCH_F 0  // fp32: the extra shared-memory traffic costs more than the latency it hides
+#endif
+#ifndef B200_MRHS_L1
+#define B200_MRHS_L1 0          // 1: batched kernels let the neighbour spinors allocate in L1 (x/y neighbours of a warp overlap)
+#endif
+template <typename R> struct MrhsPrefetch { static constexpr bool on = sizeof(R) == 4 ? (B200_MRHS_PREFETCH_F != 0) : (B200_MRHS_PREFETCH != 0); };
+
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
 // SM: the spinor was prefetched into shared memory (plane stride = `stride` = 32), see dslash_site_pf.
 template <typename R, int MU, bool MR = false, bool SM = false>
 __device__ __forceinline__ void load_project(Cx<R> h0[3], Cx<R> h1[3], const Cx<R>* __restrict__ p, int stride, R sg, uint64_t keep) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const Cx<R> a0 = SM ? p[(0 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (0 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a1 = SM ? p[(1 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (1 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a2 = SM ? p[(2 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (2 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
-    const Cx<R> a3 = SM ? p[(3 * 3 + c) * stride] : MR ? ld_keep_nol1(p + (3 * 3 + c) * (size_t)stride, keep) : ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a0 = SM ? p[(0 * 3 + c) * stride] : MR ? (B200_MRHS_L1 ? ld_keep(p + (0 * 3 + c) * (size_t)stride, keep) : ld_keep_nol1(p + (0 * 3 + c) * (size_t)stride, keep)) : ld_keep(p + (0 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a1 = SM ? p[(1 * 3 + c) * stride] : MR ? (B200_MRHS_L1 ? ld_keep(p + (1 * 3 + c) * (size_t)stride, keep) : ld_keep_nol1(p + (1 * 3 + c) * (size_t)stride, keep)) : ld_keep(p + (1 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a2 = SM ? p[(2 * 3 + c) * stride] : MR ? (B200_MRHS_L1 ? ld_keep(p + (2 * 3 + c) * (size_t)stride, keep) : ld_keep_nol1(p + (2 * 3 + c) * (size_t)stride, keep)) : ld_keep(p + (2 * 3 + c) * (size_t)stride, keep);
+    const Cx<R> a3 = SM ? p[(3 * 3 + c) * stride] : MR ? (B200_MRHS_L1 ? ld_keep(p + (3 * 3 + c) * (size_t)stride, keep) : ld_keep_nol1(p + (3 * 3 + c) * (size_t)stride, keep)) : ld_keep(p + (3 * 3 + c) * (size_t)stride, keep);
     if (MU == 0) {          // h0 = a0 + sg*i*a3, h1 = a1 + sg*i*a2
       h0[c] = mk<R>(a0.x - sg * a3.y, a0.y + sg * a3.x);
       h1[c] = mk<R>(a1.x - sg * a2.y, a1.y + sg * a2.x);
@@ -315,7 +327,7 @@ __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& 
 template <typename R>
 __device__ __forceinline__ void prefetch_spinor(Cx<R>* sp, const Cx<R>* __restrict__ p, int stride, uint64_t pol) {
 #pragma unroll
-  for (int k = 0; k < 12; ++k) cp_async_hint(sp + k * 32, p + (size_t)k * stride, pol);
+  for (int k = 0; k < 12; ++k) cp_async_hint<B200_MRHS_L1 != 0>(sp + k * 32, p + (size_t)k * stride, pol);
   cp_async_commit();
 }
 template <typename R, int MU, bool ADJ, bool RECON12>
@@ -635,16 +647,13 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
 #ifndef B200_MRHS_MINB_F
 #define B200_MRHS_MINB_F 2
 #endif
-#ifndef B200_MRHS_PREFETCH
-#define B200_MRHS_PREFETCH 1  // 1: neighbour spinors software-pipelined through shared memory (dslash_site_pf); 0: direct loads
-#endif
 template <typename R, int EPI, bool RECON12> struct MrhsSmem {
   static constexpr int NG = RECON12 ? 6 : 9;
   static constexpr int NL = 8 * NG;                                 // link slots
   static constexpr int NS = NL + (EPI == EPI_DSLASH ? 0 : 36);      // + clover slots
   static constexpr size_t bytes = (size_t)NS * 32 * sizeof(Cx<R>);
   // + one 12-plane spinor buffer per right-hand side (warp) of the CTA
-  static constexpr size_t total(int nrb) { return bytes + (B200_MRHS_PREFETCH ? (size_t)nrb * 12 * 32 * sizeof(Cx<R>) : 0); }
+  static constexpr size_t total(int nrb) { return bytes + (MrhsPrefetch<R>::on ? (size_t)nrb * 12 * 32 * sizeof(Cx<R>) : 0); }
 };
 template <typename R, int EPI, bool RECON12, int NRB>
 __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
@@ -706,15 +715,15 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   if (active) {
     const L2Policy pol = make_l2_policy();
     C acc[12];
-#if B200_MRHS_PREFETCH
-    C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;
-    constexpr bool XS = (EPI >= EPI_M);
-    dslash_site_pf<R, RECON12>(acc, a, ls, idx, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
-    site_epilogue<R, EPI, true, MODE_ASYM, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
-#else
-    dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x);
-    site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
-#endif
+    if (MrhsPrefetch<R>::on) {
+      C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;
+      constexpr bool XS = (EPI >= EPI_M) && MrhsPrefetch<R>::on;
+      dslash_site_pf<R, RECON12>(acc, a, ls, idx, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
+      site_epilogue<R, EPI, true, MODE_ASYM, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
+    } else {
+      dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x);
+      site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
+    }
   }
 
   const int sb = site_block;   // block_offset of a split step is applied inside warp_grid_reduce
