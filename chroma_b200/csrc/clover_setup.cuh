@@ -2,8 +2,8 @@
 //   field strength  F_mu,nu = 1/8 (Q - Q^dag), Q = sum of the four plaquette leaves   (lib/meas/glue/mesfield.cc:44-74)
 //   makeClov        A = diag_mass + sum c_mu,nu sigma_mu,nu F_mu,nu, packed triangular  (clover_term_qdp_w.h:398-553)
 //   ldagdlinv       per-site LDL^dagger factorisation + inverse of both 6x6 blocks      (clover_term_qdp_w.h:619-846)
-// These replace the QDP-JIT kernels ptx_make_clov / ptx_ldagdlinv (clover_term_ptx_w.h:780,1102).  One thread
-// per site, arithmetic always in double (also for the fp32 engine); they run once per gauge field.
+// These replace the QDP-JIT kernels ptx_make_clov / ptx_ldagdlinv (clover_term_ptx_w.h:780,1102).  Arithmetic is always
+// in double (also for the fp32 engine); they run once per gauge field.
 #pragma once
 #include "common.cuh"
 #include "reduce.cuh"
@@ -37,22 +37,34 @@ __device__ __forceinline__ Z zdiv(Z a, Z b) {
 }
 // r = a b, r = a b^dag, r = a^dag b on 3x3 complex matrices
 __device__ __forceinline__ void mm(Z* r, const Z* a, const Z* b) {
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
     Z s = make_double2(0, 0);
+#pragma unroll
     for (int k = 0; k < 3; ++k) s = zadd(s, zmul(a[i * 3 + k], b[k * 3 + j]));
     r[i * 3 + j] = s;
   }
 }
 __device__ __forceinline__ void mm_adj(Z* r, const Z* a, const Z* b) {
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
     Z s = make_double2(0, 0);
+#pragma unroll
     for (int k = 0; k < 3; ++k) s = zadd(s, zmul(a[i * 3 + k], zconj(b[j * 3 + k])));
     r[i * 3 + j] = s;
   }
 }
 __device__ __forceinline__ void adj_mm(Z* r, const Z* a, const Z* b) {
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
     Z s = make_double2(0, 0);
+#pragma unroll
     for (int k = 0; k < 3; ++k) s = zadd(s, zmul(zconj(a[k * 3 + i]), b[k * 3 + j]));
     r[i * 3 + j] = s;
   }
@@ -60,14 +72,15 @@ __device__ __forceinline__ void adj_mm(Z* r, const Z* a, const Z* b) {
 
 // The link U_mu at local coordinates c (on a split lattice c[3] may be -1 or Lt and c[2] may be -1 or Lz, both at once
 // for the corner links; everything else wraps), as Chroma's state->getLinks() holds it: boundary phase included,
-// anisotropy NOT included.
+// anisotropy NOT included.  Coordinates are at most one step outside the local lattice.
 template <typename R>
-__device__ void fetch_link(Z U[9], const CloverSetupArgs<R>& a, int mu, int cx, int cy, int cz, int ct) {
+__device__ __forceinline__ void fetch_link(Z U[9], const CloverSetupArgs<R>& a, int mu, int cx, int cy, int cz, int ct) {
   const Geom& g = a.g;
   const int Lx = 2 * g.Lxh;
-  cx = (cx + Lx) % Lx; cy = (cy + g.Ly) % g.Ly;
-  if (!g.zsplit) cz = (cz + g.Lz) % g.Lz;
-  if (!g.tsplit) ct = (ct + g.Lt) % g.Lt;
+  cx = cx < 0 ? cx + Lx : (cx >= Lx ? cx - Lx : cx);
+  cy = cy < 0 ? cy + g.Ly : (cy >= g.Ly ? cy - g.Ly : cy);
+  if (!g.zsplit) cz = cz < 0 ? cz + g.Lz : (cz >= g.Lz ? cz - g.Lz : cz);
+  if (!g.tsplit) ct = ct < 0 ? ct + g.Lt : (ct >= g.Lt ? ct - g.Lt : ct);
   // parity of the site: ghost slices keep the parity of their global coordinate; local extents are even, so
   // (t = -1) and (t = Lt) have the parity of an odd / even t respectively (same for z).
   const int par = (cx + cy + cz + ct + 4) & 1;
@@ -76,6 +89,7 @@ __device__ void fetch_link(Z U[9], const CloverSetupArgs<R>& a, int mu, int cx, 
     const size_t sze = (size_t)g.Lxh * g.Ly * (g.Lt + 2);
     const int f = ((ct + 1) * g.Ly + cy) * g.Lxh + cx / 2;
     const Cx<R>* p = a.ghost_links_z + ((size_t)((face * 4 + mu) * 2 + par) * 9) * sze + f;
+#pragma unroll
     for (int k = 0; k < 9; ++k) { const Cx<R> v = p[(size_t)k * sze]; U[k] = make_double2((double)v.x, (double)v.y); }
     return;
   }
@@ -83,110 +97,156 @@ __device__ void fetch_link(Z U[9], const CloverSetupArgs<R>& a, int mu, int cx, 
     const int face = ct < 0 ? 0 : 1;
     const int s3 = (cz * g.Ly + cy) * g.Lxh + cx / 2;
     const Cx<R>* p = a.ghost_links + ((size_t)((face * 4 + mu) * 2 + par) * 9) * g.S3h + s3;
+#pragma unroll
     for (int k = 0; k < 9; ++k) { const Cx<R> v = p[(size_t)k * g.S3h]; U[k] = make_double2((double)v.x, (double)v.y); }
     return;
   }
   const int idx = ((ct * g.Lz + cz) * g.Ly + cy) * g.Lxh + cx / 2;
   const int NG = a.recon12 ? 6 : 9;
   const Cx<R>* p = a.gauge + ((size_t)(mu * 2 + par) * NG) * g.Vh + idx;
-  for (int k = 0; k < NG; ++k) { const Cx<R> v = p[(size_t)k * g.Vh]; U[k] = make_double2((double)v.x, (double)v.y); }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) if (k < NG) { const Cx<R> v = __ldg(p + (size_t)k * g.Vh); U[k] = make_double2((double)v.x, (double)v.y); }
   if (a.recon12) {
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
       U[6 + c] = zconj(zsub(zmul(U[c1], U[3 + c2]), zmul(U[c2], U[3 + c1])));
     }
-    if (mu == 3 && a.bc_t == -1 && a.t_is_last && ct == g.Lt - 1)
+    if (mu == 3 && a.bc_t == -1 && a.t_is_last && ct == g.Lt - 1) {
+#pragma unroll
       for (int k = 0; k < 9; ++k) { U[k].x = -U[k].x; U[k].y = -U[k].y; }
+    }
   } else {
     const double s = a.inv_aniso[mu];
+#pragma unroll
     for (int k = 0; k < 9; ++k) { U[k].x *= s; U[k].y *= s; }
   }
 }
 
-template <typename R>
-__global__ void __launch_bounds__(CLOV_BLOCK) make_clover_kernel(const CloverSetupArgs<R> a) {
-  const Geom& g = a.g;
-  const int idx = blockIdx.x * CLOV_BLOCK + threadIdx.x;
-  if (idx >= g.Vh) return;
-  int q = idx;
-  const int xh = q % g.Lxh; q /= g.Lxh;
-  const int y = q % g.Ly; q /= g.Ly;
-  const int z = q % g.Lz;
-  const int t = q / g.Lz;
-  const int x = 2 * xh + ((y + z + t + a.parity) & 1);
-  const int c0[4] = {x, y, z, t};
-
-  Z F[6][9];
-  int plane = 0;
-#pragma unroll 1
-  for (int mu = 0; mu < 3; ++mu) {
-#pragma unroll 1
-    for (int nu = mu + 1; nu < 4; ++nu, ++plane) {
-      int em[4] = {0, 0, 0, 0}, en[4] = {0, 0, 0, 0};
-      em[mu] = 1; en[nu] = 1;
-#define LNK(U, dir, sm, sn) fetch_link<R>(U, a, dir, c0[0] + (sm) * em[0] + (sn) * en[0], c0[1] + (sm) * em[1] + (sn) * en[1], \
-                                          c0[2] + (sm) * em[2] + (sn) * en[2], c0[3] + (sm) * em[3] + (sn) * en[3])
-      Z A[9], B[9], C[9], D[9], t1[9], t2[9], Q[9];
-      // leaf 1: U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag
-      LNK(A, mu, 0, 0); LNK(B, nu, 1, 0); LNK(C, mu, 0, 1); LNK(D, nu, 0, 0);
-      mm(t1, A, B); mm(t2, D, C);           // t2 = U_nu(x) U_mu(x+nu)
-      mm_adj(Q, t1, t2);
-      // leaf 2: U_mu(x-mu)^dag U_nu(x-mu-nu)^dag U_mu(x-mu-nu) U_nu(x-nu)
-      LNK(A, mu, -1, 0); LNK(B, nu, -1, -1); LNK(C, mu, -1, -1); LNK(D, nu, 0, -1);
-      mm(t1, B, A);                          // U_nu(x-mu-nu) U_mu(x-mu)
-      mm(t2, C, D);                          // U_mu(x-mu-nu) U_nu(x-nu)
-      adj_mm(A, t1, t2);
-      for (int k = 0; k < 9; ++k) Q[k] = zadd(Q[k], A[k]);
-      // leaf 3: U_nu(x-nu)^dag U_mu(x-nu) U_nu(x-nu+mu) U_mu(x)^dag
-      LNK(A, nu, 0, -1); LNK(B, mu, 0, -1); LNK(C, nu, 1, -1); LNK(D, mu, 0, 0);
-      adj_mm(t1, A, B); mm_adj(t2, C, D);
-      mm(A, t1, t2);
-      for (int k = 0; k < 9; ++k) Q[k] = zadd(Q[k], A[k]);
-      // leaf 4: U_nu(x) U_mu(x-mu+nu)^dag U_nu(x-mu)^dag U_mu(x-mu)
-      LNK(A, nu, 0, 0); LNK(B, mu, -1, 1); LNK(C, nu, -1, 0); LNK(D, mu, -1, 0);
-      mm_adj(t1, A, B); adj_mm(t2, C, D);
-      mm(A, t1, t2);
-      for (int k = 0; k < 9; ++k) Q[k] = zadd(Q[k], A[k]);
+// Field strength of ONE plane (MU < NU) at one site, times the clover coefficient of the plane:
+// F = coef/8 (Q - Q^dag), Q = sum of the four leaves (mesfield.cc:44-74; getCloverCoeff, clover_term_qdp_w.h:1524-1544).
+// At most two links and two products are live at a time (the one-thread-per-site version kept seven 3x3 matrices and
+// the six F planes in local memory).
+template <typename R, int MU, int NU>
+__device__ __forceinline__ void field_strength_plane(Z Fout[9], const CloverSetupArgs<R>& a, int x, int y, int z, int t) {
+  constexpr int ex = (MU == 0), ey = (MU == 1), ez = (MU == 2), et = (MU == 3);     // unit vector mu
+  constexpr int fx = (NU == 0), fy = (NU == 1), fz = (NU == 2), ft = (NU == 3);     // unit vector nu
+#define LNK(U, dir, sm, sn) fetch_link<R>(U, a, dir, x + (sm) * ex + (sn) * fx, y + (sm) * ey + (sn) * fy, z + (sm) * ez + (sn) * fz, t + (sm) * et + (sn) * ft)
+  Z A[9], B[9], t1[9], t2[9], Q[9];
+  // leaf 1: U_mu(x) U_nu(x+mu) U_mu(x+nu)^dag U_nu(x)^dag
+  LNK(A, MU, 0, 0); LNK(B, NU, 1, 0); mm(t1, A, B);
+  LNK(A, NU, 0, 0); LNK(B, MU, 0, 1); mm(t2, A, B);            // t2 = U_nu(x) U_mu(x+nu)
+  mm_adj(Q, t1, t2);
+  // leaf 2: U_mu(x-mu)^dag U_nu(x-mu-nu)^dag U_mu(x-mu-nu) U_nu(x-nu)
+  LNK(A, NU, -1, -1); LNK(B, MU, -1, 0); mm(t1, A, B);         // U_nu(x-mu-nu) U_mu(x-mu)
+  LNK(A, MU, -1, -1); LNK(B, NU, 0, -1); mm(t2, A, B);         // U_mu(x-mu-nu) U_nu(x-nu)
+  adj_mm(A, t1, t2);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Q[k] = zadd(Q[k], A[k]);
+  // leaf 3: U_nu(x-nu)^dag U_mu(x-nu) U_nu(x-nu+mu) U_mu(x)^dag
+  LNK(A, NU, 0, -1); LNK(B, MU, 0, -1); adj_mm(t1, A, B);
+  LNK(A, NU, 1, -1); LNK(B, MU, 0, 0); mm_adj(t2, A, B);
+  mm(A, t1, t2);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Q[k] = zadd(Q[k], A[k]);
+  // leaf 4: U_nu(x) U_mu(x-mu+nu)^dag U_nu(x-mu)^dag U_mu(x-mu)
+  LNK(A, NU, 0, 0); LNK(B, MU, -1, 1); mm_adj(t1, A, B);
+  LNK(A, NU, -1, 0); LNK(B, MU, -1, 0); adj_mm(t2, A, B);
+  mm(A, t1, t2);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Q[k] = zadd(Q[k], A[k]);
 #undef LNK
-      // F = 1/8 (Q - Q^dag), times the clover coefficient of this plane (getCloverCoeff, :1524-1544)
-      const double coef = (a.aniso && (mu == a.t_dir || nu == a.t_dir)) ? a.ct : a.cr;
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        const Z d = zsub(Q[i * 3 + j], zconj(Q[j * 3 + i]));
-        F[plane][i * 3 + j] = make_double2(0.125 * d.x * coef, 0.125 * d.y * coef);
-      }
-    }
-  }
-
-  // makeClovSiteLoop, clover_term_qdp_w.h:416-519
-  double diag[2][6]; Z offd[2][15];
-  for (int b = 0; b < 2; ++b) for (int i = 0; i < 6; ++i) diag[b][i] = a.diag_mass;
-  for (int i = 0; i < 3; ++i) {
-    const Z d0 = zsub(F[5][i * 3 + i], F[0][i * 3 + i]);
-    diag[0][i] += d0.y; diag[0][i + 3] -= d0.y;
-    const Z d1 = zadd(F[5][i * 3 + i], F[0][i * 3 + i]);
-    diag[1][i] -= d1.y; diag[1][i + 3] += d1.y;
-  }
-  for (int i = 1; i < 3; ++i)
-    for (int j = 0; j < i; ++j) {
-      const int eij = i * (i - 1) / 2 + j, etmp = (i + 3) * (i + 2) / 2 + j + 3;
-      offd[0][eij] = ztimesI(zsub(F[0][i * 3 + j], F[5][i * 3 + j]));
-      offd[0][etmp] = make_double2(-offd[0][eij].x, -offd[0][eij].y);
-      offd[1][eij] = ztimesI(zadd(F[5][i * 3 + j], F[0][i * 3 + j]));
-      offd[1][etmp] = make_double2(-offd[1][eij].x, -offd[1][eij].y);
-    }
+  const double coef = (a.aniso && (MU == a.t_dir || NU == a.t_dir)) ? a.ct : a.cr;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int eij = (i + 3) * (i + 2) / 2 + j;
-      const Z Em = zadd(ztimesI(F[2][i * 3 + j]), F[4][i * 3 + j]);
-      const Z Bm = zsub(ztimesI(F[3][i * 3 + j]), F[1][i * 3 + j]);
-      offd[0][eij] = zsub(Bm, Em);
-      offd[1][eij] = zadd(Em, Bm);
+      const Z d = zsub(Q[i * 3 + j], zconj(Q[j * 3 + i]));
+      Fout[i * 3 + j] = make_double2(0.125 * d.x * coef, 0.125 * d.y * coef);
     }
+}
+
+// One entry of the packed clover term of a site from its six field-strength planes (makeClovSiteLoop,
+// clover_term_qdp_w.h:416-519).  q = 0..2: the diagonal pairs (2q, 2q+1) of chiral block b; q = 3..17: off-diagonal k = q-3.
+// F(p, e) reads element e of plane p of this site.  Planes: 0 (0,1), 1 (0,2), 2 (0,3), 3 (1,2), 4 (1,3), 5 (2,3).
+template <typename FS>
+__device__ __forceinline__ Z clover_entry(int b, int q, double diag_mass, const FS& F) {
+  if (q < 3) {
+    double d[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i6 = 2 * q + h, i = i6 % 3;          // diag index 0..5 -> colour i, upper (i6 < 3) or lower half
+      const Z f5 = F(5, i * 3 + i), f0 = F(0, i * 3 + i);
+      const double im = (b == 0) ? (f5.y - f0.y) : (f5.y + f0.y);
+      const bool plus = (b == 0) ? (i6 < 3) : (i6 >= 3);
+      d[h] = diag_mass + (plus ? im : -im);
+    }
+    return make_double2(d[0], d[1]);
+  }
+  const int k = q - 3;
+  // colour-colour entries inside the upper (k = 0,1,2) and lower (k = 9,13,14) 3x3 sub-blocks
+  if (k < 3 || k == 9 || k == 13 || k == 14) {
+    const int kk = k < 3 ? k : (k == 9 ? 0 : k - 12);
+    const int i = kk == 0 ? 1 : 2, j = kk == 2 ? 1 : 0;
+    const Z f0 = F(0, i * 3 + j), f5 = F(5, i * 3 + j);
+    Z v = (b == 0) ? ztimesI(zsub(f0, f5)) : ztimesI(zadd(f5, f0));
+    if (k >= 3) { v.x = -v.x; v.y = -v.y; }
+    return v;
+  }
+  // entries coupling the lower to the upper half: eij = (i+3)(i+2)/2 + j
+  const int i = k < 6 ? 0 : (k < 9 ? 1 : 2);
+  const int j = k - (i == 0 ? 3 : (i == 1 ? 6 : 10));
+  const Z Em = zadd(ztimesI(F(2, i * 3 + j)), F(4, i * 3 + j));
+  const Z Bm = zsub(ztimesI(F(3, i * 3 + j)), F(1, i * 3 + j));
+  return (b == 0) ? zsub(Bm, Em) : zadd(Em, Bm);
+}
+
+// CTA = CLOV_SITES sites x 6 planes: warp p computes plane p of the field strength for 32 consecutive sites (6x the
+// parallelism of one thread per site, no local-memory arrays), the planes meet in shared memory, and the 192 threads
+// then assemble the 36 output planes, 6 each.  48^3x96: 45 ms -> see profiles/ (per parity).
+constexpr int CLOV_SITES = 32;
+#ifndef B200_CLOV_MINB
+#define B200_CLOV_MINB 2   // CTAs/SM the register allocator plans for.  B200, 48^3x96: 1 (230 registers, no spills) 56 ms per parity; 2 (168 registers, ~400 B of spills) 28 ms -- the kernel is latency-bound, occupancy wins
+#endif
+struct SmemF {
+  const Z* f; int lane;
+  __device__ __forceinline__ Z operator()(int plane, int e) const { return f[(plane * 9 + e) * CLOV_SITES + lane]; }
+};
+template <typename R>
+__global__ void __launch_bounds__(CLOV_SITES * 6, B200_CLOV_MINB) make_clover_kernel(const CloverSetupArgs<R> a) {
+  __shared__ Z Fs[6 * 9 * CLOV_SITES];
+  const Geom& g = a.g;
+  const int lane = threadIdx.x, plane = threadIdx.y;
+  const int idx = blockIdx.x * CLOV_SITES + lane;
+  const bool active = idx < g.Vh;
+  if (active) {
+    int q = idx;
+    const int xh = q % g.Lxh; q /= g.Lxh;
+    const int y = q % g.Ly; q /= g.Ly;
+    const int z = q % g.Lz;
+    const int t = q / g.Lz;
+    const int x = 2 * xh + ((y + z + t + a.parity) & 1);
+    Z F[9];
+    switch (plane) {       // uniform per warp
+      case 0: field_strength_plane<R, 0, 1>(F, a, x, y, z, t); break;
+      case 1: field_strength_plane<R, 0, 2>(F, a, x, y, z, t); break;
+      case 2: field_strength_plane<R, 0, 3>(F, a, x, y, z, t); break;
+      case 3: field_strength_plane<R, 1, 2>(F, a, x, y, z, t); break;
+      case 4: field_strength_plane<R, 1, 3>(F, a, x, y, z, t); break;
+      default: field_strength_plane<R, 2, 3>(F, a, x, y, z, t); break;
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Fs[(plane * 9 + e) * CLOV_SITES + lane] = F[e];
+  }
+  __syncthreads();
+  if (!active) return;
+  const SmemF F{Fs, lane};
   const size_t Vh = g.Vh;
-  for (int b = 0; b < 2; ++b) {
-    Cx<R>* o = a.clov_out + (size_t)(18 * b) * Vh + idx;
-    for (int k = 0; k < 3; ++k) o[(size_t)k * Vh] = mk<R>((R)diag[b][2 * k], (R)diag[b][2 * k + 1]);
-    for (int k = 0; k < 15; ++k) o[(size_t)(3 + k) * Vh] = mk<R>((R)offd[b][k].x, (R)offd[b][k].y);
+#pragma unroll
+  for (int n = 0; n < 6; ++n) {
+    const int p = plane * 6 + n;                  // output plane 0..35 = block*18 + q
+    const Z v = clover_entry(p / 18, p % 18, a.diag_mass, F);
+    a.clov_out[(size_t)p * Vh + idx] = mk<R>((R)v.x, (R)v.y);
   }
 }
 

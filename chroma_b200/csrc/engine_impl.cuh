@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstdarg>
+#include <thread>
 
 #include "engine.cuh"
 #include "dslash.cuh"
@@ -23,6 +24,21 @@ namespace b200 {
 constexpr int DSLASH_BLOCK_MAX = B200_DSLASH_BLOCK > B200_DSLASH_BLOCK_F ? B200_DSLASH_BLOCK : B200_DSLASH_BLOCK_F;
 constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
 constexpr size_t STAGING_BYTES = 256u << 20;
+constexpr size_t PIN_BYTES = 32u << 20;      // one pinned bounce buffer of the pageable-host copy pipeline (two per engine)
+
+// memcpy with a small team of threads: one core moves ~10 GB/s, PCIe 5 x16 wants ~50
+inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int nthreads) {
+  if (nthreads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+  const size_t per = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+  std::vector<std::thread> team;
+  for (int t = 1; t < nthreads; ++t) {
+    const size_t off = per * t;
+    if (off >= bytes) break;
+    team.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (auto& th : team) th.join();
+}
 
 // status != nullptr: a solver launch -- return at once when the solve has stopped / when slot run_if is clear
 template <typename R, int BLOCK>
@@ -79,6 +95,13 @@ class Engine : public EngineBase {
   double* h_scal = nullptr; int* h_status = nullptr;   // pinned; [MAX_RHS][S_COUNT] and 2 slots of [MAX_RHS][ST_COUNT]
   cudaEvent_t ev_poll[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
   void* staging = nullptr;
+  // Host buffers the caller hands over (QDP++ fields) are pageable: a plain cudaMemcpy moves them at ~10 GB/s through the
+  // driver's own bounce buffer.  We bounce them ourselves: a team of host threads fills one pinned buffer while the DMA
+  // engine drains the other (and the reverse for downloads).  Pinned / registered host memory takes the direct path.
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  int pin_next = 0;
+  int copy_threads = 4;
   b200_field* ws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Halo<R> halo;
   int blas_grid = 148 * 8;
@@ -131,6 +154,13 @@ class Engine : public EngineBase {
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
     B200_CUDA(cudaMalloc(&staging, STAGING_BYTES));
+    for (int i = 0; i < 2; ++i) {
+      B200_CUDA(cudaHostAlloc(&pin[i], PIN_BYTES, cudaHostAllocDefault));
+      B200_CUDA(cudaEventCreateWithFlags(&pin_ev[i], cudaEventDisableTiming));
+    }
+    // the ranks of one box share its cores: half of them, split over the ranks, at most 8 per rank
+    copy_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / (2u * (unsigned)(cfg.pgrid[2] * cfg.pgrid[3]))));
+    if (const char* e = getenv("B200_COPY_THREADS")) copy_threads = std::max(0, atoi(e));   // 0: plain cudaMemcpy from pageable memory
     if (split()) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
@@ -146,6 +176,7 @@ class Engine : public EngineBase {
     cudaFree(gauge); cudaFree(clov); cudaFree(invclov); cudaFree(tr_log); cudaFree(invclov_oo); cudaFree(tr_log_oo); cudaFree(ms_dev);
     if (owns_scalars) { cudaFree(scal); cudaFree(status); }
     cudaFree(partial); cudaFree(ticket); cudaFree(staging);
+    for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (pin_ev[i]) cudaEventDestroy(pin_ev[i]); pin[i] = nullptr; pin_ev[i] = nullptr; }
     cudaFreeHost(h_scal); cudaFreeHost(h_status);
     for (int i = 0; i < 2; ++i) if (ev_poll[i]) cudaEventDestroy(ev_poll[i]);
     if (ev_t0) cudaEventDestroy(ev_t0);
@@ -179,6 +210,54 @@ class Engine : public EngineBase {
     return rb;
   }
 
+  // ------------------------------------------------------------------ host <-> device copies
+  static bool is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+  }
+  // Enqueue host -> device; on return the host buffer has been read completely (pageable) or the copy is in the stream (pinned).
+  int h2d(void* dst_dev, const void* src, size_t bytes) {
+    if (copy_threads == 0 || !is_pageable(src)) {
+      B200_CUDA(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyHostToDevice, stream));
+      return B200_OK;
+    }
+    for (size_t off = 0; off < bytes; off += PIN_BYTES) {
+      const size_t n = std::min(PIN_BYTES, bytes - off);
+      const int k = pin_next; pin_next ^= 1;
+      B200_CUDA(cudaEventSynchronize(pin_ev[k]));                 // the DMA that last read this bounce buffer is done
+      parallel_memcpy(pin[k], (const char*)src + off, n, copy_threads);
+      B200_CUDA(cudaMemcpyAsync((char*)dst_dev + off, pin[k], n, cudaMemcpyHostToDevice, stream));
+      B200_CUDA(cudaEventRecord(pin_ev[k], stream));
+    }
+    return B200_OK;
+  }
+  // Device -> host, complete on return.
+  int d2h(void* dst, const void* src_dev, size_t bytes) {
+    if (copy_threads == 0 || !is_pageable(dst)) {
+      B200_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+      B200_CUDA(cudaStreamSynchronize(stream));
+      return B200_OK;
+    }
+    size_t prev_off = 0, prev_n = 0; int prev_k = -1;
+    for (size_t off = 0; off < bytes || prev_k >= 0; off += PIN_BYTES) {
+      int k = -1; size_t n = 0;
+      if (off < bytes) {
+        n = std::min(PIN_BYTES, bytes - off);
+        k = pin_next; pin_next ^= 1;
+        B200_CUDA(cudaEventSynchronize(pin_ev[k]));
+        B200_CUDA(cudaMemcpyAsync(pin[k], (const char*)src_dev + off, n, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaEventRecord(pin_ev[k], stream));
+      }
+      if (prev_k >= 0) {                                          // drain the previous piece while this one is in flight
+        B200_CUDA(cudaEventSynchronize(pin_ev[prev_k]));
+        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads);
+      }
+      prev_k = k; prev_off = off; prev_n = n;
+    }
+    return B200_OK;
+  }
+
   // ------------------------------------------------------------------ host <-> device reordering
   template <typename H, int NR, int NPL, typename Map>
   int upload_aos(const H* src, int nsites, C* dst, size_t stride, Map map, double scale) {
@@ -186,7 +265,7 @@ class Engine : public EngineBase {
     int chunk = (int)std::min<size_t>((size_t)nsites, (STAGING_BYTES / rec) / PACK_SITES * PACK_SITES);
     for (int off = 0; off < nsites; off += chunk) {
       const int n = std::min(chunk, nsites - off);
-      B200_CUDA(cudaMemcpyAsync(staging, (const char*)src + (size_t)off * rec, (size_t)n * rec, cudaMemcpyHostToDevice, stream));
+      { int rch = h2d(staging, (const char*)src + (size_t)off * rec, (size_t)n * rec); if (rch) return rch; }
       aos_to_soa_kernel<H, R, NR, NPL, Map><<<(n + PACK_SITES - 1) / PACK_SITES, PACK_BLOCK, 0, stream>>>(
           (const H*)staging, dst, n, stride, (size_t)off, map, scale);
       int rc = launched("aos_to_soa"); if (rc) return rc;
@@ -203,7 +282,8 @@ class Engine : public EngineBase {
       soa_to_aos_kernel<H, R, NR, NPL, Map><<<(n + PACK_SITES - 1) / PACK_SITES, PACK_BLOCK, 0, stream>>>(
           (H*)staging, src, n, stride, (size_t)off, map);
       int rc = launched("soa_to_aos"); if (rc) return rc;
-      B200_CUDA(cudaMemcpyAsync((char*)dst + (size_t)off * rec, staging, (size_t)n * rec, cudaMemcpyDeviceToHost, stream));
+      // the next chunk's kernel overwrites the device staging buffer: d2h returns only when this chunk has left it
+      { int rch = d2h((char*)dst + (size_t)off * rec, staging, (size_t)n * rec); if (rch) return rch; }
     }
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
@@ -318,7 +398,7 @@ class Engine : public EngineBase {
     if (split()) { rc = halo.exchange_gauge_ghost(a, launches); if (rc) return rc; }
     for (int par = 0; par < 2; ++par) {
       a.parity = par; a.clov_out = clov + (size_t)par * 36 * g.Vh;
-      make_clover_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(a);
+      make_clover_kernel<R><<<(g.Vh + CLOV_SITES - 1) / CLOV_SITES, dim3(CLOV_SITES, 6), 0, stream>>>(a);
       rc = launched("make_clover"); if (rc) return rc;
     }
     B200_CUDA(cudaMemcpyAsync(invclov, clov, sizeof(C) * 36 * (size_t)g.Vh, cudaMemcpyDeviceToDevice, stream));
