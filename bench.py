@@ -451,6 +451,22 @@ def run_b200(args):
         del psi_d
     except Exception as e:  # noqa
         e2e["breakdown_ms"] = {"error": str(e)}
+    # the same call on PAGEABLE host buffers (what QDP++ fields are): the engine bounces them through pinned double
+    # buffers with a team of host threads (engine_impl.cuh::h2d / d2h)
+    try:
+        chi_pg, psi_pg = np.array(chi_np, copy=True), np.zeros_like(chi_np)
+        barrier()
+        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e8.record(stream)
+        L.check(ctx.lib.b200_invert(ctx.h, C.c_void_p(psi_pg.ctypes.data), C.c_void_p(chi_pg.ctypes.data), ctx.prec, solver, 0.0,
+                                    args.steps, C.byref(L.SolveInfo())))
+        e9.record(stream)
+        barrier()
+        ms_pg = max_over_ranks(e8.elapsed_time(e9))
+        e2e["pageable_host_buffers"] = {"ms_per_call": ms_pg, "value": flop_iter * Vh_global * args.steps / (ms_pg * 1e-3) * 1e-9}
+        del chi_pg, psi_pg
+    except Exception as e:  # noqa
+        e2e["pageable_host_buffers"] = {"error": str(e)}
     t_clock_end = time.time()
 
     # ---------------- optional: a real solve to 1e-8 (time to solution)
