@@ -24,11 +24,11 @@ namespace b200 {
 constexpr int DSLASH_BLOCK_MAX = B200_DSLASH_BLOCK > B200_DSLASH_BLOCK_F ? B200_DSLASH_BLOCK : B200_DSLASH_BLOCK_F;
 constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
 constexpr size_t STAGING_BYTES = 256u << 20;
-constexpr size_t PIN_BYTES = 32u << 20;      // one pinned bounce buffer of the pageable-host copy pipeline (two per engine)
+constexpr size_t PIN_BYTES_DEFAULT = 32u << 20;   // one pinned bounce buffer of the pageable-host copy pipeline (two per engine)
 
 // memcpy with a small team of threads: one core moves ~10 GB/s, PCIe 5 x16 wants ~50
-inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int nthreads) {
-  if (nthreads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int nthreads, size_t serial_below) {
+  if (nthreads <= 1 || bytes < serial_below) { memcpy(dst, src, bytes); return; }
   const size_t per = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
   std::vector<std::thread> team;
   for (int t = 1; t < nthreads; ++t) {
@@ -102,6 +102,7 @@ class Engine : public EngineBase {
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   int pin_next = 0;
   int copy_threads = 4;
+  size_t PIN_BYTES = PIN_BYTES_DEFAULT;   // B200_PIN_KB shrinks it (tests: many pieces and the thread team on small lattices)
   b200_field* ws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Halo<R> halo;
   int blas_grid = 148 * 8;
@@ -154,6 +155,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
     B200_CUDA(cudaMalloc(&staging, STAGING_BYTES));
+    if (const char* e = getenv("B200_PIN_KB")) PIN_BYTES = std::max<size_t>(4096, (size_t)atol(e) << 10);
     for (int i = 0; i < 2; ++i) {
       B200_CUDA(cudaHostAlloc(&pin[i], PIN_BYTES, cudaHostAllocDefault));
       B200_CUDA(cudaEventCreateWithFlags(&pin_ev[i], cudaEventDisableTiming));
@@ -226,7 +228,7 @@ class Engine : public EngineBase {
       const size_t n = std::min(PIN_BYTES, bytes - off);
       const int k = pin_next; pin_next ^= 1;
       B200_CUDA(cudaEventSynchronize(pin_ev[k]));                 // the DMA that last read this bounce buffer is done
-      parallel_memcpy(pin[k], (const char*)src + off, n, copy_threads);
+      parallel_memcpy(pin[k], (const char*)src + off, n, copy_threads, PIN_BYTES / 8);
       B200_CUDA(cudaMemcpyAsync((char*)dst_dev + off, pin[k], n, cudaMemcpyHostToDevice, stream));
       B200_CUDA(cudaEventRecord(pin_ev[k], stream));
     }
@@ -251,7 +253,7 @@ class Engine : public EngineBase {
       }
       if (prev_k >= 0) {                                          // drain the previous piece while this one is in flight
         B200_CUDA(cudaEventSynchronize(pin_ev[prev_k]));
-        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads);
+        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads, PIN_BYTES / 8);
       }
       prev_k = k; prev_off = off; prev_n = n;
     }
