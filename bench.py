@@ -455,14 +455,16 @@ def run_b200(args):
     # buffers with a team of host threads (engine_impl.cuh::h2d / d2h)
     try:
         chi_pg, psi_pg = np.array(chi_np, copy=True), np.zeros_like(chi_np)
-        barrier()
-        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e8.record(stream)
-        L.check(ctx.lib.b200_invert(ctx.h, C.c_void_p(psi_pg.ctypes.data), C.c_void_p(chi_pg.ctypes.data), ctx.prec, solver, 0.0,
-                                    args.steps, C.byref(L.SolveInfo())))
-        e9.record(stream)
-        barrier()
-        ms_pg = max_over_ranks(e8.elapsed_time(e9))
+        for rep in range(2):      # the first call also pays the page faults of the freshly allocated arrays
+            psi_pg[...] = 0
+            barrier()
+            e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e8.record(stream)
+            L.check(ctx.lib.b200_invert(ctx.h, C.c_void_p(psi_pg.ctypes.data), C.c_void_p(chi_pg.ctypes.data), ctx.prec, solver, 0.0,
+                                        args.steps, C.byref(L.SolveInfo())))
+            e9.record(stream)
+            barrier()
+            ms_pg = max_over_ranks(e8.elapsed_time(e9))
         e2e["pageable_host_buffers"] = {"ms_per_call": ms_pg, "value": flop_iter * Vh_global * args.steps / (ms_pg * 1e-3) * 1e-9}
         del chi_pg, psi_pg
     except Exception as e:  # noqa

@@ -88,6 +88,9 @@ typedef struct {
   int reserved;
 } b200_solve_info;
 
+/* Environment knobs read at b200_create: B200_COPY_THREADS (host threads of the pageable-buffer bounce pipeline; 0 = plain
+ * cudaMemcpy), B200_PIN_KB (size of its pinned bounce buffers, default 32768), B200_MRHS_L2_KB (L2 budget of the batched
+ * traversal), B200_QPROP_BATCH (cap on the right-hand sides b200_qprop solves at once). */
 const char* b200_last_error(void);
 const char* b200_version(void);
 int b200_device_count(void);   /* CUDA devices visible to this process (<= 0: none); for rank -> device mapping */
@@ -146,7 +149,7 @@ int b200_set_preconditioning(b200_ctx* ctx, int preconditioning);
  * Replaces Dslash<REAL>::operator() (cpp_dslash_scalar.h:20-105; cpp_dslash_scalar_64bit.cc:35-65)
  * as called from CPPWilsonDslashD::apply (lwldslash_w_cppd.cc:174-215). */
 int b200_dslash(b200_ctx* ctx, void* out_cb_host, const void* in_cb_host, int host_prec, int isign, int out_cb);
-/* Clover term (inverse = 0) or its cb-0 inverse (inverse = 1) on checkerboard cb:
+/* Clover term (inverse = 0) or its inverse (inverse = 1; cb 0 only, unless symmetric preconditioning is on) on checkerboard cb:
  * QDPCloverTermT::apply (clover_term_qdp_w.h:2138-2160). */
 int b200_clover_apply(b200_ctx* ctx, void* out_cb_host, const void* in_cb_host, int host_prec, int cb, int inverse);
 /* out_odd = M in_odd (isign=+1) or M^dagger in_odd (-1): EvenOddPrecCloverLinOp::operator()
