@@ -11,6 +11,7 @@
 #include "chromabase.h"
 #include "handle.h"
 #include "state.h"
+#include "linearop.h"
 #include "io/aniso_io.h"
 #include "actions/ferm/invert/b200_solvers/syssolver_b200_clover_params.h"
 
@@ -55,7 +56,7 @@ namespace Chroma
     B200CloverEngine(Handle< FermState<T,Q,Q> > state, const SysSolverB200CloverParams& p) : ctx(0), invParam(p)
     {
       host_prec = (sizeof(REALT) == 4) ? B200_SINGLE : B200_DOUBLE;
-      int dev_prec = host_prec;
+      dev_prec = host_prec;
       if (p.precision == B200_PREC_SINGLE) dev_prec = B200_SINGLE;
       if (p.precision == B200_PREC_DOUBLE) dev_prec = B200_DOUBLE;
       const bool reliable = p.solverType == B200_RELIABLE_CG_SOLVER || p.solverType == B200_RELIABLE_BICGSTAB_SOLVER;
@@ -114,6 +115,28 @@ namespace Chroma
     }
 
     ~B200CloverEngine() { if (ctx) b200_destroy(ctx); }
+
+    //! Guard against a parameter group that does not describe the operator the factory handed us (the creator's
+    //! signature carries no such information): apply the caller's A and the engine's M to one Gaussian vector and
+    //! compare.  Catches a wrong SymmetricLinop, Mass / clovCoeff / anisotropy that differ from the fermion action's,
+    //! or a wrong AntiPeriodicT, at construction instead of as a failed residual check after the first solve.
+    void checkOperator(const LinearOperator<T>& A) const
+    {
+      T x = zero, want = zero, got = zero;
+      gaussian(x, rb[1]);
+      A(want, x, PLUS);
+      const void* in = (const void*)&(x.elem(rb[1].start()).elem(0).elem(0).real());
+      void* out = (void*)&(got.elem(rb[1].start()).elem(0).elem(0).real());
+      check(b200_clover_matpc(ctx, out, in, host_prec, B200_PLUS), "b200_clover_matpc");
+      got[rb[1]] -= want;
+      const Double rel = sqrt(norm2(got, rb[1])) / sqrt(norm2(want, rb[1]));
+      const Double tol = (dev_prec == B200_DOUBLE && host_prec == B200_DOUBLE) ? Double(1.0e-10) : Double(1.0e-4);
+      if (toBool(rel > tol)) {
+        QDPIO::cerr << "B200_CLOVER_INVERTER: the engine's operator differs from the fermion action's linear operator (rel. diff "
+                    << rel << "): check SymmetricLinop, CloverParams and AntiPeriodicT in the InvertParam group" << std::endl;
+        QDP_abort(1);
+      }
+    }
 
     //! psi, chi live on rb[1]; cb2 layout makes that one contiguous block starting at rb[1].start()
     b200_solve_info solve(T& psi, const T& chi, bool mdagm) const
@@ -183,6 +206,7 @@ namespace Chroma
     int comm_rs[2];   // {rank, size} handed to the b200_comm callbacks
     const SysSolverB200CloverParams invParam;
     int host_prec;
+    int dev_prec;
     bool mixed;
   };
 }

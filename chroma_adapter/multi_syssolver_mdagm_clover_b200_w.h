@@ -39,7 +39,9 @@ namespace Chroma
     MdagMMultiSysSolverB200Clover(Handle< LinearOperator<T> > A_, Handle< FermState<T,Q,Q> > state_,
                                   const SysSolverB200CloverParams& invParam_)
       : A(A_), invParam(invParam_), engine(new B200CloverEngine(state_, invParam_))
-    {}
+    {
+      engine->checkOperator(*A);
+    }
 
     ~MdagMMultiSysSolverB200Clover() {}
 

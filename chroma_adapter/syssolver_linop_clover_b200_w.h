@@ -38,6 +38,7 @@ namespace Chroma
                              const SysSolverB200CloverParams& invParam_)
       : A(A_), invParam(invParam_), engine(new B200CloverEngine(state_, invParam_))
     {
+      engine->checkOperator(*A);
       QDPIO::cout << "LinOpSysSolverB200Clover: engine ready" << std::endl;
     }
 

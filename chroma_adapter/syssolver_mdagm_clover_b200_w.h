@@ -40,7 +40,9 @@ namespace Chroma
     MdagMSysSolverB200Clover(Handle< LinearOperator<T> > A_, Handle< FermState<T,Q,Q> > state_,
                              const SysSolverB200CloverParams& invParam_)
       : A(A_), invParam(invParam_), engine(new B200CloverEngine(state_, invParam_))
-    {}
+    {
+      engine->checkOperator(*A);
+    }
 
     ~MdagMSysSolverB200Clover() {}
 

@@ -78,6 +78,7 @@ class LatticeColorMatrix {
 };
 template <typename T> struct WordType { typedef REAL Type_t; };
 inline Double norm2(const LatticeFermion&, const Subset&) { return Double(1.0); }
+inline void gaussian(LatticeFermion&, const Subset&) {}
 
 namespace Layout {
 const multi1d<int>& lattSize();
