@@ -515,6 +515,9 @@ struct FinBiOmega {
 #ifndef B200_DSLASH_MINBLOCKS
 #define B200_DSLASH_MINBLOCKS 1
 #endif
+#ifndef B200_SPLIT_REDUCE
+#define B200_SPLIT_REDUCE 0   // 1: single-RHS reducing epilogues store partials only, a one-CTA kernel finishes (reduce.cuh)
+#endif
 #ifndef B200_DSLASH_MINBLOCKS_F
 #define B200_DSLASH_MINBLOCKS_F 4   // fp32: 64-bit loads need 4 CTAs/SM in flight (tuned on B200: 1 -> 80 %, 3 -> 96 %, 4 -> 100 % of HBM peak)
 #endif
@@ -615,11 +618,31 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
     site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
   }
 
+#if B200_SPLIT_REDUCE
+  // partials only; dslash_finish_kernel (launched behind the last piece of the step) sums them and runs the finaliser
+  if (EPI == EPI_M_NORM || EPI == EPI_M_CG || EPI == EPI_M_CGREL) block_partials<1, BLOCK>(red, a.red);
+  if (EPI == EPI_M_DOTR0) block_partials<2, BLOCK>(red, a.red);
+  if (EPI == EPI_M_DOTX) block_partials<3, BLOCK>(red, a.red);
+#else
   if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal});
   if (EPI == EPI_M_CG) grid_reduce<1, BLOCK>(red, a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_CGREL) grid_reduce<1, BLOCK>(red, a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status});
   if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status});
+#endif
+}
+
+// The one-CTA tail of a reducing single-RHS step (B200_SPLIT_REDUCE): same early-outs as the step itself, so that a
+// stopped / predicated-off step leaves the scalars alone.
+template <typename R, int EPI, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) dslash_finish_kernel(const DslashArgs<R> a) {
+  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  if (a.run_if && a.status[a.run_if] == 0) return;
+  if (EPI == EPI_M_NORM) finish_partials<1, BLOCK>(a.red, FinCgD{a.scal});
+  if (EPI == EPI_M_CG) finish_partials<1, BLOCK>(a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_CGREL) finish_partials<1, BLOCK>(a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_DOTR0) finish_partials<2, BLOCK>(a.red, FinBiAlpha{a.scal, a.status});
+  if (EPI == EPI_M_DOTX) finish_partials<3, BLOCK>(a.red, FinBiOmega{a.scal, a.status});
 }
 
 // ---- multi-RHS variant ------------------------------------------------------------------------------------------

@@ -528,14 +528,27 @@ class Engine : public EngineBase {
         a.box[k++] = SiteBox{inner.t0, inner.nt, g.Lz - 1, 1};
       }
       a.nbox = k; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total);
-      return launch_one<EPI>(a, nb_face);
+      rc = launch_one<EPI>(a, nb_face); if (rc) return rc;
+      return launch_finish<EPI>(a);
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr; a.ghost_zfwd = nullptr; a.ghost_zbwd = nullptr;
     a.box[0] = SiteBox{0, g.Lt, 0, g.Lz}; a.nbox = 1; a.nsites = g.Vh;
     a.zc_sites = nb > 1 ? zchunk_sites(g.Lz) : 0;
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
-    return launch_one<EPI>(a, blocks);
+    { int rc1 = launch_one<EPI>(a, blocks); if (rc1) return rc1; }
+    return launch_finish<EPI>(a);
+  }
+  // B200_SPLIT_REDUCE: the one-CTA tail of a reducing single-RHS step (sums the partials of all its launches)
+  template <int EPI>
+  int launch_finish(const DslashArgs<R>& a) {
+#if B200_SPLIT_REDUCE
+    if (nb == 1 && (EPI == EPI_M_NORM || EPI == EPI_M_CG || EPI == EPI_M_CGREL || EPI == EPI_M_DOTR0 || EPI == EPI_M_DOTX)) {
+      dslash_finish_kernel<R, EPI, DSLASH_BLOCK><<<1, DSLASH_BLOCK, 0, stream>>>(a);
+      return launched("dslash_finish_kernel");
+    }
+#endif
+    return B200_OK;
   }
   template <int EPI>
   int launch_one(const DslashArgs<R>& a, int blocks) {

@@ -123,6 +123,39 @@ __device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fi
   }
 }
 
+// Split variant for the big single-RHS Dslash grids (B200_SPLIT_REDUCE): in grid_reduce every CTA must wait for its
+// ticket atomic to come back before it may exit (it has to learn whether it is the last one), and with one CTA per SM
+// that round trip -- tens of thousands of CTAs hammering one address -- is dead time on the SM.  Here the CTAs only
+// store their partials and leave; a one-CTA kernel launched behind the step sums them in the SAME fixed order, combines
+// across GPUs and runs the finaliser.
+template <int N, int BLOCK>
+__device__ __forceinline__ void block_partials(double v[N], const ReduceBuf& rb) {
+  __shared__ double smem[BLOCK / 32];
+  double s[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) s[k] = block_sum<BLOCK>(v[k], smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + rb.block_offset + blockIdx.x] = s[k];
+  }
+}
+template <int N, int BLOCK, typename Fin>
+__device__ __forceinline__ void finish_partials(const ReduceBuf& rb, Fin fin) {
+  __shared__ double smem[BLOCK / 32];
+  double tot[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < rb.total_blocks; b += BLOCK) acc += __ldcg(rb.partial + (size_t)k * rb.total_blocks + b);
+    tot[k] = block_sum<BLOCK>(acc, smem);
+  }
+  if (threadIdx.x == 0) {
+    peer_allreduce<N>(rb.peer, tot);
+    fin(tot);
+    __threadfence();
+  }
+}
+
 // Warp-synchronous variant for the multi-RHS Dslash kernels, where one WARP (32 consecutive sites of one right-hand
 // side) is the reduction unit: shuffle tree -> one partial per (rhs, site block) -> the warp that draws the last
 // ticket of its right-hand side sums that right-hand side's partials (lane-strided, then the same shuffle tree: a
