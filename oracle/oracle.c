@@ -21,7 +21,10 @@
  * (tests/test_oracle_vs_ref.py).  The clover build, LDL^dagger inverse and the solver
  * loops are restated-and-self-consistent (A*A^-1=1, gamma5-hermiticity, free field,
  * constant abelian field strength): the reference holds no golden vectors for them
- * that can be reproduced without QDP++'s RNG.
+ * that can be reproduced without QDP++'s RNG.  The same holds for the
+ * section-8(f) additions restated here -- the symmetric operator (seoprec_clover_linop_w.cc),
+ * its qprop decomposition and MInvCG2_a: parity unpinned, self-consistency checked in
+ * tests/test_oracle.py.
  */
 #include <math.h>
 #include <stdlib.h>
