@@ -1,4 +1,4 @@
-"""Multi-GPU parity (T and T x Z process grids, NVLink peer-memory halos and reductions): spawns scripts/mgpu_check.py
+"""Multi-GPU parity (T and T x Z process grids, NVLink peer-memory halos and reductions): spawns tests/mgpu_check.py
 under torchrun.  The N-GPU cases need >= N GPUs on the box and are skipped otherwise (`gpurun --gpus N` runs them); the
 `one_device` cases put every rank on cuda:0 (time-sliced contexts sharing memory through CUDA IPC), so the whole
 multi-rank protocol -- face packing, arrival flags, ghost reads, corner links of the clover build, in-kernel cross-rank
@@ -21,7 +21,7 @@ def ngpu():
 def run_check(world, env_extra, port):
     env = dict(os.environ, **env_extra)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "scripts", "mgpu_check.py")]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU_CHECK PASSED" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
 
