@@ -347,9 +347,11 @@ class SysSolverB200CloverParams:
     CloverParams: CloverFermActParams = field(default_factory=CloverFermActParams)
     RsdTarget: float = 1e-8
     MaxIter: int = 5000
-    SolverType: str = "CG"              # CG | BICGSTAB
+    SolverType: str = "CG"              # CG | BICGSTAB | RELIABLE_CG | RELIABLE_BICGSTAB
     AntiPeriodicT: bool = True
-    Precision: str = "DOUBLE"           # SINGLE | DOUBLE  (device precision)
+    Precision: str = "DOUBLE"           # SINGLE | DOUBLE  (device precision; XML tag CudaPrecision)
+    SloppyPrecision: str = "DEFAULT"    # DEFAULT | SINGLE | DOUBLE; SINGLE under DOUBLE = mixed-precision reliable updates (CudaSloppyPrecision)
+    Delta: float = 0.1                  # reliable-update threshold (syssolver_rel_cg_clover_params.cc, syssolver_rel_bicgstab_clover_params.cc:15-18)
     Reconstruct: str = "RECONS_NONE"    # RECONS_NONE | RECONS_12
     RsdToleranceFactor: float = 10.0
     SilentFail: bool = False
@@ -379,14 +381,27 @@ class LinOpSysSolverB200Clover:
     name = "B200_CLOVER_INVERTER"
 
     def __init__(self, global_dims, links, params: SysSolverB200CloverParams, clov=None, invclov=None, device=0,
-                 proc_grid=(1, 1, 1, 1), proc_coord=(0, 0, 0, 0), comm=None):
+                 proc_grid=(1, 1, 1, 1), proc_coord=(0, 0, 0, 0), comm=None, ctx=None):
         self.p = params
-        if params.SolverType not in ("CG", "BICGSTAB"):
-            raise ValueError("SolverType must be CG or BICGSTAB")        # adapter: QDPIO::cerr + QDP_abort(1)
+        if params.SolverType not in ("CG", "BICGSTAB", "RELIABLE_CG", "RELIABLE_BICGSTAB"):
+            raise ValueError("SolverType must be CG, BICGSTAB, RELIABLE_CG or RELIABLE_BICGSTAB")   # adapter: QDPIO::cerr + QDP_abort(1)
         if params.Precision not in ("SINGLE", "DOUBLE"):
             raise ValueError("Precision must be SINGLE or DOUBLE")
+        if params.SloppyPrecision not in ("DEFAULT", "SINGLE", "DOUBLE"):
+            raise ValueError("SloppyPrecision must be DEFAULT, SINGLE or DOUBLE")
         if params.Reconstruct not in ("RECONS_NONE", "RECONS_12"):
             raise ValueError("Reconstruct must be RECONS_NONE or RECONS_12")
+        # as B200CloverEngine's constructor (chroma_adapter/b200_clover_engine.h): mixed precision needs an fp64 engine
+        reliable = params.SolverType in ("RELIABLE_CG", "RELIABLE_BICGSTAB")
+        if reliable and params.Precision != "DOUBLE":
+            raise ValueError("RELIABLE_CG / RELIABLE_BICGSTAB need Precision DOUBLE")
+        self.mixed = params.Precision == "DOUBLE" and (params.SloppyPrecision == "SINGLE" or reliable)
+        self.bicg = params.SolverType in ("BICGSTAB", "RELIABLE_BICGSTAB")
+        self.solver = L.B200_SOLVER_BICGSTAB if self.bicg else L.B200_SOLVER_CG
+        self.last_info = None
+        if ctx is not None:          # an existing engine context (tests of the dispatch logic; several plugins on one engine)
+            self.ctx = ctx
+            return
         self.ctx = Context(global_dims, prec=params.Precision.lower(), device=device, proc_grid=proc_grid,
                            proc_coord=proc_coord, comm=comm)
         cp = params.CloverParams
@@ -399,15 +414,24 @@ class LinOpSysSolverB200Clover:
             self.ctx.make_clover(dm, cr, ct, aniso=cp.anisoParam.anisoP, t_dir=cp.anisoParam.t_dir)
         if params.SymmetricLinop:
             self.ctx.set_preconditioning(True)
-        self.solver = L.B200_SOLVER_CG if params.SolverType == "CG" else L.B200_SOLVER_BICGSTAB
-        self.last_info = None
 
     def subset(self):
         return 1   # rb[1]
 
+    def _solve(self, psi_odd, chi_odd, mdagm):
+        """B200CloverEngine::solve (chroma_adapter/b200_clover_engine.h): which ABI entry serves which parameter set."""
+        p = self.p
+        if self.mixed and not self.bicg:
+            return self.ctx.invert_reliable(chi_odd, psi_odd, rsd=p.RsdTarget, delta=p.Delta, max_iter=p.MaxIter, mdagm=mdagm)
+        if self.mixed:
+            return self.ctx.invert_reliable_bicgstab(chi_odd, psi_odd, rsd=p.RsdTarget, delta=p.Delta, max_iter=p.MaxIter, mdagm=mdagm)
+        if mdagm:
+            return self.ctx.invert_mdagm(chi_odd, psi_odd, solver=self.solver, rsd=p.RsdTarget, max_iter=p.MaxIter)
+        return self.ctx.invert(chi_odd, psi_odd, solver=self.solver, rsd=p.RsdTarget, max_iter=p.MaxIter)
+
     def __call__(self, psi_odd, chi_odd):
         """psi_odd: initial guess (modified in place), chi_odd: source; both [Vh,4,3,2] on rb[1]."""
-        sol, info = self.ctx.invert(chi_odd, psi_odd, solver=self.solver, rsd=self.p.RsdTarget, max_iter=self.p.MaxIter)
+        sol, info = self._solve(psi_odd, chi_odd, False)
         psi_odd[...] = sol.reshape(psi_odd.shape)
         self.last_info = info
         res = SystemSolverResults(n_count=info.n_count, resid=info.resid)
@@ -439,3 +463,25 @@ class MdagMMultiSysSolverB200Clover(LinOpSysSolverB200Clover):
         if worst > self.p.RsdToleranceFactor * self.p.RsdTarget and not self.p.SilentFail:
             raise SolverFailure("B200 multi-shift CG: rel resid %g > %g * %g" % (worst, self.p.RsdToleranceFactor, self.p.RsdTarget))
         return psi, SystemSolverResults(n_count=infos[0].n_count, resid=max(i.resid for i in infos))
+
+
+class MdagMSysSolverB200Clover(LinOpSysSolverB200Clover):
+    """Mirror of the HMC-side plugin (chroma_adapter/syssolver_mdagm_clover_b200_w.h; twin of MdagMSysSolverQUDAClover):
+    M^dag M psi = chi, with the optional chronological-predictor overload of MdagMSysSolverCG
+    (syssolver_mdagm_cg.h:104-123): `predictor(psi, chi)` supplies the initial guess, `predictor.new_vector(psi)`
+    records the solution (AbsChronologicalPredictor4D::operator() / newVector)."""
+
+    def __call__(self, psi_odd, chi_odd, predictor=None):
+        if predictor is not None:
+            predictor(psi_odd, chi_odd)
+        sol, info = self._solve(psi_odd, chi_odd, True)
+        psi_odd[...] = sol.reshape(psi_odd.shape)
+        self.last_info = info
+        if self.p.Verbose:
+            print("B200_CLOVER_SOLVER (MdagM): %d iterations. Rsd = %g Relative Rsd = %g" % (info.n_count, info.resid, info.rel_resid))
+        if info.rel_resid > self.p.RsdToleranceFactor * self.p.RsdTarget and not self.p.SilentFail:
+            raise SolverFailure("B200 MdagM solver residuum is outside tolerance: rel resid %g > %g * %g" %
+                                (info.rel_resid, self.p.RsdToleranceFactor, self.p.RsdTarget))
+        if predictor is not None:
+            predictor.new_vector(psi_odd)
+        return SystemSolverResults(n_count=info.n_count, resid=info.resid)
