@@ -489,3 +489,21 @@ def test_reliable_bicgstab_restatement(oracle):
     assert n_upd >= 2 and res / nchi < 5e-8
     ref, _, _ = op.solve_mdagm_cg(chi, z, 1e-11, 500)
     assert np.abs(psi - ref)[Vh:].max() < 1e-6 * np.abs(ref[Vh:]).max()
+
+
+def test_multishift_unsorted_shifts_and_anisotropy(oracle):
+    """MInvCG2_a does not assume sorted shifts (it searches the smallest one, minvcg2.cc:104-110) and works for the
+    anisotropic operator; the solutions do not depend on the order in which the shifts are given."""
+    L = (4, 4, 4, 8)
+    u = fields.apply_bc(L, fields.weak_gauge(L, seed=11))
+    op = oracle.Op(L, u, 0.1, 0.91, 1.07, anisoP=True, t_dir=3, xi_0=2.464, nu=0.95)
+    chi = fields.gaussian_fermion(L, seed=12, cb=1)
+    Vh = chi.shape[0] // 2
+    shifts = [0.7, 0.003, 2.5, 0.04]
+    psi, n, rel = op.solve_multishift(chi, shifts, 1e-9, 1000)
+    assert 0 < n < 1000 and max(rel) < 5e-9
+    order = np.argsort(shifts)
+    psi_s, n_s, _ = op.solve_multishift(chi, [shifts[i] for i in order], 1e-9, 1000)
+    assert n_s == n
+    for k, i in enumerate(order):
+        assert np.abs(psi_s[k] - psi[i])[Vh:].max() < 1e-12 * np.abs(psi[i][Vh:]).max()
