@@ -114,3 +114,52 @@ def test_clover_parameter_derivations():
     iso = CloverFermActParams.from_kappa(0.115, 1.27)
     assert iso.Mass == pytest.approx(1.0 / 0.23 - 4.0) and iso.derived() == pytest.approx((1.0 + 3.0 + iso.Mass, 0.635, 0.635))
     assert iso.ferm_coeffs() == (1.0, 1.0, 1.0, 1.0)
+
+
+def test_constructor_sequence_with_a_stand_in_engine(monkeypatch):
+    """The constructor's call sequence on the engine (as LinOpSysSolverQUDAClover's ctor: create, load gauge with the
+    anisotropy factors and the boundary sign, build or load the clover term, select the preconditioning), with
+    chroma_b200.solver.Context replaced by a recorder."""
+    from chroma_b200 import solver as S
+
+    class FakeContext(RecordingContext):
+        def __init__(self, global_dims, prec="double", device=0, proc_grid=(1, 1, 1, 1), proc_coord=(0, 0, 0, 0), comm=None):
+            super().__init__()
+            self.calls.append(("create", dict(dims=tuple(global_dims), prec=prec, device=device, grid=tuple(proc_grid))))
+
+        def load_gauge(self, u, aniso_coeff, t_boundary, reconstruct):
+            self.calls.append(("load_gauge", dict(aniso=tuple(aniso_coeff), t_boundary=t_boundary, reconstruct=reconstruct)))
+
+        def make_clover(self, dm, cr, ct, aniso=False, t_dir=3):
+            self.calls.append(("make_clover", dict(dm=dm, cr=cr, ct=ct, aniso=aniso, t_dir=t_dir)))
+
+        def load_clover(self, clov, invclov):
+            self.calls.append(("load_clover", {}))
+
+        def set_preconditioning(self, sym):
+            self.calls.append(("set_preconditioning", dict(sym=sym)))
+
+        def close(self):
+            self.calls.append(("close", {}))
+
+    monkeypatch.setattr(S, "Context", FakeContext)
+    cp = CloverFermActParams(Mass=0.1, clovCoeffR=1.0, clovCoeffT=1.0)
+    p = SysSolverB200CloverParams(CloverParams=cp, RsdTarget=1e-8, MaxIter=1000, SolverType="BICGSTAB", AntiPeriodicT=True,
+                                  Reconstruct="RECONS_12", SymmetricLinop=True)
+    sol = LinOpSysSolverB200Clover((8, 8, 8, 8), "links", p, device=3)
+    names = [c[0] for c in sol.ctx.calls]
+    assert names == ["create", "load_gauge", "make_clover", "set_preconditioning"]
+    assert sol.ctx.calls[0][1] == dict(dims=(8, 8, 8, 8), prec="double", device=3, grid=(1, 1, 1, 1))
+    assert sol.ctx.calls[1][1] == dict(aniso=(1.0, 1.0, 1.0, 1.0), t_boundary=-1, reconstruct=L.B200_RECONS_12)
+    assert sol.ctx.calls[2][1] == dict(dm=4.1, cr=0.5, ct=0.5, aniso=False, t_dir=3)
+    psi, chi = np.zeros((8, 4, 3, 2)), np.ones((8, 4, 3, 2))
+    assert sol(psi, chi).n_count == 7 and sol.ctx.calls[-1] == ("invert", dict(solver=L.B200_SOLVER_BICGSTAB, rsd=1e-8, max_iter=1000))
+    sol.close()
+    assert sol.ctx.calls[-1][0] == "close"
+    # handing over Chroma's own clover buffers instead (the loadCloverQuda path); periodic T; fp32 engine
+    p2 = SysSolverB200CloverParams(CloverParams=cp, AntiPeriodicT=False, Precision="SINGLE")
+    m = MdagMMultiSysSolverB200Clover((4, 4, 4, 4), "links", p2, clov="clov", invclov="invclov")
+    assert [c[0] for c in m.ctx.calls] == ["create", "load_gauge", "load_clover"]
+    assert m.ctx.calls[0][1]["prec"] == "single" and m.ctx.calls[1][1]["t_boundary"] == 1
+    h = MdagMSysSolverB200Clover((4, 4, 4, 4), "links", SysSolverB200CloverParams(CloverParams=cp, SolverType="RELIABLE_CG"))
+    assert h(psi, chi).n_count == 7 and h.ctx.calls[-1][0] == "invert_reliable" and h.ctx.calls[-1][1]["mdagm"] is True
