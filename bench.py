@@ -8,10 +8,16 @@ weak-field SU(3) gauge field, Mass 0.1, clovCoeff 1.0, antiperiodic T, Gaussian 
 
   value     GFLOP/s of K iterations with every field resident in HBM (Chroma's count: 7824 flop per odd site per
             iteration = 2*3792 + 240, invcg2.cc:67,101-220), CUDA events on the engine's stream, max over ranks.
-  e2e       same metric through the plugin-facing C ABI call b200_invert() with HOST (pinned) chi / psi buffers:
-            H2D of source + initial guess, M^dag chi, the solver preamble, K iterations, true-residual check, D2H of psi.
-  roofline  dominant kernel = dslash_kernel<EPI_M> (chi = A_oo x - 1/4 D_oe t): algorithmic bytes (144+8G)*8 = 2304 B
-            per odd site / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+  e2e       same metric through the plugin-facing C ABI call b200_invert() with PAGEABLE host chi / psi buffers (what
+            QDP++ fields are): H2D of source + initial guess, M^dag chi, the solver preamble, K iterations, true-residual
+            check, D2H of psi.  The same call on pinned buffers is reported beside it (e2e.pinned_host_buffers).
+  roofline  the kernels the CG loop really launches, each timed with CUDA events on the engine's stream inside the loop
+            (b200_dev_time_solver_kernels): EPI_AINV (x2), EPI_M_NORM, EPI_M_CG, cg_update.  The dominant one is the
+            kernel with the largest share of the iteration; achieved = its algorithmic bytes /
+            its duration, against MEASURED_PEAKS.json hbm_gbs.
+  solve     the BASELINE metric's second half: a real solve to 1e-8 at every N -- seconds, iterations, the TRUE relative
+            residual, and two N-independent checksums (|M chi|^2, |psi|^2 as cross-rank sums) compared with the N=1
+            values in tests/golden/bench_expected.json; a mismatch makes the run exit non-zero.
   cpu_baseline  the reference's own Dslash<double> (oracle/_ref, compiled from /root/reference) composed into the same
             CG iteration by the CPU restatement, all host cores, on a bounded 24^3x48 sample (rank 0, N=1 only).
 
@@ -49,7 +55,9 @@ def parse():
     ap.add_argument("--solver", default="CG", choices=["CG", "BICGSTAB"])
     ap.add_argument("--nrhs", type=int, default=12, help="right-hand sides of the batched (propagator) leg; 1 = skip it")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--solve", action="store_true", help="also run a full solve to 1e-8 and report time-to-solution")
+    ap.add_argument("--no-solve", action="store_true", help="skip the full solve to 1e-8 (time to solution + N-independent checksums)")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 leg (per-kernel roofline of the single-precision engine)")
+    ap.add_argument("--write-expected", action="store_true", help="record this run's solve checksums in tests/golden/bench_expected.json")
     ap.add_argument("--grid", type=int, nargs=2, default=None, metavar=("PZ", "PT"),
                     help="process grid in Z x T (PZ*PT = --gpus); default: T split only (1 x N)")
     return ap.parse_args()
@@ -70,6 +78,12 @@ def cpu_arm(steps, warmup):
     """Seconds per CG iteration of the CPU reference path on a bounded sample; returns the cpu_baseline dict."""
     from oracle import oracle as orc
     from chroma_b200 import fields
+    # every core this process may use: torchrun exports OMP_NUM_THREADS=1, which would make this a 1-core baseline
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
+    orc.set_num_threads(ncores)
     latt = SAMPLE_LATT
     u = fields.apply_bc(latt, fields.weak_gauge(latt, seed=11))
     op = orc.Op(latt, u, 0.1, 1.0)
@@ -97,7 +111,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_cg_iteration_on_sample"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
@@ -110,7 +124,9 @@ def workload_config(args, n):
             % (tuple(args.lattice) + (args.solver, "fp64" if args.prec == "double" else "fp32", args.recon)),
             "lattice": list(args.lattice),
             "partition": ("T-split x%d" % n) if not args.grid or args.grid[0] == 1 else "Z x T grid %d x %d" % tuple(args.grid),
-            "l2_policy": "working set per step (gauge+clover+vectors, >10 GB) exceeds the 126 MB L2; no flush needed"}
+            "l2_policy": "working set per step (gauge+clover+vectors, >10 GB) exceeds the 126 MB L2; no flush needed",
+            "cpu_reference_sample": "the CPU reference arm (--impl reference, cpu_baseline) times the same operator and CG iteration on a "
+                                    "%dx%dx%dx%d sub-lattice with every host core; GFLOP/s is per-site work x sites / time, so it carries over" % SAMPLE_LATT}
 
 
 # ----------------------------------------------------------------------------------------------- clocks sampler
@@ -249,6 +265,95 @@ def make_comm(dist, rank, world):
     return comm
 
 
+EXPECTED = os.path.join(ROOT, "tests", "golden", "bench_expected.json")
+
+
+def load_expected():
+    try:
+        return json.load(open(EXPECTED))
+    except Exception:
+        return {}
+
+
+def expected_key(args):
+    return "%dx%dx%dx%d %s %s recon%d" % (tuple(args.lattice) + (args.solver, args.prec, args.recon))
+
+
+def dram_traffic(kernel_name):
+    """dram__bytes_read+write per launch of `kernel_name` from the newest `ncu --set full` capture of THIS build, if one was
+    committed (profiles/dram_traffic.json: {"kernels": {name: bytes}, "build": ...}); None otherwise."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        for k, v in t.get("kernels", {}).items():
+            if k in kernel_name:
+                return v
+    except Exception:
+        pass
+    return None
+
+
+def kernel_table(solver_name, kms, R, G, Vh, peak):
+    """Per-launch table of one solver iteration: algorithmic bytes per odd site (every array element once
+    per pass, neighbour re-reads served by L2) and the measured duration of every launch, in launch order."""
+    ainv, m, mcg, upd = (120 + 8 * G) * R, (144 + 8 * G) * R, (168 + 8 * G) * R, 120 * R
+    if solver_name == "CG":
+        rows = [("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo p", ainv), ("dslash_kernel<EPI_M_NORM> mp = A_oo p - 1/4 D_oe t, |mp|^2", m),
+                ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo^dag mp", ainv), ("dslash_kernel<EPI_M_CG> r -= a(A_oo mp - 1/4 D_oe^dag t), |r|^2", mcg),
+                ("cg_update_kernel psi += a p, p = r + b p", upd)]
+    else:
+        rows = [("bicg_p_kernel p = r + beta(p - omega v)", 96 * R), ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo p", ainv),
+                ("dslash_kernel<EPI_M_DOTR0> v = M p, <r0|v>", mcg), ("bicg_s_kernel r -= alpha v", 72 * R),
+                ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo r", ainv), ("dslash_kernel<EPI_M_DOTX> t = M r, <t|r>, |t|^2", m),
+                ("bicg_update_kernel psi += omega r + alpha p, r -= omega t, |r|^2, <r0|r>", 192 * R)]
+    if len(kms) != len(rows):       # symmetric preconditioning adds a clover pass; not the default bench path
+        rows = [("launch %d" % i, 0) for i in range(len(kms))]
+    total = sum(kms)
+    merged = {}
+    for (name, nbytes), ms in zip(rows, kms):
+        key = name.split(" ")[0]
+        d = merged.setdefault(key, {"kernel": key, "what": [], "ms": [], "bytes": nbytes})
+        d["what"].append(name); d["ms"].append(ms)
+    out = []
+    for key, d in merged.items():
+        ms = sum(d["ms"]) / len(d["ms"])
+        ach = d["bytes"] * Vh / (ms * 1e-3) * 1e-9 if ms > 0 else 0.0
+        out.append({"kernel": key, "what": d["what"], "launches_per_iteration": len(d["ms"]), "ms_per_launch": ms,
+                    "algorithmic_bytes_per_site": d["bytes"], "algorithmic_bytes_per_launch": d["bytes"] * Vh,
+                    "achieved": ach, "frac": ach / peak, "share_of_iteration": sum(d["ms"]) / total if total > 0 else 0.0})
+    return out
+
+
+def fp32_leg(args, torch, dev, latt, solver, flop_iter, peak, barrier_main):
+    """The CG loop on a single-precision engine (its own context: same gauge recipe, fp32 storage + arithmetic)."""
+    from chroma_b200.solver import Context
+    ctx = Context(latt, prec="single", device=dev.index)
+    u = torch_weak_gauge(latt, 0, latt, 11, 0.2, dev)
+    apply_bc_local(u, latt, True)
+    ctx.load_gauge(u.astype(np.float32), t_boundary=-1, reconstruct=args.recon)
+    del u
+    ctx.make_clover(1.0 + 3.0 + 0.1, 0.5, 0.5)
+    chi = torch_gaussian_source(latt, 0, 12, dev, torch.float32).numpy()
+    chi_f, psi_f = ctx.field(chi), ctx.field(np.zeros_like(chi))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    ctx.dev_iterate_begin(psi_f, chi_f, solver)
+    ctx.dev_iterate(solver, args.warmup)
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.dev_iterate(solver, args.steps)
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1) / args.steps
+    kms = ctx.dev_time_solver_kernels(solver, max(5, args.steps))
+    out = {"ms_per_step": ms, "gflops": flop_iter * ctx.Vh / (ms * 1e-3) * 1e-9,
+           "kernels_in_loop": kernel_table(args.solver, kms, 4, args.recon, ctx.Vh, peak)}
+    psi_f.zero()
+    inf = ctx.dev_invert(psi_f, chi_f, solver=solver, rsd=1e-6, max_iter=10000)
+    out["solve_to_1e-6"] = {"seconds": inf.secs, "iterations": inf.n_count, "rel_resid": inf.rel_resid, "converged": bool(inf.converged)}
+    ctx.close()
+    return out
+
+
 def run_b200(args):
     import torch
     from chroma_b200 import lib as L
@@ -335,34 +440,40 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = flop_iter * Vh_global / (ms_step * 1e-3) * 1e-9
 
-    # ---------------- leg 2: operator alone + per-kernel roofline (single GPU only: events around each kernel)
+    # ---------------- leg 2: per-kernel roofline of the kernels the loop launches (CUDA events behind every launch of
+    # the running CG / BiCGStab recurrences, b200_dev_time_solver_kernels), and the operator alone
+    R = 8 if args.prec == "double" else 4
+    G = args.recon
+    peak, how = peaks()
     roof = None
+    kern = None
+    try:
+        ctx.dev_time_solver_kernels(solver, 2)
+        barrier()
+        kms = ctx.dev_time_solver_kernels(solver, max(5, args.steps))
+        kern = kernel_table(args.solver, kms, R, G, Vh, peak)
+        dom = max(kern, key=lambda k: k["share_of_iteration"])
+        roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "peak_source": how, "traffic": dram_traffic(dom["kernel"]), "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                "ms_per_launch": dom["ms_per_launch"], "launches_per_iteration": dom["launches_per_iteration"],
+                "share_of_iteration": dom["share_of_iteration"],
+                "how": "CUDA events behind every launch of %d running %s iterations (engine stream)%s"
+                       % (max(5, args.steps), args.solver, "" if world == 1 else "; rank 0 of %d, the kernel includes the halo wait" % world),
+                "kernels_in_loop": kern}
+    except Exception as e:  # noqa
+        roof = {"error": str(e)}
     dsl = None
     out_f = ctx.field()
     if world == 1:
         ctx.dev_time_matpc(out_f, chi_f, +1, 3)
         barrier()
         ms_a, ms_b = ctx.dev_time_matpc(out_f, chi_f, +1, max(5, args.steps))
-        R = 8 if args.prec == "double" else 4
-        G = args.recon
         bytes_a, bytes_b = (120 + 8 * G) * R, (144 + 8 * G) * R
-        peak, how = peaks()
-        achieved = bytes_b * Vh / (ms_b * 1e-3) * 1e-9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dslash_kernel_EPI_M_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roof = {"bound": "hbm", "kernel": "dslash_kernel<EPI_M> (chi = A_oo x - 1/4 D_oe t)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": how, "traffic": traffic,
-                "algorithmic_bytes_per_launch": bytes_b * Vh, "ms_per_launch": ms_b,
-                "other_kernels": {"dslash_kernel<EPI_AINV> (t = A_ee^-1 D_eo x)": {
-                    "achieved": bytes_a * Vh / (ms_a * 1e-3) * 1e-9, "frac": bytes_a * Vh / (ms_a * 1e-3) * 1e-9 / peak, "ms_per_launch": ms_a}}}
         dsl = {"gflops": FLOP_M * Vh / ((ms_a + ms_b) * 1e-3) * 1e-9,
                "hbm_gbs": (bytes_a + bytes_b) * Vh / ((ms_a + ms_b) * 1e-3) * 1e-9,
-               "frac_of_peak": (bytes_a + bytes_b) * Vh / ((ms_a + ms_b) * 1e-3) * 1e-9 / peak, "ms_per_apply": ms_a + ms_b}
+               "frac_of_peak": (bytes_a + bytes_b) * Vh / ((ms_a + ms_b) * 1e-3) * 1e-9 / peak, "ms_per_apply": ms_a + ms_b,
+               "kernels": {"EPI_AINV": {"ms": ms_a, "frac": bytes_a * Vh / (ms_a * 1e-3) * 1e-9 / peak},
+                           "EPI_M": {"ms": ms_b, "frac": bytes_b * Vh / (ms_b * 1e-3) * 1e-9 / peak}}}
     else:
         ctx.dev_matpc(out_f, chi_f, +1)
         barrier()
@@ -412,31 +523,43 @@ def run_b200(args):
         except Exception as e:  # noqa
             mrhs = {"error": str(e)}
 
-    # ---------------- leg 3: end to end through the host-pointer ABI call (what the Chroma adapter calls)
-    # rsd = 0 never converges (cp <= 0 is false), so exactly `steps` iterations run.
-    psi_np[...] = 0
-    ctx.invert(chi_np, psi_np, solver=solver, rsd=0.0, max_iter=max(1, args.warmup))   # warm the path once
-    barrier()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    psi_np[...] = 0
-    e4.record(stream)
-    info = L.SolveInfo()
-    rc = ctx.lib.b200_invert(ctx.h, C.c_void_p(psi_np.ctypes.data), C.c_void_p(chi_np.ctypes.data), ctx.prec, solver, 0.0,
-                             args.steps, C.byref(info))
-    L.check(rc)
-    e5.record(stream)
-    barrier()
-    ms_e2e = max_over_ranks(e4.elapsed_time(e5))
-    e2e_value = flop_iter * Vh_global * args.steps / (ms_e2e * 1e-3) * 1e-9
+    # ---------------- leg 3: end to end through the host-pointer ABI call (what the Chroma adapter calls) on PAGEABLE host
+    # buffers -- QDP++ fields are ordinary heap memory; the engine bounces them through pinned double buffers with a
+    # team of host threads (engine_impl.cuh::h2d / d2h).  rsd = 0 never converges (cp <= 0 is false), so exactly `steps`
+    # iterations run.  The same call on pinned buffers is the side note.
+    def timed_invert(chi_a, psi_a):
+        psi_a[...] = 0
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        L.check(ctx.lib.b200_invert(ctx.h, C.c_void_p(psi_a.ctypes.data), C.c_void_p(chi_a.ctypes.data), ctx.prec, solver, 0.0,
+                                    args.steps, C.byref(L.SolveInfo())))
+        eb.record(stream)
+        barrier()
+        return max_over_ranks(ea.elapsed_time(eb))
+
+    chi_pg, psi_pg = np.array(chi_np, copy=True), np.zeros_like(chi_np)       # plain numpy = pageable
+    ctx.invert(chi_pg, psi_pg, solver=solver, rsd=0.0, max_iter=max(1, args.warmup))   # warm the path (and fault the pages in)
+    timed_invert(chi_pg, psi_pg)
+    ms_e2e = timed_invert(chi_pg, psi_pg)
     cb_bytes = Vh * 24 * (8 if args.prec == "double" else 4)
-    e2e = {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 2 * cb_bytes * world / args.steps,
-           "d2h_bytes_per_step": cb_bytes * world / args.steps, "ms_per_call": ms_e2e,
-           "call": "b200_invert(host psi, host chi, max_iter=steps): H2D chi+psi0, M^dag chi, preamble, %d iterations, "
-                   "true residual, D2H psi" % args.steps}
+    e2e = {"value": flop_iter * Vh_global * args.steps / (ms_e2e * 1e-3) * 1e-9, "unit": "GFLOP/s",
+           "h2d_bytes_per_step": 2 * cb_bytes * world / args.steps, "d2h_bytes_per_step": cb_bytes * world / args.steps,
+           "ms_per_call": ms_e2e, "host_buffers": "pageable",
+           "call": "b200_invert(host psi, host chi, max_iter=steps) on pageable numpy buffers: H2D chi+psi0, M^dag chi, preamble, "
+                   "%d iterations, true residual, D2H psi" % args.steps}
+    del chi_pg, psi_pg
+    try:
+        timed_invert(chi_np, psi_np)
+        ms_pin = timed_invert(chi_np, psi_np)
+        e2e["pinned_host_buffers"] = {"ms_per_call": ms_pin, "value": flop_iter * Vh_global * args.steps / (ms_pin * 1e-3) * 1e-9}
+    except Exception as e:  # noqa
+        e2e["pinned_host_buffers"] = {"error": str(e)}
     # where the end-to-end time goes (untimed diagnostics, after the headline call): each stage between two events
     try:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         psi_d = ctx.field()
+        psi_np[...] = 0
         barrier()
         ev[0].record(stream)
         chi_f.upload(chi_np); psi_d.upload(psi_np)
@@ -446,54 +569,70 @@ def run_b200(args):
         L.check(ctx.lib.b200_mfield_download(ctx.h, psi_d.h, 0, C.c_void_p(psi_np.ctypes.data), ctx.prec))
         ev[3].record(stream)
         barrier()
-        e2e["breakdown_ms"] = {"h2d_chi_psi0": ev[0].elapsed_time(ev[1]), "device_solve": ev[1].elapsed_time(ev[2]),
-                               "d2h_psi": ev[2].elapsed_time(ev[3]), "iterations_only": ms_step * args.steps}
+        e2e["breakdown_ms_pinned"] = {"h2d_chi_psi0": ev[0].elapsed_time(ev[1]), "device_solve": ev[1].elapsed_time(ev[2]),
+                                      "d2h_psi": ev[2].elapsed_time(ev[3]), "iterations_only": ms_step * args.steps}
         del psi_d
     except Exception as e:  # noqa
-        e2e["breakdown_ms"] = {"error": str(e)}
-    # the same call on PAGEABLE host buffers (what QDP++ fields are): the engine bounces them through pinned double
-    # buffers with a team of host threads (engine_impl.cuh::h2d / d2h)
-    try:
-        chi_pg, psi_pg = np.array(chi_np, copy=True), np.zeros_like(chi_np)
-        for rep in range(2):      # the first call also pays the page faults of the freshly allocated arrays
-            psi_pg[...] = 0
-            barrier()
-            e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e8.record(stream)
-            L.check(ctx.lib.b200_invert(ctx.h, C.c_void_p(psi_pg.ctypes.data), C.c_void_p(chi_pg.ctypes.data), ctx.prec, solver, 0.0,
-                                        args.steps, C.byref(L.SolveInfo())))
-            e9.record(stream)
-            barrier()
-            ms_pg = max_over_ranks(e8.elapsed_time(e9))
-        e2e["pageable_host_buffers"] = {"ms_per_call": ms_pg, "value": flop_iter * Vh_global * args.steps / (ms_pg * 1e-3) * 1e-9}
-        del chi_pg, psi_pg
-    except Exception as e:  # noqa
-        e2e["pageable_host_buffers"] = {"error": str(e)}
+        e2e["breakdown_ms_pinned"] = {"error": str(e)}
     t_clock_end = time.time()
 
-    # ---------------- optional: a real solve to 1e-8 (time to solution)
+    # ---------------- the BASELINE metric's second half: CG/BiCGStab time to solution, with N-independent checksums
     solve = None
-    if args.solve:
+    solve_ok = True
+    if not args.no_solve:
+        rsd = 1e-8 if args.prec == "double" else 1e-6
         psi2 = ctx.field(np.zeros_like(chi_np))
+        ctx.dev_invert(psi2, chi_f, solver=solver, rsd=rsd, max_iter=3)              # warm the solve path
+        psi2.zero()
         barrier()
-        inf = ctx.dev_invert(psi2, chi_f, solver=solver, rsd=1e-8 if args.prec == "double" else 1e-6, max_iter=10000)
+        inf = ctx.dev_invert(psi2, chi_f, solver=solver, rsd=rsd, max_iter=10000)
         barrier()
-        solve = {"solver": args.solver, "seconds": max_over_ranks(inf.secs), "iterations": inf.n_count, "converged": bool(inf.converged),
-                 "rel_resid": inf.rel_resid, "gflops": flop_iter * Vh_global * inf.n_count / max(inf.secs, 1e-9) * 1e-9}
-        if args.prec == "double":
+        ctx.dev_matpc(out_f, chi_f, +1)
+        sums = {"norm2_M_chi": ctx.dev_norm2(out_f), "norm2_psi": ctx.dev_norm2(psi2), "norm2_chi": ctx.dev_norm2(chi_f)}
+        solve = {"solver": args.solver, "rsd_target": rsd, "seconds": max_over_ranks(inf.secs), "iterations": inf.n_count,
+                 "converged": bool(inf.converged), "rel_resid": inf.rel_resid,
+                 "rel_resid_how": "|chi - M psi| / |chi| recomputed with one more application of M after the loop (syssolver_linop_cg.h:80-87)",
+                 "gflops": flop_iter * Vh_global * inf.n_count / max(inf.secs, 1e-9) * 1e-9, "checksums": sums}
+        key = expected_key(args)
+        exp = load_expected().get(key)
+        if args.write_expected and rank == 0 and world == 1:
+            allx = load_expected()
+            allx[key] = {"iterations": inf.n_count, "checksums": sums, "written_by": "bench.py --write-expected on 1 GPU"}
+            json.dump(allx, open(EXPECTED, "w"), indent=1, sort_keys=True)
+            exp = allx[key]
+        if exp is None:
+            solve["check"] = "no N=1 record for this configuration in tests/golden/bench_expected.json"
+        else:
+            bad = []
+            if not inf.converged or not (inf.rel_resid < 20 * rsd):
+                bad.append("not converged: true rel resid %.3e" % inf.rel_resid)
+            if abs(inf.n_count - exp["iterations"]) > max(1, round(0.03 * exp["iterations"])):
+                bad.append("iterations %d vs %d at N=1" % (inf.n_count, exp["iterations"]))
+            tol = {"norm2_M_chi": 1e-10, "norm2_chi": 1e-10, "norm2_psi": 1e-6} if args.prec == "double" else \
+                  {"norm2_M_chi": 1e-5, "norm2_chi": 1e-5, "norm2_psi": 1e-3}
+            for k, v in sums.items():
+                if abs(v - exp["checksums"][k]) > tol[k] * abs(exp["checksums"][k]):
+                    bad.append("%s %.15e vs %.15e at N=1" % (k, v, exp["checksums"][k]))
+            solve["iterations_n1"] = exp["iterations"]
+            solve["check"] = "ok: converged, iteration count and checksums match the N=1 record" if not bad else "FAILED: " + "; ".join(bad)
+            solve_ok = not bad
+        if args.prec == "double" and args.solver == "CG":
             # the same system by mixed-precision reliable-update CG (fp32 inner, fp64 outer; reliable_cg.cc)
-            psi3 = ctx.field(np.zeros_like(chi_np))
-            barrier()
-            ctx.dev_invert_reliable(psi3, chi_f, rsd=1e-8, delta=0.1, max_iter=50)      # builds the fp32 twin (untimed)
-            solve["mixed_precision_cg"] = []
-            for delta in (0.1, 0.01):
+            try:
+                psi3 = ctx.field(np.zeros_like(chi_np))
+                barrier()
+                ctx.dev_invert_reliable(psi3, chi_f, rsd=1e-8, delta=0.1, max_iter=50)      # builds the fp32 twin (untimed)
                 psi3.zero()
                 barrier()
-                inf = ctx.dev_invert_reliable(psi3, chi_f, rsd=1e-8, delta=delta, max_iter=10000)
+                inf = ctx.dev_invert_reliable(psi3, chi_f, rsd=1e-8, delta=0.1, max_iter=10000)
                 barrier()
-                solve["mixed_precision_cg"].append({"delta": delta, "seconds": max_over_ranks(inf.secs), "iterations": inf.n_count,
-                                                    "fp64_residual_replacements": inf.n_updates, "converged": bool(inf.converged),
-                                                    "rel_resid": inf.rel_resid})
+                solve["mixed_precision_cg"] = {"delta": 0.1, "seconds": max_over_ranks(inf.secs), "iterations": inf.n_count,
+                                               "fp64_residual_replacements": inf.n_updates, "converged": bool(inf.converged),
+                                               "rel_resid": inf.rel_resid}
+                del psi3
+            except Exception as e:  # noqa
+                solve["mixed_precision_cg"] = {"error": str(e)}
+        del psi2
 
     clocks.stop()
     ck = clocks.summary(wall0, t_clock_end)
@@ -505,19 +644,30 @@ def run_b200(args):
         except Exception as e:  # noqa
             cpu = {"error": str(e)}
 
+    # ---------------- fp32 leg: the same loop on the single-precision engine (per-kernel roofline fractions)
+    fp32 = None
+    if world == 1 and args.prec == "double" and not args.no_fp32:
+        try:
+            fp32 = fp32_leg(args, torch, dev, latt, solver, flop_iter, peak, barrier)
+        except Exception as e:  # noqa
+            fp32 = {"error": str(e)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.prec == "double" else "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": ck, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu, "clover_dslash": dsl, "multi_rhs": mrhs, "solve": solve,
+            "roofline": roof, "cpu_baseline": cpu, "clover_dslash": dsl, "multi_rhs": mrhs, "solve": solve, "fp32": fp32,
             "setup_s": t_setup, "timed_wall_s": wall1 - wall0,
         }
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+    if not solve_ok:
+        sys.stderr.write("bench.py: solve check failed: %s\n" % (solve or {}).get("check"))
+        sys.exit(3)
 
 
 def main():

@@ -39,7 +39,7 @@ __device__ void scale_planes_body(C2* p, int nplanes, size_t stride, size_t off,
 __global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
 __global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f) { scale_planes_body(p, nplanes, stride, off, count, f); }
 
-__global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* status, int check_stop, int run_if) {
+__global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* status, int check_stop, int run_if, long long spin) {
   if (check_stop && status && (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0)) return;
   if (run_if && status && status[run_if] == 0) return;
   const long long t0 = clock64();
@@ -47,7 +47,7 @@ __global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* stat
     if (!w.f[f]) continue;
     const volatile unsigned long long* v = w.f[f];
     while (*v < seq) {
-      if (clock64() - t0 > PEER_SPIN_CYCLES) { if (status) status[ST_BREAKDOWN] = 90; break; }
+      if (clock64() - t0 > spin) { if (status) status[ST_BREAKDOWN] = 90; break; }
     }
   }
   __threadfence_system();
@@ -279,6 +279,12 @@ int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter) {
   CHECK_CTX(ctx);
   if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
   return ctx->eng->iterate(solver, n_iter);
+}
+
+int b200_dev_time_solver_kernels(b200_ctx* ctx, int solver, int reps, double* ms, int max_ms, int* n_ms) {
+  CHECK_CTX(ctx);
+  if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
+  return ctx->eng->time_solver_kernels(solver, reps, ms, max_ms, n_ms);
 }
 
 int b200_dslash(b200_ctx* ctx, void* out, const void* in, int host_prec, int isign, int out_cb) {

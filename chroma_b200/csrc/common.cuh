@@ -176,7 +176,8 @@ enum StatusSlot {
   ST_COUNT = 8
 };
 
-// Spin-wait budget for peer flags (SM clock cycles, ~5 s): a lost peer must not hang the GPU forever.
-constexpr long long PEER_SPIN_CYCLES = 10000000000LL;
+// Default spin-wait budget for peer flags (SM clock cycles, ~60 s; B200_PEER_TIMEOUT_S overrides): a lost peer must not
+// hang the GPU forever, but ranks may legitimately be seconds apart (lazy module loading, I/O on one rank).
+constexpr long long PEER_SPIN_CYCLES = 120000000000LL;
 
 }  // namespace b200

@@ -55,7 +55,7 @@ struct DslashArgs {
   Geom g;
   int parity;       // target parity
   int isign;        // +1: D, -1: D^dagger
-  SiteBox box[4];   // target sites of this launch: the union of nbox boxes (whole lattice / interior / boundary pieces)
+  SiteBox box[5];   // target sites of this launch: the union of nbox boxes (whole lattice / interior / boundary pieces)
   int nbox;
   int nsites;       // total number of target sites of this launch
   int iter;         // solver iteration this launch belongs to (for the stop flag)
@@ -91,10 +91,24 @@ __device__ __forceinline__ int launch_site(const DslashArgs<R>& a, int local) {
   }
   local -= n0;
 #pragma unroll
-  for (int k = 1; k < 4; ++k) {
+  for (int k = 1; k < 5; ++k) {
     if (k < a.nbox) {
       const int n = box_count(g, a.box[k]);
       if (local < n) return box_site(g, a.box[k], local);
+      local -= n;
+    }
+  }
+  return 0;
+}
+
+// The `local`-th target site among boxes kbegin.. of a launch (the boundary pieces of a fused split-lattice launch).
+template <typename R>
+__device__ __forceinline__ int launch_site_from(const DslashArgs<R>& a, int local, int kbegin) {
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k >= kbegin && k < a.nbox) {
+      const int n = box_count(a.g, a.box[k]);
+      if (local < n) return box_site(a.g, a.box[k], local);
       local -= n;
     }
   }
@@ -209,7 +223,8 @@ __device__ __forceinline__ void hop(Cx<R> acc[12], const Cx<R>* __restrict__ psi
   recons_acc<R, MU>(acc, r0, r1, sg);
 }
 
-// Hops across a rank boundary (split direction MU).  Forward: the half spinor was already projected by the +mu
+// Hops across a rank boundary (split direction MU).  The ghost faces are written by a PEER GPU during this very launch
+// (fused split-lattice kernel, halo.cuh), so they are read through the coherent path, never ld.global.nc.  Forward: the half spinor was already projected by the +mu
 // neighbour rank, only the link multiply is left.  Backward: U^dag (1 +/- g_mu) psi was computed by the -mu neighbour
 // rank (it owns that link): just reconstruct.  gp points at this site's entry of the ghost face, fs = face stride.
 template <typename R, int MU, bool RECON12, bool MR>
@@ -217,7 +232,7 @@ __device__ __forceinline__ void ghost_hop_fwd(Cx<R> acc[12], const Cx<R>* __rest
                                               R sg, R scale, const L2Policy& pol) {
   Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { h0[c] = ld_stream(gp + (size_t)c * fs, pol.stream); h1[c] = ld_stream(gp + (size_t)(3 + c) * fs, pol.stream); }
+  for (int c = 0; c < 3; ++c) { h0[c] = ld_stream_rw(gp + (size_t)c * fs, pol.stream); h1[c] = ld_stream_rw(gp + (size_t)(3 + c) * fs, pol.stream); }
   load_link<R, RECON12, MR>(U, link, lstride, pol.stream);
   if (RECON12) {
 #pragma unroll
@@ -230,7 +245,7 @@ template <typename R, int MU>
 __device__ __forceinline__ void ghost_hop_bwd(Cx<R> acc[12], const Cx<R>* __restrict__ gp, int fs, R sg, const L2Policy& pol) {
   Cx<R> r0[3], r1[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { r0[c] = ld_stream(gp + (size_t)c * fs, pol.stream); r1[c] = ld_stream(gp + (size_t)(3 + c) * fs, pol.stream); }
+  for (int c = 0; c < 3; ++c) { r0[c] = ld_stream_rw(gp + (size_t)c * fs, pol.stream); r1[c] = ld_stream_rw(gp + (size_t)(3 + c) * fs, pol.stream); }
   recons_acc<R, MU>(acc, r0, r1, sg);
 }
 
@@ -515,9 +530,6 @@ struct FinBiOmega {
 #ifndef B200_DSLASH_MINBLOCKS
 #define B200_DSLASH_MINBLOCKS 1
 #endif
-#ifndef B200_SPLIT_REDUCE
-#define B200_SPLIT_REDUCE 0   // 1: single-RHS reducing epilogues store partials only, a one-CTA kernel finishes (reduce.cuh)
-#endif
 #ifndef B200_DSLASH_MINBLOCKS_F
 #define B200_DSLASH_MINBLOCKS_F 4   // fp32: 64-bit loads need 4 CTAs/SM in flight (tuned on B200: 1 -> 80 %, 3 -> 96 %, 4 -> 100 % of HBM peak)
 #endif
@@ -618,31 +630,11 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
     site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
   }
 
-#if B200_SPLIT_REDUCE
-  // partials only; dslash_finish_kernel (launched behind the last piece of the step) sums them and runs the finaliser
-  if (EPI == EPI_M_NORM || EPI == EPI_M_CG || EPI == EPI_M_CGREL) block_partials<1, BLOCK>(red, a.red);
-  if (EPI == EPI_M_DOTR0) block_partials<2, BLOCK>(red, a.red);
-  if (EPI == EPI_M_DOTX) block_partials<3, BLOCK>(red, a.red);
-#else
   if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal});
   if (EPI == EPI_M_CG) grid_reduce<1, BLOCK>(red, a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_CGREL) grid_reduce<1, BLOCK>(red, a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status});
   if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status});
-#endif
-}
-
-// The one-CTA tail of a reducing single-RHS step (B200_SPLIT_REDUCE): same early-outs as the step itself, so that a
-// stopped / predicated-off step leaves the scalars alone.
-template <typename R, int EPI, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) dslash_finish_kernel(const DslashArgs<R> a) {
-  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
-  if (a.run_if && a.status[a.run_if] == 0) return;
-  if (EPI == EPI_M_NORM) finish_partials<1, BLOCK>(a.red, FinCgD{a.scal});
-  if (EPI == EPI_M_CG) finish_partials<1, BLOCK>(a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
-  if (EPI == EPI_M_CGREL) finish_partials<1, BLOCK>(a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
-  if (EPI == EPI_M_DOTR0) finish_partials<2, BLOCK>(a.red, FinBiAlpha{a.scal, a.status});
-  if (EPI == EPI_M_DOTX) finish_partials<3, BLOCK>(a.red, FinBiOmega{a.scal, a.status});
 }
 
 // ---- multi-RHS variant ------------------------------------------------------------------------------------------

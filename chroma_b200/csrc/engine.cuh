@@ -71,6 +71,7 @@ class EngineBase {
   virtual int invert(b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, int mdagm, b200_solve_info* info) = 0;   // info[nrhs]
   virtual int iterate_begin(b200_field* psi, const b200_field* chi, int solver) = 0;
   virtual int iterate(int solver, int n_iter) = 0;
+  virtual int time_solver_kernels(int solver, int reps, double* ms, int max_ms, int* n_ms) = 0;
   virtual int qprop(void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter,
                     b200_solve_info* infos) = 0;
   virtual int sync() = 0;

@@ -22,7 +22,7 @@ namespace b200 {
 #define B200_DSLASH_BLOCK_F 128
 #endif
 constexpr int DSLASH_BLOCK_MAX = B200_DSLASH_BLOCK > B200_DSLASH_BLOCK_F ? B200_DSLASH_BLOCK : B200_DSLASH_BLOCK_F;
-constexpr int ITER_BATCH = 16;        // iterations enqueued between two status polls
+constexpr int ITER_BATCH = 8;         // iterations enqueued between two status polls
 constexpr size_t STAGING_BYTES = 256u << 20;
 constexpr size_t PIN_BYTES_DEFAULT = 32u << 20;   // one pinned bounce buffer of the pageable-host copy pipeline (two per engine)
 
@@ -92,7 +92,8 @@ class Engine : public EngineBase {
   MsState* ms_dev = nullptr; b200_field* ms_p = nullptr; C* ms_psi = nullptr;
   double* scal = nullptr; int* status = nullptr;
   double* partial = nullptr; unsigned int* ticket = nullptr; size_t partial_cap = 0;   // partial: doubles; ticket: [MAX_RHS]
-  double* h_scal = nullptr; int* h_status = nullptr;   // pinned; [MAX_RHS][S_COUNT] and 2 slots of [MAX_RHS][ST_COUNT]
+  double* gpartial = nullptr; unsigned int* gticket = nullptr;                          // two-level reductions (reduce.cuh)
+  double* h_scal = nullptr; int* h_status = nullptr;   // pinned; [MAX_RHS][S_COUNT] and 3 slots of [MAX_RHS][ST_COUNT] (2 for the solver poll, 1 for comm_check)
   cudaEvent_t ev_poll[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
   void* staging = nullptr;
   // Host buffers the caller hands over (QDP++ fields) are pageable: a plain cudaMemcpy moves them at ~10 GB/s through the
@@ -150,7 +151,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaMalloc(&ticket, sizeof(unsigned int) * MAX_RHS));
     B200_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int) * MAX_RHS, stream));
     B200_CUDA(cudaHostAlloc(&h_scal, sizeof(double) * S_COUNT * MAX_RHS, cudaHostAllocDefault));
-    B200_CUDA(cudaHostAlloc(&h_status, sizeof(int) * ST_COUNT * MAX_RHS * 2, cudaHostAllocDefault));
+    B200_CUDA(cudaHostAlloc(&h_status, sizeof(int) * ST_COUNT * MAX_RHS * 3, cudaHostAllocDefault));
     for (int i = 0; i < 2; ++i) B200_CUDA(cudaEventCreateWithFlags(&ev_poll[i], cudaEventDisableTiming));
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
@@ -177,26 +178,50 @@ class Engine : public EngineBase {
     if (ms_p) { field_free(ms_p); ms_p = nullptr; }
     cudaFree(gauge); cudaFree(clov); cudaFree(invclov); cudaFree(tr_log); cudaFree(invclov_oo); cudaFree(tr_log_oo); cudaFree(ms_dev);
     if (owns_scalars) { cudaFree(scal); cudaFree(status); }
-    cudaFree(partial); cudaFree(ticket); cudaFree(staging);
+    cudaFree(partial); cudaFree(gpartial); cudaFree(gticket); cudaFree(ticket); cudaFree(staging);
     for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (pin_ev[i]) cudaEventDestroy(pin_ev[i]); pin[i] = nullptr; pin_ev[i] = nullptr; }
     cudaFreeHost(h_scal); cudaFreeHost(h_status);
     for (int i = 0; i < 2; ++i) if (ev_poll[i]) cudaEventDestroy(ev_poll[i]);
+    for (auto& e : trace_ev) cudaEventDestroy(e);
+    trace_ev.clear();
     if (ev_t0) cudaEventDestroy(ev_t0);
     if (ev_t1) cudaEventDestroy(ev_t1);
     if (owns_stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
 
-  // reduction scratch: `doubles` partial sums (grown on demand by the batched kernels: N x nrhs x blocks)
+  // reduction scratch: `doubles` partial sums (grown on demand by the batched kernels: N x nrhs x blocks), plus the
+  // group sums and group tickets of the two-level reductions (reduce.cuh): one per RED_GROUP partials
   int ensure_partial(size_t doubles) {
     if (doubles <= partial_cap) return B200_OK;
-    if (partial) { B200_CUDA(cudaStreamSynchronize(stream)); cudaFree(partial); partial = nullptr; }
+    if (partial) { B200_CUDA(cudaStreamSynchronize(stream)); cudaFree(partial); cudaFree(gpartial); cudaFree(gticket); partial = nullptr; gpartial = nullptr; gticket = nullptr; }
+    const size_t ng = doubles / RED_GROUP + 8 * MAX_RHS;
     B200_CUDA(cudaMalloc(&partial, sizeof(double) * doubles));
+    B200_CUDA(cudaMalloc(&gpartial, sizeof(double) * ng));
+    B200_CUDA(cudaMalloc(&gticket, sizeof(unsigned int) * ng));
+    B200_CUDA(cudaMemsetAsync(gticket, 0, sizeof(unsigned int) * ng, stream));
     partial_cap = doubles;
     return B200_OK;
   }
 
-  int sync() override { B200_CUDA(cudaSetDevice(cfg.device)); B200_CUDA(cudaStreamSynchronize(stream)); return B200_OK; }
+  int sync() override { B200_CUDA(cudaSetDevice(cfg.device)); B200_CUDA(cudaStreamSynchronize(stream)); return comm_check(); }
+
+  // Split lattices: a peer wait that ran out of its spin budget (status 90 = halo flag, 91 = reduction mailbox) left stale
+  // ghost / mailbox data behind.  The solver loops see that in their status poll; every other path calls this before a
+  // result reaches the host (fetch_scalars, the end of a download, b200_sync), so a lost peer is B200_ERR_COMM, never a
+  // silently wrong number.
+  int comm_check() {
+    if (!split()) return B200_OK;
+    int* hs3 = h_status + 2 * ST_COUNT * MAX_RHS;
+    B200_CUDA(cudaMemcpyAsync(hs3, status, sizeof(int) * ST_COUNT * MAX_RHS, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
+    for (int r = 0; r < MAX_RHS; ++r) if (hs3[r * ST_COUNT + ST_BREAKDOWN] >= 90) return comm_timeout(hs3[r * ST_COUNT + ST_BREAKDOWN]);
+    return B200_OK;
+  }
+
+  // b200_dev_time_solver_kernels: while trace_n >= 0 every hot-loop launch is followed by an event on the stream
+  std::vector<cudaEvent_t> trace_ev; int trace_n = -1;
+  void mark() { if (trace_n >= 0 && trace_n < (int)trace_ev.size()) cudaEventRecord(trace_ev[trace_n++], stream); }
 
   int launched(const char* what) {
     ++launches;
@@ -207,7 +232,7 @@ class Engine : public EngineBase {
 
   ReduceBuf make_red(int block_offset, int total_blocks) {
     ReduceBuf rb;
-    rb.partial = partial; rb.ticket = ticket; rb.block_offset = block_offset; rb.total_blocks = total_blocks;
+    rb.partial = partial; rb.ticket = ticket; rb.gpartial = gpartial; rb.gticket = gticket; rb.block_offset = block_offset; rb.total_blocks = total_blocks;
     rb.peer = halo.peer_reduce();
     return rb;
   }
@@ -288,7 +313,7 @@ class Engine : public EngineBase {
       { int rch = d2h((char*)dst + (size_t)off * rec, staging, (size_t)n * rec); if (rch) return rch; }
     }
     B200_CUDA(cudaStreamSynchronize(stream));
-    return B200_OK;
+    return comm_check();
   }
 
   int load_gauge(const void* const u[4], int host_prec, const double aniso[4], int t_boundary, int recon_) override {
@@ -506,49 +531,62 @@ class Engine : public EngineBase {
     int rc;
     for (auto& b : a.box) b = SiteBox{0, 0, 0, 0};
     if (split()) {
-      // pack + send the faces over NVLink, run the interior while they fly, then the boundary slices / planes
-      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, nb, a.fstride, launches); if (rc) return rc;
-      a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
       const SiteBox inner{g.tsplit ? 1 : 0, g.tsplit ? g.Lt - 2 : g.Lt, g.zsplit ? 1 : 0, g.zsplit ? g.Lz - 2 : g.Lz};
       const int n_int = box_count(g, inner);
       const int n_face = g.Vh - n_int;
       const int nb_int = (n_int + bs - 1) / bs;
       const int nb_face = (n_face + bs - 1) / bs;
       const int total = nb_int + nb_face;
+      SiteBox faces[4]; int nf = 0;
+      if (g.tsplit) { faces[nf++] = SiteBox{0, 1, 0, g.Lz}; faces[nf++] = SiteBox{g.Lt - 1, 1, 0, g.Lz}; }
+      if (g.zsplit && inner.nt > 0) {
+        faces[nf++] = SiteBox{inner.t0, inner.nt, 0, 1};
+        faces[nf++] = SiteBox{inner.t0, inner.nt, g.Lz - 1, 1};
+      }
+      if (nb == 1) {
+        // ONE launch: pack CTAs, interior CTAs, boundary CTAs that poll the arrival flags themselves (halo.cuh)
+        HaloFuse<R> h;
+        halo.prepare(h.pack, a.in, gauge, recon, ls, a.isign, a.parity, 1, a.fstride);
+        for (int f = 0; f < 4; ++f) h.wait[f] = halo.local_flag(f);
+        h.seq = halo.seq; h.spin = halo.spin_cycles;
+        h.n_pack = (halo.pack_threads() + DSLASH_BLOCK - 1) / DSLASH_BLOCK; h.n_int = nb_int; h.n_int_sites = n_int;
+        a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
+        a.box[0] = inner; for (int k = 0; k < nf; ++k) a.box[1 + k] = faces[k];
+        a.nbox = 1 + nf; a.nsites = g.Vh; a.zc_sites = 0; a.red = make_red(0, total);
+        return launch_halo<EPI>(a, h, h.n_pack + total);
+      }
+      // batched right-hand sides: pack + send the faces over NVLink, run the interior while they fly, then the boundary
+      rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, nb, a.fstride, launches); if (rc) return rc;
+      a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
       if (n_int > 0) {
         a.box[0] = inner; a.nbox = 1; a.nsites = n_int; a.red = make_red(0, total);
-        a.zc_sites = nb > 1 ? zchunk_sites(inner.nz) : 0;
+        a.zc_sites = zchunk_sites(inner.nz);
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
       rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, nb, launches); if (rc) return rc;
-      int k = 0;
-      if (g.tsplit) { a.box[k++] = SiteBox{0, 1, 0, g.Lz}; a.box[k++] = SiteBox{g.Lt - 1, 1, 0, g.Lz}; }
-      if (g.zsplit && inner.nt > 0) {
-        a.box[k++] = SiteBox{inner.t0, inner.nt, 0, 1};
-        a.box[k++] = SiteBox{inner.t0, inner.nt, g.Lz - 1, 1};
-      }
-      a.nbox = k; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total);
-      rc = launch_one<EPI>(a, nb_face); if (rc) return rc;
-      return launch_finish<EPI>(a);
+      for (int k = 0; k < nf; ++k) a.box[k] = faces[k];
+      a.nbox = nf; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total);
+      return launch_one<EPI>(a, nb_face);
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr; a.ghost_zfwd = nullptr; a.ghost_zbwd = nullptr;
     a.box[0] = SiteBox{0, g.Lt, 0, g.Lz}; a.nbox = 1; a.nsites = g.Vh;
     a.zc_sites = nb > 1 ? zchunk_sites(g.Lz) : 0;
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
-    { int rc1 = launch_one<EPI>(a, blocks); if (rc1) return rc1; }
-    return launch_finish<EPI>(a);
+    return launch_one<EPI>(a, blocks);
   }
-  // B200_SPLIT_REDUCE: the one-CTA tail of a reducing single-RHS step (sums the partials of all its launches)
+  // the fused split-lattice launch (single right-hand side): dslash_halo_kernel, halo.cuh
   template <int EPI>
-  int launch_finish(const DslashArgs<R>& a) {
-#if B200_SPLIT_REDUCE
-    if (nb == 1 && (EPI == EPI_M_NORM || EPI == EPI_M_CG || EPI == EPI_M_CGREL || EPI == EPI_M_DOTR0 || EPI == EPI_M_DOTX)) {
-      dslash_finish_kernel<R, EPI, DSLASH_BLOCK><<<1, DSLASH_BLOCK, 0, stream>>>(a);
-      return launched("dslash_finish_kernel");
-    }
-#endif
-    return B200_OK;
+  int launch_halo(const DslashArgs<R>& a, const HaloFuse<R>& h, int blocks) {
+    if (EPI >= EPI_M && a.mmode == MODE_SYM_PLUS) launch_halo_mode<EPI, (EPI >= EPI_M ? MODE_SYM_PLUS : MODE_ASYM)>(a, h, blocks);
+    else if (EPI >= EPI_M && a.mmode == MODE_SYM_MINUS) launch_halo_mode<EPI, (EPI >= EPI_M ? MODE_SYM_MINUS : MODE_ASYM)>(a, h, blocks);
+    else launch_halo_mode<EPI, MODE_ASYM>(a, h, blocks);
+    return launched("dslash_halo_kernel");
+  }
+  template <int EPI, int MODE>
+  void launch_halo_mode(const DslashArgs<R>& a, const HaloFuse<R>& h, int blocks) {
+    if (recon == 12) dslash_halo_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, h);
+    else dslash_halo_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, h);
   }
   template <int EPI>
   int launch_one(const DslashArgs<R>& a, int blocks) {
@@ -616,24 +654,28 @@ class Engine : public EngineBase {
     if (sym && isign < 0) {
       clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, 1), 128, 0, stream>>>(in, W(8), invclov_oo, g.Vh, nelem(), (check || run_if) ? status : nullptr, run_if);
       int rc0 = launched("clover_kernel"); if (rc0) return rc0;
+      mark();
       src = W(8);
     }
     DslashArgs<R> a{};
     a.in = src; a.out = W(0); a.clov = invclov; a.parity = 0; a.isign = isign; a.iter = iter; a.check_stop = check; a.run_if = run_if;
     int rc = launch_dslash<EPI_AINV>(a); if (rc) return rc;
+    mark();
     DslashArgs<R> b{};
     b.in = W(0); b.out = out; b.clov = clov + (size_t)36 * g.Vh; b.x = in; b.r = r; b.r0 = r0;
     if (sym) { b.clov = invclov_oo; b.mmode = isign > 0 ? MODE_SYM_PLUS : MODE_SYM_MINUS; }
     b.parity = 1; b.isign = isign; b.iter = iter; b.check_stop = check; b.run_if = run_if;
     switch (epi) {
-      case EPI_M_CGREL: return launch_dslash<EPI_M_CGREL>(b);
-      case EPI_M: return launch_dslash<EPI_M>(b);
-      case EPI_M_NORM: return launch_dslash<EPI_M_NORM>(b);
-      case EPI_M_CG: return launch_dslash<EPI_M_CG>(b);
-      case EPI_M_DOTR0: return launch_dslash<EPI_M_DOTR0>(b);
-      case EPI_M_DOTX: return launch_dslash<EPI_M_DOTX>(b);
+      case EPI_M_CGREL: rc = launch_dslash<EPI_M_CGREL>(b); break;
+      case EPI_M: rc = launch_dslash<EPI_M>(b); break;
+      case EPI_M_NORM: rc = launch_dslash<EPI_M_NORM>(b); break;
+      case EPI_M_CG: rc = launch_dslash<EPI_M_CG>(b); break;
+      case EPI_M_DOTR0: rc = launch_dslash<EPI_M_DOTR0>(b); break;
+      case EPI_M_DOTX: rc = launch_dslash<EPI_M_DOTX>(b); break;
+      default: set_error("bad epilogue"); return B200_ERR_ARG;
     }
-    set_error("bad epilogue"); return B200_ERR_ARG;
+    mark();
+    return rc;
   }
 
   int dslash(b200_field* out, const b200_field* in, int isign, int out_cb) override {
@@ -706,7 +748,7 @@ class Engine : public EngineBase {
   int fetch_scalars() {
     B200_CUDA(cudaMemcpyAsync(h_scal, scal, sizeof(double) * S_COUNT * MAX_RHS, cudaMemcpyDeviceToHost, stream));
     B200_CUDA(cudaStreamSynchronize(stream));
-    return B200_OK;
+    return comm_check();
   }
   double hs(int rhs, int slot) const { return h_scal[rhs * S_COUNT + slot]; }
   int set_scalars(const ScalarSet& s) {
@@ -760,18 +802,24 @@ class Engine : public EngineBase {
     int rc = apply_M(W(1), W(2), +1, EPI_M_NORM, nullptr, nullptr, k, check); if (rc) return rc;      // mp = M p, d, a
     rc = apply_M(nullptr, W(1), -1, EPI_M_CG, W(3), nullptr, k, check); if (rc) return rc;            // r -= a M^dag mp, cp, b
     cg_update_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(psi, W(2), W(3), nelem(), ctl(k, check));
-    return launched("cg_update");
+    rc = launched("cg_update");
+    mark();
+    return rc;
   }
   // one BiCGStab iteration, invbicgstab.cc:74-170.  W(1)=r, W(2)=r0, W(3)=p, W(4)=v, W(5)=t
   int bicg_iteration(C* psi, int k, int check, int isign = +1) {
     bicg_p_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(W(3), W(1), W(4), nelem(), ctl(k, check));
     int rc = launched("bicg_p"); if (rc) return rc;
+    mark();
     rc = apply_M(W(4), W(3), isign, EPI_M_DOTR0, nullptr, W(2), k, check); if (rc) return rc;         // v = M p, alpha
     bicg_s_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(W(1), W(4), nelem(), ctl(k, check));
     rc = launched("bicg_s"); if (rc) return rc;
+    mark();
     rc = apply_M(W(5), W(1), isign, EPI_M_DOTX, nullptr, nullptr, k, check); if (rc) return rc;       // t = M r, omega
     bicg_update_kernel<R><<<bgrid(), BLAS_BLOCK, 0, stream>>>(psi, W(1), W(3), W(5), W(2), nelem(), ctl(k, check));
-    return launched("bicg_update");
+    rc = launched("bicg_update");
+    mark();
+    return rc;
   }
 
   // one multi-shift CG iteration, minvcg2.cc:243-342 (the p updates of :246-262 were done by the previous ms_update).
@@ -1078,6 +1126,31 @@ class Engine : public EngineBase {
       if (rc) return rc;
     }
     return B200_OK;
+  }
+
+  // Measurement aid behind b200_dev_time_solver_kernels: `reps` iterations of the loop set up by iterate_begin, with an
+  // event behind every launch; ms[i] = average duration of the i-th launch of one iteration (CG: EPI_AINV, EPI_M_NORM,
+  // EPI_AINV^dag, EPI_M_CG, cg_update; BiCGStab: bicg_p, EPI_AINV, EPI_M_DOTR0, bicg_s, EPI_AINV, EPI_M_DOTX, bicg_update).
+  int time_solver_kernels(int solver, int reps, double* ms, int max_ms, int* n_ms) override {
+    B200_CUDA(cudaSetDevice(cfg.device));
+    if (!it_psi) { set_error("b200_dev_time_solver_kernels: call b200_dev_iterate_begin first"); return B200_ERR_STATE; }
+    if (reps < 1 || !ms || !n_ms || max_ms < 1) { set_error("b200_dev_time_solver_kernels: bad argument"); return B200_ERR_ARG; }
+    { int rcb = set_batch(it_nb); if (rcb) return rcb; }
+    if (trace_ev.empty()) { trace_ev.resize(17); for (auto& e : trace_ev) B200_CUDA(cudaEventCreate(&e)); }
+    std::vector<double> acc(16, 0.0);
+    int n = 0;
+    for (int i = 0; i < reps; ++i) {
+      ++it_k;
+      trace_n = 0; mark();
+      int rc = (solver == B200_SOLVER_CG) ? cg_iteration(it_psi, it_k, 0) : bicg_iteration(it_psi, it_k, 0);
+      n = trace_n - 1; trace_n = -1;
+      if (rc) return rc;
+      B200_CUDA(cudaEventSynchronize(trace_ev[n]));
+      for (int k = 0; k < n; ++k) { float t = 0.f; B200_CUDA(cudaEventElapsedTime(&t, trace_ev[k], trace_ev[k + 1])); acc[k] += t; }
+    }
+    *n_ms = n;
+    for (int k = 0; k < n && k < max_ms; ++k) ms[k] = acc[k] / reps;
+    return comm_check();
   }
 
   // ------------------------------------------------------------------ full-lattice propagator (section 8f, rank 1)

@@ -80,18 +80,18 @@ __device__ __forceinline__ void pack_project_mul(Cx<R>* __restrict__ dst, int f,
   for (int c = 0; c < 3; ++c) { dst[(size_t)c * fs + f] = r0[c]; dst[(size_t)(3 + c) * fs + f] = r1[c]; }
 }
 
-template <typename R, bool RECON12>
-__global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
+// Body of the face pack for CTA `bx` of `nbx` (x RHS `rhs` of `nby`), BLOCK threads each.
+template <typename R, bool RECON12, int BLOCK>
+__device__ __forceinline__ void pack_faces_body(const PackArgs<R>& a, int bx, int nbx, int rhs, int nby) {
   typedef Cx<R> C;
-  // A converged right-hand side sends nothing.  With a single right-hand side the whole Dslash (wait kernel included)
+  // A converged right-hand side sends nothing.  With a single right-hand side the whole Dslash (wait included)
   // is skipped; in a batch the flags are still published so that the other right-hand sides can proceed.
-  const int rhs = blockIdx.y;
   bool skip = false;
   if (a.status) { const int* st = a.status + rhs * ST_COUNT; skip = st[ST_STOP] != 0 || st[ST_BREAKDOWN] != 0; }
   if (a.nrhs == 1 && skip) return;
   if (a.pred && *a.pred == 0) return;
   const Geom& g = a.g;
-  int tid = blockIdx.x * 128 + threadIdx.x;
+  int tid = bx * BLOCK + threadIdx.x;
   const int stride = g.Vh, st = g.S3h, sz = g.SZh, row = g.Lxh * g.Ly;
   const R s = (R)a.isign;
   const L2Policy pol = make_l2_policy();
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(a.ticket, 1u);
-    is_last = (t == gridDim.x * gridDim.y - 1);
+    is_last = (t == (unsigned int)(nbx * nby) - 1u);
   }
   __syncthreads();
   if (is_last && threadIdx.x == 0) {
@@ -134,9 +134,79 @@ __global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
     __threadfence_system();
   }
 }
+template <typename R, bool RECON12>
+__global__ void __launch_bounds__(128) pack_faces_kernel(const PackArgs<R> a) {
+  pack_faces_body<R, RECON12, 128>(a, blockIdx.x, gridDim.x, blockIdx.y, gridDim.y);
+}
+
+// ---- the whole split-lattice Dslash in ONE launch (single right-hand side) ------------------------------------------
+// Round 1 issued pack -> interior -> wait<<<1,1>>> -> boundary as four kernels on one stream: three extra kernel tails
+// per Dslash, the pack overlapped with nothing, and the boundary could not start before the last interior CTA had
+// left (17 launches per CG iteration on a split lattice).  Here the roles are CTA ranges of one grid, in dispatch order:
+//   [0, n_pack)                 project the faces, store them into the neighbours' ghost buffers, last one publishes seq
+//   [n_pack, n_pack + n_int)    interior sites (no ghost dependence): run while the faces are in flight
+//   the rest                    boundary sites: thread 0 spins on the local arrival flags, then the CTA proceeds
+// The boundary CTAs are the last of the grid, so they only occupy SM slots once every pack / interior CTA has been
+// dispatched; what they wait for is the NEIGHBOURS' pack CTAs, the first CTAs of the neighbours' launch of the same
+// Dslash, which need nothing from this rank's launch.  A CG iteration on a split lattice is 5 launches, as on one GPU.
+template <typename R>
+struct HaloFuse {
+  PackArgs<R> pack;
+  const unsigned long long* wait[4];   // local arrival flags of the faces in use (null = not split)
+  unsigned long long seq;
+  long long spin;                      // spin budget (SM cycles) before a lost peer raises status 90
+  int n_pack, n_int;                   // CTAs of the first two roles
+  int n_int_sites;                     // sites of box[0] (the interior); boundary CTAs enumerate box[1..]
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename R, int EPI, bool RECON12, int BLOCK, int MODE = MODE_ASYM>
+__global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS))
+dslash_halo_kernel(const DslashArgs<R> a, const LinkScale ls, const HaloFuse<R> h) {
+  typedef Cx<R> C;
+  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  if (a.run_if && a.status[a.run_if] == 0) return;
+  int b = blockIdx.x;
+  if (b < h.n_pack) { pack_faces_body<R, RECON12, BLOCK>(h.pack, b, h.n_pack, 0, 1); return; }
+  b -= h.n_pack;
+  const bool boundary = b >= h.n_int;
+  if (boundary) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        if (!h.wait[f]) continue;
+        while (ld_acquire_sys(h.wait[f]) < h.seq) {
+          if (clock64() - t0 > h.spin) { a.status[ST_BREAKDOWN] = 90; break; }
+          __nanosleep(64);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int stride = a.g.Vh;
+  const int local = boundary ? (b - h.n_int) * BLOCK + threadIdx.x : b * BLOCK + threadIdx.x;
+  const bool active = boundary ? local < a.nsites - h.n_int_sites : local < h.n_int_sites;
+  double red[3] = {0.0, 0.0, 0.0};
+  if (active) {
+    const int idx = boundary ? launch_site_from<R>(a, local, 1) : box_site(a.g, a.box[0], local);
+    const L2Policy pol = make_l2_policy();
+    C acc[12];
+    dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
+    site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
+  }
+  if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal}, b);
+  if (EPI == EPI_M_CG) grid_reduce<1, BLOCK>(red, a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop}, b);
+  if (EPI == EPI_M_CGREL) grid_reduce<1, BLOCK>(red, a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop}, b);
+  if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status}, b);
+  if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status}, b);
+}
 
 struct WaitFlags { const unsigned long long* f[4]; };   // local arrival flags of the faces in use (null = not split)
-__global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* status, int check_stop, int run_if);
+__global__ void wait_flags_kernel(WaitFlags w, unsigned long long seq, int* status, int check_stop, int run_if, long long spin);
 
 // One-time push of the boundary links the field strength needs (clover leaves reach x +/- mu +/- nu).
 // T faces: face 0 of the receiver = slice t=-1 (sender's last slice), face 1 = slice t=Lt (sender's first slice).
@@ -237,6 +307,7 @@ class Halo {
     }
     nbr[0] = rank_of(cfg, cfg.pcoord[2], cfg.pcoord[3] - 1); nbr[1] = rank_of(cfg, cfg.pcoord[2], cfg.pcoord[3] + 1);
     nbr[2] = rank_of(cfg, cfg.pcoord[2] - 1, cfg.pcoord[3]); nbr[3] = rank_of(cfg, cfg.pcoord[2] + 1, cfg.pcoord[3]);
+    if (const char* e = getenv("B200_PEER_TIMEOUT_S")) spin_cycles = (long long)(atof(e) * 2.0e9);
     lay = layout(g);
     B200_CUDA(cudaMalloc(&arena, lay.total));
     B200_CUDA(cudaMemset(arena, 0, lay.total));
@@ -287,7 +358,7 @@ class Halo {
   PeerReduce peer_reduce() const {
     PeerReduce p;
     memset(&p, 0, sizeof(p));
-    p.nranks = nranks; p.rank = rank; p.status = status_dev;
+    p.nranks = nranks; p.rank = rank; p.status = status_dev; p.spin = spin_cycles;
     if (nranks > 1) {
       p.seq = (unsigned long long*)(arena + lay.seq_off);
       for (int r = 0; r < nranks; ++r) p.mailbox[r] = (double*)(peer[r] + lay.mailbox_off);
@@ -295,24 +366,33 @@ class Halo {
     return p;
   }
 
-  // Pack + send all faces of `in` for the Dslash that targets `parity`.
-  int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, int run_if, int nrhs,
-            size_t fstride, long long& launches) {
+  long long spin_cycles = PEER_SPIN_CYCLES;   // budget of every peer wait (SM clock cycles); B200_PEER_TIMEOUT_S overrides
+  int pack_threads() const { return (g.tsplit ? 2 * g.S3h : 0) + (g.zsplit ? 2 * g.SZh : 0); }
+  const unsigned long long* local_flag(int f) const { return face_on(f) ? flag_ptr(arena, (int)(seq & 1), f) : nullptr; }
+
+  // Start Dslash number ++seq: fill the arguments of its face pack (source `in`, target `parity`).
+  void prepare(PackArgs<R>& a, const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, int nrhs, size_t fstride) {
     ++seq;
     const int slot = (int)(seq & 1);
-    PackArgs<R> a;
     a.in = in; a.gauge = gauge;
     for (int f = 0; f < 4; ++f) {
       a.to[f] = face_on(f) ? ghost_ptr(peer[nbr[f]], slot, f) : nullptr;
       a.flag[f] = face_on(f) ? flag_ptr(peer[nbr[f]], slot, f) : nullptr;
     }
-    a.seq = seq; a.ticket = ticket; a.status = status; a.pred = run_if ? status_dev + run_if : nullptr; a.g = g;
+    a.seq = seq; a.ticket = ticket; a.status = nullptr; a.pred = nullptr; a.g = g;
     a.src_par = 1 - parity; a.isign = isign; a.recon12 = recon == 12;
     a.scale_b[0] = ls.aniso[3] * (ls.t_is_last ? (double)ls.bc_t : 1.0);
     a.scale_b[1] = ls.aniso[2];
     a.nrhs = nrhs; a.fstride = fstride; a.gstride[0] = lay.face_t; a.gstride[1] = lay.face_z;
-    const int nthreads = (g.tsplit ? 2 * g.S3h : 0) + (g.zsplit ? 2 * g.SZh : 0);
-    const dim3 blocks((nthreads + 127) / 128, nrhs);
+  }
+
+  // Pack + send all faces of `in` for the Dslash that targets `parity` (stand-alone pack kernel: batched right-hand sides).
+  int start(const C* in, const C* gauge, int recon, const LinkScale& ls, int isign, int parity, const int* status, int run_if, int nrhs,
+            size_t fstride, long long& launches) {
+    PackArgs<R> a;
+    prepare(a, in, gauge, recon, ls, isign, parity, nrhs, fstride);
+    a.status = status; a.pred = run_if ? status_dev + run_if : nullptr;
+    const dim3 blocks((pack_threads() + 127) / 128, nrhs);
     if (recon == 12) pack_faces_kernel<R, true><<<blocks, 128, 0, stream>>>(a);
     else pack_faces_kernel<R, false><<<blocks, 128, 0, stream>>>(a);
     ++launches;
@@ -326,7 +406,7 @@ class Halo {
     WaitFlags w;
     for (int f = 0; f < 4; ++f) w.f[f] = face_on(f) ? flag_ptr(arena, slot, f) : nullptr;
     // a batch always waits: its flags are always published, and one right-hand side's stop flag says nothing about the others
-    wait_flags_kernel<<<1, 1, 0, stream>>>(w, seq, status_dev, (status && nrhs == 1) ? 1 : 0, run_if);
+    wait_flags_kernel<<<1, 1, 0, stream>>>(w, seq, status_dev, (status && nrhs == 1) ? 1 : 0, run_if, spin_cycles);
     ++launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("wait_flags launch failed: %s", cudaGetErrorString(e)); return B200_ERR_CUDA; }

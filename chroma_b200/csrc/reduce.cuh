@@ -16,20 +16,34 @@ struct PeerReduce {
   unsigned long long* seq;  // device counters [MAX_RHS]: cross-GPU reductions done so far for each right-hand side
   double* mailbox[8];       // mailbox[r] = rank r's mailbox base (peer pointer), layout [rhs][slot 2][src rank 8][4 values + seq]
   int* status;              // device status block (ST_BREAKDOWN = 91 on timeout)
+  long long spin;           // spin budget in SM cycles
 };
 
+// Reductions over more than RED_FLAT_MAX blocks are summed in TWO levels: blocks form groups of RED_GROUP consecutive
+// partial slots with one ticket per group; the block that draws the last ticket of its group sums the group (one
+// warp, two loads per lane) and then draws the step's ticket; the last group finisher sums the group sums.  With a flat
+// ticket the last of the 41 472 CTAs of a 48^3x96 Dslash summed all partials alone -- 324 dependent L2 round trips per
+// thread, ~8 % of the kernel (round-1 ncu: EPI_M_NORM 2.05 ms against 1.89 ms for the same traffic).  Order of
+// summation is fixed in both levels, so results stay bitwise reproducible.
+constexpr int RED_GROUP = 64;
+constexpr int RED_FLAT_MAX = 2048;
 struct ReduceBuf {
   double* partial;       // [N][total_blocks]
   unsigned int* ticket;  // zero between kernels
+  double* gpartial;      // [N][ngroups] group sums (two-level reductions)
+  unsigned int* gticket; // [ngroups], zero between kernels
   int block_offset;      // first partial slot of this launch (a step may be split into several launches)
   int total_blocks;      // blocks over all launches of the step
   PeerReduce peer;
-  // The view of right-hand side `rhs` of a batched step reducing N quantities: own partials, ticket, mailbox, status.
+  __host__ __device__ __forceinline__ int ngroups() const { return (total_blocks + RED_GROUP - 1) / RED_GROUP; }
+  // The view of right-hand side `rhs` of a batched step reducing N quantities: own partials, tickets, mailbox, status.
   template <int N>
   __device__ __forceinline__ ReduceBuf for_rhs(int rhs) const {
     ReduceBuf r = *this;
     r.partial += (size_t)rhs * N * total_blocks;
     r.ticket += rhs;
+    r.gpartial += (size_t)rhs * N * ngroups();
+    r.gticket += (size_t)rhs * ngroups();
     if (r.peer.nranks > 1) {
       r.peer.seq += rhs;
       for (int i = 0; i < r.peer.nranks; ++i) r.peer.mailbox[i] += (size_t)rhs * MAILBOX_DOUBLES;
@@ -80,7 +94,7 @@ __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, double vals
     volatile unsigned long long* tag = (volatile unsigned long long*)(mb + 4);
     const long long t0 = clock64();
     while (*tag != s) {
-      if (clock64() - t0 > PEER_SPIN_CYCLES) { if (pr.status) pr.status[ST_BREAKDOWN] = 91; break; }
+      if (clock64() - t0 > pr.spin) { if (pr.status) pr.status[ST_BREAKDOWN] = 91; break; }
     }
     __threadfence_system();
     for (int k = 0; k < N; ++k) tot[k] += mb[k];
@@ -89,81 +103,94 @@ __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, double vals
   *pr.seq = s;
 }
 
-// v[N]: this thread's contributions.  fin(tot) runs in exactly one thread of the whole step.
-template <int N, int BLOCK, typename Fin>
-__device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fin fin) {
-  __shared__ double smem[BLOCK / 32];
-  __shared__ bool is_last;
-  double s[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) s[k] = block_sum<BLOCK>(v[k], smem);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + rb.block_offset + blockIdx.x] = s[k];
-    __threadfence();
-    unsigned int t = atomicAdd(rb.ticket, 1u);
-    is_last = (t == (unsigned int)rb.total_blocks - 1u);
+// Sum of n doubles at p by the calling thread group: thread `tid` of `nthr` takes p[tid], p[tid+nthr], ... four
+// independent loads at a time (a fixed order, and four L2 round trips in flight instead of one).
+__device__ __forceinline__ double strided_sum(const double* p, int n, int tid, int nthr) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int b = tid;
+  for (; b + 3 * nthr < n; b += 4 * nthr) {
+    const double x0 = __ldcg(p + b), x1 = __ldcg(p + b + nthr), x2 = __ldcg(p + b + 2 * nthr), x3 = __ldcg(p + b + 3 * nthr);
+    a0 += x0; a1 += x1; a2 += x2; a3 += x3;
   }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    double tot[N];
+  for (; b < n; b += nthr) a0 += __ldcg(p + b);
+  return (a0 + a1) + (a2 + a3);
+}
+// Sum of the <= RED_GROUP partials of group `grp` by one warp (fixed order: lane, lane+32, then the shuffle tree).
+__device__ __forceinline__ double group_sum(const double* p, int gsize, int lane) {
+  double x = (lane < gsize ? __ldcg(p + lane) : 0.0) + (lane + 32 < gsize ? __ldcg(p + lane + 32) : 0.0);
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double acc = 0.0;
-      for (int b = threadIdx.x; b < rb.total_blocks; b += BLOCK) acc += __ldcg(rb.partial + (size_t)k * rb.total_blocks + b);
-      tot[k] = block_sum<BLOCK>(acc, smem);
-    }
-    if (threadIdx.x == 0) {
-      peer_allreduce<N>(rb.peer, tot);
-      fin(tot);
-      *rb.ticket = 0u;
-      __threadfence();
-    }
-  }
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
 }
 
-// Split variant for the big single-RHS Dslash grids (B200_SPLIT_REDUCE): in grid_reduce every CTA must wait for its
-// ticket atomic to come back before it may exit (it has to learn whether it is the last one), and with one CTA per SM
-// that round trip -- tens of thousands of CTAs hammering one address -- is dead time on the SM.  Here the CTAs only
-// store their partials and leave; a one-CTA kernel launched behind the step sums them in the SAME fixed order, combines
-// across GPUs and runs the finaliser.
-template <int N, int BLOCK>
-__device__ __forceinline__ void block_partials(double v[N], const ReduceBuf& rb) {
+// v[N]: this thread's contributions.  fin(tot) runs in exactly one thread of the whole step.  blk = this block's
+// index among the reducing blocks of its launch (blockIdx.x unless the launch has other CTAs in front).
+template <int N, int BLOCK, typename Fin>
+__device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fin fin, int blk = -1) {
   __shared__ double smem[BLOCK / 32];
+  __shared__ int role1, role2;    // role1: this block drew the last ticket of its group (flat: of the step); role2: ... of the step
+  if (blk < 0) blk = blockIdx.x;
+  blk += rb.block_offset;
+  const bool flat = rb.total_blocks <= RED_FLAT_MAX;
+  const int grp = blk / RED_GROUP, ngrp = rb.ngroups();
+  const int gsize = min(RED_GROUP, rb.total_blocks - grp * RED_GROUP);
   double s[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) s[k] = block_sum<BLOCK>(v[k], smem);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + rb.block_offset + blockIdx.x] = s[k];
+    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + blk] = s[k];
+    __threadfence();
+    if (flat) role1 = atomicAdd(rb.ticket, 1u) == (unsigned int)rb.total_blocks - 1u;
+    else role1 = atomicAdd(rb.gticket + grp, 1u) == (unsigned int)gsize - 1u;
   }
-}
-template <int N, int BLOCK, typename Fin>
-__device__ __forceinline__ void finish_partials(const ReduceBuf& rb, Fin fin) {
-  __shared__ double smem[BLOCK / 32];
+  __syncthreads();
+  if (!role1) return;
+  if (!flat) {
+    if (threadIdx.x < 32) {
+      __threadfence();
+      double gs[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) gs[k] = group_sum(rb.partial + (size_t)k * rb.total_blocks + grp * RED_GROUP, gsize, threadIdx.x);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) rb.gpartial[(size_t)k * ngrp + grp] = gs[k];
+        rb.gticket[grp] = 0u;
+        __threadfence();
+        role2 = atomicAdd(rb.ticket, 1u) == (unsigned int)ngrp - 1u;
+      }
+    }
+    __syncthreads();
+    if (!role2) return;
+  }
+  __threadfence();
   double tot[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    double acc = 0.0;
-    for (int b = threadIdx.x; b < rb.total_blocks; b += BLOCK) acc += __ldcg(rb.partial + (size_t)k * rb.total_blocks + b);
+    const double acc = flat ? strided_sum(rb.partial + (size_t)k * rb.total_blocks, rb.total_blocks, threadIdx.x, BLOCK)
+                            : strided_sum(rb.gpartial + (size_t)k * ngrp, ngrp, threadIdx.x, BLOCK);
     tot[k] = block_sum<BLOCK>(acc, smem);
   }
   if (threadIdx.x == 0) {
     peer_allreduce<N>(rb.peer, tot);
     fin(tot);
+    *rb.ticket = 0u;
     __threadfence();
   }
 }
 
 // Warp-synchronous variant for the multi-RHS Dslash kernels, where one WARP (32 consecutive sites of one right-hand
-// side) is the reduction unit: shuffle tree -> one partial per (rhs, site block) -> the warp that draws the last
-// ticket of its right-hand side sums that right-hand side's partials (lane-strided, then the same shuffle tree: a
-// fixed order) and lane 0 runs the finaliser.  rb must already be the for_rhs() view.  No __syncthreads: warps of
-// one CTA belong to different right-hand sides and may have returned early (converged).
+// side) is the reduction unit: shuffle tree -> one partial per (rhs, site block) -> two-level tickets as above (the
+// warp that draws the last ticket of its group sums the group, the last group finisher sums the group sums, lane-strided
+// and then the same shuffle tree: a fixed order) and lane 0 runs the finaliser.  rb must already be the for_rhs() view.
+// No __syncthreads: warps of one CTA belong to different right-hand sides and may have returned early (converged).
 template <int N, typename Fin>
 __device__ __forceinline__ void warp_grid_reduce(double v[N], const ReduceBuf& rb, int site_block, Fin fin) {
   const int lane = threadIdx.x & 31;
+  const int blk = rb.block_offset + site_block;
+  const bool flat = rb.total_blocks <= RED_FLAT_MAX;
+  const int grp = blk / RED_GROUP, ngrp = rb.ngroups();
+  const int gsize = min(RED_GROUP, rb.total_blocks - grp * RED_GROUP);
   double s[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -172,21 +199,38 @@ __device__ __forceinline__ void warp_grid_reduce(double v[N], const ReduceBuf& r
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     s[k] = x;
   }
-  unsigned int t = 0;
+  int role = 0;
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + rb.block_offset + site_block] = s[k];
+    for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + blk] = s[k];
     __threadfence();
-    t = atomicAdd(rb.ticket, 1u);
+    if (flat) role = (atomicAdd(rb.ticket, 1u) == (unsigned int)rb.total_blocks - 1u) ? 2 : 0;
+    else role = (atomicAdd(rb.gticket + grp, 1u) == (unsigned int)gsize - 1u) ? 1 : 0;
   }
-  t = __shfl_sync(0xffffffffu, t, 0);
-  if (t != (unsigned int)rb.total_blocks - 1u) return;
+  role = __shfl_sync(0xffffffffu, role, 0);
+  if (role == 0) return;
+  if (!flat) {
+    __threadfence();
+    double gs[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) gs[k] = group_sum(rb.partial + (size_t)k * rb.total_blocks + grp * RED_GROUP, gsize, lane);
+    role = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) rb.gpartial[(size_t)k * ngrp + grp] = gs[k];
+      rb.gticket[grp] = 0u;
+      __threadfence();
+      role = (atomicAdd(rb.ticket, 1u) == (unsigned int)ngrp - 1u) ? 2 : 0;
+    }
+    role = __shfl_sync(0xffffffffu, role, 0);
+    if (role == 0) return;
+  }
   __threadfence();
   double tot[N];
 #pragma unroll
   for (int k = 0; k < N; ++k) {
-    double acc = 0.0;
-    for (int b = lane; b < rb.total_blocks; b += 32) acc += __ldcg(rb.partial + (size_t)k * rb.total_blocks + b);
+    double acc = flat ? strided_sum(rb.partial + (size_t)k * rb.total_blocks, rb.total_blocks, lane, 32)
+                      : strided_sum(rb.gpartial + (size_t)k * ngrp, ngrp, lane, 32);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     tot[k] = acc;

@@ -94,6 +94,7 @@ SYMBOLS = {
     "b200_dev_invert_multishift": (_i, [_vp, _vp, _vp, _i, C.POINTER(_d), C.POINTER(_d), _i, C.POINTER(SolveInfo)]),
     "b200_dev_iterate_begin": (_i, [_vp, _vp, _vp, _i]),
     "b200_dev_iterate": (_i, [_vp, _i, _i]),
+    "b200_dev_time_solver_kernels": (_i, [_vp, _i, _i, C.POINTER(_d), _i, C.POINTER(_i)]),
     "b200_stream": (_vp, [_vp]),
     "b200_sync": (_i, [_vp]),
     "b200_launch_count": (C.c_longlong, [_vp]),

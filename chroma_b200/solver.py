@@ -293,6 +293,12 @@ class Context:
     def dev_iterate(self, solver, n):
         L.check(self.lib.b200_dev_iterate(self.h, int(solver), int(n)))
 
+    def dev_time_solver_kernels(self, solver, reps=5):
+        """Average device time (ms) of every launch of one solver iteration, in launch order (after dev_iterate_begin)."""
+        ms, n = (C.c_double * 16)(), C.c_int(0)
+        L.check(self.lib.b200_dev_time_solver_kernels(self.h, int(solver), int(reps), ms, 16, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
     def sync(self):
         L.check(self.lib.b200_sync(self.h))
 

@@ -256,6 +256,13 @@ int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter);
  * A_oo x - 1/4 D_oe t.  Used by bench.py for the roofline line. */
 int b200_dev_time_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int reps, double ms[2]);
 
+/* Measurement aid for the roofline line of bench.py: with the recurrences of b200_dev_iterate_begin set up, run `reps`
+ * iterations of the solver loop with a CUDA event behind every launch and return in ms[0..*n_ms) the average device time
+ * (milliseconds) of each launch of one iteration, in launch order -- CG (invcg2.cc:158-220): A_ee^-1 D_eo p | A_oo p -
+ * 1/4 D_oe t with |Mp|^2 | A_ee^-1 D_eo^dag Mp | r -= a(..) with |r|^2 | psi += a p, p = r + b p.  BiCGStab
+ * (invbicgstab.cc:74-170): p update | A^-1 D | M with <r0|v> | r -= alpha v | A^-1 D | M with <t|r>,|t|^2 | psi, r update. */
+int b200_dev_time_solver_kernels(b200_ctx* ctx, int solver, int reps, double* ms, int max_ms, int* n_ms);
+
 /* ---- plumbing -------------------------------------------------------------------------------- */
 void* b200_stream(b200_ctx* ctx);              /* cudaStream_t the engine launches on (for event timing) */
 int b200_sync(b200_ctx* ctx);

@@ -18,7 +18,7 @@
  *
  * Parity pinning: orc_dslash and orc_clover_apply are checked against the reference's
  * own Dslash<double> / CloverSchur4D<double> compiled unmodified into oracle/_ref
- * (tests/test_oracle_vs_ref.py).  The clover build, LDL^dagger inverse and the solver
+ * (tests/test_oracle.py).  The clover build, LDL^dagger inverse and the solver
  * loops are restated-and-self-consistent (A*A^-1=1, gamma5-hermiticity, free field,
  * constant abelian field strength): the reference holds no golden vectors for them
  * that can be reproduced without QDP++'s RNG.  The same holds for the
@@ -62,6 +62,16 @@ int orc_num_threads(void) {
   return omp_get_max_threads();
 #else
   return 1;
+#endif
+}
+
+/* bench.py --impl reference runs under torchrun, which exports OMP_NUM_THREADS=1: the CPU arm sets its team itself
+ * (the reference's OpenMP dispatcher in oracle/_ref shares this libgomp, so it follows). */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
 #endif
 }
 

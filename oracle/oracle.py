@@ -71,6 +71,11 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP team size of the CPU arm (torchrun exports OMP_NUM_THREADS=1; bench.py asks for every core it may use)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
 def site_index(L, c):
     return lib().orc_site_index(c_int4(*L), c_int4(*c))
 
