@@ -112,18 +112,28 @@ namespace Chroma
       check(b200_make_clover(ctx, diag_mass, clov_r, clov_t, aniso.anisoP ? 1 : 0, aniso.t_dir), "b200_make_clover");
       // SymEvenOddPrecCloverLinOp::create also inverts the odd block (seoprec_clover_linop_w.cc:31-33): done on the GPU
       if (p.SymmetricLinopP) check(b200_set_preconditioning(ctx, B200_PRECOND_SYMMETRIC), "b200_set_preconditioning");
+      // twisted-mass term of the clover operators (eoprec_clover_linop_w.cc:174-184, seoprec_clover_linop_w.cc:174-184)
+      if (p.CloverParams.twisted_m_usedP)
+        check(b200_set_twisted_mass(ctx, toDouble(p.CloverParams.twisted_m)), "b200_set_twisted_mass");
     }
 
     ~B200CloverEngine() { if (ctx) b200_destroy(ctx); }
 
     //! Guard against a parameter group that does not describe the operator the factory handed us (the creator's
-    //! signature carries no such information): apply the caller's A and the engine's M to one Gaussian vector and
-    //! compare.  Catches a wrong SymmetricLinop, Mass / clovCoeff / anisotropy that differ from the fermion action's,
-    //! or a wrong AntiPeriodicT, at construction instead of as a failed residual check after the first solve.
+    //! signature carries no such information): apply the caller's A and the engine's M to one test vector and
+    //! compare.  Catches a wrong SymmetricLinop, Mass / clovCoeff / anisotropy / TwistedM that differ from the fermion
+    //! action's, or a wrong AntiPeriodicT, at construction instead of as a failed residual check after the first solve.
+    //! The test vector is Gaussian but QDP++'s global RNG is left exactly as found (RNG::savern / setrn): solvers are
+    //! constructed many times per HMC trajectory and a run must reproduce the random sequence of the same XML and seed
+    //! run with the CPU or QUDA solvers (their constructors draw nothing).  <CheckOperator>false</CheckOperator> skips it.
     void checkOperator(const LinearOperator<T>& A) const
     {
+      if (!invParam.CheckOperatorP) return;
       T x = zero, want = zero, got = zero;
+      Seed saved;
+      QDP::RNG::savern(saved);
       gaussian(x, rb[1]);
+      QDP::RNG::setrn(saved);
       A(want, x, PLUS);
       const void* in = (const void*)&(x.elem(rb[1].start()).elem(0).elem(0).real());
       void* out = (void*)&(got.elem(rb[1].start()).elem(0).elem(0).real());

@@ -40,7 +40,7 @@ namespace Chroma
   SysSolverB200CloverParams::SysSolverB200CloverParams()
     : AntiPeriodicT(true), MaxIter(5000), RsdTarget(Real(1.0e-8)), Delta(Real(0.1)), solverType(B200_CG_SOLVER),
       precision(B200_PREC_DEFAULT), sloppyPrecision(B200_PREC_DEFAULT), reconstruct(B200_RECONS_NONE_T),
-      SilentFailP(false), RsdToleranceFactor(Real(10)), verboseP(false), device(-1), SymmetricLinopP(false)
+      SilentFailP(false), RsdToleranceFactor(Real(10)), verboseP(false), device(-1), SymmetricLinopP(false), CheckOperatorP(true)
   {}
 
   SysSolverB200CloverParams::SysSolverB200CloverParams(XMLReader& xml, const std::string& path)
@@ -63,6 +63,7 @@ namespace Chroma
     if (paramtop.count("Verbose") > 0) read(paramtop, "Verbose", verboseP);
     if (paramtop.count("Device") > 0) read(paramtop, "Device", device);
     if (paramtop.count("SymmetricLinop") > 0) read(paramtop, "SymmetricLinop", SymmetricLinopP);
+    if (paramtop.count("CheckOperator") > 0) read(paramtop, "CheckOperator", CheckOperatorP);
   }
 
   void read(XMLReader& xml, const std::string& path, SysSolverB200CloverParams& p)
@@ -89,6 +90,7 @@ namespace Chroma
     write(xml, "Verbose", p.verboseP);
     write(xml, "Device", p.device);
     write(xml, "SymmetricLinop", p.SymmetricLinopP);
+    write(xml, "CheckOperator", p.CheckOperatorP);
     pop(xml);
   }
 }

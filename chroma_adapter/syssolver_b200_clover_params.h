@@ -6,7 +6,7 @@
  *  The schema is the subset of SysSolverQUDACloverParams (quda_solvers/syssolver_quda_clover_params.h) that has a
  *  meaning for this engine, under the same tag names where one exists, so that an existing QUDA XML group works after
  *  changing <invType>: MaxIter, RsdTarget, CloverParams, AntiPeriodicT, SolverType, Delta, CudaPrecision,
- *  CudaSloppyPrecision, CudaReconstruct, RsdToleranceFactor, SilentFail, Verbose.  Tags this engine ignores
+ *  CudaSloppyPrecision, CudaReconstruct, RsdToleranceFactor, SilentFail, Verbose; own tags: Device, SymmetricLinop, CheckOperator.  Tags this engine ignores
  *  (AsymmetricLinop -- QUDA's internal choice; here the operator solved is always the caller's own A, see
  *  SymmetricLinop --, AxialGaugeFix, AutotuneDslash, Pipeline,
  *  GCRInnerParams, BackupSolverParam, DumpOnFail) are accepted and skipped.
@@ -46,6 +46,8 @@ namespace Chroma
     //! true: a SymEvenOddPrecCloverLinOp (SEOPREC_CLOVER, seoprec_clover_fermact_w.cc).  The engine must solve the
     //! caller's own A for the plugin's residual check with A to pass.
     bool SymmetricLinopP;
+    //! true (default): compare the engine's operator with the caller's A on one vector at construction (RNG state preserved)
+    bool CheckOperatorP;
   };
 
   void read(XMLReader& xml, const std::string& path, SysSolverB200CloverParams& p);

@@ -201,6 +201,8 @@ int b200_set_preconditioning(b200_ctx* ctx, int mode) {
   return ctx->eng->set_preconditioning(mode);   // the fp32 twin of b200_invert_reliable re-syncs through operator_epoch
 }
 
+int b200_set_twisted_mass(b200_ctx* ctx, double mu) { CHECK_CTX(ctx); return ctx->eng->set_twisted_mass(mu); }
+
 int b200_field_alloc(b200_ctx* ctx, b200_field** f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_alloc(f); }
 void b200_field_free(b200_ctx* ctx, b200_field* f) { if (ctx && ctx->eng) ctx->eng->field_free(f); }
 int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_upload(f, host, host_prec); }

@@ -68,6 +68,7 @@ struct DslashArgs {
   size_t gstride_z; // ... and the Z ghost faces (6*SZh)
   int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice (box 0)
   int mmode;        // OperatorMode of the EPI_M* epilogues (selects the kernel instantiation; single-RHS kernels only)
+  double twist;     // EPI_M*: isign * twisted_m -- m += twist * i gamma_5 x (eoprec_clover_linop_w.cc:174-184); 0 = no twisted term
 };
 
 // The `local`-th target site of a launch (local < a.nsites).  ZC: the batched kernels sweep box 0 in z-chunks.
@@ -557,6 +558,7 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
     // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
     // and would cost one exposed DRAM round trip each.
     C m[12], ex[12];
+    const R tw = (R)a.twist;
     if (XS) cp_async_wait_all();
     if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
 #pragma unroll
@@ -578,6 +580,10 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
         if (MODE == MODE_ASYM) m[6 * b + k] = mk<R>(o[k].x - (R)0.25 * acc[6 * b + k].x, o[k].y - (R)0.25 * acc[6 * b + k].y);
         if (MODE == MODE_SYM_PLUS) m[6 * b + k] = mk<R>(xi[k].x - (R)0.25 * o[k].x, xi[k].y - (R)0.25 * o[k].y);
         if (MODE == MODE_SYM_MINUS) m[6 * b + k] = mk<R>(xi[k].x - (R)0.25 * acc[6 * b + k].x, xi[k].y - (R)0.25 * acc[6 * b + k].y);
+        if (tw != (R)0) {   // twisted-mass term: i gamma_5 = +i on the upper chiral block (b = 0), -i on the lower one
+          const R t = b == 0 ? tw : -tw;
+          m[6 * b + k].x -= t * xi[k].y; m[6 * b + k].y += t * xi[k].x;
+        }
         if (EPI == EPI_M_DOTX) {                              // <m|x>, |m|^2
           const C mm = m[6 * b + k];
           red[0] += (double)mm.x * xi[k].x + (double)mm.y * xi[k].y;

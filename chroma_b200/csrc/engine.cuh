@@ -55,6 +55,7 @@ class EngineBase {
   virtual int get_clover(void* clov, void* invclov, int host_prec) = 0;
   virtual int clover_logdet(double* out, int cb) = 0;
   virtual int set_preconditioning(int mode) = 0;
+  virtual int set_twisted_mass(double mu) = 0;
   virtual int invert_multishift(b200_field* psi, const b200_field* chi, int n_shift, const double* shifts, const double* rsd,
                                 int max_iter, b200_solve_info* info) = 0;   // info[n_shift]
   virtual int field_alloc(b200_field** f, int nrhs = 1) = 0;

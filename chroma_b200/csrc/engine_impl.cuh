@@ -402,6 +402,15 @@ class Engine : public EngineBase {
     return B200_OK;
   }
 
+  // Twisted-mass term of the clover operators: chi += (+/-) mu i gamma_5 psi for PLUS / MINUS
+  // (eoprec_clover_linop_w.cc:174-184, seoprec_clover_linop_w.cc:174-184; CloverFermActParams::twisted_m).  0 = none.
+  double twisted_m = 0.0;
+  int set_twisted_mass(double mu) override {
+    if (!(mu == mu)) { set_error("b200_set_twisted_mass: NaN"); return B200_ERR_ARG; }
+    if (mu != twisted_m) { twisted_m = mu; ++operator_epoch; it_psi = nullptr; }
+    return B200_OK;
+  }
+
   int alloc_clover() {
     if (!clov) B200_CUDA(cudaMalloc(&clov, sizeof(C) * 72 * (size_t)g.Vh));
     if (!invclov) B200_CUDA(cudaMalloc(&invclov, sizeof(C) * 36 * (size_t)g.Vh));
@@ -665,6 +674,7 @@ class Engine : public EngineBase {
     b.in = W(0); b.out = out; b.clov = clov + (size_t)36 * g.Vh; b.x = in; b.r = r; b.r0 = r0;
     if (sym) { b.clov = invclov_oo; b.mmode = isign > 0 ? MODE_SYM_PLUS : MODE_SYM_MINUS; }
     b.parity = 1; b.isign = isign; b.iter = iter; b.check_stop = check; b.run_if = run_if;
+    b.twist = isign * twisted_m;
     switch (epi) {
       case EPI_M_CGREL: rc = launch_dslash<EPI_M_CGREL>(b); break;
       case EPI_M: rc = launch_dslash<EPI_M>(b); break;
@@ -724,6 +734,7 @@ class Engine : public EngineBase {
       DslashArgs<R> b{};
       b.in = W(0); b.out = (C*)out->d; b.clov = clov + (size_t)36 * g.Vh; b.x = (const C*)in->d; b.parity = 1; b.isign = isign;
       if (sym) { b.clov = invclov_oo; b.mmode = isign > 0 ? MODE_SYM_PLUS : MODE_SYM_MINUS; }
+      b.twist = isign * twisted_m;
       B200_CUDA(cudaEventRecord(e[0], stream));
       if (sym && isign < 0) {   // the A_oo^-1 pass of the symmetric M^dag is booked with the first kernel
         clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, 1), 128, 0, stream>>>((const C*)in->d, W(8), invclov_oo, g.Vh, nelem());

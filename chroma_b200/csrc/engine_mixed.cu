@@ -141,6 +141,7 @@ static int adopt(Engine<float>& lo, Engine<double>& hi) {
   lo.have_trlog = false;
   // symmetric preconditioning: the fp32 twin takes an fp32 copy of A_oo^-1 as well
   lo.sym = hi.sym;
+  lo.twisted_m = hi.twisted_m;
   if (hi.sym) {
     if (!lo.invclov_oo) B200_CUDA(cudaMalloc(&lo.invclov_oo, sizeof(float2) * 36 * Vh));
     planes_d2f_kernel<<<hi.blas_grid, BLAS_BLOCK, 0, hi.stream>>>(lo.invclov_oo, hi.invclov_oo, 36 * Vh);

@@ -63,6 +63,7 @@ SYMBOLS = {
     "b200_clover_logdet": (_i, [_vp, C.POINTER(_d)]),
     "b200_clover_logdet_oo": (_i, [_vp, C.POINTER(_d)]),
     "b200_set_preconditioning": (_i, [_vp, _i]),
+    "b200_set_twisted_mass": (_i, [_vp, _d]),
     "b200_dslash": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "b200_clover_apply": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "b200_clover_matpc": (_i, [_vp, _vp, _vp, _i, _i]),

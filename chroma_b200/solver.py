@@ -135,6 +135,11 @@ class Context:
         """False: EvenOddPrecCloverLinOp (default); True: SymEvenOddPrecCloverLinOp (seoprec_clover_linop_w.cc:147-193)."""
         L.check(self.lib.b200_set_preconditioning(self.h, L.B200_PRECOND_SYMMETRIC if symmetric else L.B200_PRECOND_ASYMMETRIC))
 
+    def set_twisted_mass(self, mu):
+        """CloverFermActParams::twisted_m: M psi += mu i gamma_5 psi (PLUS) / -= (MINUS); 0 = off
+        (eoprec_clover_linop_w.cc:174-184, seoprec_clover_linop_w.cc:174-184)."""
+        L.check(self.lib.b200_set_twisted_mass(self.h, float(mu)))
+
     # -- host-buffer operators (what the adapter calls)
     def _cb_out(self, like):
         return np.empty((self.Vh, 4, 3, 2), dtype=like.dtype)
@@ -328,6 +333,8 @@ class CloverFermActParams:
     clovCoeffR: float = 1.0
     clovCoeffT: float = 1.0
     anisoParam: AnisoParam = field(default_factory=AnisoParam)
+    twisted_m: float = 0.0            # <TwistedM>; twisted_m_usedP = the tag is present (clover_fermact_params_w.cc:90-97)
+    twisted_m_usedP: bool = False
 
     @staticmethod
     def from_kappa(Kappa, clovCoeff, **kw):
@@ -366,6 +373,9 @@ class SysSolverB200CloverParams:
     # (seoprec_clover_fermact_w.cc) -- the operator solved must be the caller's A so that its residual check passes
     # (cf. AsymmetricLinop of the QUDA plugin, syssolver_linop_clover_quda_w.h:318-325)
     SymmetricLinop: bool = False
+    # True (default): the constructor compares the engine's M with the caller's A on one test vector (checkOperator,
+    # chroma_adapter/b200_clover_engine.h); the vector is deterministic, QDP++'s RNG is never touched
+    CheckOperator: bool = True
 
 
 @dataclass
@@ -420,6 +430,8 @@ class LinOpSysSolverB200Clover:
             self.ctx.make_clover(dm, cr, ct, aniso=cp.anisoParam.anisoP, t_dir=cp.anisoParam.t_dir)
         if params.SymmetricLinop:
             self.ctx.set_preconditioning(True)
+        if cp.twisted_m_usedP:
+            self.ctx.set_twisted_mass(cp.twisted_m)
 
     def subset(self):
         return 1   # rb[1]

@@ -145,6 +145,13 @@ int b200_clover_logdet_oo(b200_ctx* ctx, double* tr_log_oo);
  * refused (B200_ERR_ARG): right-hand sides are then solved one at a time. */
 int b200_set_preconditioning(b200_ctx* ctx, int preconditioning);
 
+/* Twisted-mass term of the clover operators (CloverFermActParams::twisted_m, clover_fermact_params_w.cc:90-97): every
+ * later application adds chi += mu i gamma_5 psi (PLUS) / chi -= mu i gamma_5 psi (MINUS) on the odd checkerboard, with
+ * either preconditioning -- EvenOddPrecCloverLinOp::operator() (eoprec_clover_linop_w.cc:174-184) and
+ * SymEvenOddPrecCloverLinOp::operator() (seoprec_clover_linop_w.cc:174-184).  gamma_5 = Gamma(15) = diag(1,1,-1,-1) in
+ * Chroma's basis.  mu = 0 (the default) switches the term off.  Single- and multi-RHS kernels, all solvers. */
+int b200_set_twisted_mass(b200_ctx* ctx, double mu);
+
 /* Wilson hopping term on one checkerboard: out (parity out_cb) = D in (parity 1-out_cb).
  * Replaces Dslash<REAL>::operator() (cpp_dslash_scalar.h:20-105; cpp_dslash_scalar_64bit.cc:35-65)
  * as called from CPPWilsonDslashD::apply (lwldslash_w_cppd.cc:174-215). */

@@ -500,6 +500,7 @@ typedef struct {
   double* tmp1; double* tmp2;
   double* tr_log_diag;
   int sym;            /* 0: EvenOddPrecCloverLinOp, 1: SymEvenOddPrecCloverLinOp (invclov cb 1 inverted too) */
+  double twisted_m;   /* CloverFermActParams::twisted_m; 0 = twisted_m_usedP false */
 } orc_op;
 
 /* EvenOddPrecCloverLinOp::create, eoprec_clover_linop_w.cc:19-39: clov.create (mesField +
@@ -545,7 +546,29 @@ void orc_op_dslash(const orc_op* op, double* chi, const double* psi, int isign, 
   orc_dslash(op->g, chi, psi, op->packed_u, isign, 1 - cb);
 }
 
-/* EvenOddPrecCloverLinOp::operator(), eoprec_clover_linop_w.cc:142-187 (no twisted mass):
+/* The twisted-mass term both operators end with (eoprec_clover_linop_w.cc:174-184, seoprec_clover_linop_w.cc:174-184):
+ * tmp1 = Gamma(15) * timesI(psi); chi += twisted_m * tmp1 (PLUS) / chi -= twisted_m * tmp1 (MINUS), odd checkerboard.
+ * Gamma(15) = gamma_0 gamma_1 gamma_2 gamma_3 = diag(1,1,-1,-1) in the basis of the projectors above. */
+void orc_op_set_twisted_mass(orc_op* op, double mu) { op->twisted_m = mu; }
+static void orc_twisted_term(const orc_op* op, double* chi, const double* psi, int isign) {
+  if (op->twisted_m == 0.0) return;
+  int Vh = op->g->Vh;
+  const double mu = (isign > 0 ? 1.0 : -1.0) * op->twisted_m;
+#pragma omp parallel for
+  for (int i = Vh; i < 2*Vh; ++i) {
+    for (int s = 0; s < 4; ++s) {
+      const double g5 = s < 2 ? 1.0 : -1.0;
+      for (int c = 0; c < 3; ++c) {
+        const double* p = psi + (size_t)i*SPINOR + (s*3 + c)*2;
+        double* x = chi + (size_t)i*SPINOR + (s*3 + c)*2;
+        const double tr = g5 * (-p[1]), ti = g5 * p[0];     /* Gamma(15) * (i psi) */
+        x[0] += mu * tr; x[1] += mu * ti;
+      }
+    }
+  }
+}
+
+/* EvenOddPrecCloverLinOp::operator(), eoprec_clover_linop_w.cc:142-187:
  * tmp1 = D_eo psi; tmp2 = A_ee^-1 tmp1; tmp1 = D_oe tmp2; chi = A_oo psi; chi -= 1/4 tmp1.
  * Fields are full-lattice arrays; only the odd half of chi is written. */
 static void orc_sym_apply(orc_op* op, double* chi, const double* psi, int isign);
@@ -560,6 +583,7 @@ void orc_op_apply(orc_op* op, double* chi, const double* psi, int isign) {
   size_t n = (size_t)Vh*SPINOR;
 #pragma omp parallel for
   for (size_t i = 0; i < n; ++i) c[i] += -0.25*t[i];
+  orc_twisted_term(op, chi, psi, isign);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -603,6 +627,7 @@ static void orc_sym_apply(orc_op* op, double* chi, const double* psi, int isign)
   const double* t = op->tmp2 + n; const double* x = psi + n; double* c = chi + n;
 #pragma omp parallel for
   for (size_t i = 0; i < n; ++i) c[i] = x[i] + -0.25*t[i];
+  orc_twisted_term(op, chi, psi, isign);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -206,6 +206,11 @@ class Op:
         apply(), the solvers and the qprop prepare / reconstruct steps all follow the switch."""
         lib().orc_op_set_symmetric(self.h, C.c_int(int(bool(sym))))
 
+    def set_twisted_mass(self, mu):
+        """CloverFermActParams::twisted_m: apply() then ends with chi +/-= mu * Gamma(15) * timesI(psi)
+        (eoprec_clover_linop_w.cc:174-184, seoprec_clover_linop_w.cc:174-184); 0 switches the term off."""
+        lib().orc_op_set_twisted_mass(self.h, C.c_double(float(mu)))
+
     @property
     def symmetric(self):
         return bool(lib().orc_op_is_symmetric(self.h))

@@ -1,7 +1,7 @@
 #ifndef MOCK_HANDLE_H
 #define MOCK_HANDLE_H
 namespace Chroma {
-template <typename T> class Handle {   // lib/handle.h:37-92
+template <typename T> class Handle {   // lib/handle.h:37-92 (reference counting left out: the test owns the objects)
  public:
   Handle() : p(0) {}
   Handle(T* q) : p(q) {}

@@ -507,3 +507,44 @@ def test_multishift_unsorted_shifts_and_anisotropy(oracle):
     assert n_s == n
     for k, i in enumerate(order):
         assert np.abs(psi_s[k] - psi[i])[Vh:].max() < 1e-12 * np.abs(psi[i][Vh:]).max()
+
+
+def test_twisted_mass_term_restatement(oracle):
+    """a10: both clover operators end with chi +/-= twisted_m * Gamma(15) * timesI(psi) (eoprec_clover_linop_w.cc:174-184,
+    seoprec_clover_linop_w.cc:174-184).  Gamma(15) = gamma_0 gamma_1 gamma_2 gamma_3 is rebuilt here from the four gamma
+    matrices the spin projectors of the hopping term define, as explicit 4x4 algebra."""
+    gam = [np.zeros((4, 4), complex) for _ in range(4)]
+    gam[0][0, 3] = 1j; gam[0][1, 2] = 1j
+    gam[1][0, 3] = -1; gam[1][1, 2] = 1
+    gam[2][0, 2] = 1j; gam[2][1, 3] = -1j
+    gam[3][0, 2] = 1; gam[3][1, 3] = 1
+    for m in gam:
+        m += m.conj().T
+    g5 = gam[0] @ gam[1] @ gam[2] @ gam[3]
+    assert np.allclose(g5, np.diag([1, 1, -1, -1]))
+    L = (4, 4, 4, 4)
+    u = fields.apply_bc(L, fields.weak_gauge(L, seed=81))
+    psi = fields.gaussian_fermion(L, seed=82, cb=1)
+    chi = fields.gaussian_fermion(L, seed=83, cb=1)
+    mu = 0.21
+    for symmetric in (False, True):
+        op = oracle.Op(L, u, 0.1, 1.0)
+        op.set_symmetric(symmetric)
+        Vh = op.Vh
+        base = {s: op.apply(psi, s) for s in (+1, -1)}
+        op.set_twisted_mass(mu)
+        for isign in (+1, -1):
+            got = op.apply(psi, isign)
+            tw = np.einsum("st,xtc->xsc", g5, 1j * cplx_field(psi[Vh:]))          # Gamma(15) * timesI(psi)
+            want = cplx_field(base[isign][Vh:]) + isign * mu * tw
+            assert np.abs(cplx_field(got[Vh:]) - want).max() < 1e-14
+            assert np.array_equal(got[:Vh], base[isign][:Vh])                      # rb[1] only
+        a = np.vdot(cplx(chi), cplx(op.apply(psi, +1)))
+        b = np.vdot(cplx(op.apply(chi, -1)), cplx(psi))
+        assert abs(a - b) < 1e-11 * abs(a)
+        op.set_twisted_mass(0.0)
+        assert np.array_equal(op.apply(psi, +1), base[+1])
+
+
+def cplx_field(a):
+    return a[..., 0] + 1j * a[..., 1]
