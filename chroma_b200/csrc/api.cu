@@ -26,6 +26,8 @@ __global__ void set_scalars_kernel(double* scal, int* status, ScalarSet s) {
   }
 }
 
+__global__ void l2_policy_kernel(L2Policy* out) { *out = make_l2_policy(); }
+
 template <typename C2>
 __device__ void scale_planes_body(C2* p, int nplanes, size_t stride, size_t off, int count, double f) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

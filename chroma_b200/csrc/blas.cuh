@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(BLAS_BLOCK) xmy_norm_kernel(Cx<R>* out, Cx<R>*
   grid_reduce<1, BLAS_BLOCK>(s, red, FinStore{dst, 1});
 }
 
-// out = a*x + b*y (real a,b from the host; setup only)
+// out = a*x + b*y (real a,b from the host; setup only).  out may alias x or y (b200_qprop updates in place): no __restrict__.
 template <typename R>
-__global__ void __launch_bounds__(BLAS_BLOCK) axpby_kernel(Cx<R>* __restrict__ out, double a, const Cx<R>* __restrict__ x, double b,
-                                                          const Cx<R>* __restrict__ y, size_t n, size_t fstride) {
+__global__ void __launch_bounds__(BLAS_BLOCK) axpby_kernel(Cx<R>* out, double a, const Cx<R>* x, double b,
+                                                          const Cx<R>* y, size_t n, size_t fstride) {
   out += blockIdx.y * fstride; x += blockIdx.y * fstride; y += blockIdx.y * fstride;
   for (size_t i = (size_t)blockIdx.x * BLAS_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * BLAS_BLOCK) {
     const Cx<R> xv = x[i], yv = y[i];

@@ -68,6 +68,10 @@ struct DslashArgs {
   size_t gstride_z; // ... and the Z ghost faces (6*SZh)
   int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice (box 0)
   int mmode;        // OperatorMode of the EPI_M* epilogues (selects the kernel instantiation; single-RHS kernels only)
+  L2Policy pol;     // L2 residency descriptors, created once per engine and passed as kernel arguments: they then live in the
+                    // constant bank / uniform registers.  (ncu source view, round 2: with createpolicy inside the kernel the
+                    // reducing epilogues kept the descriptors in vector registers and paid one R2UR in front of EVERY hinted
+                    // load/store -- 284 extra instructions per warp, +12 % of the instruction count.)
   double twist;     // EPI_M*: isign * twisted_m -- m += twist * i gamma_5 x (eoprec_clover_linop_w.cc:174-184); 0 = no twisted term
 };
 
@@ -630,7 +634,7 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
 
   if (active) {
     const int idx = launch_site<R, false>(a, local);
-    const L2Policy pol = make_l2_policy();
+    const L2Policy pol = a.pol;
     C acc[12];
     dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
     site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
@@ -641,6 +645,20 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
   if (EPI == EPI_M_CGREL) grid_reduce<1, BLOCK>(red, a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
   if (EPI == EPI_M_DOTR0) grid_reduce<2, BLOCK>(red, a.red, FinBiAlpha{a.scal, a.status});
   if (EPI == EPI_M_DOTX) grid_reduce<3, BLOCK>(red, a.red, FinBiOmega{a.scal, a.status});
+}
+
+// The one-CTA tail of a reducing single-RHS step whose CTAs only stored their partials (ReduceBuf::split, reduce.cuh):
+// same early-outs as the step itself, so that a stopped / predicated-off step leaves the scalars alone.
+constexpr int FINISH_BLOCK = 1024;
+template <typename R, int EPI>
+__global__ void __launch_bounds__(FINISH_BLOCK) dslash_finish_kernel(const DslashArgs<R> a) {
+  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  if (a.run_if && a.status[a.run_if] == 0) return;
+  if (EPI == EPI_M_NORM) reduce_finish<1, FINISH_BLOCK>(a.red, FinCgD{a.scal});
+  if (EPI == EPI_M_CG) reduce_finish<1, FINISH_BLOCK>(a.red, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_CGREL) reduce_finish<1, FINISH_BLOCK>(a.red, FinRelCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_DOTR0) reduce_finish<2, FINISH_BLOCK>(a.red, FinBiAlpha{a.scal, a.status});
+  if (EPI == EPI_M_DOTX) reduce_finish<3, FINISH_BLOCK>(a.red, FinBiOmega{a.scal, a.status});
 }
 
 // ---- multi-RHS variant ------------------------------------------------------------------------------------------
@@ -734,7 +752,7 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {
-    const L2Policy pol = make_l2_policy();
+    const L2Policy pol = a.pol;
     C acc[12];
     if (MrhsPrefetch<R>::on) {
       C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;

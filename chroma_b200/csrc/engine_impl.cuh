@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(BLOCK) clover_kernel(const Cx<R>* __restrict__
 
 struct ScalarSet { int n; int slots[12]; double vals[12]; int reset_status; int rhs; };
 __global__ void set_scalars_kernel(double* scal, int* status, ScalarSet s);
+__global__ void l2_policy_kernel(L2Policy* out);
 __global__ void scale_planes_kernel(double2* p, int nplanes, size_t stride, size_t off, int count, double f);
 __global__ void scale_planes_kernel(float2* p, int nplanes, size_t stride, size_t off, int count, double f);
 
@@ -104,6 +105,7 @@ class Engine : public EngineBase {
   int pin_next = 0;
   int copy_threads = 4;
   size_t PIN_BYTES = PIN_BYTES_DEFAULT;   // B200_PIN_KB shrinks it (tests: many pieces and the thread team on small lattices)
+  L2Policy l2pol{};         // createpolicy descriptors (evict_last for neighbour spinors, evict_first for streams), made once
   b200_field* ws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Halo<R> halo;
   int blas_grid = 148 * 8;
@@ -136,6 +138,7 @@ class Engine : public EngineBase {
     if (prop.major < 10) { set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); return B200_ERR_CUDA; }
     blas_grid = prop.multiProcessorCount * 8;
     if (const char* e = getenv("B200_MRHS_L2_KB")) l2_budget = atol(e) << 10;
+    if (const char* e = getenv("B200_SPLIT_MIN_BLOCKS")) split_min_blocks = atoi(e);
     g.Lxh = cfg.ldims[0] / 2; g.Ly = cfg.ldims[1]; g.Lz = cfg.ldims[2]; g.Lt = cfg.ldims[3];
     g.S3h = g.Lxh * g.Ly * g.Lz;
     g.Vh = g.S3h * g.Lt;
@@ -156,6 +159,9 @@ class Engine : public EngineBase {
     B200_CUDA(cudaEventCreate(&ev_t0));
     B200_CUDA(cudaEventCreate(&ev_t1));
     B200_CUDA(cudaMalloc(&staging, STAGING_BYTES));
+    l2_policy_kernel<<<1, 1, 0, stream>>>((L2Policy*)staging);
+    B200_CUDA(cudaMemcpyAsync(&l2pol, staging, sizeof(L2Policy), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));
     if (const char* e = getenv("B200_PIN_KB")) PIN_BYTES = std::max<size_t>(4096, (size_t)atol(e) << 10);
     for (int i = 0; i < 2; ++i) {
       B200_CUDA(cudaHostAlloc(&pin[i], PIN_BYTES, cudaHostAllocDefault));
@@ -233,6 +239,7 @@ class Engine : public EngineBase {
   ReduceBuf make_red(int block_offset, int total_blocks) {
     ReduceBuf rb;
     rb.partial = partial; rb.ticket = ticket; rb.gpartial = gpartial; rb.gticket = gticket; rb.block_offset = block_offset; rb.total_blocks = total_blocks;
+    rb.split = 0;
     rb.peer = halo.peer_reduce();
     return rb;
   }
@@ -296,6 +303,10 @@ class Engine : public EngineBase {
       aos_to_soa_kernel<H, R, NR, NPL, Map><<<(n + PACK_SITES - 1) / PACK_SITES, PACK_BLOCK, 0, stream>>>(
           (const H*)staging, dst, n, stride, (size_t)off, map, scale);
       int rc = launched("aos_to_soa"); if (rc) return rc;
+      if (NR == 18 && r12_check) {   // 12-real compression: every link must be SU(3) up to the one phase the engine carries itself
+        recon12_check_kernel<H><<<(n + 255) / 256, 256, 0, stream>>>((const H*)staging, n, (size_t)off, r12_flip_lo, r12_flip_hi, r12_check);
+        rc = launched("recon12_check"); if (rc) return rc;
+      }
       // the staging buffer is reused by the next chunk: same stream, so ordering is implicit
     }
     return B200_OK;
@@ -316,6 +327,8 @@ class Engine : public EngineBase {
     return comm_check();
   }
 
+  unsigned long long* r12_check = nullptr;    // device word: max |reconstructed row 2 - given row 2| of the upload in progress
+  size_t r12_flip_lo = 0, r12_flip_hi = 0;
   int load_gauge(const void* const u[4], int host_prec, const double aniso[4], int t_boundary, int recon_) override {
     B200_CUDA(cudaSetDevice(cfg.device));
     if (recon_ != B200_RECONS_NONE && recon_ != B200_RECONS_12) { set_error("reconstruct must be 18 or 12"); return B200_ERR_ARG; }
@@ -327,10 +340,15 @@ class Engine : public EngineBase {
     B200_CUDA(cudaMalloc(&gauge, sizeof(C) * 8 * (size_t)NG * g.Vh));
     recon = recon_; t_boundary_ = t_boundary;
     const bool last_rank = cfg.pcoord[3] == cfg.pgrid[3] - 1;
+    unsigned long long* chk = nullptr;
+    if (recon == 12) { B200_CUDA(cudaMalloc(&chk, sizeof(unsigned long long))); B200_CUDA(cudaMemsetAsync(chk, 0, sizeof(unsigned long long), stream)); }
     for (int mu = 0; mu < 4; ++mu) {
       aniso_[mu] = aniso[mu];
       ls.aniso[mu] = aniso[mu];
       for (int par = 0; par < 2; ++par) {
+        r12_check = chk;
+        const bool flip = mu == 3 && t_boundary == -1 && last_rank;      // the -1 of the antiperiodic T boundary lives on the last slice
+        r12_flip_lo = flip ? (size_t)(g.Lt - 1) * g.S3h : 0; r12_flip_hi = flip ? (size_t)g.Vh : 0;
         C* dst = gauge + (size_t)(mu * 2 + par) * NG * g.Vh;
         int rc;
         const double sc = (recon == 18) ? aniso[mu] : 1.0;
@@ -343,7 +361,8 @@ class Engine : public EngineBase {
           rc = (recon == 18) ? upload_aos<float, 18, 9>(src, g.Vh, dst, (size_t)g.Vh, MapIdentity(), sc)
                              : upload_aos<float, 18, 6>(src, g.Vh, dst, (size_t)g.Vh, MapIdentity(), sc);
         }
-        if (rc) return rc;
+        r12_check = nullptr;
+        if (rc) { cudaFree(chk); return rc; }
         if (recon == 12 && mu == 3 && t_boundary == -1 && last_rank) {
           // strip the antiperiodic phase so that rows 0,1 are rows of an SU(3) matrix again; the kernel
           // re-applies it (LinkScale::bc_t), as the QUDA / QPhiX adapters do
@@ -357,6 +376,20 @@ class Engine : public EngineBase {
     ls.t_is_last = last_rank ? 1 : 0;
     ++operator_epoch;
     B200_CUDA(cudaStreamSynchronize(stream));
+    if (chk) {
+      unsigned long long bits = 0;
+      B200_CUDA(cudaMemcpy(&bits, chk, sizeof(bits), cudaMemcpyDeviceToHost));
+      cudaFree(chk);
+      double dev; memcpy(&dev, &bits, sizeof(dev));
+      const double tol = host_prec == B200_DOUBLE ? 1e-9 : 1e-3;
+      if (!(dev <= tol)) {
+        cudaFree(gauge); gauge = nullptr;
+        set_error("RECONS_12 needs SU(3) links whose only extra phase is the antiperiodic T boundary (t_boundary = %d): the third row "
+                  "rebuilt from rows 0,1 differs from the given one by %.3e -- spatial fermion boundary phases, a wrong AntiPeriodicT "
+                  "or non-unitary links; use RECONS_NONE", t_boundary, dev);
+        return B200_ERR_ARG;
+      }
+    }
     return B200_OK;
   }
 
@@ -534,7 +567,7 @@ class Engine : public EngineBase {
   static constexpr int NRB = sizeof(R) == 4 ? B200_MRHS_NRB_F : B200_MRHS_NRB;   // right-hand sides per CTA (tuned per precision)
   template <int EPI>
   int launch_dslash(DslashArgs<R>& a) {
-    a.gauge = gauge; a.scal = scal; a.status = status; a.g = g;
+    a.gauge = gauge; a.scal = scal; a.status = status; a.g = g; a.pol = l2pol;
     a.nrhs = nb; a.fstride = nelem(); a.gstride = (size_t)6 * g.S3h; a.gstride_z = (size_t)6 * g.SZh;
     const int bs = nb > 1 ? 32 : DSLASH_BLOCK;          // target sites per CTA
     int rc;
@@ -562,7 +595,9 @@ class Engine : public EngineBase {
         a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
         a.box[0] = inner; for (int k = 0; k < nf; ++k) a.box[1 + k] = faces[k];
         a.nbox = 1 + nf; a.nsites = g.Vh; a.zc_sites = 0; a.red = make_red(0, total);
-        return launch_halo<EPI>(a, h, h.n_pack + total);
+        a.red.split = split_reduce<EPI>(total);
+        rc = launch_halo<EPI>(a, h, h.n_pack + total); if (rc) return rc;
+        return launch_finish<EPI>(a);
       }
       // batched right-hand sides: pack + send the faces over NVLink, run the interior while they fly, then the boundary
       rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, nb, a.fstride, launches); if (rc) return rc;
@@ -582,7 +617,21 @@ class Engine : public EngineBase {
     a.zc_sites = nb > 1 ? zchunk_sites(g.Lz) : 0;
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
-    return launch_one<EPI>(a, blocks);
+    if (nb == 1) a.red.split = split_reduce<EPI>(blocks);
+    { int rc1 = launch_one<EPI>(a, blocks); if (rc1) return rc1; }
+    return launch_finish<EPI>(a);
+  }
+  // Big single-RHS grids: the CTAs only store their partial sums, a one-CTA kernel behind the step finishes (reduce.cuh)
+  int split_min_blocks = RED_FLAT_MAX;   // B200_SPLIT_MIN_BLOCKS overrides (tests: exercise the split path on small lattices)
+  template <int EPI>
+  int split_reduce(int blocks) const {
+    return (EPI == EPI_M_NORM || EPI == EPI_M_CG || EPI == EPI_M_CGREL || EPI == EPI_M_DOTR0 || EPI == EPI_M_DOTX) && blocks > split_min_blocks;
+  }
+  template <int EPI>
+  int launch_finish(const DslashArgs<R>& a) {
+    if (!a.red.split) return B200_OK;
+    dslash_finish_kernel<R, EPI><<<1, FINISH_BLOCK, 0, stream>>>(a);
+    return launched("dslash_finish_kernel");
   }
   // the fused split-lattice launch (single right-hand side): dslash_halo_kernel, halo.cuh
   template <int EPI>

@@ -193,7 +193,7 @@ dslash_halo_kernel(const DslashArgs<R> a, const LinkScale ls, const HaloFuse<R> 
   double red[3] = {0.0, 0.0, 0.0};
   if (active) {
     const int idx = boundary ? launch_site_from<R>(a, local, 1) : box_site(a.g, a.box[0], local);
-    const L2Policy pol = make_l2_policy();
+    const L2Policy pol = a.pol;
     C acc[12];
     dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
     site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
@@ -327,15 +327,20 @@ class Halo {
       peer[r] = (char*)p;
     }
     if (comm.barrier(comm.user) != 0) { set_error("barrier failed"); return B200_ERR_COMM; }
+    ready = true;
     return B200_OK;
   }
 
+  bool ready = false;   // init() completed on this rank (and therefore, after its last barrier, on every rank)
   void destroy() {
     if (!arena) return;
     cudaDeviceSynchronize();
-    if (comm.barrier) comm.barrier(comm.user);     // nobody may still be writing into a peer arena
-    for (int r = 0; r < nranks; ++r) if (r != rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
-    if (comm.barrier) comm.barrier(comm.user);
+    // the barriers pair with those of the other ranks' destroy(); a rank whose init() failed half way must not wait for
+    // peers that never got here (they would be waiting in init's own collective)
+    if (ready && comm.barrier) comm.barrier(comm.user);     // nobody may still be writing into a peer arena
+    for (int r = 0; r < (int)peer.size(); ++r) if (r != rank && peer[r]) cudaIpcCloseMemHandle(peer[r]);
+    if (ready && comm.barrier) comm.barrier(comm.user);
+    ready = false;
     cudaFree(arena); cudaFree(ticket);
     arena = nullptr;
   }

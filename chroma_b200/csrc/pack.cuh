@@ -44,6 +44,34 @@ __global__ void __launch_bounds__(PACK_BLOCK) aos_to_soa_kernel(const H* __restr
   }
 }
 
+// 12-real link compression keeps rows 0 and 1 and rebuilds row 2 = conj(row0 x row1) in the kernels.  That is only right
+// for SU(3) links; the one non-unit factor the engine carries separately is the -1 of an antiperiodic T boundary on the
+// last global time slice.  Links with any other phase (spatially antiperiodic or twisted fermion boundaries, U(3) links)
+// would be reconstructed wrongly, so the upload checks every link: |conj(row0 x row1) - sgn * row2| with sgn = -1 for
+// sites in [flip_lo, flip_hi) (index within this parity field), +1 elsewhere; the maximum is kept as the bit pattern of a
+// non-negative double (ordered like an unsigned integer).
+template <typename H>
+__global__ void __launch_bounds__(256) recon12_check_kernel(const H* __restrict__ aos, int nsites, size_t site_off, size_t flip_lo, size_t flip_hi,
+                                                          unsigned long long* maxdev) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double dev = 0.0;
+  if (i < nsites) {
+    const H* u = aos + (size_t)i * 18;
+    const size_t site = site_off + i;
+    const double sg = (site >= flip_lo && site < flip_hi) ? -1.0 : 1.0;
+    for (int c = 0; c < 3; ++c) {
+      const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+      const double ar = u[2 * c1], ai = u[2 * c1 + 1], br = u[6 + 2 * c2], bi = u[6 + 2 * c2 + 1];
+      const double cr = u[2 * c2], ci = u[2 * c2 + 1], dr = u[6 + 2 * c1], di = u[6 + 2 * c1 + 1];
+      const double tr = (ar * br - ai * bi) - (cr * dr - ci * di), ti = (ar * bi + ai * br) - (cr * di + ci * dr);
+      const double er = tr - sg * (double)u[12 + 2 * c], ei = -ti - sg * (double)u[12 + 2 * c + 1];
+      dev = fmax(dev, fmax(fabs(er), fabs(ei)));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+  if ((threadIdx.x & 31) == 0 && dev > 0.0) atomicMax(maxdev, (unsigned long long)__double_as_longlong(dev));
+}
+
 template <typename H, typename R, int NR, int NPL, typename Map>
 __global__ void __launch_bounds__(PACK_BLOCK) soa_to_aos_kernel(H* __restrict__ dst, const Cx<R>* __restrict__ src, int nsites,
                                                                size_t stride, size_t src_off, Map map) {

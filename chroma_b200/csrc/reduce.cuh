@@ -32,6 +32,7 @@ struct ReduceBuf {
   unsigned int* ticket;  // zero between kernels
   double* gpartial;      // [N][ngroups] group sums (two-level reductions)
   unsigned int* gticket; // [ngroups], zero between kernels
+  int split;             // != 0: the blocks only store their partials; reduce_finish (a one-CTA kernel behind the step) sums them
   int block_offset;      // first partial slot of this launch (a step may be split into several launches)
   int total_blocks;      // blocks over all launches of the step
   PeerReduce peer;
@@ -165,6 +166,9 @@ __device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fi
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + blk] = s[k];
+  }
+  if (rb.split) return;            // uniform over the grid: no ticket, nobody waits (see reduce_finish)
+  if (threadIdx.x == 0) {
 #if B200_RED_PROBE == 2
     role1 = 0;
 #else
@@ -203,6 +207,56 @@ __device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fi
     fin(tot);
     *rb.ticket = 0u;
     __threadfence();
+  }
+}
+
+// Split reductions (the big single-RHS Dslash grids).  Drawing a ticket costs every CTA an L2 atomic round trip before it
+// may leave -- it has to learn whether it is the last one -- and with two 255-register CTAs per SM that ~1 us tail, during
+// which the CTA's slot issues no loads, is 7-8 % of a 13 us CTA (measured on B200, profiles/r02_reduce_tail_ab.json:
+// accumulate only +2.5 %, + block sums and partial stores +4-5 %, + ticket +7.6 %; a release atomic instead of
+// __threadfence + atomic changes nothing).  With rb.split the CTAs store their partial and leave; this one-CTA kernel,
+// launched behind the step, sums the partials in the same two-level fixed order (groups of RED_GROUP by one warp each,
+// then the group sums), combines across GPUs and runs the finaliser: ~5 us instead of ~150 us of tails.
+template <int N, int BLOCK, typename Fin>
+__device__ __forceinline__ void reduce_finish(const ReduceBuf& rb, Fin fin) {
+  __shared__ double smem[BLOCK / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = BLOCK / 32;
+  const int ngrp = rb.ngroups();
+  for (int g0 = w; g0 < ngrp; g0 += 4 * nw) {            // four groups per warp in flight
+    double x[N][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int grp = g0 + j * nw;
+      const int gsize = grp < ngrp ? min(RED_GROUP, rb.total_blocks - grp * RED_GROUP) : 0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double* p = rb.partial + (size_t)k * rb.total_blocks + (size_t)grp * RED_GROUP;
+        x[k][j] = (lane < gsize ? __ldcg(p + lane) : 0.0) + (lane + 32 < gsize ? __ldcg(p + lane + 32) : 0.0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int grp = g0 + j * nw;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        double v = x[k][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && grp < ngrp) rb.gpartial[(size_t)k * ngrp + grp] = v;
+      }
+    }
+  }
+  __syncthreads();                                        // one CTA: the group sums are visible to all its threads
+  double tot[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double acc = 0.0;                                     // plain loads: written by this CTA
+    for (int b = threadIdx.x; b < ngrp; b += BLOCK) acc += rb.gpartial[(size_t)k * ngrp + b];
+    tot[k] = block_sum<BLOCK>(acc, smem);
+  }
+  if (threadIdx.x == 0) {
+    peer_allreduce<N>(rb.peer, tot);
+    fin(tot);
   }
 }
 

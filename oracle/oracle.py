@@ -551,3 +551,119 @@ def cg_bench(op, chi, n_warm, n_timed, use_reference_dslash=True):
     lib().orc_set_dslash_hook(None, None)
     del keep
     return out[0], out[1], kind
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's Chroma-level code for the path, compiled unmodified into oracle/_ref/libref_chroma.so against
+# tests/mock_chroma (oracle/Makefile, oracle/ref_chroma_shim.cc): clover site loops of clover_term_qdp_w.h and the solver
+# loops invcg2.cc / invbicgstab.cc / minvcg2.cc / reliable_cg.cc / reliable_bicgstab.cc.  Used by tests/test_oracle.py to
+# pin the restatements above and by tests/golden/make_golden.py to write fixtures.
+_REFC = None
+
+
+def have_ref_chroma():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_chroma.so"))
+
+
+def ref_chroma(L):
+    """dlopen the library and set its (global, single-rank) layout to lattice L."""
+    global _REFC
+    if _REFC is None:
+        _REFC = C.CDLL(os.path.join(_HERE, "_ref", "libref_chroma.so"))
+    _REFC.refc_setup(c_int4(*L))
+    return _REFC
+
+
+def _apply_ptr():
+    """orc_op_apply(op, chi, psi, isign) as the C callback the reference solvers iterate on."""
+    return C.cast(lib().orc_op_apply, C.c_void_p)
+
+
+def ref_mesfield(L, u):
+    """The reference's mesField (lib/meas/glue/mesfield.cc:30-78) on a periodic single-rank lattice."""
+    R = ref_chroma(L)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    f = np.zeros((6,) + u.shape[1:], dtype=np.float64)
+    R.refc_mesfield(_p(u), _p(f))
+    return f
+
+
+def ref_make_clov(L, f, diag_mass, cR, cT, anisoP=False, t_dir=3):
+    """QDPCloverTermT::makeClov with the reference's own makeClovSiteLoop (clover_term_qdp_w.h:398-553)."""
+    R = ref_chroma(L)
+    pmu, pnu = (0, 0, 0, 1, 1, 2), (1, 2, 3, 2, 3, 3)
+    coef = (C.c_double * 6)(*[(cT if (anisoP and (pmu[k] == t_dir or pnu[k] == t_dir)) else cR) for k in range(6)])
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    tri = np.zeros((f.shape[1], 72), dtype=np.float64)
+    R.refc_make_clov(_p(f), coef, C.c_double(diag_mass), _p(tri))
+    return tri
+
+
+def ref_ldagdlinv(L, tri, cb):
+    """QDPCloverTermT::ldagdlinv with the reference's own LDagDLInvSiteLoop (:619-846)."""
+    R = ref_chroma(L)
+    out = np.ascontiguousarray(tri, dtype=np.float64).copy()
+    trlog = np.zeros(out.shape[0], dtype=np.float64)
+    R.refc_ldagdlinv(_p(out), C.c_int(cb), _p(trlog))
+    return out, trlog
+
+
+def ref_clover_apply(L, psi, tri, cb):
+    """QDPCloverTermT::apply with the reference's own applySiteLoop (:1562-1634)."""
+    R = ref_chroma(L)
+    psi = np.ascontiguousarray(psi, dtype=np.float64)
+    chi = np.zeros_like(psi)
+    R.refc_clover_apply(_p(np.ascontiguousarray(tri, dtype=np.float64)), _p(psi), _p(chi), C.c_int(cb))
+    return chi
+
+
+def ref_invcg2(op, chi, psi0, rsd, maxit, trace_cap=4096):
+    """The reference's InvCG2 on the oracle operator `op`.  Returns (psi, n_count, resid, trace) with trace[i] = |input|^2 of
+    the i-th operator application -- an iteration-by-iteration fingerprint of the Krylov sequence."""
+    R = ref_chroma(op.L)
+    psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+    out, trace = (C.c_double * 4)(), np.zeros(trace_cap)
+    R.refc_invcg2(_apply_ptr(), op.h, _p(np.ascontiguousarray(chi, dtype=np.float64)), _p(psi), C.c_double(rsd), C.c_int(maxit),
+                  out, _p(trace), C.c_int(trace_cap))
+    return psi, int(out[0]), out[1], trace[:min(int(out[2]), trace_cap)]
+
+
+def ref_invbicgstab(op, chi, psi0, rsd, maxit, isign=+1, trace_cap=4096):
+    R = ref_chroma(op.L)
+    psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+    out, trace = (C.c_double * 4)(), np.zeros(trace_cap)
+    R.refc_invbicgstab(_apply_ptr(), op.h, _p(np.ascontiguousarray(chi, dtype=np.float64)), _p(psi), C.c_double(rsd),
+                       C.c_int(maxit), C.c_int(isign), out, _p(trace), C.c_int(trace_cap))
+    return psi, int(out[0]), out[1], trace[:min(int(out[2]), trace_cap)]
+
+
+def ref_minvcg2(op, chi, shifts, rsd, maxit, trace_cap=4096):
+    R = ref_chroma(op.L)
+    shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+    rsd = np.ascontiguousarray(np.broadcast_to(np.asarray(rsd, dtype=np.float64), shifts.shape))
+    chi = np.ascontiguousarray(chi, dtype=np.float64)
+    psi = np.zeros((len(shifts),) + chi.shape)
+    out, trace = (C.c_double * 4)(), np.zeros(trace_cap)
+    R.refc_minvcg2(_apply_ptr(), op.h, _p(chi), _p(psi), _p(shifts), _p(rsd), C.c_int(len(shifts)), C.c_int(maxit), out,
+                   _p(trace), C.c_int(trace_cap))
+    return psi, int(out[0]), trace[:min(int(out[2]), trace_cap)]
+
+
+def ref_reliable_cg(op, chi, psi0, rsd, delta, maxit):
+    """The reference's InvCGReliable(A, AF, ...) with the oracle operator in fp64 and the same operator rounded through
+    float fields as the fp32 one.  Returns (psi, n_count, resid, fp64 applications, fp32 applications)."""
+    R = ref_chroma(op.L)
+    psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+    out = (C.c_double * 4)()
+    R.refc_reliable_cg(_apply_ptr(), op.h, _p(np.ascontiguousarray(chi, dtype=np.float64)), _p(psi), C.c_double(rsd),
+                       C.c_double(delta), C.c_int(maxit), out)
+    return psi, int(out[0]), out[1], int(out[2]), int(out[3])
+
+
+def ref_reliable_bicgstab(op, chi, psi0, rsd, delta, maxit, isign=+1):
+    R = ref_chroma(op.L)
+    psi = np.ascontiguousarray(psi0, dtype=np.float64).copy()
+    out = (C.c_double * 4)()
+    R.refc_reliable_bicgstab(_apply_ptr(), op.h, _p(np.ascontiguousarray(chi, dtype=np.float64)), _p(psi), C.c_double(rsd),
+                             C.c_double(delta), C.c_int(maxit), C.c_int(isign), out)
+    return psi, int(out[0]), out[1], int(out[2]), int(out[3])

@@ -1,4 +1,4 @@
-"""Generates tests/golden/ref_*.npz: outputs of the REFERENCE'S OWN code on seeded inputs.
+"""Generates tests/golden/ref_*.npz and tests/golden/chroma_*.npz: outputs of the REFERENCE'S OWN code on seeded inputs.
 
 Run in the build container only (needs /root/reference, through oracle/_ref/libref_dslash.so which oracle/Makefile
 compiles, unmodified and in place, from /root/reference/other_libs/cpp_wilson_dslash/lib):
@@ -69,5 +69,50 @@ def main():
         print(path, "%.0f KB" % (os.path.getsize(path) / 1024))
 
 
+def main_chroma():
+    """tests/golden/chroma_*.npz: outputs of the reference's Chroma-level code for the path -- mesField, the clover site
+    loops of clover_term_qdp_w.h and the solver loops invcg2 / invbicgstab / minvcg2 / reliable_cg / reliable_bicgstab --
+    compiled unmodified into oracle/_ref/libref_chroma.so (oracle/Makefile).  The operator the solvers iterate on is the
+    oracle's (pinned to the reference Dslash / CloverSchur4D by the ref_*.npz fixtures above)."""
+    assert orc.have_ref_chroma(), "oracle/_ref/libref_chroma.so missing: run `make -C oracle` where /root/reference exists"
+    for name, L, seed, aniso in (("4x4x4x8", (4, 4, 4, 8), 301, False), ("6x4x4x4_aniso", (6, 4, 4, 4), 401, True)):
+        g = orc.Geom(L)
+        u = fields.apply_bc(L, fields.weak_gauge(L, seed=seed))
+        an = dict(anisoP=True, t_dir=3, xi_0=2.464, nu=0.95) if aniso else {}
+        cR, cT = (0.91, 1.07) if aniso else (1.0, 1.0)
+        dm, r, t = orc.clover_coeffs(0.1, cR, cT, **{k: v for k, v in an.items() if k != "t_dir"})
+        f = orc.ref_mesfield(L, u)
+        tri = orc.ref_make_clov(L, f, dm, r, t, anisoP=aniso, t_dir=3)
+        inv0, trlog0 = orc.ref_ldagdlinv(L, tri, 0)
+        inv1, trlog1 = orc.ref_ldagdlinv(L, tri, 1)
+        psi = fields.gaussian_fermion(L, seed=seed + 1)
+        out = {"L": np.array(L, dtype=np.int32), "u": u, "Mass": 0.1, "clovCoeffR": cR, "clovCoeffT": cT, "aniso": int(aniso),
+               "xi_0": an.get("xi_0", 1.0), "nu": an.get("nu", 1.0),
+               "f": f, "tri": tri, "invtri_cb0": inv0[:g.Vh], "invtri_cb1": inv1[g.Vh:], "trlog_cb0": trlog0[:g.Vh], "trlog_cb1": trlog1[g.Vh:],
+               "psi": psi, "clover_apply_cb0": orc.ref_clover_apply(L, psi, tri, 0)[:g.Vh],
+               "clover_apply_cb1": orc.ref_clover_apply(L, psi, tri, 1)[g.Vh:],
+               "invclover_apply_cb0": orc.ref_clover_apply(L, psi, inv0, 0)[:g.Vh]}
+        op = orc.Op(L, u, 0.1, cR, cT, **an)
+        chi = fields.gaussian_fermion(L, seed=seed + 2, cb=1)
+        zero = np.zeros_like(chi)
+        out["chi"] = chi[g.Vh:]
+        p, n, res, tr = orc.ref_invcg2(op, chi, zero, 1e-8, 1000)
+        out.update(cg_psi=p[g.Vh:], cg_n=n, cg_resid=res, cg_trace=tr)
+        for isign, key in ((+1, "p"), (-1, "m")):
+            p, n, res, tr = orc.ref_invbicgstab(op, chi, zero, 1e-8, 1000, isign)
+            out.update({"bicg_%s_psi" % key: p[g.Vh:], "bicg_%s_n" % key: n, "bicg_%s_resid" % key: res, "bicg_%s_trace" % key: tr})
+        shifts = np.array([0.7, 0.001, 0.05])      # unsorted on purpose: minvcg2.cc:153-164 finds the smallest itself
+        p, n, tr = orc.ref_minvcg2(op, chi, shifts, 1e-8, 1000)
+        out.update(ms_shifts=shifts, ms_psi=p[:, g.Vh:], ms_n=n, ms_trace=tr)
+        p, n, res, c64, c32 = orc.ref_reliable_cg(op, chi, zero, 1e-10, 0.1, 1000)
+        out.update(relcg_psi=p[g.Vh:], relcg_n=n, relcg_resid=res, relcg_calls=np.array([c64, c32]))
+        p, n, res, c64, c32 = orc.ref_reliable_bicgstab(op, chi, zero, 1e-10, 0.1, 1000)
+        out.update(relbicg_psi=p[g.Vh:], relbicg_n=n, relbicg_resid=res, relbicg_calls=np.array([c64, c32]))
+        path = os.path.join(HERE, "chroma_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print(path, "%.0f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     main()
+    main_chroma()

@@ -111,7 +111,14 @@ template <typename R> struct OReal {
   OReal& operator+=(const OReal& o) { e.e.e.v += o.val(); return *this; }
   OReal& operator/=(const OReal& o) { e.e.e.v /= o.val(); return *this; }
 };
+template <typename T> struct OScalar;     // only the spelling QDP++ code uses for Real: OScalar<PScalar<PScalar<RScalar<R>>>>
+template <typename R> struct OScalar<PScalar<PScalar<RScalar<R> > > > : OReal<R> {
+  OScalar() {}
+  OScalar(double x) : OReal<R>(x) {}
+  template <typename R2> OScalar(const OReal<R2>& o) : OReal<R>(o) {}
+};
 typedef OReal<float> RealF;
+const double fuzz = 1.0e-5;              // QDP++'s "fuzz" constant (qdp_globalfuncs)
 typedef OReal<double> RealD;
 typedef RealD Real;      // a double-precision build of Chroma
 typedef RealD Double;
@@ -139,6 +146,9 @@ MOCK_REAL_CMP(<=)
 MOCK_REAL_CMP(>=)
 MOCK_REAL_CMP(==)
 #undef MOCK_REAL_CMP
+inline Boolean operator&&(const Boolean& a, const Boolean& b) { Boolean r = {a.b && b.b}; return r; }
+inline Boolean operator||(const Boolean& a, const Boolean& b) { Boolean r = {a.b || b.b}; return r; }
+inline Boolean operator!(const Boolean& a) { Boolean r = {!a.b}; return r; }
 inline bool toBool(const Boolean& b) { return b.b; }
 inline bool toBool(bool b) { return b; }
 template <typename A> inline double toDouble(const OReal<A>& r) { return (double)r.val(); }
@@ -198,6 +208,17 @@ template <> class multi1d<bool> {     // std::vector<bool> has no addressable el
   std::vector<unsigned char> d;
 };
 
+template <typename T> class multi2d {     // multi2d<T> z(n2, n1); z[j][i]
+ public:
+  multi2d() : n1(0) {}
+  multi2d(int n2_, int n1_) : n1(n1_), d((size_t)n2_ * n1_) {}
+  T* operator[](int j) { return d.data() + (size_t)j * n1; }
+  const T* operator[](int j) const { return d.data() + (size_t)j * n1; }
+ private:
+  int n1;
+  std::vector<T> d;
+};
+
 namespace Layout {
 // test harness: the LOCAL lattice of this rank, the process grid and this rank's coordinate in it
 void mockSetup(const int local_dims[4], const int grid[4], const int coord[4], int node, int nodes);
@@ -231,6 +252,8 @@ extern Zero zero;
 
 // ---------------------------------------------------------------------------------------------- lattice fields
 template <typename L> struct SubsetProxy;
+template <typename T> struct SiteWord { typedef typename T::Word type; };
+template <typename R> struct SiteWord<PScalar<PScalar<RScalar<R> > > > { typedef R type; };   // LatticeReal
 template <typename T> class OLattice {
  public:
   typedef T Site;
@@ -241,7 +264,7 @@ template <typename T> class OLattice {
   const T& elem(int i) const { return d[i]; }
   SubsetProxy<OLattice> operator[](const Subset& s) { SubsetProxy<OLattice> p = {*this, s}; return p; }
   // flat view in words of the site type
-  typedef typename T::Word Word;
+  typedef typename SiteWord<T>::type Word;
   Word* words() { return reinterpret_cast<Word*>(d.data()); }
   const Word* words() const { return reinterpret_cast<const Word*>(d.data()); }
   static int wordsPerSite() { return (int)(sizeof(T) / sizeof(Word)); }
@@ -262,11 +285,12 @@ typedef OLattice<FermSite<double, Ns> > LatticeFermionD;
 typedef LatticeFermionD LatticeFermion;
 typedef OLattice<FermSite<float, 1> > LatticeStaggeredFermionF;
 typedef OLattice<FermSite<double, 1> > LatticeStaggeredFermionD;
+typedef LatticeStaggeredFermionD LatticeStaggeredFermion;
 typedef OLattice<CMSite<float> > LatticeColorMatrixF;
 typedef OLattice<CMSite<double> > LatticeColorMatrixD;
 typedef LatticeColorMatrixD LatticeColorMatrix;
 template <typename T> struct WordType;
-template <typename S> struct WordType<OLattice<S> > { typedef typename S::Word Type_t; };
+template <typename S> struct WordType<OLattice<S> > { typedef typename SiteWord<S>::type Type_t; };
 
 // eager "expressions": every operator returns a whole field
 #define MOCK_FOR_WORDS(L, x) const int n_ = Layout::sitesOnNode() * L::wordsPerSite(); for (int x = 0; x < n_; ++x)
@@ -277,12 +301,12 @@ template <typename S> inline OLattice<S> operator-(const OLattice<S>& a, const O
   OLattice<S> r; MOCK_FOR_WORDS(OLattice<S>, i) r.words()[i] = a.words()[i] - b.words()[i]; return r;
 }
 template <typename S, typename R> inline OLattice<S> operator*(const OReal<R>& a, const OLattice<S>& b) {
-  typedef typename S::Word W; const W s = (W)a.val();
+  typedef typename SiteWord<S>::type W; const W s = (W)a.val();
   OLattice<S> r; MOCK_FOR_WORDS(OLattice<S>, i) r.words()[i] = s * b.words()[i]; return r;
 }
 template <typename S, typename R> inline OLattice<S> operator*(const OLattice<S>& b, const OReal<R>& a) { return a * b; }
 template <typename S, typename R> inline OLattice<S> operator*(const OComplex<R>& a, const OLattice<S>& b) {
-  typedef typename S::Word W; const W ar = (W)a.re, ai = (W)a.im;
+  typedef typename SiteWord<S>::type W; const W ar = (W)a.re, ai = (W)a.im;
   OLattice<S> r;
   const int n = Layout::sitesOnNode() * OLattice<S>::wordsPerSite() / 2;
   for (int i = 0; i < n; ++i) {
@@ -297,11 +321,50 @@ template <typename L> struct SubsetProxy {
   int w0() const { return s.start() * L::wordsPerSite(); }
   int w1() const { return (s.end() + 1) * L::wordsPerSite(); }
   SubsetProxy& operator=(const L& o) { for (int i = w0(); i < w1(); ++i) l.words()[i] = o.words()[i]; return *this; }
+  // precision-converting assignment (LatticeFermionF <-> LatticeFermionD, reliable_cg.cc:58,124)
+  template <typename S2> SubsetProxy& operator=(const OLattice<S2>& o) { for (int i = w0(); i < w1(); ++i) l.words()[i] = (W)o.words()[i]; return *this; }
+  template <typename S2> SubsetProxy& operator+=(const OLattice<S2>& o) { for (int i = w0(); i < w1(); ++i) l.words()[i] += (W)o.words()[i]; return *this; }
   SubsetProxy& operator+=(const L& o) { for (int i = w0(); i < w1(); ++i) l.words()[i] += o.words()[i]; return *this; }
   SubsetProxy& operator-=(const L& o) { for (int i = w0(); i < w1(); ++i) l.words()[i] -= o.words()[i]; return *this; }
   template <typename R> SubsetProxy& operator*=(const OReal<R>& a) { const W x = (W)a.val(); for (int i = w0(); i < w1(); ++i) l.words()[i] *= x; return *this; }
   SubsetProxy& operator=(const Zero&) { for (int i = w0(); i < w1(); ++i) l.words()[i] = 0; return *this; }
 };
+// colour-matrix fields: products, adjoint, nearest-neighbour shifts (what mesField needs, lib/meas/glue/mesfield.cc:30-78)
+enum { BACKWARD = -1, FORWARD = 1 };
+namespace Layout { const int* mockNeighbourTable(int dir, int mu); }    // [sitesOnNode]: site of x + dir*mu, periodic, cb2 order
+template <typename R> inline OLattice<CMSite<R> > operator*(const OLattice<CMSite<R> >& a, const OLattice<CMSite<R> >& b) {
+  OLattice<CMSite<R> > r;
+  const int n = Layout::sitesOnNode();
+  for (int s = 0; s < n; ++s)
+    for (int i = 0; i < Nc; ++i)
+      for (int j = 0; j < Nc; ++j) {
+        RComplex<R> acc = a.elem(s).elem().elem(i, 0) * b.elem(s).elem().elem(0, j);
+        for (int k = 1; k < Nc; ++k) acc += a.elem(s).elem().elem(i, k) * b.elem(s).elem().elem(k, j);
+        r.elem(s).elem().elem(i, j) = acc;
+      }
+  return r;
+}
+template <typename R> inline OLattice<CMSite<R> > adj(const OLattice<CMSite<R> >& a) {
+  OLattice<CMSite<R> > r;
+  const int n = Layout::sitesOnNode();
+  for (int s = 0; s < n; ++s)
+    for (int i = 0; i < Nc; ++i)
+      for (int j = 0; j < Nc; ++j) r.elem(s).elem().elem(i, j) = adj(a.elem(s).elem().elem(j, i));
+  return r;
+}
+template <typename S> inline OLattice<S> shift(const OLattice<S>& a, int dir, int mu) {
+  OLattice<S> r;
+  const int* nb = Layout::mockNeighbourTable(dir, mu);
+  const int n = Layout::sitesOnNode();
+  for (int s = 0; s < n; ++s) r.elem(s) = a.elem(nb[s]);
+  return r;
+}
+template <typename S> inline OLattice<S>& operator+=(OLattice<S>& a, const OLattice<S>& b) { MOCK_FOR_WORDS(OLattice<S>, i) a.words()[i] += b.words()[i]; return a; }
+template <typename S> inline OLattice<S>& operator-=(OLattice<S>& a, const OLattice<S>& b) { MOCK_FOR_WORDS(OLattice<S>, i) a.words()[i] -= b.words()[i]; return a; }
+template <typename S, typename R> inline OLattice<S>& operator*=(OLattice<S>& a, const OReal<R>& f) {
+  typedef typename SiteWord<S>::type W; const W x = (W)f.val(); MOCK_FOR_WORDS(OLattice<S>, i) a.words()[i] *= x; return a;
+}
+
 // reductions: site order, double accumulation (scalar QDP++)
 template <typename S> inline Double norm2(const OLattice<S>& a, const Subset& s) {
   double acc = 0;
@@ -330,7 +393,7 @@ double gauss();
 }
 template <typename S> inline void gaussian(OLattice<S>& x, const Subset& s) {
   const int w = OLattice<S>::wordsPerSite();
-  for (int i = s.start() * w; i < (s.end() + 1) * w; ++i) x.words()[i] = (typename S::Word)RNG::gauss();
+  for (int i = s.start() * w; i < (s.end() + 1) * w; ++i) x.words()[i] = (typename SiteWord<S>::type)RNG::gauss();
 }
 
 namespace Hints {
@@ -346,6 +409,7 @@ void globalSum(int& x);
 }
 namespace QDPIO { extern std::ostream& cout; extern std::ostream& cerr; }
 void QDP_abort(int);
+void QDP_error_exit(const char* fmt, ...);
 
 // A flat key -> value store stands in for libxml2: XMLReader(top, "path") narrows the prefix.
 class XMLReader {

@@ -32,6 +32,29 @@ void mockSetup(const int local_dims[4], const int grid[4], const int coord[4], i
   rb[0].make(0, g_sites / 2);          // cb2 order: checkerboard 0 first (shift_table_scalar.cc:190-214)
   rb[1].make(g_sites / 2, g_sites);
 }
+// cb2 site index of local coordinate c (shift_table_scalar.cc:190-214)
+static int cb2_index(const int c[4]) {
+  const int* L = g_sub.slice();
+  const int cb = (c[0] + c[1] + c[2] + c[3]) & 1;
+  return cb * (g_sites / 2) + ((c[3] * L[2] + c[2]) * L[1] + c[1]) * (L[0] / 2) + c[0] / 2;
+}
+const int* mockNeighbourTable(int dir, int mu) {
+  static std::vector<int> tab[2][4];
+  static int built_for = -1;
+  if (built_for != g_sites) { for (int d = 0; d < 2; ++d) for (int m = 0; m < 4; ++m) tab[d][m].clear(); built_for = g_sites; }
+  std::vector<int>& t = tab[dir > 0 ? 1 : 0][mu];
+  if (t.empty()) {
+    const int* L = g_sub.slice();
+    t.resize(g_sites);
+    int c[4];
+    for (c[3] = 0; c[3] < L[3]; ++c[3]) for (c[2] = 0; c[2] < L[2]; ++c[2]) for (c[1] = 0; c[1] < L[1]; ++c[1]) for (c[0] = 0; c[0] < L[0]; ++c[0]) {
+      int n[4] = {c[0], c[1], c[2], c[3]};
+      n[mu] = (c[mu] + (dir > 0 ? 1 : L[mu] - 1)) % L[mu];
+      t[cb2_index(c)] = cb2_index(n);
+    }
+  }
+  return t.data();
+}
 const multi1d<int>& lattSize() { return g_latt; }
 const multi1d<int>& subgridLattSize() { return g_sub; }
 const multi1d<int>& logicalSize() { return g_grid; }
@@ -77,6 +100,8 @@ void globalSum(int& x) { globalSumArray(&x, 1); }
 namespace QDPIO { std::ostream& cout = std::cout; std::ostream& cerr = std::cerr; }
 void QDP_abort(int rc) { std::ostringstream m; m << "QDP_abort(" << rc << ")"; throw std::runtime_error(m.str()); }
 
+void QDP_error_exit(const char* fmt, ...) { QDPIO::cerr << "QDP_error_exit: " << fmt << std::endl; QDP_abort(1); }
+
 std::string XMLReader::get(const std::string& tag) const {
   std::map<std::string, std::string>::const_iterator it = kv.find(join(prefix, tag));
   if (it == kv.end()) { QDPIO::cerr << "XMLReader: no tag " << join(prefix, tag) << std::endl; QDP_abort(1); }
@@ -118,13 +143,13 @@ void read(XMLReader& xml, const std::string& path, CloverFermActParams& p) {
   if (top.count("Mass")) read(top, "Mass", p.Mass);
   else if (top.count("Kappa")) { Real k; read(top, "Kappa", k); p.Mass = Real(1.0 / (2.0 * toDouble(k)) - 4.0); }
   else { QDPIO::cerr << "CloverFermActParams: neither Mass nor Kappa" << std::endl; QDP_abort(1); }
-  if (top.count("clovCoeff")) { read(top, "clovCoeff", p.clovCoeffR); p.clovCoeffT = p.clovCoeffR; }
-  else { read(top, "clovCoeffR", p.clovCoeffR); read(top, "clovCoeffT", p.clovCoeffT); }
   if (top.count("AnisoParam")) {
     XMLReader a(top, "AnisoParam");
     read(a, "anisoP", p.anisoParam.anisoP); read(a, "t_dir", p.anisoParam.t_dir);
     read(a, "xi_0", p.anisoParam.xi_0); read(a, "nu", p.anisoParam.nu);
   }
+  if (p.anisoParam.anisoP) { read(top, "clovCoeffR", p.clovCoeffR); read(top, "clovCoeffT", p.clovCoeffT); }   // :66-77
+  else { read(top, "clovCoeff", p.clovCoeffR); p.clovCoeffT = p.clovCoeffR; }
   if (top.count("TwistedM")) { p.twisted_m_usedP = true; read(top, "TwistedM", p.twisted_m); }
 }
 void write(XMLWriter& xml, const std::string& path, const CloverFermActParams& p) {

@@ -734,3 +734,28 @@ def test_twisted_mass_operator_parity(oracle, prec, symmetric):
     for isign in (+1, -1):
         assert np.array_equal(ctx.matpc(psi[Vh:].astype(NP[prec]), isign), plain[isign])
     ctx.close()
+
+
+@pytest.mark.parametrize("solver", ["CG", "BICGSTAB"])
+def test_split_reduction_path(oracle, solver, monkeypatch):
+    """Large single-RHS grids let the CTAs store their partial sums and a one-CTA kernel finish the reduction
+    (ReduceBuf::split, reduce.cuh); B200_SPLIT_MIN_BLOCKS=0 forces that path on a small lattice.  Same iteration count as
+    the CPU restatement, bit-identical solution to the in-kernel ticket path (both sum in the same two-level order only
+    above RED_FLAT_MAX blocks, so here: equal to rounding), true residual below target."""
+    latt = (8, 8, 8, 8)
+    code = L.B200_SOLVER_CG if solver == "CG" else L.B200_SOLVER_BICGSTAB
+    u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
+    Vh = ctx.Vh
+    chi = fields.gaussian_fermion(latt, seed=41, cb=1)
+    ref_sol, ref_info = ctx.invert(chi[Vh:], None, solver=code, rsd=1e-9, max_iter=500)
+    ctx.close()
+    monkeypatch.setenv("B200_SPLIT_MIN_BLOCKS", "0")
+    u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
+    sol, info = ctx.invert(chi[Vh:], None, solver=code, rsd=1e-9, max_iter=500)
+    n_launch = ctx.launch_count
+    ctx.close()
+    assert info.converged and abs(info.n_count - ref_info.n_count) <= 1
+    assert np.abs(sol - ref_sol).max() < 1e-9 * np.abs(ref_sol).max()
+    full = np.zeros_like(chi); full[Vh:] = sol
+    res = chi - op.apply(full, +1)
+    assert np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(chi[Vh:] ** 2)) < 2e-8

@@ -78,3 +78,13 @@ def test_one_device_grid_parity(grid, latt, prec, recon):
         pytest.skip("disabled by B200_SKIP_ONE_DEVICE_TESTS")
     world = int(grid.split(",")[0]) * int(grid.split(",")[1])
     run_check(world, {"MGPU_LATT": latt, "MGPU_GRID": grid, "MGPU_PREC": prec, "MGPU_RECON": recon, "MGPU_ONE_DEVICE": "1"}, 29527)
+
+
+def test_one_device_split_reduction():
+    """The fused single-launch split-lattice Dslash with the split reduction path (partials + one-CTA finish kernel that
+    also does the cross-rank mailbox sum), forced on a small lattice by B200_SPLIT_MIN_BLOCKS=0."""
+    if ngpu() < 1:
+        pytest.skip("needs a GPU")
+    if os.environ.get("B200_SKIP_ONE_DEVICE_TESTS"):
+        pytest.skip("disabled by B200_SKIP_ONE_DEVICE_TESTS")
+    run_check(2, {"MGPU_LATT": "4,4,4,8", "MGPU_GRID": "1,2", "MGPU_ONE_DEVICE": "1", "B200_SPLIT_MIN_BLOCKS": "0"}, 29528)
