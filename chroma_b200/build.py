@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         for _, log in results:
             sys.stderr.write(log)
     cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
-                                                 "-Xcompiler", "-fPIC", "-lcudart"]
+                                                 "-Xcompiler", "-fPIC", "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: a no-op unless a profiler (nsys / ncu --nvtx) is attached
+
 #include "engine_impl.cuh"
 
 namespace b200 {
@@ -107,6 +109,16 @@ __global__ void __launch_bounds__(BLAS_BLOCK) sum_double_kernel(const double* x,
 
 using namespace b200;
 
+// Every ABI entry that does device work is an NVTX range named after itself (the reference brackets
+// its solves with QDP++ StopWatch / FlopCounter reports, syssolver_linop_clover_quda_w.h:586-648; a timeline tool sees these).
+namespace {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define B200_RANGE() NvtxRange nvtx_range_(__func__)
+
 #define CHECK_CTX(c)                                                     \
   do {                                                                   \
     if (!(c) || !(c)->eng) { set_error("null b200_ctx"); return B200_ERR_ARG; } \
@@ -188,18 +200,18 @@ void b200_destroy(b200_ctx* ctx) {
 }
 
 int b200_load_gauge(b200_ctx* ctx, const void* const u[4], int host_prec, const double aniso_coeff[4], int t_boundary, int reconstruct) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   if (!u) { set_error("null gauge array"); return B200_ERR_ARG; }
   const double one[4] = {1, 1, 1, 1};
   return ctx->eng->load_gauge(u, host_prec, aniso_coeff ? aniso_coeff : one, t_boundary, reconstruct);
 }
-int b200_load_clover(b200_ctx* ctx, const void* clov, const void* invclov, int host_prec) { CHECK_CTX(ctx); return ctx->eng->load_clover(clov, invclov, host_prec); }
-int b200_make_clover(b200_ctx* ctx, double diag_mass, double clov_r, double clov_t, int aniso, int t_dir) { CHECK_CTX(ctx); return ctx->eng->make_clover(diag_mass, clov_r, clov_t, aniso, t_dir); }
-int b200_get_clover(b200_ctx* ctx, void* clov, void* invclov, int host_prec) { CHECK_CTX(ctx); return ctx->eng->get_clover(clov, invclov, host_prec); }
+int b200_load_clover(b200_ctx* ctx, const void* clov, const void* invclov, int host_prec) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->load_clover(clov, invclov, host_prec); }
+int b200_make_clover(b200_ctx* ctx, double diag_mass, double clov_r, double clov_t, int aniso, int t_dir) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->make_clover(diag_mass, clov_r, clov_t, aniso, t_dir); }
+int b200_get_clover(b200_ctx* ctx, void* clov, void* invclov, int host_prec) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->get_clover(clov, invclov, host_prec); }
 int b200_clover_logdet(b200_ctx* ctx, double* out) { CHECK_CTX(ctx); if (!out) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->clover_logdet(out, 0); }
 int b200_clover_logdet_oo(b200_ctx* ctx, double* out) { CHECK_CTX(ctx); if (!out) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->clover_logdet(out, 1); }
 int b200_set_preconditioning(b200_ctx* ctx, int mode) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return ctx->eng->set_preconditioning(mode);   // the fp32 twin of b200_invert_reliable re-syncs through operator_epoch
 }
 
@@ -207,52 +219,52 @@ int b200_set_twisted_mass(b200_ctx* ctx, double mu) { CHECK_CTX(ctx); return ctx
 
 int b200_field_alloc(b200_ctx* ctx, b200_field** f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_alloc(f); }
 void b200_field_free(b200_ctx* ctx, b200_field* f) { if (ctx && ctx->eng) ctx->eng->field_free(f); }
-int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_upload(f, host, host_prec); }
-int b200_field_download(b200_ctx* ctx, const b200_field* f, void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_download(f, host, host_prec); }
+int b200_field_upload(b200_ctx* ctx, b200_field* f, const void* host, int host_prec) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->field_upload(f, host, host_prec); }
+int b200_field_download(b200_ctx* ctx, const b200_field* f, void* host, int host_prec) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->field_download(f, host, host_prec); }
 int b200_mfield_alloc(b200_ctx* ctx, int nrhs, b200_field** f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_alloc(f, nrhs); }
-int b200_mfield_upload(b200_ctx* ctx, b200_field* f, int irhs, const void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_upload(f, host, host_prec, irhs); }
-int b200_mfield_download(b200_ctx* ctx, const b200_field* f, int irhs, void* host, int host_prec) { CHECK_CTX(ctx); return ctx->eng->field_download(f, host, host_prec, irhs); }
+int b200_mfield_upload(b200_ctx* ctx, b200_field* f, int irhs, const void* host, int host_prec) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->field_upload(f, host, host_prec, irhs); }
+int b200_mfield_download(b200_ctx* ctx, const b200_field* f, int irhs, void* host, int host_prec) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->field_download(f, host, host_prec, irhs); }
 int b200_field_nrhs(const b200_field* f) { return f ? f->nrhs : 0; }
 int b200_field_zero(b200_ctx* ctx, b200_field* f) { CHECK_CTX(ctx); if (!f) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->field_zero(f); }
 
-int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb) { CHECK_CTX(ctx); return ctx->eng->dslash(out, in, isign, out_cb); }
-int b200_dev_clover_apply(b200_ctx* ctx, b200_field* out, const b200_field* in, int cb, int inverse) { CHECK_CTX(ctx); return ctx->eng->clover_apply(out, in, cb, inverse); }
-int b200_dev_clover_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign) { CHECK_CTX(ctx); return ctx->eng->matpc(out, in, isign); }
+int b200_dev_dslash(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int out_cb) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->dslash(out, in, isign, out_cb); }
+int b200_dev_clover_apply(b200_ctx* ctx, b200_field* out, const b200_field* in, int cb, int inverse) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->clover_apply(out, in, cb, inverse); }
+int b200_dev_clover_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign) { CHECK_CTX(ctx); B200_RANGE(); return ctx->eng->matpc(out, in, isign); }
 int b200_dev_time_matpc(b200_ctx* ctx, b200_field* out, const b200_field* in, int isign, int reps, double ms[2]) { CHECK_CTX(ctx); if (!ms) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->time_matpc(out, in, isign, reps, ms); }
-int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* r) { CHECK_CTX(ctx); if (!x || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->norm2(x, r); }
-int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double r[2]) { CHECK_CTX(ctx); if (!x || !y || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->inner(x, y, r); }
+int b200_dev_norm2(b200_ctx* ctx, const b200_field* x, double* r) { CHECK_CTX(ctx); B200_RANGE(); if (!x || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->norm2(x, r); }
+int b200_dev_inner(b200_ctx* ctx, const b200_field* x, const b200_field* y, double r[2]) { CHECK_CTX(ctx); B200_RANGE(); if (!x || !y || !r) { set_error("null pointer"); return B200_ERR_ARG; } return ctx->eng->inner(x, y, r); }
 int b200_dev_invert(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return ctx->eng->invert(psi, chi, solver, rsd, max_iter, 0, info);
 }
 int b200_dev_invert_mdagm(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver, double rsd, int max_iter, b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return ctx->eng->invert(psi, chi, solver, rsd, max_iter, 1, info);
 }
 int b200_dev_invert_reliable(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd, double delta, int max_iter, int mdagm,
                              b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return reliable_solve(ctx->eng, &ctx->sloppy, psi, chi, rsd, delta, max_iter, mdagm, info);
 }
 int b200_dev_invert_reliable_bicgstab(b200_ctx* ctx, b200_field* psi, const b200_field* chi, double rsd, double delta, int max_iter, int mdagm,
                                       b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return reliable_bicgstab_solve(ctx->eng, &ctx->sloppy, psi, chi, rsd, delta, max_iter, mdagm, info);
 }
 int b200_invert_reliable_bicgstab(b200_ctx* ctx, void* psi, const void* chi, int host_prec, double rsd, double delta, int max_iter, int mdagm,
                                   b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return host_solve(ctx, psi, chi, host_prec, info,
                     [&](b200_field* p, b200_field* c) { return reliable_bicgstab_solve(ctx->eng, &ctx->sloppy, p, c, rsd, delta, max_iter, mdagm, info); });
 }
 int b200_dev_invert_multishift(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int n_shift, const double* shifts, const double* rsd,
                                int max_iter, b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return ctx->eng->invert_multishift(psi, chi, n_shift, shifts, rsd, max_iter, info);
 }
 int b200_invert_multishift(b200_ctx* ctx, void* const psi[], const void* chi, int host_prec, int n_shift, const double* shifts,
                            const double* rsd, int max_iter, b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   if (!psi || !chi || !shifts || !rsd || !info) { set_error("b200_invert_multishift: null pointer"); return B200_ERR_ARG; }
   if (n_shift < 1 || n_shift > B200_MAX_SHIFTS) { set_error("b200_invert_multishift: 1..%d shifts (got %d)", (int)B200_MAX_SHIFTS, n_shift); return B200_ERR_ARG; }
   for (int s = 0; s < n_shift; ++s) if (!psi[s]) { set_error("b200_invert_multishift: null psi[%d]", s); return B200_ERR_ARG; }
@@ -280,7 +292,7 @@ int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi
   return ctx->eng->iterate_begin(psi, chi, solver);
 }
 int b200_dev_iterate(b200_ctx* ctx, int solver, int n_iter) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   if (solver != B200_SOLVER_CG && solver != B200_SOLVER_BICGSTAB) { set_error("unknown solver %d", solver); return B200_ERR_ARG; }
   return ctx->eng->iterate(solver, n_iter);
 }
@@ -292,42 +304,42 @@ int b200_dev_time_solver_kernels(b200_ctx* ctx, int solver, int reps, double* ms
 }
 
 int b200_dslash(b200_ctx* ctx, void* out, const void* in, int host_prec, int isign, int out_cb) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   TmpFields t(ctx); int rc = t.get(2); if (rc) return rc;
   if ((rc = ctx->eng->field_upload(t.f[0], in, host_prec))) return rc;
   if ((rc = ctx->eng->dslash(t.f[1], t.f[0], isign, out_cb))) return rc;
   return ctx->eng->field_download(t.f[1], out, host_prec);
 }
 int b200_clover_apply(b200_ctx* ctx, void* out, const void* in, int host_prec, int cb, int inverse) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   TmpFields t(ctx); int rc = t.get(2); if (rc) return rc;
   if ((rc = ctx->eng->field_upload(t.f[0], in, host_prec))) return rc;
   if ((rc = ctx->eng->clover_apply(t.f[1], t.f[0], cb, inverse))) return rc;
   return ctx->eng->field_download(t.f[1], out, host_prec);
 }
 int b200_clover_matpc(b200_ctx* ctx, void* out, const void* in, int host_prec, int isign) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   TmpFields t(ctx); int rc = t.get(2); if (rc) return rc;
   if ((rc = ctx->eng->field_upload(t.f[0], in, host_prec))) return rc;
   if ((rc = ctx->eng->matpc(t.f[1], t.f[0], isign))) return rc;
   return ctx->eng->field_download(t.f[1], out, host_prec);
 }
 int b200_invert(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int solver, double rsd, int max_iter, b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return host_solve(ctx, psi, chi, host_prec, info, [&](b200_field* p, b200_field* c) { return ctx->eng->invert(p, c, solver, rsd, max_iter, 0, info); });
 }
 int b200_invert_mdagm(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int solver, double rsd, int max_iter, b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return host_solve(ctx, psi, chi, host_prec, info, [&](b200_field* p, b200_field* c) { return ctx->eng->invert(p, c, solver, rsd, max_iter, 1, info); });
 }
 int b200_invert_reliable(b200_ctx* ctx, void* psi, const void* chi, int host_prec, double rsd, double delta, int max_iter, int mdagm,
                          b200_solve_info* info) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return host_solve(ctx, psi, chi, host_prec, info,
                     [&](b200_field* p, b200_field* c) { return reliable_solve(ctx->eng, &ctx->sloppy, p, c, rsd, delta, max_iter, mdagm, info); });
 }
 int b200_qprop(b200_ctx* ctx, void* psi, const void* chi, int host_prec, int nrhs, int solver, double rsd, int max_iter, b200_solve_info* infos) {
-  CHECK_CTX(ctx);
+  CHECK_CTX(ctx); B200_RANGE();
   return ctx->eng->qprop(psi, chi, host_prec, nrhs, solver, rsd, max_iter, infos);
 }
 

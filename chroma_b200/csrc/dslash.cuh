@@ -694,7 +694,7 @@ template <typename R, int EPI, bool RECON12> struct MrhsSmem {
   // + one 12-plane spinor buffer per right-hand side (warp) of the CTA
   static constexpr size_t total(int nrb) { return bytes + (MrhsPrefetch<R>::on ? (size_t)nrb * 12 * 32 * sizeof(Cx<R>) : 0); }
 };
-template <typename R, int EPI, bool RECON12, int NRB>
+template <typename R, int EPI, bool RECON12, int NRB, int MODE = MODE_ASYM>
 __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
   typedef Cx<R> C;
   typedef MrhsSmem<R, EPI, RECON12> SM;
@@ -758,10 +758,10 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
       C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;
       constexpr bool XS = (EPI >= EPI_M) && MrhsPrefetch<R>::on;
       dslash_site_pf<R, RECON12>(acc, a, ls, idx, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
-      site_epilogue<R, EPI, true, MODE_ASYM, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
+      site_epilogue<R, EPI, true, MODE, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
     } else {
       dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x);
-      site_epilogue<R, EPI, true>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
+      site_epilogue<R, EPI, true, MODE>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
     }
   }
 

@@ -556,7 +556,6 @@ class Engine : public EngineBase {
   // for the BLAS grid as well as for the Dslash grids (32 sites per block when batched).
   int set_batch(int n) {
     if (n < 1 || n > MAX_RHS) { set_error("the batched kernels take 1..%d right-hand sides (field holds %d)", MAX_RHS, n); return B200_ERR_ARG; }
-    if (n > 1 && sym) { set_error("batched right-hand sides are not available with symmetric preconditioning"); return B200_ERR_ARG; }
     nb = n;
     const size_t dblocks = n > 1 ? (size_t)(g.Vh + 31) / 32 + 4 : (size_t)(g.Vh + DSLASH_BLOCK - 1) / DSLASH_BLOCK + 8;
     return ensure_partial(4 * (size_t)n * std::max<size_t>((size_t)blas_grid, dblocks));
@@ -674,21 +673,26 @@ class Engine : public EngineBase {
   template <int EPI>
   int launch_mrhs(const DslashArgs<R>& a, int site_blocks) {
     if (EPI == EPI_M_CGREL) { set_error("the reliable-update epilogue has no multi-RHS variant"); return B200_ERR_ARG; }
-    else {
-      const int ngroups = (nb + NRB - 1) / NRB;
-      const dim3 block(32, NRB);
-      constexpr int E = (EPI == EPI_M_CGREL ? EPI_M_CG : EPI);
-      if (recon == 12) {
-        auto k = dslash_mrhs_kernel<R, E, true, NRB>;
-        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, true>::total(NRB)));
-        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::total(NRB), stream>>>(a, ls, ngroups);
-      } else {
-        auto k = dslash_mrhs_kernel<R, E, false, NRB>;
-        B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, false>::total(NRB)));
-        k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::total(NRB), stream>>>(a, ls, ngroups);
-      }
-      return launched("dslash_mrhs_kernel");
+    constexpr int E = (EPI == EPI_M_CGREL ? EPI_M_CG : EPI);
+    // the symmetric operator's epilogues (MODE_SYM_*) exist for the EPI_M* family only
+    if (E >= EPI_M && a.mmode == MODE_SYM_PLUS) return launch_mrhs_mode<E, (E >= EPI_M ? MODE_SYM_PLUS : MODE_ASYM)>(a, site_blocks);
+    if (E >= EPI_M && a.mmode == MODE_SYM_MINUS) return launch_mrhs_mode<E, (E >= EPI_M ? MODE_SYM_MINUS : MODE_ASYM)>(a, site_blocks);
+    return launch_mrhs_mode<E, MODE_ASYM>(a, site_blocks);
+  }
+  template <int E, int MODE>
+  int launch_mrhs_mode(const DslashArgs<R>& a, int site_blocks) {
+    const int ngroups = (nb + NRB - 1) / NRB;
+    const dim3 block(32, NRB);
+    if (recon == 12) {
+      auto k = dslash_mrhs_kernel<R, E, true, NRB, MODE>;
+      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, true>::total(NRB)));
+      k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::total(NRB), stream>>>(a, ls, ngroups);
+    } else {
+      auto k = dslash_mrhs_kernel<R, E, false, NRB, MODE>;
+      B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, false>::total(NRB)));
+      k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::total(NRB), stream>>>(a, ls, ngroups);
     }
+    return launched("dslash_mrhs_kernel");
   }
 
   int ready() {
@@ -710,7 +714,7 @@ class Engine : public EngineBase {
   int apply_M(C* out, const C* in, int isign, int epi, C* r, const C* r0, int iter, int check, int run_if = 0) {
     const C* src = in;
     if (sym && isign < 0) {
-      clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, 1), 128, 0, stream>>>(in, W(8), invclov_oo, g.Vh, nelem(), (check || run_if) ? status : nullptr, run_if);
+      clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, nb), 128, 0, stream>>>(in, W(8), invclov_oo, g.Vh, nelem(), (check || run_if) ? status : nullptr, run_if);
       int rc0 = launched("clover_kernel"); if (rc0) return rc0;
       mark();
       src = W(8);
@@ -786,7 +790,7 @@ class Engine : public EngineBase {
       b.twist = isign * twisted_m;
       B200_CUDA(cudaEventRecord(e[0], stream));
       if (sym && isign < 0) {   // the A_oo^-1 pass of the symmetric M^dag is booked with the first kernel
-        clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, 1), 128, 0, stream>>>((const C*)in->d, W(8), invclov_oo, g.Vh, nelem());
+        clover_kernel<R, 128><<<dim3((g.Vh + 127) / 128, nb), 128, 0, stream>>>((const C*)in->d, W(8), invclov_oo, g.Vh, nelem());
         rc = launched("clover_kernel"); if (rc) return rc;
         a.in = W(8);
       }
@@ -1232,7 +1236,6 @@ class Engine : public EngineBase {
     if (const char* e = getenv("B200_QPROP_BATCH")) cap = std::min(cap, std::max(1, atoi(e)));
     if (cap < 1) { set_error("b200_qprop: not enough free device memory for even one right-hand side"); return B200_ERR_CUDA; }
     cap = std::min(cap, nrhs);
-    if (sym) cap = 1;     // the symmetric operator has no batched kernels: one right-hand side at a time
     const size_t cbbytes = (size_t)g.Vh * 24 * host_prec;
     b200_field *chi_e = nullptr, *chi_o = nullptr, *psi_o = nullptr, *t1 = nullptr, *t2 = nullptr;
     if ((rc = field_alloc(&chi_e, cap)) || (rc = field_alloc(&chi_o, cap)) || (rc = field_alloc(&psi_o, cap)) ||
@@ -1254,11 +1257,12 @@ class Engine : public EngineBase {
       if (rc) break;
       if (sym) {
         // SymEvenOddPrecActQprop::operator(), seoprec_fermact_qprop.cc:45-89 with M_oe = A_oo^-1 (-1/2 Dslash),
-        // M_eo = A_ee^-1 (-1/2 Dslash) (lib/seoprec_linop.h:170-204):
+        // M_eo = A_ee^-1 (-1/2 Dslash) (lib/seoprec_linop.h:170-204), for the whole batch:
         //   chi'_e = A_ee^-1 chi_e ; chi'_o = A_oo^-1 (chi_o + 1/2 Dslash chi'_e) ; S psi_o = chi'_o ;
         //   psi_e = chi'_e + 1/2 A_ee^-1 Dslash psi_o
         if ((rc = clover_apply(t1, chi_e, 0, 1))) break;
         if ((rc = dslash(t2, t1, +1, 1))) break;
+        if ((rc = set_batch(n))) break;
         if ((rc = axpby_dev((C*)chi_o->d, 1.0, (const C*)chi_o->d, 0.5, (const C*)t2->d))) break;
         if ((rc = clover_apply(t2, chi_o, 1, 1))) break;
         rc = invert(psi_o, t2, solver, rsd, max_iter, 0, &infos[i0]);
@@ -1266,10 +1270,13 @@ class Engine : public EngineBase {
         if (rc) break;
         if ((rc = dslash(chi_o, psi_o, +1, 0))) break;
         if ((rc = clover_apply(t2, chi_o, 0, 1))) break;
+        if ((rc = set_batch(n))) break;
         if ((rc = axpby_dev((C*)chi_e->d, 1.0, (const C*)t1->d, 0.5, (const C*)t2->d))) break;
-        char* ph = (char*)psi_h + (size_t)i0 * 2 * cbbytes;
-        if ((rc = field_download(chi_e, ph, host_prec, 0))) break;
-        rc = field_download(psi_o, ph + cbbytes, host_prec, 0);
+        for (int j = 0; j < n && !rc; ++j) {
+          char* ph = (char*)psi_h + (size_t)(i0 + j) * 2 * cbbytes;
+          if ((rc = field_download(chi_e, ph, host_prec, j))) break;
+          rc = field_download(psi_o, ph + cbbytes, host_prec, j);
+        }
         continue;
       }
       // chi' = chi_o - D_oe A_ee^-1 chi_e = chi_o + 1/2 Dslash(A_ee^-1 chi_e)

@@ -141,8 +141,8 @@ int b200_clover_logdet_oo(b200_ctx* ctx, double* tr_log_oo);
  * A_oo^-1 is derived on the device from the clover term that is (or later gets) loaded or built -- the LDL^dagger
  * inverse of clover_term_qdp_w.h:619-846 on cb 1, i.e. SymEvenOddPrecCloverLinOp::create's invclov.choles(1)
  * (seoprec_clover_linop_w.cc:31-33).  With the symmetric operator b200_clover_apply accepts inverse = 1 on cb 1,
- * b200_qprop follows SymEvenOddPrecActQprop (seoprec_fermact_qprop.cc:41-100), and batched (multi-RHS) fields are
- * refused (B200_ERR_ARG): right-hand sides are then solved one at a time. */
+ * b200_qprop follows SymEvenOddPrecActQprop (seoprec_fermact_qprop.cc:41-100); batched (multi-RHS) fields go through the
+ * same multi-RHS kernels as with the asymmetric operator. */
 int b200_set_preconditioning(b200_ctx* ctx, int preconditioning);
 
 /* Twisted-mass term of the clover operators (CloverFermActParams::twisted_m, clover_fermact_params_w.cc:90-97): every

@@ -463,10 +463,22 @@ def test_symmetric_operator_parity(oracle, prec, recon, aniso, gpu_clover):
     ctx.dev_matpc(fo2, fc, -1)
     a, b = ctx.dev_inner(fc, fo), ctx.dev_inner(fo2, fx)
     assert abs(a - b) < (1e-11 if prec == "double" else 1e-4) * abs(a)
-    # batched fields are refused, the asymmetric operator comes back bit-identical
-    with pytest.raises(L.B200Error) as e:
-        ctx.dev_matpc(ctx.mfield(2), ctx.mfield(2), +1)
-    assert e.value.code == L.B200_ERR_ARG
+    # batched fields run the multi-RHS kernels with the symmetric epilogues (MODE_SYM_PLUS / MODE_SYM_MINUS + the A_oo^-1 pass)
+    nr = 5
+    srcs = np.stack([fields.gaussian_fermion(latt, seed=60 + i, cb=1) for i in range(nr)])
+    fin, fout = ctx.mfield(nr, srcs[:, Vh:].astype(NP[prec])), ctx.mfield(nr)
+    for isign in (+1, -1):
+        ctx.dev_matpc(fout, fin, isign)
+        outs = fout.download()
+        for i in range(nr):
+            assert rel_site_err(outs[i], op.apply(srcs[i], isign)[Vh:]) < 2 * tol, (isign, i)
+    infos = ctx.dev_invert(fout, fin, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-8 if prec == "double" else 1e-5, max_iter=500)
+    sols = fout.download()
+    for i in range(nr):
+        full = np.zeros_like(srcs[i]); full[Vh:] = sols[i]
+        r = srcs[i] - op.apply(full, +1)
+        assert infos[i].converged == 1 and np.sqrt(np.sum(r[Vh:] ** 2) / np.sum(srcs[i][Vh:] ** 2)) < (2e-7 if prec == "double" else 2e-4)
+    # the asymmetric operator comes back bit-identical
     ctx.set_preconditioning(False)
     assert np.array_equal(ctx.matpc(x, +1), asym_plus)
     with pytest.raises(L.B200Error):
@@ -514,18 +526,24 @@ def test_symmetric_solvers(oracle, solver):
     ctx.close()
 
 
-def test_symmetric_qprop_and_plugin(oracle):
+def test_symmetric_qprop_and_plugin(oracle, monkeypatch):
     """SymEvenOddPrecActQprop (seoprec_fermact_qprop.cc:41-100) on the device solves the same unpreconditioned system;
     the plugin mirror with SymmetricLinop solves the caller's symmetric A."""
     latt = (4, 4, 4, 8)
     u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
     ctx.set_preconditioning(True)
     srcs = np.stack([fields.point_source(latt, s, c) for s, c in ((0, 0), (3, 2))] + [fields.gaussian_fermion(latt, seed=31)])
-    sol, infos = ctx.qprop(srcs, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-10, max_iter=500)
-    for i in range(len(srcs)):
-        r = op.unprec_apply(sol[i], +1) - srcs[i]
-        assert np.linalg.norm(r) / np.linalg.norm(srcs[i]) < 1e-8
-        assert infos[i].converged == 1
+    launches = {}
+    for batch in ("12", "1"):          # all right-hand sides through the batched symmetric kernels, then one at a time
+        monkeypatch.setenv("B200_QPROP_BATCH", batch)
+        l0 = ctx.launch_count
+        sol, infos = ctx.qprop(srcs, solver=L.B200_SOLVER_BICGSTAB, rsd=1e-10, max_iter=500)
+        launches[batch] = ctx.launch_count - l0
+        for i in range(len(srcs)):
+            r = op.unprec_apply(sol[i], +1) - srcs[i]
+            assert np.linalg.norm(r) / np.linalg.norm(srcs[i]) < 1e-8
+            assert infos[i].converged == 1
+    assert launches["12"] < 0.6 * launches["1"]      # the batch really went through in lockstep
     ctx.close()
     op.set_symmetric(True)
     chi = fields.gaussian_fermion(latt, seed=32, cb=1)
