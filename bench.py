@@ -279,11 +279,16 @@ def expected_key(args):
     return "%dx%dx%dx%d %s %s recon%d" % (tuple(args.lattice) + (args.solver, args.prec, args.recon))
 
 
+LATTICE_OF_RUN, PREC_OF_RUN, RECON_OF_RUN = [48, 48, 48, 96], "double", 18     # set by run_b200 from its arguments
+
+
 def dram_traffic(kernel_name):
     """dram__bytes_read+write per launch of `kernel_name` from the newest `ncu --set full` capture of THIS build, if one was
     committed (profiles/dram_traffic.json: {"kernels": {name: bytes}, "build": ...}); None otherwise."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        if list(t.get("lattice", [])) != list(LATTICE_OF_RUN) or t.get("prec") != PREC_OF_RUN or t.get("recon") != RECON_OF_RUN:
+            return None              # the capture was taken on another workload: no traffic figure for this run
         for k, v in t.get("kernels", {}).items():
             if k in kernel_name:
                 return v
@@ -377,6 +382,8 @@ def run_b200(args):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         comm = make_comm(dist, rank, world)
 
+    global LATTICE_OF_RUN, PREC_OF_RUN, RECON_OF_RUN
+    LATTICE_OF_RUN, PREC_OF_RUN, RECON_OF_RUN = (list(args.lattice) if world == 1 else None), args.prec, args.recon   # the capture is a 1-GPU one
     latt = tuple(args.lattice)
     pz, pt = tuple(args.grid) if args.grid else (1, world)
     assert pz * pt == world, "--grid PZ PT must multiply to the number of ranks"

@@ -633,7 +633,9 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {
-    const int idx = launch_site<R, false>(a, local);
+    // ZC: on lattices whose three live time slices of neighbour spinors outgrow the L2 budget (64^3: 75 MB) the launch
+    // sweeps t inside z-chunks, like the batched kernels (zc_sites = 0 keeps the natural order)
+    const int idx = launch_site<R, true>(a, local);
     const L2Policy pol = a.pol;
     C acc[12];
     dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);

@@ -613,7 +613,7 @@ class Engine : public EngineBase {
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr; a.ghost_zfwd = nullptr; a.ghost_zbwd = nullptr;
     a.box[0] = SiteBox{0, g.Lt, 0, g.Lz}; a.nbox = 1; a.nsites = g.Vh;
-    a.zc_sites = nb > 1 ? zchunk_sites(g.Lz) : 0;
+    a.zc_sites = zchunk_sites(g.Lz);
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
     if (nb == 1) a.red.split = split_reduce<EPI>(blocks);
