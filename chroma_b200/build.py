@@ -6,6 +6,7 @@ import concurrent.futures
 import os
 import subprocess
 import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -53,6 +54,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     os.makedirs(OBJDIR, exist_ok=True)
+    t_start = time.time()
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     objs = [o for o, _ in results]
@@ -64,6 +66,7 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    os.utime(OUT, (t_start, t_start))      # a source edited WHILE this build ran must make the library stale
     return OUT
 
 

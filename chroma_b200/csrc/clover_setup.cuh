@@ -250,52 +250,99 @@ __global__ void __launch_bounds__(CLOV_SITES * 6, B200_CLOV_MINB) make_clover_ke
   }
 }
 
-// In-place inverse of the cb-0 clover planes; tr_log[idx] = sum_i log|d_i| over both blocks.
+// In-place inverse of one checkerboard's clover planes and tr_log[idx] = sum_i log|d_i| over both chiral blocks: what
+// invclov.choles(cb) leaves behind (clover_term_qdp_w.h:560-571; the reference's site loop, :619-818, factorises A = L D L^dag
+// and then solves for A^-1 one column at a time by forward and backward substitution).
+//
+// Here: one thread per (site, chiral block) -- 2 Vh threads, twice the parallelism of a thread per site -- and the whole
+// 6x6 Hermitian block lives in registers: every loop below is fully unrolled, so the triangular index i(i-1)/2+j is a
+// compile-time constant and no array is ever addressed dynamically (the round-1 kernel kept inv_offd[15] and v[6] in
+// local memory).  The inverse is formed as an explicit congruence instead of 6 triangular solves:
+//     A = L D L^dag   (left-looking, d_j real)
+//     W = L^-1        (unit lower triangular, by forward substitution on the 15 strictly-lower entries)
+//     A^-1 = W^dag D^-1 W,   (A^-1)_ij = sum_{k >= i} conj(W_ki) W_kj / d_k   for i >= j, W_kk = 1
+// which needs no division beyond the six 1/d_k.  Arithmetic in double for both engine precisions.
+constexpr __host__ __device__ int tri_idx(int i, int j) { return i * (i - 1) / 2 + j; }   // i > j
 template <typename R>
 __global__ void __launch_bounds__(CLOV_BLOCK) ldagdlinv_kernel(Cx<R>* __restrict__ tri, double* __restrict__ tr_log, int Vh_) {
-  const int idx = blockIdx.x * CLOV_BLOCK + threadIdx.x;
-  if (idx >= Vh_) return;
+  const int tid = blockIdx.x * CLOV_BLOCK + threadIdx.x;
+  const int idx = tid >> 1, block = tid & 1;           // the two blocks of a site sit in adjacent lanes
+  const bool active = idx < Vh_;
   const size_t Vh = Vh_;
-  const int N = 6;
   double tl = 0.0;
-  for (int block = 0; block < 2; ++block) {
+  if (active) {
     Cx<R>* p = tri + (size_t)(18 * block) * Vh + idx;
-    double inv_d[6], diag_g[6]; Z inv_offd[15], v[6];
-    for (int k = 0; k < 3; ++k) { const Cx<R> d = p[(size_t)k * Vh]; inv_d[2 * k] = (double)d.x; inv_d[2 * k + 1] = (double)d.y; }
-    for (int k = 0; k < 15; ++k) { const Cx<R> o = p[(size_t)(3 + k) * Vh]; inv_offd[k] = make_double2((double)o.x, (double)o.y); }
-    for (int j = 0; j < N; ++j) {
-      for (int i = 0; i < j; ++i) {
-        const int eji = j * (j - 1) / 2 + i;
-        v[i] = zmul(make_double2(inv_d[i], 0.0), zconj(inv_offd[eji]));
+    double d[6]; Z l[15];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const Cx<R> v = p[(size_t)k * Vh]; d[2 * k] = (double)v.x; d[2 * k + 1] = (double)v.y; }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) { const Cx<R> o = p[(size_t)(3 + k) * Vh]; l[k] = make_double2((double)o.x, (double)o.y); }
+    // ---- A = L D L^dag, in place: l[tri_idx(i,j)] becomes L_ij, d[j] the pivots
+    double rd[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+      for (int k = 0; k < j; ++k) {
+        const Z ljk = l[tri_idx(j, k)];
+        d[j] -= (ljk.x * ljk.x + ljk.y * ljk.y) * d[k];
       }
-      v[j] = make_double2(inv_d[j], 0.0);
-      for (int k = 0; k < j; ++k) v[j] = zsub(v[j], zmul(inv_offd[j * (j - 1) / 2 + k], v[k]));
-      inv_d[j] = v[j].x;
-      for (int k = j + 1; k < N; ++k) {
-        const int ekj = k * (k - 1) / 2 + j;
-        for (int l = 0; l < j; ++l) inv_offd[ekj] = zsub(inv_offd[ekj], zmul(inv_offd[k * (k - 1) / 2 + l], v[l]));
-        inv_offd[ekj] = zdiv(inv_offd[ekj], v[j]);
+      rd[j] = 1.0 / d[j];
+      tl += log(fabs(d[j]));
+#pragma unroll
+      for (int i = j + 1; i < 6; ++i) {
+        Z s = l[tri_idx(i, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) {            // s -= L_ik d_k conj(L_jk)
+          const Z lik = l[tri_idx(i, k)], ljk = l[tri_idx(j, k)];
+          const double tr = (lik.x * ljk.x + lik.y * ljk.y) * d[k], ti = (lik.y * ljk.x - lik.x * ljk.y) * d[k];
+          s.x -= tr; s.y -= ti;
+        }
+        l[tri_idx(i, j)] = make_double2(s.x * rd[j], s.y * rd[j]);
       }
     }
-    for (int i = 0; i < N; ++i) { diag_g[i] = 1.0 / inv_d[i]; tl += log(fabs(inv_d[i])); }
-    for (int k = 0; k < N; ++k) {
-      for (int i = 0; i < k; ++i) v[i] = make_double2(0, 0);
-      v[k] = make_double2(diag_g[k], 0.0);
-      for (int i = k + 1; i < N; ++i) {
-        v[i] = make_double2(0, 0);
-        for (int j = k; j < i; ++j)
-          v[i] = zsub(v[i], zmul(zmul(inv_offd[i * (i - 1) / 2 + j], make_double2(inv_d[j], 0.0)), v[j]));
-        v[i].x *= diag_g[i]; v[i].y *= diag_g[i];
+    // ---- W = L^-1: W_ij = -L_ij - sum_{j<k<i} L_ik W_kj
+    Z w[15];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+#pragma unroll
+      for (int i = j + 1; i < 6; ++i) {
+        Z s = make_double2(-l[tri_idx(i, j)].x, -l[tri_idx(i, j)].y);
+#pragma unroll
+        for (int k = j + 1; k < i; ++k) {
+          const Z lik = l[tri_idx(i, k)], wkj = w[tri_idx(k, j)];
+          s.x -= lik.x * wkj.x - lik.y * wkj.y; s.y -= lik.x * wkj.y + lik.y * wkj.x;
+        }
+        w[tri_idx(i, j)] = s;
       }
-      for (int i = N - 2; i >= k; --i)
-        for (int j = i + 1; j < N; ++j) v[i] = zsub(v[i], zmul(zconj(inv_offd[j * (j - 1) / 2 + i]), v[j]));
-      inv_d[k] = v[k].x;
-      for (int i = k + 1; i < N; ++i) inv_offd[i * (i - 1) / 2 + k] = v[i];
     }
-    for (int k = 0; k < 3; ++k) p[(size_t)k * Vh] = mk<R>((R)inv_d[2 * k], (R)inv_d[2 * k + 1]);
-    for (int k = 0; k < 15; ++k) p[(size_t)(3 + k) * Vh] = mk<R>((R)inv_offd[k].x, (R)inv_offd[k].y);
+    // ---- A^-1 = W^dag D^-1 W (lower triangle), written straight back to the planes
+    double od[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double s = rd[i];
+#pragma unroll
+      for (int k = i + 1; k < 6; ++k) { const Z wki = w[tri_idx(k, i)]; s += (wki.x * wki.x + wki.y * wki.y) * rd[k]; }
+      od[i] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[(size_t)k * Vh] = mk<R>((R)od[2 * k], (R)od[2 * k + 1]);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        Z s = make_double2(w[tri_idx(i, j)].x * rd[i], w[tri_idx(i, j)].y * rd[i]);      // k = i term: conj(W_ii = 1) W_ij / d_i
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) {       // + conj(W_ki) W_kj / d_k
+          const Z wki = w[tri_idx(k, i)], wkj = w[tri_idx(k, j)];
+          s.x += (wki.x * wkj.x + wki.y * wkj.y) * rd[k]; s.y += (wki.x * wkj.y - wki.y * wkj.x) * rd[k];
+        }
+        p[(size_t)(3 + tri_idx(i, j)) * Vh] = mk<R>((R)s.x, (R)s.y);
+      }
+    }
   }
-  tr_log[idx] = tl;
+  // tr_log of the site = sum over its two blocks (adjacent lanes)
+  tl += __shfl_xor_sync(0xffffffffu, tl, 1);
+  if (active && block == 0) tr_log[idx] = tl;
 }
 
 __global__ void sum_double_kernel(const double* x, size_t n, ReduceBuf red, double* dst);

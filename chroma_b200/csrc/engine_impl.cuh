@@ -4,6 +4,10 @@
 #include <cstdlib>
 #include <cstdarg>
 #include <thread>
+#include <stdint.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "engine.cuh"
 #include "dslash.cuh"
@@ -26,17 +30,40 @@ constexpr int ITER_BATCH = 8;         // iterations enqueued between two status 
 constexpr size_t STAGING_BYTES = 256u << 20;
 constexpr size_t PIN_BYTES_DEFAULT = 32u << 20;   // one pinned bounce buffer of the pageable-host copy pipeline (two per engine)
 
-// memcpy with a small team of threads: one core moves ~10 GB/s, PCIe 5 x16 wants ~50
-inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int nthreads, size_t serial_below) {
-  if (nthreads <= 1 || bytes < serial_below) { memcpy(dst, src, bytes); return; }
+// Copy with non-temporal stores: the destination of a download is a gigabyte of pageable user memory that is not read
+// again soon, so ordinary stores would first read every destination line into the cache (read-for-ownership) and double
+// the memory traffic of the copy.  Falls back to memcpy without AVX2.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) inline void stream_copy_avx2(void* dst, const void* src, size_t bytes) {
+  char* d = (char*)dst; const char* s = (const char*)src;
+  const size_t head = ((uintptr_t)d & 31) ? 32 - ((uintptr_t)d & 31) : 0;
+  if (head >= bytes) { memcpy(d, s, bytes); return; }
+  memcpy(d, s, head); d += head; s += head; bytes -= head;
+  const size_t n32 = bytes / 32;
+  for (size_t i = 0; i < n32; ++i) _mm256_stream_si256((__m256i*)d + i, _mm256_loadu_si256((const __m256i*)s + i));
+  _mm_sfence();
+  memcpy(d + n32 * 32, s + n32 * 32, bytes - n32 * 32);
+}
+inline void stream_copy(void* dst, const void* src, size_t bytes) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2 && bytes >= 4096) stream_copy_avx2(dst, src, bytes); else memcpy(dst, src, bytes);
+}
+#else
+inline void stream_copy(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+#endif
+
+// memcpy with a small team of threads: one core moves ~10 GB/s, PCIe 5 x16 wants ~50.  nt: non-temporal stores (downloads).
+inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int nthreads, size_t serial_below, bool nt = false) {
+  auto cp = [nt](void* d, const void* s, size_t n) { if (nt) stream_copy(d, s, n); else memcpy(d, s, n); };
+  if (nthreads <= 1 || bytes < serial_below) { cp(dst, src, bytes); return; }
   const size_t per = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
   std::vector<std::thread> team;
   for (int t = 1; t < nthreads; ++t) {
     const size_t off = per * t;
     if (off >= bytes) break;
-    team.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
+    team.emplace_back([=] { cp((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
   }
-  memcpy(dst, src, std::min(per, bytes));
+  cp(dst, src, std::min(per, bytes));
   for (auto& th : team) th.join();
 }
 
@@ -109,6 +136,7 @@ class Engine : public EngineBase {
   b200_field* ws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   Halo<R> halo;
   int blas_grid = 148 * 8;
+  int num_sms = 148;
   bool owns_stream = true, owns_scalars = true;   // false once a mixed-precision partner lent us its stream / scalar block
   long long operator_epoch = 0;                   // bumped whenever gauge or clover change (the fp32 twin re-syncs on it)
   // fixed-iteration (benchmark) state
@@ -137,6 +165,7 @@ class Engine : public EngineBase {
     B200_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
     if (prop.major < 10) { set_error("device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); return B200_ERR_CUDA; }
     blas_grid = prop.multiProcessorCount * 8;
+    num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("B200_MRHS_L2_KB")) l2_budget = atol(e) << 10;
     if (const char* e = getenv("B200_SPLIT_MIN_BLOCKS")) split_min_blocks = atoi(e);
     g.Lxh = cfg.ldims[0] / 2; g.Ly = cfg.ldims[1]; g.Lz = cfg.ldims[2]; g.Lt = cfg.ldims[3];
@@ -285,7 +314,7 @@ class Engine : public EngineBase {
       }
       if (prev_k >= 0) {                                          // drain the previous piece while this one is in flight
         B200_CUDA(cudaEventSynchronize(pin_ev[prev_k]));
-        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads, PIN_BYTES / 8);
+        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads, PIN_BYTES / 8, true);
       }
       prev_k = k; prev_off = off; prev_n = n;
     }
@@ -420,7 +449,7 @@ class Engine : public EngineBase {
     if (!invclov_oo) B200_CUDA(cudaMalloc(&invclov_oo, sizeof(C) * 36 * (size_t)g.Vh));
     if (!tr_log_oo) B200_CUDA(cudaMalloc(&tr_log_oo, sizeof(double) * (size_t)g.Vh));
     B200_CUDA(cudaMemcpyAsync(invclov_oo, clov + (size_t)36 * g.Vh, sizeof(C) * 36 * (size_t)g.Vh, cudaMemcpyDeviceToDevice, stream));
-    ldagdlinv_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov_oo, tr_log_oo, g.Vh);
+    ldagdlinv_kernel<R><<<(2 * g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov_oo, tr_log_oo, g.Vh);
     return launched("ldagdlinv(oo)");
   }
   int set_preconditioning(int mode) override {
@@ -471,7 +500,7 @@ class Engine : public EngineBase {
       rc = launched("make_clover"); if (rc) return rc;
     }
     B200_CUDA(cudaMemcpyAsync(invclov, clov, sizeof(C) * 36 * (size_t)g.Vh, cudaMemcpyDeviceToDevice, stream));
-    ldagdlinv_kernel<R><<<(g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov, tr_log, g.Vh);
+    ldagdlinv_kernel<R><<<(2 * g.Vh + CLOV_BLOCK - 1) / CLOV_BLOCK, CLOV_BLOCK, 0, stream>>>(invclov, tr_log, g.Vh);
     rc = launched("ldagdlinv"); if (rc) return rc;
     have_trlog = true;
     rc = refresh_sym(); if (rc) return rc;
@@ -590,7 +619,9 @@ class Engine : public EngineBase {
         halo.prepare(h.pack, a.in, gauge, recon, ls, a.isign, a.parity, 1, a.fstride);
         for (int f = 0; f < 4; ++f) h.wait[f] = halo.local_flag(f);
         h.seq = halo.seq; h.spin = halo.spin_cycles;
-        h.n_pack = (halo.pack_threads() + DSLASH_BLOCK - 1) / DSLASH_BLOCK; h.n_int = nb_int; h.n_int_sites = n_int;
+        // one pack CTA per SM at most (they stride over the face sites): the other CTA slot of every SM starts interior
+        // work at once, so the pack overlaps the interior instead of preceding it
+        h.n_pack = std::min((halo.pack_threads() + DSLASH_BLOCK - 1) / DSLASH_BLOCK, num_sms); h.n_int = nb_int; h.n_int_sites = n_int;
         a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
         a.box[0] = inner; for (int k = 0; k < nf; ++k) a.box[1 + k] = faces[k];
         a.nbox = 1 + nf; a.nsites = g.Vh; a.zc_sites = 0; a.red = make_red(0, total);

@@ -80,7 +80,9 @@ __device__ __forceinline__ void pack_project_mul(Cx<R>* __restrict__ dst, int f,
   for (int c = 0; c < 3; ++c) { dst[(size_t)c * fs + f] = r0[c]; dst[(size_t)(3 + c) * fs + f] = r1[c]; }
 }
 
-// Body of the face pack for CTA `bx` of `nbx` (x RHS `rhs` of `nby`), BLOCK threads each.
+// Body of the face pack for CTA `bx` of `nbx` (x RHS `rhs` of `nby`), BLOCK threads each.  The CTA strides over the
+// face sites (nbx may be smaller than the number of BLOCK-sized pieces: the fused kernel uses one pack CTA per SM so that
+// interior CTAs start in the other slot of every SM at once and the pack overlaps them instead of preceding them).
 template <typename R, bool RECON12, int BLOCK>
 __device__ __forceinline__ void pack_faces_body(const PackArgs<R>& a, int bx, int nbx, int rhs, int nby) {
   typedef Cx<R> C;
@@ -91,37 +93,41 @@ __device__ __forceinline__ void pack_faces_body(const PackArgs<R>& a, int bx, in
   if (a.nrhs == 1 && skip) return;
   if (a.pred && *a.pred == 0) return;
   const Geom& g = a.g;
-  int tid = bx * BLOCK + threadIdx.x;
   const int stride = g.Vh, st = g.S3h, sz = g.SZh, row = g.Lxh * g.Ly;
   const R s = (R)a.isign;
   const L2Policy pol = make_l2_policy();
   constexpr int NG = RECON12 ? 6 : 9;
   const C* __restrict__ in = a.in + rhs * a.fstride;
   const int nT = g.tsplit ? 2 * st : 0, nZ = g.zsplit ? 2 * sz : 0;
-  if (skip) {
-  } else if (tid < nT) {
-    if (tid < st) {
-      pack_project<R, 3>(a.to[0] + rhs * a.gstride[0], tid, st, in + tid, stride, -s, pol);
-    } else {
-      const int f = tid - st, idx = (g.Lt - 1) * st + f;
-      pack_project_mul<R, 3, RECON12>(a.to[1] + rhs * a.gstride[0], f, st, in + idx, a.gauge + ((size_t)(3 * 2 + a.src_par) * NG) * stride + idx,
-                                      stride, s, (R)a.scale_b[0], pol);
+  if (!skip) {
+    for (int tid = bx * BLOCK + threadIdx.x; tid < nT + nZ; tid += nbx * BLOCK) {
+      if (tid < nT) {
+        if (tid < st) {
+          pack_project<R, 3>(a.to[0] + rhs * a.gstride[0], tid, st, in + tid, stride, -s, pol);
+        } else {
+          const int f = tid - st, idx = (g.Lt - 1) * st + f;
+          pack_project_mul<R, 3, RECON12>(a.to[1] + rhs * a.gstride[0], f, st, in + idx, a.gauge + ((size_t)(3 * 2 + a.src_par) * NG) * stride + idx,
+                                          stride, s, (R)a.scale_b[0], pol);
+        }
+      } else {
+        const int tz = tid - nT;
+        const bool back = tz >= sz;
+        const int f = back ? tz - sz : tz;                 // face index (t*Ly + y)*Lxh + xh
+        const int t = f / row, w = f - t * row;
+        const int idx = t * st + (back ? (g.Lz - 1) * row : 0) + w;
+        if (!back) pack_project<R, 2>(a.to[2] + rhs * a.gstride[1], f, sz, in + idx, stride, -s, pol);
+        else pack_project_mul<R, 2, RECON12>(a.to[3] + rhs * a.gstride[1], f, sz, in + idx, a.gauge + ((size_t)(2 * 2 + a.src_par) * NG) * stride + idx,
+                                             stride, s, (R)a.scale_b[1], pol);
+      }
     }
-  } else if (tid < nT + nZ) {
-    tid -= nT;
-    const bool back = tid >= sz;
-    const int f = back ? tid - sz : tid;                 // face index (t*Ly + y)*Lxh + xh
-    const int t = f / row, w = f - t * row;
-    const int idx = t * st + (back ? (g.Lz - 1) * row : 0) + w;
-    if (!back) pack_project<R, 2>(a.to[2] + rhs * a.gstride[1], f, sz, in + idx, stride, -s, pol);
-    else pack_project_mul<R, 2, RECON12>(a.to[3] + rhs * a.gstride[1], f, sz, in + idx, a.gauge + ((size_t)(2 * 2 + a.src_par) * NG) * stride + idx,
-                                         stride, s, (R)a.scale_b[1], pol);
   }
-  // last block publishes the arrival flags
-  __threadfence_system();
+  // The last CTA publishes the arrival flags.  One system-scope fence per CTA, by the thread that draws the ticket, after
+  // a CTA barrier: the barrier orders every thread's peer stores before thread 0's fence, and fences are cumulative, so
+  // the stores are visible to the peer GPU before the flag written behind the last ticket.
   __shared__ bool is_last;
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned int t = atomicAdd(a.ticket, 1u);
     is_last = (t == (unsigned int)(nbx * nby) - 1u);
   }
