@@ -131,6 +131,7 @@ class Engine : public EngineBase {
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   int pin_next = 0;
   int copy_threads = 4;
+  bool nt_copy = true;      // downloads leave the pinned bounce buffer with non-temporal stores (B200_NT_COPY=0: plain memcpy)
   size_t PIN_BYTES = PIN_BYTES_DEFAULT;   // B200_PIN_KB shrinks it (tests: many pieces and the thread team on small lattices)
   L2Policy l2pol{};         // createpolicy descriptors (evict_last for neighbour spinors, evict_first for streams), made once
   b200_field* ws[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -198,7 +199,8 @@ class Engine : public EngineBase {
     }
     // the ranks of one box share its cores: half of them, split over the ranks, at most 8 per rank
     copy_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / (2u * (unsigned)(cfg.pgrid[2] * cfg.pgrid[3]))));
-    if (const char* e = getenv("B200_COPY_THREADS")) copy_threads = std::max(0, atoi(e));   // 0: plain cudaMemcpy from pageable memory
+    if (const char* e = getenv("B200_COPY_THREADS")) copy_threads = std::max(0, atoi(e));
+    if (const char* e = getenv("B200_NT_COPY")) nt_copy = atoi(e) != 0;   // 0: plain cudaMemcpy from pageable memory
     if (split()) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;
@@ -314,7 +316,7 @@ class Engine : public EngineBase {
       }
       if (prev_k >= 0) {                                          // drain the previous piece while this one is in flight
         B200_CUDA(cudaEventSynchronize(pin_ev[prev_k]));
-        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads, PIN_BYTES / 8, true);
+        parallel_memcpy((char*)dst + prev_off, pin[prev_k], prev_n, copy_threads, PIN_BYTES / 8, nt_copy);
       }
       prev_k = k; prev_off = off; prev_n = n;
     }

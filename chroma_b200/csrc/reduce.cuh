@@ -68,40 +68,55 @@ __device__ __forceinline__ double block_sum(double v, double* smem /* [BLOCK/32]
   return s;
 }
 
-// Combine `vals[N]` (N<=4) across ranks in fixed rank order.  Executed by ONE thread of the last block.
-// Each rank writes its values + a sequence tag into every peer's mailbox (slot = seq&1), then polls its
-// own mailbox until all N ranks' tags match.  Two slots suffice because a rank cannot start reduction
-// s+2 before every peer has finished reading reduction s (they all needed this rank's s+1 contribution).
+// Combine `vals[N]` (N<=4) across ranks in fixed rank order.  Executed by ONE WARP (all 32 lanes call it with the same
+// vals; lane r talks to rank r); on return every lane holds the totals.
+// Protocol (NCCL's "LL" idea): every 8-byte word that crosses NVLink carries 4 bytes of payload and a 4-byte tag, and
+// 8-byte stores are never torn, so a word is either old or complete -- no fence between data and flag, no fence at all.
+// A double travels as two such words.  Rank `me` writes its N values into slot (seq&1, me) of EVERY rank's mailbox (lane =
+// destination: eight posted stores in flight at once), then lane r polls slot (seq&1, r) of the LOCAL mailbox until both
+// tags of every value match, and the totals are formed in rank order with shuffles, so all ranks get bit-identical sums.
+// Round 1 did this in one thread with two system fences and serial polling: ~20 us per reduction at 8 GPUs.
+// Two slots suffice because a rank cannot start reduction s+2 before every peer has finished reading reduction s (they
+// all needed this rank's s+1 contribution).
 template <int N>
 __device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, double vals[N]) {
   if (pr.nranks <= 1) return;
+  const int lane = threadIdx.x & 31;
   const unsigned long long s = *pr.seq + 1ull;
   const int slot = (int)(s & 1ull);
-  for (int dst = 0; dst < pr.nranks; ++dst) {
-    volatile double* mb = pr.mailbox[dst] + ((size_t)slot * 8 + pr.rank) * 8;
-    for (int k = 0; k < N; ++k) mb[k] = vals[k];
-  }
-  __threadfence_system();
-  for (int dst = 0; dst < pr.nranks; ++dst) {
-    volatile unsigned long long* tag =
-        (volatile unsigned long long*)(pr.mailbox[dst] + ((size_t)slot * 8 + pr.rank) * 8 + 4);
-    *tag = s;
-  }
-  __threadfence_system();
-  double tot[N];
-  for (int k = 0; k < N; ++k) tot[k] = 0.0;
-  for (int src = 0; src < pr.nranks; ++src) {
-    volatile double* mb = pr.mailbox[pr.rank] + ((size_t)slot * 8 + src) * 8;
-    volatile unsigned long long* tag = (volatile unsigned long long*)(mb + 4);
-    const long long t0 = clock64();
-    while (*tag != s) {
-      if (clock64() - t0 > pr.spin) { if (pr.status) pr.status[ST_BREAKDOWN] = 91; break; }
+  const unsigned long long tag = ((s & 0x7fffffffull) | 0x80000000ull) << 32;
+  if (lane < pr.nranks) {
+    volatile unsigned long long* mb = (volatile unsigned long long*)(pr.mailbox[lane] + ((size_t)slot * 8 + pr.rank) * 8);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[k]);
+      mb[2 * k] = tag | (bits & 0xffffffffull);
+      mb[2 * k + 1] = tag | (bits >> 32);
     }
-    __threadfence_system();
-    for (int k = 0; k < N; ++k) tot[k] += mb[k];
   }
-  for (int k = 0; k < N; ++k) vals[k] = tot[k];
-  *pr.seq = s;
+  double mine[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) mine[k] = 0.0;
+  if (lane < pr.nranks) {
+    const volatile unsigned long long* mb = (const volatile unsigned long long*)(pr.mailbox[pr.rank] + ((size_t)slot * 8 + lane) * 8);
+    const long long t0 = clock64();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      unsigned long long lo, hi;
+      while ((((lo = mb[2 * k]) ^ tag) >> 32) != 0ull || (((hi = mb[2 * k + 1]) ^ tag) >> 32) != 0ull) {
+        if (clock64() - t0 > pr.spin) { if (pr.status) pr.status[ST_BREAKDOWN] = 91; lo = hi = 0ull; break; }
+      }
+      mine[k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double tot = 0.0;
+    for (int src = 0; src < pr.nranks; ++src) tot += __shfl_sync(0xffffffffu, mine[k], src);
+    vals[k] = tot;
+  }
+  if (lane == 0) *pr.seq = s;
+  __syncwarp();
 }
 
 // Draw a ticket.  The release semantics of the atomic order this thread's partial-sum stores before the ticket becomes
@@ -202,11 +217,13 @@ __device__ __forceinline__ void grid_reduce(double v[N], const ReduceBuf& rb, Fi
                             : strided_sum(rb.gpartial + (size_t)k * ngrp, ngrp, threadIdx.x, BLOCK);
     tot[k] = block_sum<BLOCK>(acc, smem);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {          // every thread holds the totals; warp 0 combines them across GPUs
     peer_allreduce<N>(rb.peer, tot);
-    fin(tot);
-    *rb.ticket = 0u;
-    __threadfence();
+    if (threadIdx.x == 0) {
+      fin(tot);
+      *rb.ticket = 0u;
+      __threadfence();
+    }
   }
 }
 
@@ -254,9 +271,9 @@ __device__ __forceinline__ void reduce_finish(const ReduceBuf& rb, Fin fin) {
     for (int b = threadIdx.x; b < ngrp; b += BLOCK) acc += rb.gpartial[(size_t)k * ngrp + b];
     tot[k] = block_sum<BLOCK>(acc, smem);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     peer_allreduce<N>(rb.peer, tot);
-    fin(tot);
+    if (threadIdx.x == 0) fin(tot);
   }
 }
 
@@ -314,8 +331,8 @@ __device__ __forceinline__ void warp_grid_reduce(double v[N], const ReduceBuf& r
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     tot[k] = acc;
   }
+  peer_allreduce<N>(rb.peer, tot);       // the whole warp (the butterfly left the totals in every lane)
   if (lane == 0) {
-    peer_allreduce<N>(rb.peer, tot);
     fin(tot);
     *rb.ticket = 0u;
     __threadfence();
