@@ -187,6 +187,7 @@ int b200_create(b200_ctx** out, int device, const int global_dims[4], const int 
   ctx->eng = e;
   ctx->sloppy = nullptr;
   for (auto& f : ctx->host_tmp) f = nullptr;
+  ctx->ms_sol = nullptr;
   *out = ctx;
   return B200_OK;
 }
@@ -194,6 +195,7 @@ int b200_create(b200_ctx** out, int device, const int global_dims[4], const int 
 void b200_destroy(b200_ctx* ctx) {
   if (!ctx) return;
   for (auto f : ctx->host_tmp) if (f && ctx->eng) ctx->eng->field_free(f);
+  if (ctx->ms_sol && ctx->eng) ctx->eng->field_free(ctx->ms_sol);
   delete ctx->sloppy;   // first: it borrows the main engine's stream and scalar block
   delete ctx->eng;
   delete ctx;
@@ -273,8 +275,9 @@ int b200_invert_multishift(b200_ctx* ctx, void* const psi[], const void* chi, in
   B200_CUDA(cudaEventCreate(&e0)); B200_CUDA(cudaEventCreate(&e1));
   B200_CUDA(cudaEventRecord(e0, ctx->eng->stream));
   TmpFields t(ctx); int rc = t.get(1);
-  b200_field* sol = nullptr;
-  if (!rc) rc = ctx->eng->field_alloc(&sol, n_shift);
+  if (!rc && ctx->ms_sol && ctx->ms_sol->nrhs < n_shift) { ctx->eng->field_free(ctx->ms_sol); ctx->ms_sol = nullptr; }
+  if (!rc && !ctx->ms_sol) rc = ctx->eng->field_alloc(&ctx->ms_sol, n_shift);
+  b200_field* sol = ctx->ms_sol;
   if (!rc) rc = ctx->eng->field_upload(t.f[0], chi, host_prec);
   if (!rc) rc = ctx->eng->invert_multishift(sol, t.f[0], n_shift, shifts, rsd, max_iter, info);
   for (int s = 0; s < n_shift && !rc; ++s) rc = ctx->eng->field_download(sol, psi[s], host_prec, s);
@@ -282,7 +285,6 @@ int b200_invert_multishift(b200_ctx* ctx, void* const psi[], const void* chi, in
   float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
   if (!rc) for (int s = 0; s < n_shift; ++s) info[s].secs_total = ms * 1e-3;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  if (sol) ctx->eng->field_free(sol);
   return rc;
 }
 int b200_dev_iterate_begin(b200_ctx* ctx, b200_field* psi, const b200_field* chi, int solver) {

@@ -103,4 +103,7 @@ struct b200_ctx {
   // life of the context (Chroma calls operator() 12 times per propagator, quarkprop4_w.cc:70-117; a cudaMalloc/cudaFree
   // pair of 1 GB per call costs more than the transfers)
   b200_field* host_tmp[3];
+  // device twin of the n_shift host solutions of b200_invert_multishift: kept (and grown on demand) for the life of the
+  // context -- the rational monomials of RHMC call the multi-shift solver once per force / action evaluation
+  b200_field* ms_sol;
 };
