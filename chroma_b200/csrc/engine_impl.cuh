@@ -197,8 +197,10 @@ class Engine : public EngineBase {
       B200_CUDA(cudaHostAlloc(&pin[i], PIN_BYTES, cudaHostAllocDefault));
       B200_CUDA(cudaEventCreateWithFlags(&pin_ev[i], cudaEventDisableTiming));
     }
-    // the ranks of one box share its cores: half of them, split over the ranks, at most 8 per rank
-    copy_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / (2u * (unsigned)(cfg.pgrid[2] * cfg.pgrid[3]))));
+    // the ranks of one box share its cores: all of them, split over the ranks, at most 16 per rank (the host has nothing else
+    // to do while a field is copied).  16-core box, 1 rank: gauge upload 189 / 161 / 140 ms with 8 / 12 / 16 threads, 1 GB
+    // fermion down 33 / 29 / 28 ms (profiles/r02_copy_threads.json)
+    copy_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)(cfg.pgrid[2] * cfg.pgrid[3])));
     if (const char* e = getenv("B200_COPY_THREADS")) copy_threads = std::max(0, atoi(e));
     if (const char* e = getenv("B200_NT_COPY")) nt_copy = atoi(e) != 0;   // 0: plain cudaMemcpy from pageable memory
     if (split()) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
