@@ -551,9 +551,10 @@ def run_b200(args):
     ms_e2e = timed_invert(chi_pg, psi_pg)
     cb_bytes = Vh * 24 * (8 if args.prec == "double" else 4)
     e2e = {"value": flop_iter * Vh_global * args.steps / (ms_e2e * 1e-3) * 1e-9, "unit": "GFLOP/s",
-           "h2d_bytes_per_step": 2 * cb_bytes * world / args.steps, "d2h_bytes_per_step": cb_bytes * world / args.steps,
+           "h2d_bytes_per_step": cb_bytes * world / args.steps, "d2h_bytes_per_step": cb_bytes * world / args.steps,
            "ms_per_call": ms_e2e, "host_buffers": "pageable",
-           "call": "b200_invert(host psi, host chi, max_iter=steps) on pageable numpy buffers: H2D chi+psi0, M^dag chi, preamble, "
+           "call": "b200_invert(host psi, host chi, max_iter=steps) on pageable numpy buffers: H2D chi (the initial guess psi0 = 0, as "
+                   "quarkprop4_w.cc:74 passes it, is recognised by a host scan and set on the device, not copied), M^dag chi, preamble, "
                    "%d iterations, true residual, D2H psi" % args.steps}
     del chi_pg, psi_pg
     try:

@@ -145,7 +145,12 @@ int host_solve(b200_ctx* ctx, void* psi, const void* chi, int host_prec, b200_so
   B200_CUDA(cudaEventRecord(e0, ctx->eng->stream));
   TmpFields t(ctx); int rc = t.get(2);
   if (!rc) rc = ctx->eng->field_upload(t.f[0], chi, host_prec);
-  if (!rc) rc = ctx->eng->field_upload(t.f[1], psi, host_prec);
+  if (!rc) {
+    // a zero initial guess (what quarkprop4_w.cc:74 hands over) is set on the device instead of being copied
+    const size_t bytes = (size_t)ctx->eng->g.Vh * 24 * (size_t)host_prec;
+    if ((host_prec == B200_SINGLE || host_prec == B200_DOUBLE) && host_all_zero(psi, bytes, ctx->eng->host_copy_threads)) rc = ctx->eng->field_zero(t.f[1]);
+    else rc = ctx->eng->field_upload(t.f[1], psi, host_prec);
+  }
   if (!rc) rc = solve(t.f[1], t.f[0]);
   if (!rc || rc == B200_ERR_BREAKDOWN) { int r2 = ctx->eng->field_download(t.f[1], psi, host_prec); if (!rc) rc = r2; }
   cudaEventRecord(e1, ctx->eng->stream); cudaEventSynchronize(e1);

@@ -81,6 +81,7 @@ class EngineBase {
   Geom g;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  int host_copy_threads = 4;   // size of the host thread team of the pageable-copy pipeline (set by init)
 };
 
 // Mixed-precision reliable-update CG (engine_mixed.cu): hi must be the fp64 engine; *lo_slot is created on first use.

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstdarg>
 #include <thread>
+#include <atomic>
 #include <stdint.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -65,6 +66,33 @@ inline void parallel_memcpy(void* dst, const void* src, size_t bytes, int nthrea
   }
   cp(dst, src, std::min(per, bytes));
   for (auto& th : team) th.join();
+}
+
+// True if every byte of a host buffer is zero.  The propagator call site hands the solver psi = zero as the initial guess
+// (quarkprop4_w.cc:74: "LatticeFermion psi = zero"), and scanning a gigabyte with the thread team (read-only, early exit at
+// the first non-zero word -- a real initial guess costs one cache line) is 2-3x cheaper than bouncing it over PCIe just to
+// hold zeros on the device.
+inline bool host_all_zero(const void* p, size_t bytes, int nthreads) {
+  if (bytes % 8 != 0 || ((uintptr_t)p & 7)) return false;
+  const unsigned long long* w = (const unsigned long long*)p;
+  const size_t n = bytes / 8;
+  if (n == 0 || w[0] != 0ull || w[n - 1] != 0ull || w[n / 2] != 0ull) return false;
+  std::atomic<bool> nonzero(false);
+  auto scan = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi && !nonzero.load(std::memory_order_relaxed); i += 512) {
+      unsigned long long acc = 0ull;
+      const size_t e = std::min(hi, i + 512);
+      for (size_t j = i; j < e; ++j) acc |= w[j];
+      if (acc) nonzero.store(true, std::memory_order_relaxed);
+    }
+  };
+  const int nt = std::max(1, nthreads);
+  const size_t per = (n + nt - 1) / nt;
+  std::vector<std::thread> team;
+  for (int t = 1; t < nt; ++t) if (per * t < n) team.emplace_back(scan, per * t, std::min(n, per * (t + 1)));
+  scan(0, std::min(n, per));
+  for (auto& th : team) th.join();
+  return !nonzero.load();
 }
 
 // status != nullptr: a solver launch -- return at once when the solve has stopped / when slot run_if is clear
@@ -202,7 +230,8 @@ class Engine : public EngineBase {
     // fermion down 33 / 29 / 28 ms (profiles/r02_copy_threads.json)
     copy_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)(cfg.pgrid[2] * cfg.pgrid[3])));
     if (const char* e = getenv("B200_COPY_THREADS")) copy_threads = std::max(0, atoi(e));
-    if (const char* e = getenv("B200_NT_COPY")) nt_copy = atoi(e) != 0;   // 0: plain cudaMemcpy from pageable memory
+    if (const char* e = getenv("B200_NT_COPY")) nt_copy = atoi(e) != 0;
+    host_copy_threads = copy_threads;   // 0: plain cudaMemcpy from pageable memory
     if (split()) { int rc = halo.init(cfg, g, stream); if (rc) return rc; halo.status_dev = status; }
     B200_CUDA(cudaStreamSynchronize(stream));
     return B200_OK;

@@ -777,3 +777,23 @@ def test_split_reduction_path(oracle, solver, monkeypatch):
     full = np.zeros_like(chi); full[Vh:] = sol
     res = chi - op.apply(full, +1)
     assert np.sqrt(np.sum(res[Vh:] ** 2) / np.sum(chi[Vh:] ** 2)) < 2e-8
+
+
+def test_zero_initial_guess_is_not_copied(oracle):
+    """b200_invert sets an all-zero initial guess on the device instead of copying it (host_all_zero, engine_impl.cuh; the
+    propagator call site passes psi = zero, quarkprop4_w.cc:74).  The result must be bit-identical to the copied path,
+    which a single -0.0 in the guess forces (its bit pattern is not zero), and a real guess must still be honoured."""
+    latt = (8, 8, 8, 8)
+    u, op, ctx, _ = setup(oracle, latt, "double", gauge="weak")
+    Vh = ctx.Vh
+    chi = fields.gaussian_fermion(latt, seed=51, cb=1)[Vh:]
+    zero = np.zeros_like(chi)
+    negzero = zero.copy(); negzero[Vh // 2, 1, 2, 0] = -0.0
+    assert negzero.tobytes() != zero.tobytes()
+    s0, i0 = ctx.invert(chi, zero, solver=L.B200_SOLVER_CG, rsd=1e-9, max_iter=500)
+    s1, i1 = ctx.invert(chi, negzero, solver=L.B200_SOLVER_CG, rsd=1e-9, max_iter=500)
+    assert i0.n_count == i1.n_count and np.array_equal(s0, s1)
+    # starting from the solution: converged at once (the guess was used, not replaced by zero)
+    s2, i2 = ctx.invert(chi, s0, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=500)
+    assert i2.n_count <= 1 and i2.converged
+    ctx.close()
