@@ -9,8 +9,8 @@ weak-field SU(3) gauge field, Mass 0.1, clovCoeff 1.0, antiperiodic T, Gaussian 
   value     GFLOP/s of K iterations with every field resident in HBM (Chroma's count: 7824 flop per odd site per
             iteration = 2*3792 + 240, invcg2.cc:67,101-220), CUDA events on the engine's stream, max over ranks.
   e2e       same metric through the plugin-facing C ABI call b200_invert() with PAGEABLE host chi / psi buffers (what
-            QDP++ fields are): H2D of source + initial guess, M^dag chi, the solver preamble, K iterations, true-residual
-            check, D2H of psi.  The same call on pinned buffers is reported beside it (e2e.pinned_host_buffers).
+            QDP++ fields are): H2D of the source (the zero initial guess the propagator call site passes is set on the
+            device, not copied), M^dag chi, the solver preamble, K iterations, true-residual check, D2H of psi.  The same call on pinned buffers is reported beside it (e2e.pinned_host_buffers).
   roofline  the kernels the CG loop really launches, each timed with CUDA events on the engine's stream inside the loop
             (b200_dev_time_solver_kernels): EPI_AINV (x2), EPI_M_NORM, EPI_M_CG, cg_update.  The dominant one is the
             kernel with the largest share of the iteration; achieved = its algorithmic bytes /
