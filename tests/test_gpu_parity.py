@@ -797,3 +797,26 @@ def test_zero_initial_guess_is_not_copied(oracle):
     s2, i2 = ctx.invert(chi, s0, solver=L.B200_SOLVER_CG, rsd=1e-8, max_iter=500)
     assert i2.n_count <= 1 and i2.converged
     ctx.close()
+
+
+def test_recon12_rejects_links_it_cannot_rebuild(oracle):
+    """12-real compression keeps rows 0,1 of every link and rebuilds row 2 as conj(row0 x row1): right only for SU(3) links
+    whose one extra phase is the antiperiodic T boundary the engine carries itself.  The upload checks every link
+    (recon12_check_kernel) and refuses anything else with B200_ERR_ARG instead of producing diag(1,1,-1) U silently:
+    spatially antiperiodic fermion boundaries, a wrong t_boundary, non-unitary links."""
+    latt = (4, 4, 4, 8)
+    u0 = fields.random_gauge(latt, seed=71)
+    ctx = Context(latt, prec="double")
+    ctx.load_gauge(fields.apply_bc(latt, u0, (1, 1, 1, -1)), t_boundary=-1, reconstruct=L.B200_RECONS_12)      # fine
+    ctx.load_gauge(fields.apply_bc(latt, u0, (1, 1, 1, 1)), t_boundary=+1, reconstruct=L.B200_RECONS_12)       # fine
+    for bc, tb in (((-1, 1, 1, -1), -1),        # antiperiodic in x as well
+                   ((1, 1, 1, -1), +1),         # the links carry the T phase but the caller says periodic
+                   ((1, 1, 1, 1), -1)):         # ... and the other way round
+        with pytest.raises(L.B200Error) as e:
+            ctx.load_gauge(fields.apply_bc(latt, u0, bc), t_boundary=tb, reconstruct=L.B200_RECONS_12)
+        assert e.value.code == L.B200_ERR_ARG and "RECONS_12" in str(e.value)
+    bad = u0.copy(); bad[2, 17] *= 1.01                                  # one non-unitary link
+    with pytest.raises(L.B200Error):
+        ctx.load_gauge(bad, t_boundary=+1, reconstruct=L.B200_RECONS_12)
+    ctx.load_gauge(fields.apply_bc(latt, u0, (-1, 1, 1, -1)), t_boundary=-1, reconstruct=L.B200_RECONS_NONE)   # uncompressed links take any phase
+    ctx.close()
