@@ -7,15 +7,17 @@
 // the backward hop the SENDER multiplies by U^dagger (decomp_hvv, cpp_dslash_parscalar_utils_64bit.cc:61-110),
 // so the hopping term needs no gauge ghost.
 //
-// Protocol per Dslash number n (all ranks issue the same sequence of Dslashes):
-//   pack kernel   projects the faces of the source field (t = 0, Lt-1; on a T x Z grid also z = 0, Lz-1) and STORES
-//                 them straight into the neighbours' ghost buffers (slot n&1) through peer-mapped pointers; its last
-//                 block then writes n into the neighbours' arrival flags (threadfence_system before the flag).
-//   interior      dslash kernel on the sites with no ghost dependence runs while the faces are in flight.
-//   wait kernel   one thread spins on the local arrival flags (2 or 4) until all equal n.
-//   boundary      dslash kernel on the boundary slices / planes, reading the ghost half spinors.
+// Protocol per Dslash number n (all ranks issue the same sequence of Dslashes).  A single-RHS Dslash is ONE launch
+// (dslash_halo_kernel below) whose CTA ranges play the roles; a batched Dslash still issues them as separate kernels:
+//   pack          projects the faces of the source field (t = 0, Lt-1; on a T x Z grid also z = 0, Lz-1) and STORES
+//                 them straight into the neighbours' ghost buffers (slot n&1) through peer-mapped pointers; the last
+//                 pack CTA then writes n into the neighbours' arrival flags (CTA barrier, one system fence, flag).
+//   interior      the sites with no ghost dependence run while the faces are in flight.
+//   wait          thread 0 of every boundary CTA (batched: a one-thread kernel) polls the local arrival flags (2 or 4)
+//                 until all equal n.
+//   boundary      the boundary slices / planes, reading the ghost half spinors through the coherent path.
 // Two slots are enough: a rank can only start packing Dslash n+2 after it finished the boundary of n+1, which
-// needed the neighbour's pack n+1, which the neighbour issued after ITS boundary kernel of n had read slot n&1.
+// needed the neighbour's pack n+1, which the neighbour issued after ITS boundary CTAs of n had read slot n&1.
 // Predicated Dslashes (run_if, used by the reliable-update solver) are skipped by ALL ranks or by none (the flag is
 // derived from a global sum) and always come in groups of four, so executed Dslashes still alternate slots.
 #pragma once

@@ -1,15 +1,16 @@
-// reduce.cuh -- deterministic block reduction + "last block finalises" pattern used by every fused
-// solver kernel.  Each block writes one partial per reduced quantity; the block that draws the last
-// ticket sums the partials in a fixed order (so the result does not depend on block scheduling),
-// optionally combines across GPUs through NVLink peer mailboxes, and hands the totals to a finaliser
-// functor that derives the solver scalars (alpha, beta, ...) ON THE DEVICE -- the host never sees them.
+// reduce.cuh -- deterministic grid reductions used by every fused solver kernel.  Each block writes one partial per
+// reduced quantity; the partials are summed in a fixed two-level order (so the result does not depend on block
+// scheduling) -- by the block that draws the last ticket (small grids) or by a one-CTA finish kernel (the big Dslash
+// grids, ReduceBuf::split) --, optionally combined across GPUs through NVLink peer mailboxes (peer_allreduce), and the
+// totals go to a finaliser functor that derives the solver scalars (alpha, beta, ...) ON THE DEVICE -- the host never
+// sees them.
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-// Cross-GPU reduction mailboxes (peer-mapped).  See comm.cuh for how they are wired up.
-constexpr int MAILBOX_DOUBLES = 2 * 8 * 8;   // per right-hand side: [slot 2][src rank 8][4 values + tag + pad]
+// Cross-GPU reduction mailboxes (peer-mapped; halo.cuh wires them up).
+constexpr int MAILBOX_DOUBLES = 2 * 8 * 8;   // per right-hand side: [slot 2][src rank 8][8 words: 4 values x (lo, hi) data+tag words]
 struct PeerReduce {
   int nranks;           // 1 => single GPU, nothing to do
   int rank;

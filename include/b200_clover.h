@@ -61,7 +61,7 @@ enum {
   B200_ERR_CUDA = 2,      /* CUDA runtime error / no usable device */
   B200_ERR_STATE = 3,     /* call out of order (e.g. solve before gauge/clover are loaded) */
   B200_ERR_BREAKDOWN = 4, /* BiCGStab breakdown (rho = 0, <r0|v> = 0, |t| = 0); invbicgstab.cc:80-83,109-112,133-136 */
-  B200_ERR_COMM = 5       /* multi-GPU bootstrap failed */
+  B200_ERR_COMM = 5       /* multi-GPU bootstrap failed, or a peer wait (halo flag / reduction mailbox) ran out of its budget */
 };
 
 /* Host-side collectives the caller lends the engine for the ONE-TIME multi-GPU bootstrap (exchange of
@@ -88,9 +88,12 @@ typedef struct {
   int reserved;
 } b200_solve_info;
 
-/* Environment knobs read at b200_create: B200_COPY_THREADS (host threads of the pageable-buffer bounce pipeline; 0 = plain
- * cudaMemcpy), B200_PIN_KB (size of its pinned bounce buffers, default 32768), B200_MRHS_L2_KB (L2 budget of the batched
- * traversal), B200_QPROP_BATCH (cap on the right-hand sides b200_qprop solves at once). */
+/* Environment knobs read at b200_create: B200_COPY_THREADS (host threads of the pageable-buffer bounce pipeline; default every
+ * core the rank may use, at most 16; 0 = plain cudaMemcpy), B200_PIN_KB (size of its pinned bounce buffers, default 32768),
+ * B200_NT_COPY (0: downloads leave the bounce buffer with plain instead of non-temporal stores), B200_PEER_TIMEOUT_S (budget of
+ * every multi-GPU peer wait, default 60 s; when it runs out the call returns B200_ERR_COMM), B200_MRHS_L2_KB (L2 budget of the
+ * z-chunked traversal), B200_QPROP_BATCH (cap on the right-hand sides b200_qprop solves at once), B200_SPLIT_MIN_BLOCKS (grid size
+ * above which the Dslash reductions are finished by a one-CTA kernel; tests). */
 const char* b200_last_error(void);
 const char* b200_version(void);
 int b200_device_count(void);   /* CUDA devices visible to this process (<= 0: none); for rank -> device mapping */
@@ -163,7 +166,8 @@ int b200_clover_apply(b200_ctx* ctx, void* out_cb_host, const void* in_cb_host, 
  * (eoprec_clover_linop_w.cc:142-187); also what CloverSchur4D fuses (cpp_clover_scalar_64bit.cc:65-102). */
 int b200_clover_matpc(b200_ctx* ctx, void* out_odd_host, const void* in_odd_host, int host_prec, int isign);
 
-/* Solve M psi = chi on the odd checkerboard.  psi holds the initial guess on entry, the solution on exit.
+/* Solve M psi = chi on the odd checkerboard.  psi holds the initial guess on entry, the solution on exit (an all-zero guess,
+ * what quarkprop4_w.cc:74 passes, is recognised by a host scan and set on the device instead of being copied).
  * solver = B200_SOLVER_CG:       LinOpSysSolverCG (syssolver_linop_cg.h:57-96): chi' = M^dag chi, then
  *                                InvCG2_a on M^dag M (invcg2.cc:70-232), stop |r|^2 <= rsd^2 |chi'|^2.
  * solver = B200_SOLVER_BICGSTAB: LinOpSysSolverBiCGStab (syssolver_linop_bicgstab.h:57-95) ->

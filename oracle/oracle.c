@@ -16,15 +16,17 @@
  *   clover       per site: diag[2][6] reals then offd[2][15] complex = 72 reals
  *                (lib/actions/ferm/linop/clover_term_qdp_w.h:19-24)
  *
- * Parity pinning: orc_dslash and orc_clover_apply are checked against the reference's
- * own Dslash<double> / CloverSchur4D<double> compiled unmodified into oracle/_ref
- * (tests/test_oracle.py).  The clover build, LDL^dagger inverse and the solver
- * loops are restated-and-self-consistent (A*A^-1=1, gamma5-hermiticity, free field,
- * constant abelian field strength): the reference holds no golden vectors for them
- * that can be reproduced without QDP++'s RNG.  The same holds for the
- * section-8(f) additions restated here -- the symmetric operator (seoprec_clover_linop_w.cc),
- * its qprop decomposition and MInvCG2_a: parity unpinned, self-consistency checked in
- * tests/test_oracle.py.
+ * Parity pinning (tests/test_oracle.py, tests/test_golden.py): every restatement in this file is compared with the
+ * reference's OWN code compiled unmodified from /root/reference (oracle/Makefile -> oracle/_ref/):
+ *   orc_dslash, the composed Schur operator   Dslash<double|float>, CloverSchur4D<double>       (_ref/libref_dslash.so)
+ *   orc_mesfield, orc_make_clov               mesField, makeClovSiteLoop: bit for bit            (_ref/libref_chroma.so)
+ *   orc_ldagdlinv, orc_clover_apply           LDagDLInvSiteLoop (1 ulp), applySiteLoop (bit for bit)
+ *   orc_invcg2, orc_invbicgstab, orc_minvcg2  InvCG2, InvBiCGStab, MInvCG2: same counts, solutions to 1e-15
+ *   reliable CG / BiCGStab (oracle.py)        InvCGReliable, InvBiCGStabReliable with an fp32 inner operator
+ * The Chroma-level sources compile against tests/mock_chroma, a functional stand-in for the slice of QDP++ they touch
+ * (QDP++ itself is not available).  The symmetric operator, the twisted-mass term and the qprop decompositions are
+ * compositions of those pinned pieces (their own source files instantiate all of Chroma) and are checked through
+ * properties: A_oo^-1 M_asym, <chi,M psi> = <M^dag chi,psi>, explicit Gamma(15) algebra, the unpreconditioned system.
  */
 #include <math.h>
 #include <stdlib.h>
