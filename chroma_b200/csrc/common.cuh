@@ -98,6 +98,8 @@ __device__ __forceinline__ void cp_async_hint(float2* smem_dst, const float2* gs
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all commit groups but the most recent one have landed (batched kernels: group 1 = staged links, group 2 = first spinor)
+__device__ __forceinline__ void cp_async_wait_staged() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 // read-modify-write streams (the CG residual) must not use the non-coherent path
 __device__ __forceinline__ double2 ld_stream_rw(const double2* p, uint64_t pol) {
   double2 v;
@@ -150,6 +152,21 @@ __host__ __device__ __forceinline__ int box_site(const Geom& g, const SiteBox& b
   const int zz = q % b.nz, tt = q / b.nz;
   return ((b.t0 + tt) * g.Lz + b.z0 + zz) * row + w;
 }
+
+// Division by a launch-invariant divisor without the ~20-instruction integer-division sequence: q = (n * mul) >> shift
+// with shift = 28 + ceil(log2 d), mul = ceil(2^shift / d) is exact for 0 <= n < 2^28, 1 <= d <= 2^28 (the error term
+// n * (mul*d - 2^shift) stays below 2^shift).  Site counts of one rank are far below 2^28 (64^3 x 128 / 2 = 2^24).
+struct FastDiv { unsigned mul, shift; };
+inline FastDiv make_fastdiv(int d) {
+  if (d < 1) d = 1;
+  unsigned s = 0;
+  while ((1ull << s) < (unsigned long long)d) ++s;
+  FastDiv f;
+  f.shift = 28 + s;
+  f.mul = (unsigned)(((1ull << f.shift) + (unsigned long long)d - 1) / (unsigned long long)d);
+  return f;
+}
+__device__ __forceinline__ int fast_div(int n, const FastDiv f) { return (int)(((unsigned long long)(unsigned)n * f.mul) >> f.shift); }
 
 // Right-hand sides solved in lockstep by the batched (multi-RHS) kernels: the 12 spin-colour sources of a propagator
 // (quarkprop4_w.cc:70-117).  Every right-hand side owns one ScalarSlot block and one StatusSlot block.

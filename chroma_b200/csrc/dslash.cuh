@@ -120,6 +120,49 @@ __device__ __forceinline__ int launch_site_from(const DslashArgs<R>& a, int loca
   return 0;
 }
 
+// Checkerboard coordinates of a target site next to its cb2 index: the batched kernels decode them ONCE per thread
+// (mrhs_site) and hand them to the staging code and to dslash_site*, instead of re-deriving them from idx.
+struct SiteCoord { int idx, xh, y, z, t; };
+// Launch-invariant divisors of the batched kernels' site decode (FastDiv, common.cuh), filled on the host per launch.
+struct MrhsDiv { FastDiv lxh, ly, lz, zc, per, row, nz0; };
+template <typename R>
+inline MrhsDiv make_mrhs_div(const DslashArgs<R>& a) {
+  MrhsDiv d;
+  d.lxh = make_fastdiv(a.g.Lxh); d.ly = make_fastdiv(a.g.Ly); d.lz = make_fastdiv(a.g.Lz);
+  d.zc = make_fastdiv(a.zc_sites); d.per = make_fastdiv(a.zc_sites * a.box[0].nt);
+  d.row = make_fastdiv(a.g.Lxh * a.g.Ly); d.nz0 = make_fastdiv(a.box[0].nz);
+  return d;
+}
+// The `local`-th target site of a batched launch, with its coordinates: same traversal order as launch_site<R, true>
+// (box 0 swept in z-chunks), without a single hardware integer division on the box-0 path.  (Round 2: the generic
+// decode + the old slot-by-slot staging loop cost ~1000 of the ~3000 instructions a warp issued per 32 sites, all of
+// them in front of its first load.)
+template <typename R>
+__device__ __forceinline__ SiteCoord mrhs_site(const DslashArgs<R>& a, const MrhsDiv& dv, int local) {
+  const Geom& g = a.g;
+  const SiteBox& b = a.box[0];
+  const int row = g.Lxh * g.Ly;
+  SiteCoord s;
+  if (local < row * b.nz * b.nt) {
+    if (a.zc_sites) {
+      const int zc = fast_div(local, dv.per), rem = local - zc * (a.zc_sites * b.nt);
+      const int tt = fast_div(rem, dv.zc), w = rem - tt * a.zc_sites;
+      local = tt * (row * b.nz) + zc * a.zc_sites + w;
+    }
+    const int q = fast_div(local, dv.row), w = local - q * row;      // local = (tt*nz + zz)*row + w
+    const int tt = fast_div(q, dv.nz0), zz = q - tt * b.nz;
+    s.t = b.t0 + tt; s.z = b.z0 + zz;
+    s.y = fast_div(w, dv.lxh); s.xh = w - s.y * g.Lxh;
+    s.idx = (s.t * g.Lz + s.z) * row + w;
+  } else {                                                            // the other boxes of a boundary launch
+    s.idx = launch_site<R, false>(a, local);
+    int q = fast_div(s.idx, dv.lxh); s.xh = s.idx - q * g.Lxh;
+    int q2 = fast_div(q, dv.ly); s.y = q - q2 * g.Ly;
+    s.t = fast_div(q2, dv.lz); s.z = q2 - s.t * g.Lz;
+  }
+  return s;
+}
+
 // Batched-kernel knobs (tuned on B200, profiles/r01_tune_mrhs_prefetch.txt):
 #ifndef B200_MRHS_PREFETCH
 #define B200_MRHS_PREFETCH 1    // fp64: neighbour spinors software-pipelined through shared memory (dslash_site_pf); 0: direct loads
@@ -266,15 +309,19 @@ struct LinkScale {
 // `sml` (slot stride 32); otherwise they stream from global memory.
 template <typename R, bool RECON12, bool MR = false>
 __device__ __forceinline__ void dslash_site(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol,
-                                            const Cx<R>* sml = nullptr) {
+                                            const Cx<R>* sml = nullptr, const SiteCoord* sc = nullptr) {
   typedef Cx<R> C;
   const Geom& g = a.g;
   const int stride = g.Vh;
-  int q = idx;
-  const int xh = q % g.Lxh; q /= g.Lxh;
-  const int y = q % g.Ly;   q /= g.Ly;
-  const int z = q % g.Lz;
-  const int t = q / g.Lz;
+  int xh, y, z, t;
+  if (sc) { xh = sc->xh; y = sc->y; z = sc->z; t = sc->t; }      // batched kernels: decoded once by mrhs_site
+  else {
+    int q = idx;
+    xh = q % g.Lxh; q /= g.Lxh;
+    y = q % g.Ly;   q /= g.Ly;
+    z = q % g.Lz;
+    t = q / g.Lz;
+  }
   const int p = a.parity;
   const int r = (y + z + t + p) & 1;      // x = 2*xh + r
   constexpr int NG = RECON12 ? 6 : 9;
@@ -365,24 +412,26 @@ __device__ __forceinline__ void hop_pf(Cx<R> acc[12], Cx<R>* sp, const Cx<R>* li
   su3_mul<R, ADJ>(r0, r1, U, h0, h1);
   recons_acc<R, MU>(acc, r0, r1, sg);
 }
-template <typename R, bool RECON12>
-__device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, int idx, const L2Policy& pol,
+// index of the +x neighbour of a target site: the first hop of dslash_site_pf (the batched kernel issues its fetch early)
+__device__ __forceinline__ int xfwd_neighbour(const Geom& g, const SiteCoord& c, int parity) {
+  const int r = (c.y + c.z + c.t + parity) & 1;
+  return r ? (c.xh + 1 == g.Lxh ? c.idx - (g.Lxh - 1) : c.idx + 1) : c.idx;
+}
+// FIRST_ISSUED: the caller has already started the fetch of the +x neighbour into `sp` (and committed it)
+template <typename R, bool RECON12, bool FIRST_ISSUED = false>
+__device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, const SiteCoord& c, const L2Policy& pol,
                                                const Cx<R>* sml, Cx<R>* sp, const Cx<R>* after) {
   typedef Cx<R> C;
   const Geom& g = a.g;
   const int stride = g.Vh;
-  int q = idx;
-  const int xh = q % g.Lxh; q /= g.Lxh;
-  const int y = q % g.Ly;   q /= g.Ly;
-  const int z = q % g.Lz;
-  const int t = q / g.Lz;
+  const int idx = c.idx, xh = c.xh, y = c.y, z = c.z, t = c.t;
   const int r = (y + z + t + a.parity) & 1;
   constexpr int NG = RECON12 ? 6 : 9;
   const C* __restrict__ in = a.in;
   const R s = (R)a.isign;
 #define B200_LF(mu) (sml + (2 * (mu)) * NG * 32)
 #define B200_LB(mu) (sml + (2 * (mu) + 1) * NG * 32)
-  const int xf = r ? (xh + 1 == g.Lxh ? idx - (g.Lxh - 1) : idx + 1) : idx;
+  const int xf = xfwd_neighbour(g, c, a.parity);
   const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
   const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
   const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
@@ -402,7 +451,7 @@ __device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = mk<R>(0, 0);
 
-  prefetch_spinor<R>(sp, in + xf, stride, pol.keep);
+  if (!FIRST_ISSUED) prefetch_spinor<R>(sp, in + xf, stride, pol.keep);
   hop_pf<R, 0, false, RECON12>(acc, sp, B200_LF(0), -s, (R)ls.aniso[0], pol, in + xb, stride, pol.keep);
   hop_pf<R, 0, true, RECON12>(acc, sp, B200_LB(0), s, (R)ls.aniso[0], pol, in + yf, stride, pol.keep);
   hop_pf<R, 1, false, RECON12>(acc, sp, B200_LF(1), -s, (R)ls.aniso[1], pol, in + yb, stride, pol.keep);
@@ -429,20 +478,19 @@ __device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R
 #undef B200_LB
 }
 
-// Indices (on the source checkerboard) of the four backward neighbours of target site idx -- where the backward links
-// live.  Same arithmetic as dslash_site; used by the multi-RHS kernels to stage the links.
-__device__ __forceinline__ void backward_neighbours(const Geom& g, int idx, int parity, int nbr[4]) {
-  int q = idx;
-  const int xh = q % g.Lxh; q /= g.Lxh;
-  const int y = q % g.Ly;   q /= g.Ly;
-  const int z = q % g.Lz;
-  const int t = q / g.Lz;
-  const int r = (y + z + t + parity) & 1;
-  nbr[0] = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
-  nbr[1] = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
+// Index (on the source checkerboard) of the backward neighbour in direction mu of a target site -- where the backward
+// link lives.  Same arithmetic as dslash_site; used by the multi-RHS kernels to stage the links.
+// `mu` is warp-uniform in the staging code, so the switch costs one uniform branch.
+__device__ __forceinline__ int backward_neighbour(const Geom& g, const SiteCoord& c, int parity, int mu) {
+  const int idx = c.idx;
+  if (mu == 0) {
+    const int r = (c.y + c.z + c.t + parity) & 1;
+    return r ? idx : (c.xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
+  }
+  if (mu == 1) return (c.y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
   const int sz = g.Ly * g.Lxh;
-  nbr[2] = (z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
-  nbr[3] = (t == 0) ? idx + (g.Lt - 1) * g.S3h : idx - g.S3h;
+  if (mu == 2) return (c.z == 0) ? idx + (g.Lz - 1) * sz : idx - sz;
+  return (c.t == 0) ? idx + (g.Lt - 1) * g.S3h : idx - g.S3h;
 }
 
 // ---- clover: one 6x6 Hermitian block times 6 complex --------------------------------------------
@@ -697,45 +745,62 @@ template <typename R, int EPI, bool RECON12> struct MrhsSmem {
   static constexpr size_t total(int nrb) { return bytes + (MrhsPrefetch<R>::on ? (size_t)nrb * 12 * 32 * sizeof(Cx<R>) : 0); }
 };
 template <typename R, int EPI, bool RECON12, int NRB, int MODE = MODE_ASYM>
-__global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups) {
+__global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups, const MrhsDiv dv) {
   typedef Cx<R> C;
   typedef MrhsSmem<R, EPI, RECON12> SM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   C* const sm = reinterpret_cast<C*>(smem_raw);
-  const int grp = blockIdx.x % ngroups, site_block = blockIdx.x / ngroups;
+  // blockIdx.x = site_block * ngroups + grp (ngroups is 1, 2 or 3: cheaper as a compare chain than as a division)
+  int site_block, grp;
+  if (ngroups == 1) { site_block = blockIdx.x; grp = 0; }
+  else if (ngroups == 2) { site_block = blockIdx.x >> 1; grp = blockIdx.x & 1; }
+  else { site_block = blockIdx.x / ngroups; grp = blockIdx.x - site_block * ngroups; }
   const int rhs = grp * NRB + threadIdx.y;
   const int stride = a0.g.Vh;
   const int local = site_block * 32 + threadIdx.x;
   const bool active = local < a0.nsites;
-  const int idx = active ? launch_site<R, true>(a0, local) : 0;
+  SiteCoord sc = {0, 0, 0, 0, 0};
+  if (active) sc = mrhs_site<R>(a0, dv, local);
+  const int idx = sc.idx;
 
   // ---- stage this CTA's operator data: the 8 links (and the clover block) of its 32 sites go to shared memory ONCE,
-  // with asynchronous copies issued by all NRB warps; every right-hand side then reads them from there.
+  // with asynchronous copies issued by all NRB warps; every right-hand side then reads them from there.  The slots
+  // form groups of NG planes with one base pointer each (8 link directions, then the clover planes NG at a time); a
+  // warp takes whole groups, so the choice of base pointer is a warp-uniform branch and the copies are a plain
+  // unrolled "base + k * stride".
   if (active) {
-    int nbr[4];
-    backward_neighbours(a0.g, idx, a0.parity, nbr);
+    constexpr int NGRP = SM::NS / SM::NG;
+    static_assert(NGRP * SM::NG == SM::NS, "slot groups");
     const size_t gplane = (size_t)SM::NG * stride, gmu = 2 * gplane;
-    const C* const Uf = a0.gauge + (size_t)a0.parity * gplane + idx;
-    const C* const Ub = a0.gauge + (size_t)(1 - a0.parity) * gplane;
 #pragma unroll
-    for (int i = 0; i < (SM::NS + NRB - 1) / NRB; ++i) {
-      const int e = threadIdx.y + i * NRB;
-      if (e < SM::NS) {
+    for (int j = 0; j < (NGRP + NRB - 1) / NRB; ++j) {
+      const int gi = threadIdx.y + j * NRB;
+      if (gi < NGRP) {
         const C* src;
-        if (e < SM::NL) {
-          const int d = e / SM::NG, k = e - d * SM::NG, mu = d >> 1;
-          src = (d & 1) ? Ub + mu * gmu + nbr[mu] + (size_t)k * stride : Uf + mu * gmu + (size_t)k * stride;
+        if (gi < 8) {
+          const int mu = gi >> 1;
+          if (gi & 1) src = a0.gauge + (size_t)(1 - a0.parity) * gplane + mu * gmu + backward_neighbour(a0.g, sc, a0.parity, mu);
+          else src = a0.gauge + (size_t)a0.parity * gplane + mu * gmu + idx;
         } else {
-          src = a0.clov + (size_t)(e - SM::NL) * stride + idx;
+          src = a0.clov + (size_t)(gi - 8) * gplane + idx;
         }
-        cp_async(sm + e * 32 + threadIdx.x, src);
+        C* const dst = sm + gi * (SM::NG * 32) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < SM::NG; ++k) cp_async(dst + k * 32, src + (size_t)k * stride);
       }
     }
   }
   cp_async_commit();
 
-  DslashArgs<R> a = a0;
   const bool have_rhs = rhs < a0.nrhs;
+  C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;     // this lane's column of the warp's spinor buffer
+  constexpr bool PF = MrhsPrefetch<R>::on;
+  // the first hop's neighbour spinor is requested BEFORE the wait on the staged links: both fetches fly together
+  if (PF && active && have_rhs)
+    prefetch_spinor<R>(sp, a0.in + rhs * a0.fstride + xfwd_neighbour(a0.g, sc, a0.parity), stride, a0.pol.keep);
+  else if (PF) cp_async_commit();
+
+  DslashArgs<R> a = a0;
   if (have_rhs) {
     a.scal = a0.scal + rhs * S_COUNT; a.status = a0.status + rhs * ST_COUNT;
     a.in = a0.in + rhs * a0.fstride;
@@ -746,23 +811,24 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
     if (a0.ghost_fwd) { a.ghost_fwd = a0.ghost_fwd + rhs * a0.gstride; a.ghost_bwd = a0.ghost_bwd + rhs * a0.gstride; }
     if (a0.ghost_zfwd) { a.ghost_zfwd = a0.ghost_zfwd + rhs * a0.gstride_z; a.ghost_zbwd = a0.ghost_zbwd + rhs * a0.gstride_z; }
   }
-  cp_async_wait_all();
+  if (PF) cp_async_wait_staged(); else cp_async_wait_all();      // the links + clover have landed (the spinor may still fly)
   __syncthreads();
   // a converged right-hand side (or an empty slot of the last group) leaves only now: its warp helped staging
-  if (!have_rhs) return;
-  if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
+  if (!have_rhs || (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0))) {
+    cp_async_wait_all();
+    return;
+  }
   double red[3] = {0.0, 0.0, 0.0};
 
   if (active) {
     const L2Policy pol = a.pol;
     C acc[12];
-    if (MrhsPrefetch<R>::on) {
-      C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;
-      constexpr bool XS = (EPI >= EPI_M) && MrhsPrefetch<R>::on;
-      dslash_site_pf<R, RECON12>(acc, a, ls, idx, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
+    if (PF) {
+      constexpr bool XS = (EPI >= EPI_M) && PF;
+      dslash_site_pf<R, RECON12, true>(acc, a, ls, sc, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
       site_epilogue<R, EPI, true, MODE, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
     } else {
-      dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x);
+      dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x, &sc);
       site_epilogue<R, EPI, true, MODE>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
     }
   }

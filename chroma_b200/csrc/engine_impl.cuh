@@ -747,14 +747,15 @@ class Engine : public EngineBase {
   int launch_mrhs_mode(const DslashArgs<R>& a, int site_blocks) {
     const int ngroups = (nb + NRB - 1) / NRB;
     const dim3 block(32, NRB);
+    const MrhsDiv dv = make_mrhs_div(a);
     if (recon == 12) {
       auto k = dslash_mrhs_kernel<R, E, true, NRB, MODE>;
       B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, true>::total(NRB)));
-      k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::total(NRB), stream>>>(a, ls, ngroups);
+      k<<<site_blocks * ngroups, block, MrhsSmem<R, E, true>::total(NRB), stream>>>(a, ls, ngroups, dv);
     } else {
       auto k = dslash_mrhs_kernel<R, E, false, NRB, MODE>;
       B200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MrhsSmem<R, E, false>::total(NRB)));
-      k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::total(NRB), stream>>>(a, ls, ngroups);
+      k<<<site_blocks * ngroups, block, MrhsSmem<R, E, false>::total(NRB), stream>>>(a, ls, ngroups, dv);
     }
     return launched("dslash_mrhs_kernel");
   }
