@@ -24,7 +24,7 @@ FLAGS = [
 ]
 # tuning knobs (defaults live in the sources): B200_DSLASH_BLOCK, B200_DSLASH_MINBLOCKS
 for _k in ("B200_DSLASH_BLOCK", "B200_DSLASH_MINBLOCKS", "B200_DSLASH_BLOCK_F", "B200_DSLASH_MINBLOCKS_F",
-           "B200_MRHS_NRB", "B200_MRHS_MINB", "B200_MRHS_NRB_F", "B200_MRHS_MINB_F", "B200_MRHS_PREFETCH", "B200_MRHS_PREFETCH_F", "B200_MRHS_L1", "B200_CLOV_MINB", "B200_RED_RELEASE", "B200_RED_PROBE"):
+           "B200_MRHS_NRB", "B200_MRHS_MINB", "B200_MRHS_NRB_F", "B200_MRHS_MINB_F", "B200_MRHS_PREFETCH", "B200_MRHS_PREFETCH_F", "B200_MRHS_L1", "B200_MRHS_DEPTH", "B200_MRHS_CLOVER_LATE", "B200_CLOV_MINB", "B200_RED_RELEASE", "B200_RED_PROBE"):
     if os.environ.get(_k):
         FLAGS += ["-D%s=%s" % (_k, os.environ[_k])]
 

@@ -98,8 +98,6 @@ __device__ __forceinline__ void cp_async_hint(float2* smem_dst, const float2* gs
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// all commit groups but the most recent one have landed (batched kernels: group 1 = staged links, group 2 = first spinor)
-__device__ __forceinline__ void cp_async_wait_staged() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 // read-modify-write streams (the CG residual) must not use the non-coherent path
 __device__ __forceinline__ double2 ld_stream_rw(const double2* p, uint64_t pol) {
   double2 v;
@@ -166,7 +164,7 @@ inline FastDiv make_fastdiv(int d) {
   f.mul = (unsigned)(((1ull << f.shift) + (unsigned long long)d - 1) / (unsigned long long)d);
   return f;
 }
-__device__ __forceinline__ int fast_div(int n, const FastDiv f) { return (int)(((unsigned long long)(unsigned)n * f.mul) >> f.shift); }
+__host__ __device__ __forceinline__ int fast_div(int n, const FastDiv f) { return (int)(((unsigned long long)(unsigned)n * f.mul) >> f.shift); }
 
 // Right-hand sides solved in lockstep by the batched (multi-RHS) kernels: the 12 spin-colour sources of a propagator
 // (quarkprop4_w.cc:70-117).  Every right-hand side owns one ScalarSlot block and one StatusSlot block.

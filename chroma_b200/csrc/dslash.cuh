@@ -173,7 +173,18 @@ __device__ __forceinline__ SiteCoord mrhs_site(const DslashArgs<R>& a, const Mrh
 #ifndef B200_MRHS_L1
 #define B200_MRHS_L1 0          // 1: batched kernels let the neighbour spinors allocate in L1 (x/y neighbours of a warp overlap)
 #endif
-template <typename R> struct MrhsPrefetch { static constexpr bool on = sizeof(R) == 4 ? (B200_MRHS_PREFETCH_F != 0) : (B200_MRHS_PREFETCH != 0); };
+#ifndef B200_MRHS_DEPTH
+#define B200_MRHS_DEPTH 1       // neighbour spinors in flight per warp (= 6 KB fp64 shared-memory buffers per warp): 1 or 2
+#endif
+#ifndef B200_MRHS_CLOVER_LATE
+#define B200_MRHS_CLOVER_LATE 0 // depth 2 only: 1 = the clover block is not staged up front but copied over the dead link slots mid-way
+#endif
+template <typename R> struct MrhsPrefetch {
+  static constexpr bool on = sizeof(R) == 4 ? (B200_MRHS_PREFETCH_F != 0) : (B200_MRHS_PREFETCH != 0);
+  static constexpr int depth = B200_MRHS_DEPTH;
+  static constexpr bool clover_late = on && depth == 2 && (B200_MRHS_CLOVER_LATE != 0);
+  static_assert(B200_MRHS_DEPTH == 1 || B200_MRHS_DEPTH == 2, "the first B200_MRHS_DEPTH fetches must be x hops");
+};
 
 // ---- spin projection while loading: (1 + sg*gamma_MU) psi, upper two components -----------------
 // SM: the spinor was prefetched into shared memory (plane stride = `stride` = 32), see dslash_site_pf.
@@ -397,13 +408,18 @@ __device__ __forceinline__ void prefetch_spinor(Cx<R>* sp, const Cx<R>* __restri
   for (int k = 0; k < 12; ++k) cp_async_hint<B200_MRHS_L1 != 0>(sp + k * 32, p + (size_t)k * stride, pol);
   cp_async_commit();
 }
+// cp.async bookkeeping of the pipelined hops: EVERY slot k = 0..8+depth-1 (8 hops, then the epilogue operand) commits
+// exactly one group -- an empty one if there is nothing to fetch (ghost hop, no operand, past the end) -- so that
+// "all but the depth-1 most recent groups have landed" always means "slot k has landed" at hop k.
+template <int PENDING> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 template <typename R, int MU, bool ADJ, bool RECON12>
 __device__ __forceinline__ void hop_pf(Cx<R> acc[12], Cx<R>* sp, const Cx<R>* link, R sg, R scale, const L2Policy& pol,
                                        const Cx<R>* __restrict__ next, int stride, uint64_t next_pol) {
   Cx<R> h0[3], h1[3], U[9], r0[3], r1[3];
-  cp_async_wait_all();
+  cp_async_wait_pending<MrhsPrefetch<R>::depth - 1>();
   load_project<R, MU, true, true>(h0, h1, sp, 32, sg, 0);
-  if (next) prefetch_spinor<R>(sp, next, stride, next_pol);      // the buffer is free again: start the next hop's fetch
+  // the buffer is free again: start the fetch of the hop `depth` slots ahead into it
+  if (next) prefetch_spinor<R>(sp, next, stride, next_pol); else cp_async_commit();
   load_link<R, RECON12, true>(U, link, 32, pol.stream);
   if (RECON12) {
 #pragma unroll
@@ -412,27 +428,42 @@ __device__ __forceinline__ void hop_pf(Cx<R> acc[12], Cx<R>* sp, const Cx<R>* li
   su3_mul<R, ADJ>(r0, r1, U, h0, h1);
   recons_acc<R, MU>(acc, r0, r1, sg);
 }
-// index of the +x neighbour of a target site: the first hop of dslash_site_pf (the batched kernel issues its fetch early)
+// index of the +x / -x neighbour of a target site: the first hops of dslash_site_pf (the batched kernel issues their
+// fetches early, next to the staging copies)
 __device__ __forceinline__ int xfwd_neighbour(const Geom& g, const SiteCoord& c, int parity) {
   const int r = (c.y + c.z + c.t + parity) & 1;
   return r ? (c.xh + 1 == g.Lxh ? c.idx - (g.Lxh - 1) : c.idx + 1) : c.idx;
 }
-// FIRST_ISSUED: the caller has already started the fetch of the +x neighbour into `sp` (and committed it)
-template <typename R, bool RECON12, bool FIRST_ISSUED = false>
+__device__ __forceinline__ int xbwd_neighbour(const Geom& g, const SiteCoord& c, int parity) {
+  const int r = (c.y + c.z + c.t + parity) & 1;
+  return r ? c.idx : (c.xh == 0 ? c.idx + (g.Lxh - 1) : c.idx - 1);
+}
+// the first `depth` fetches of a site (slots 0 and 1 are the x hops, never ghost hops); `sp` = the lane's column of
+// the warp's first buffer, consecutive buffers 12*32 elements apart
+template <typename R>
+__device__ __forceinline__ void dslash_site_pf_begin(const Cx<R>* __restrict__ in, const Geom& g, const SiteCoord& c, int parity, Cx<R>* sp, uint64_t keep) {
+  prefetch_spinor<R>(sp, in + xfwd_neighbour(g, c, parity), g.Vh, keep);
+  if (MrhsPrefetch<R>::depth > 1) prefetch_spinor<R>(sp + 12 * 32, in + xbwd_neighbour(g, c, parity), g.Vh, keep);
+}
+// The hops of one site with the neighbour spinors pipelined through the warp's `depth` shared-memory buffers; the
+// caller has run dslash_site_pf_begin.  Slot k lives in buffer k % depth; the fetch of slot k + depth goes into the
+// buffer hop k has just read.
+// H0, H1: only hops H0 <= k < H1 are done (the clover-late variant of the batched kernel splits a site's hops in two).
+template <typename R, bool RECON12, int H0 = 0, int H1 = 8>
 __device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R>& a, const LinkScale& ls, const SiteCoord& c, const L2Policy& pol,
                                                const Cx<R>* sml, Cx<R>* sp, const Cx<R>* after) {
   typedef Cx<R> C;
+  constexpr int D = MrhsPrefetch<R>::depth;
   const Geom& g = a.g;
   const int stride = g.Vh;
   const int idx = c.idx, xh = c.xh, y = c.y, z = c.z, t = c.t;
-  const int r = (y + z + t + a.parity) & 1;
   constexpr int NG = RECON12 ? 6 : 9;
   const C* __restrict__ in = a.in;
   const R s = (R)a.isign;
 #define B200_LF(mu) (sml + (2 * (mu)) * NG * 32)
 #define B200_LB(mu) (sml + (2 * (mu) + 1) * NG * 32)
-  const int xf = xfwd_neighbour(g, c, a.parity);
-  const int xb = r ? idx : (xh == 0 ? idx + (g.Lxh - 1) : idx - 1);
+#define B200_BUF(k) (sp + ((k) % D) * (12 * 32))
+  const int xb = xbwd_neighbour(g, c, a.parity);
   const int yf = (y + 1 == g.Ly) ? idx - (g.Ly - 1) * g.Lxh : idx + g.Lxh;
   const int yb = (y == 0) ? idx + (g.Ly - 1) * g.Lxh : idx - g.Lxh;
   const int sz = g.Ly * g.Lxh, st = g.S3h;
@@ -448,34 +479,43 @@ __device__ __forceinline__ void dslash_site_pf(Cx<R> acc[12], const DslashArgs<R
     if (ls.t_is_last && tl) scf *= (R)ls.bc_t;
     if (ls.t_is_last && t0 && !g.tsplit) scb *= (R)ls.bc_t;
   }
+  // what slot k fetches (nullptr: nothing -- ghost hop / no epilogue operand / past the end) and with which L2 policy
+  const C* const nb[10] = {nullptr, in + xb, in + yf, in + yb, gzf ? nullptr : in + zf, gzb ? nullptr : in + zb,
+                           gtf ? nullptr : in + tf, gtb ? nullptr : in + tb, after, nullptr};
+#define B200_NEXT(k) nb[(k) + D], stride, ((k) + D == 8 ? pol.stream : pol.keep)
+#define B200_HOP(k) if (H0 <= (k) && (k) < H1)
+  if (H0 == 0) {
 #pragma unroll
-  for (int k = 0; k < 12; ++k) acc[k] = mk<R>(0, 0);
+    for (int k = 0; k < 12; ++k) acc[k] = mk<R>(0, 0);
+  }
 
-  if (!FIRST_ISSUED) prefetch_spinor<R>(sp, in + xf, stride, pol.keep);
-  hop_pf<R, 0, false, RECON12>(acc, sp, B200_LF(0), -s, (R)ls.aniso[0], pol, in + xb, stride, pol.keep);
-  hop_pf<R, 0, true, RECON12>(acc, sp, B200_LB(0), s, (R)ls.aniso[0], pol, in + yf, stride, pol.keep);
-  hop_pf<R, 1, false, RECON12>(acc, sp, B200_LF(1), -s, (R)ls.aniso[1], pol, in + yb, stride, pol.keep);
-  hop_pf<R, 1, true, RECON12>(acc, sp, B200_LB(1), s, (R)ls.aniso[1], pol, gzf ? nullptr : in + zf, stride, pol.keep);
-  // a hop across a rank boundary reads its (already projected) half spinor from the ghost face: nothing was prefetched
-  // for it, so the buffer is free and the fetch for the hop after it starts first
-  if (gzf) {
-    if (!gzb) prefetch_spinor<R>(sp, in + zb, stride, pol.keep);
+  B200_HOP(0) hop_pf<R, 0, false, RECON12>(acc, B200_BUF(0), B200_LF(0), -s, (R)ls.aniso[0], pol, B200_NEXT(0));
+  B200_HOP(1) hop_pf<R, 0, true, RECON12>(acc, B200_BUF(1), B200_LB(0), s, (R)ls.aniso[0], pol, B200_NEXT(1));
+  B200_HOP(2) hop_pf<R, 1, false, RECON12>(acc, B200_BUF(2), B200_LF(1), -s, (R)ls.aniso[1], pol, B200_NEXT(2));
+  B200_HOP(3) hop_pf<R, 1, true, RECON12>(acc, B200_BUF(3), B200_LB(1), s, (R)ls.aniso[1], pol, B200_NEXT(3));
+  // a hop across a rank boundary reads its (already projected) half spinor from the ghost face: nothing was fetched
+  // for its slot, so its buffer is free and the fetch `depth` slots ahead starts first
+  B200_HOP(4) if (gzf) {
+    if (nb[4 + D]) prefetch_spinor<R>(B200_BUF(4), B200_NEXT(4)); else cp_async_commit();
     ghost_hop_fwd<R, 2, RECON12, true>(acc, a.ghost_zfwd + fz, g.SZh, B200_LF(2), 32, -s, (R)ls.aniso[2], pol);
-  } else hop_pf<R, 2, false, RECON12>(acc, sp, B200_LF(2), -s, (R)ls.aniso[2], pol, gzb ? nullptr : in + zb, stride, pol.keep);
-  if (gzb) {
-    if (!gtf) prefetch_spinor<R>(sp, in + tf, stride, pol.keep);
+  } else hop_pf<R, 2, false, RECON12>(acc, B200_BUF(4), B200_LF(2), -s, (R)ls.aniso[2], pol, B200_NEXT(4));
+  B200_HOP(5) if (gzb) {
+    if (nb[5 + D]) prefetch_spinor<R>(B200_BUF(5), B200_NEXT(5)); else cp_async_commit();
     ghost_hop_bwd<R, 2>(acc, a.ghost_zbwd + fz, g.SZh, s, pol);
-  } else hop_pf<R, 2, true, RECON12>(acc, sp, B200_LB(2), s, (R)ls.aniso[2], pol, gtf ? nullptr : in + tf, stride, pol.keep);
-  if (gtf) {
-    if (!gtb) prefetch_spinor<R>(sp, in + tb, stride, pol.keep);
+  } else hop_pf<R, 2, true, RECON12>(acc, B200_BUF(5), B200_LB(2), s, (R)ls.aniso[2], pol, B200_NEXT(5));
+  B200_HOP(6) if (gtf) {
+    if (nb[6 + D]) prefetch_spinor<R>(B200_BUF(6), B200_NEXT(6)); else cp_async_commit();
     ghost_hop_fwd<R, 3, RECON12, true>(acc, a.ghost_fwd + (idx - (g.Lt - 1) * st), st, B200_LF(3), 32, -s, scf, pol);
-  } else hop_pf<R, 3, false, RECON12>(acc, sp, B200_LF(3), -s, scf, pol, gtb ? nullptr : in + tb, stride, pol.keep);
-  if (gtb) {
-    if (after) prefetch_spinor<R>(sp, after, stride, pol.stream);
+  } else hop_pf<R, 3, false, RECON12>(acc, B200_BUF(6), B200_LF(3), -s, scf, pol, B200_NEXT(6));
+  B200_HOP(7) if (gtb) {
+    if (nb[7 + D]) prefetch_spinor<R>(B200_BUF(7), B200_NEXT(7)); else cp_async_commit();
     ghost_hop_bwd<R, 3>(acc, a.ghost_bwd + idx, st, s, pol);
-  } else hop_pf<R, 3, true, RECON12>(acc, sp, B200_LB(3), s, scb, pol, after, stride, pol.stream);
+  } else hop_pf<R, 3, true, RECON12>(acc, B200_BUF(7), B200_LB(3), s, scb, pol, B200_NEXT(7));
 #undef B200_LF
 #undef B200_LB
+#undef B200_BUF
+#undef B200_NEXT
+#undef B200_HOP
 }
 
 // Index (on the source checkerboard) of the backward neighbour in direction mu of a target site -- where the backward
@@ -740,9 +780,15 @@ template <typename R, int EPI, bool RECON12> struct MrhsSmem {
   static constexpr int NG = RECON12 ? 6 : 9;
   static constexpr int NL = 8 * NG;                                 // link slots
   static constexpr int NS = NL + (EPI == EPI_DSLASH ? 0 : 36);      // + clover slots
-  static constexpr size_t bytes = (size_t)NS * 32 * sizeof(Cx<R>);
-  // + one 12-plane spinor buffer per right-hand side (warp) of the CTA
-  static constexpr size_t total(int nrb) { return bytes + (MrhsPrefetch<R>::on ? (size_t)nrb * 12 * 32 * sizeof(Cx<R>) : 0); }
+  // clover-late variant: only the links are staged up front; the 36 clover planes later overwrite link slots [0, 36),
+  // which are dead once every warp is past hop HB = 36 / NG (the x and y links; with 12-number links the z links too)
+  static constexpr bool CL = MrhsPrefetch<R>::clover_late && EPI != EPI_DSLASH;
+  static constexpr int HB = 36 / NG;
+  static constexpr int NSTAGE = CL ? NL : NS;                      // slots staged before the first hop
+  static constexpr int CLOV0 = CL ? 0 : NL;                        // first clover slot
+  static constexpr size_t bytes = (size_t)NSTAGE * 32 * sizeof(Cx<R>);
+  // + `depth` 12-plane spinor buffers per right-hand side (warp) of the CTA
+  static constexpr size_t total(int nrb) { return bytes + (MrhsPrefetch<R>::on ? (size_t)nrb * MrhsPrefetch<R>::depth * 12 * 32 * sizeof(Cx<R>) : 0); }
 };
 template <typename R, int EPI, bool RECON12, int NRB, int MODE = MODE_ASYM>
 __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F : B200_MRHS_MINB)) dslash_mrhs_kernel(const DslashArgs<R> a0, const LinkScale ls, int ngroups, const MrhsDiv dv) {
@@ -768,10 +814,10 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   // form groups of NG planes with one base pointer each (8 link directions, then the clover planes NG at a time); a
   // warp takes whole groups, so the choice of base pointer is a warp-uniform branch and the copies are a plain
   // unrolled "base + k * stride".
+  const size_t gplane = (size_t)SM::NG * stride, gmu = 2 * gplane;
   if (active) {
-    constexpr int NGRP = SM::NS / SM::NG;
-    static_assert(NGRP * SM::NG == SM::NS, "slot groups");
-    const size_t gplane = (size_t)SM::NG * stride, gmu = 2 * gplane;
+    constexpr int NGRP = SM::NSTAGE / SM::NG;
+    static_assert(NGRP * SM::NG == SM::NSTAGE, "slot groups");
 #pragma unroll
     for (int j = 0; j < (NGRP + NRB - 1) / NRB; ++j) {
       const int gi = threadIdx.y + j * NRB;
@@ -793,12 +839,12 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   cp_async_commit();
 
   const bool have_rhs = rhs < a0.nrhs;
-  C* const sp = sm + SM::NS * 32 + threadIdx.y * (12 * 32) + threadIdx.x;     // this lane's column of the warp's spinor buffer
   constexpr bool PF = MrhsPrefetch<R>::on;
-  // the first hop's neighbour spinor is requested BEFORE the wait on the staged links: both fetches fly together
-  if (PF && active && have_rhs)
-    prefetch_spinor<R>(sp, a0.in + rhs * a0.fstride + xfwd_neighbour(a0.g, sc, a0.parity), stride, a0.pol.keep);
-  else if (PF) cp_async_commit();
+  constexpr int PD = MrhsPrefetch<R>::depth;
+  C* const sp = sm + SM::NSTAGE * 32 + threadIdx.y * (PD * 12 * 32) + threadIdx.x;     // this lane's column of the warp's spinor buffers
+  // the first hops' neighbour spinors are requested BEFORE the wait on the staged links: the fetches fly together
+  if (PF && active && have_rhs) dslash_site_pf_begin<R>(a0.in + rhs * a0.fstride, a0.g, sc, a0.parity, sp, a0.pol.keep);
+  else if (PF) { for (int k = 0; k < PD; ++k) cp_async_commit(); }
 
   DslashArgs<R> a = a0;
   if (have_rhs) {
@@ -811,25 +857,54 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
     if (a0.ghost_fwd) { a.ghost_fwd = a0.ghost_fwd + rhs * a0.gstride; a.ghost_bwd = a0.ghost_bwd + rhs * a0.gstride; }
     if (a0.ghost_zfwd) { a.ghost_zfwd = a0.ghost_zfwd + rhs * a0.gstride_z; a.ghost_zbwd = a0.ghost_zbwd + rhs * a0.gstride_z; }
   }
-  if (PF) cp_async_wait_staged(); else cp_async_wait_all();      // the links + clover have landed (the spinor may still fly)
+  // a converged right-hand side (or an empty slot of the last group) only helps with the staging
+  const bool work = have_rhs && !(a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0));
+  if (PF) cp_async_wait_pending<PD>(); else cp_async_wait_all();      // the links + clover have landed (the spinors may still fly)
   __syncthreads();
-  // a converged right-hand side (or an empty slot of the last group) leaves only now: its warp helped staging
-  if (!have_rhs || (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0))) {
-    cp_async_wait_all();
-    return;
-  }
   double red[3] = {0.0, 0.0, 0.0};
+  const L2Policy pol = a.pol;
+  constexpr bool XS = (EPI >= EPI_M) && PF;
 
-  if (active) {
-    const L2Policy pol = a.pol;
+  if (SM::CL) {
+    // clover-late: hops 0 .. HB-1, barrier (the links of those hops are dead in every warp), every warp copies its share
+    // of the clover block over them -- the copies join the commit group of the next hop's fetch and land while the
+    // remaining hops run -- barrier, epilogue.  Warps without work walk through the same two barriers.
     C acc[12];
-    if (PF) {
-      constexpr bool XS = (EPI >= EPI_M) && PF;
-      dslash_site_pf<R, RECON12, true>(acc, a, ls, sc, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
-      site_epilogue<R, EPI, true, MODE, XS>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x, sp);
-    } else {
-      dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x, &sc);
-      site_epilogue<R, EPI, true, MODE>(acc, a, idx, stride, pol, red, sm + SM::NL * 32 + threadIdx.x);
+    if (work && active) dslash_site_pf<R, RECON12, 0, SM::HB>(acc, a, ls, sc, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
+    __syncthreads();
+    if (active) {
+      constexpr int NCG = 36 / SM::NG;
+#pragma unroll
+      for (int j = 0; j < (NCG + NRB - 1) / NRB; ++j) {
+        const int gi = threadIdx.y + j * NRB;
+        if (gi < NCG) {
+          const C* const src = a0.clov + (size_t)gi * gplane + idx;
+          C* const dst = sm + gi * (SM::NG * 32) + threadIdx.x;
+#pragma unroll
+          for (int k = 0; k < SM::NG; ++k) cp_async(dst + k * 32, src + (size_t)k * stride);
+        }
+      }
+    }
+    if (work && active) dslash_site_pf<R, RECON12, SM::HB, 8>(acc, a, ls, sc, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
+    else cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    if (!work) return;
+    if (active) site_epilogue<R, EPI, true, MODE, XS>(acc, a, idx, stride, pol, red, sm + SM::CLOV0 * 32 + threadIdx.x, sp + (8 % PD) * (12 * 32));
+  } else {
+    if (!work) {
+      cp_async_wait_all();
+      return;
+    }
+    if (active) {
+      C acc[12];
+      if (PF) {
+        dslash_site_pf<R, RECON12>(acc, a, ls, sc, pol, sm + threadIdx.x, sp, XS ? a.x + idx : nullptr);
+        site_epilogue<R, EPI, true, MODE, XS>(acc, a, idx, stride, pol, red, sm + SM::CLOV0 * 32 + threadIdx.x, sp + (8 % PD) * (12 * 32));
+      } else {
+        dslash_site<R, RECON12, true>(acc, a, ls, idx, pol, sm + threadIdx.x, &sc);
+        site_epilogue<R, EPI, true, MODE>(acc, a, idx, stride, pol, red, sm + SM::CLOV0 * 32 + threadIdx.x);
+      }
     }
   }
 
