@@ -123,7 +123,8 @@ __device__ __forceinline__ int launch_site_from(const DslashArgs<R>& a, int loca
 // Checkerboard coordinates of a target site next to its cb2 index: the batched kernels decode them ONCE per thread
 // (mrhs_site) and hand them to the staging code and to dslash_site*, instead of re-deriving them from idx.
 struct SiteCoord { int idx, xh, y, z, t; };
-// Launch-invariant divisors of the batched kernels' site decode (FastDiv, common.cuh), filled on the host per launch.
+// Launch-invariant divisors of the kernels' site decode (FastDiv, common.cuh), filled on the host per launch and passed
+// as a kernel argument (single-RHS and batched kernels alike).
 struct MrhsDiv { FastDiv lxh, ly, lz, zc, per, row, nz0; };
 template <typename R>
 inline MrhsDiv make_mrhs_div(const DslashArgs<R>& a) {
@@ -132,6 +133,15 @@ inline MrhsDiv make_mrhs_div(const DslashArgs<R>& a) {
   d.zc = make_fastdiv(a.zc_sites); d.per = make_fastdiv(a.zc_sites * a.box[0].nt);
   d.row = make_fastdiv(a.g.Lxh * a.g.Ly); d.nz0 = make_fastdiv(a.box[0].nz);
   return d;
+}
+// coordinates of the site with cb2 index idx
+__device__ __forceinline__ SiteCoord site_coord(const Geom& g, const MrhsDiv& dv, int idx) {
+  SiteCoord s;
+  s.idx = idx;
+  const int q = fast_div(idx, dv.lxh); s.xh = idx - q * g.Lxh;
+  const int q2 = fast_div(q, dv.ly); s.y = q - q2 * g.Ly;
+  s.t = fast_div(q2, dv.lz); s.z = q2 - s.t * g.Lz;
+  return s;
 }
 // The `local`-th target site of a batched launch, with its coordinates: same traversal order as launch_site<R, true>
 // (box 0 swept in z-chunks), without a single hardware integer division on the box-0 path.  (Round 2: the generic
@@ -154,12 +164,7 @@ __device__ __forceinline__ SiteCoord mrhs_site(const DslashArgs<R>& a, const Mrh
     s.t = b.t0 + tt; s.z = b.z0 + zz;
     s.y = fast_div(w, dv.lxh); s.xh = w - s.y * g.Lxh;
     s.idx = (s.t * g.Lz + s.z) * row + w;
-  } else {                                                            // the other boxes of a boundary launch
-    s.idx = launch_site<R, false>(a, local);
-    int q = fast_div(s.idx, dv.lxh); s.xh = s.idx - q * g.Lxh;
-    int q2 = fast_div(q, dv.ly); s.y = q - q2 * g.Ly;
-    s.t = fast_div(q2, dv.lz); s.z = q2 - s.t * g.Lz;
-  }
+  } else s = site_coord(g, dv, launch_site<R, false>(a, local));       // the other boxes of a boundary launch
   return s;
 }
 
@@ -711,7 +716,7 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
 }
 
 template <typename R, int EPI, bool RECON12, int BLOCK, int MODE = MODE_ASYM>
-__global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS)) dslash_kernel(const DslashArgs<R> a, const LinkScale ls) {
+__global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS)) dslash_kernel(const DslashArgs<R> a, const LinkScale ls, const MrhsDiv dv) {
   typedef Cx<R> C;
   if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
   if (a.run_if && a.status[a.run_if] == 0) return;
@@ -723,10 +728,11 @@ __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS
   if (active) {
     // ZC: on lattices whose three live time slices of neighbour spinors outgrow the L2 budget (64^3: 75 MB) the launch
     // sweeps t inside z-chunks, like the batched kernels (zc_sites = 0 keeps the natural order)
-    const int idx = launch_site<R, true>(a, local);
+    const SiteCoord sc = mrhs_site<R>(a, dv, local);      // division-free decode, same order as launch_site<R, true>
+    const int idx = sc.idx;
     const L2Policy pol = a.pol;
     C acc[12];
-    dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
+    dslash_site<R, RECON12, false>(acc, a, ls, idx, pol, nullptr, &sc);
     site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
   }
 

@@ -706,8 +706,9 @@ class Engine : public EngineBase {
   }
   template <int EPI, int MODE>
   void launch_halo_mode(const DslashArgs<R>& a, const HaloFuse<R>& h, int blocks) {
-    if (recon == 12) dslash_halo_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, h);
-    else dslash_halo_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, h);
+    const MrhsDiv dv = make_mrhs_div(a);
+    if (recon == 12) dslash_halo_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, h, dv);
+    else dslash_halo_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, h, dv);
   }
   template <int EPI>
   int launch_one(const DslashArgs<R>& a, int blocks) {
@@ -720,8 +721,9 @@ class Engine : public EngineBase {
   }
   template <int EPI, int MODE>
   void launch_mode(const DslashArgs<R>& a, int blocks) {
-    if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
-    else dslash_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls);
+    const MrhsDiv dv = make_mrhs_div(a);
+    if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, dv);
+    else dslash_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, dv);
   }
   // z-chunk (in sites per time slice) of the batched traversal order of a box nz planes thick: the largest divisor of
   // nz for which three time slices of the batch's source spinors fit in ~1/3 of the L2 (B200: 126 MB); 0 = natural order

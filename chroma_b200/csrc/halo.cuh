@@ -173,7 +173,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 template <typename R, int EPI, bool RECON12, int BLOCK, int MODE = MODE_ASYM>
 __global__ void __launch_bounds__(BLOCK, (sizeof(R) == 4 ? B200_DSLASH_MINBLOCKS_F : B200_DSLASH_MINBLOCKS))
-dslash_halo_kernel(const DslashArgs<R> a, const LinkScale ls, const HaloFuse<R> h) {
+dslash_halo_kernel(const DslashArgs<R> a, const LinkScale ls, const HaloFuse<R> h, const MrhsDiv dv) {
   typedef Cx<R> C;
   if (a.check_stop && (a.status[ST_STOP] != 0 || a.status[ST_BREAKDOWN] != 0)) return;
   if (a.run_if && a.status[a.run_if] == 0) return;
@@ -200,10 +200,11 @@ dslash_halo_kernel(const DslashArgs<R> a, const LinkScale ls, const HaloFuse<R> 
   const bool active = boundary ? local < a.nsites - h.n_int_sites : local < h.n_int_sites;
   double red[3] = {0.0, 0.0, 0.0};
   if (active) {
-    const int idx = boundary ? launch_site_from<R>(a, local, 1) : box_site(a.g, a.box[0], local);
+    const SiteCoord sc = boundary ? site_coord(a.g, dv, launch_site_from<R>(a, local, 1)) : mrhs_site<R>(a, dv, local);
+    const int idx = sc.idx;
     const L2Policy pol = a.pol;
     C acc[12];
-    dslash_site<R, RECON12, false>(acc, a, ls, idx, pol);
+    dslash_site<R, RECON12, false>(acc, a, ls, idx, pol, nullptr, &sc);
     site_epilogue<R, EPI, false, MODE>(acc, a, idx, stride, pol, red);
   }
   if (EPI == EPI_M_NORM) grid_reduce<1, BLOCK>(red, a.red, FinCgD{a.scal}, b);

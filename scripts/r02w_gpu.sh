@@ -1,0 +1,8 @@
+#!/bin/bash
+# round-2 GPU job W (1 GPU): validation of the build with the division-free site decode in the single-RHS kernels -- pytest -m gpu, smoke, bench
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r02w_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02w_pytest.log
+tail -4 gpurun_out/r02w_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02w_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r02w_smoke.log
+( time python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02w_bench_1gpu.json 2> gpurun_out/r02w_bench_1gpu.err ) 2>&1 | grep real; echo "bench rc=$?"
+python bench.py --nrhs 12 --solver BICGSTAB --no-cpu --no-fp32 > gpurun_out/r02w_bench_bicgstab_12rhs.json 2> gpurun_out/r02w_bench_bicgstab_12rhs.err; echo "bench bicgstab 12rhs rc=$?"
