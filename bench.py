@@ -297,19 +297,23 @@ def dram_traffic(kernel_name):
     return None
 
 
-def kernel_table(solver_name, kms, R, G, Vh, peak):
+def kernel_table(solver_name, kms, R, G, Vh, peak, nrhs=1):
     """Per-launch table of one solver iteration: algorithmic bytes per odd site (every array element once
-    per pass, neighbour re-reads served by L2) and the measured duration of every launch, in launch order."""
+    per pass, neighbour re-reads served by L2) and the measured duration of every launch, in launch order.  nrhs > 1: the
+    batched kernels -- spinor streams once per right-hand side, links and clover once per batch; bytes per site for the batch."""
+    op_a = op_m = (72 + 8 * G) * R          # operator data of one site: 8 links of G reals + one clover block of 72 reals
     ainv, m, mcg, upd = (120 + 8 * G) * R, (144 + 8 * G) * R, (168 + 8 * G) * R, 120 * R
+    if nrhs > 1:
+        ainv, m, mcg, upd = (ainv - op_a) * nrhs + op_a, (m - op_m) * nrhs + op_m, (mcg - op_m) * nrhs + op_m, upd * nrhs
     if solver_name == "CG":
         rows = [("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo p", ainv), ("dslash_kernel<EPI_M_NORM> mp = A_oo p - 1/4 D_oe t, |mp|^2", m),
                 ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo^dag mp", ainv), ("dslash_kernel<EPI_M_CG> r -= a(A_oo mp - 1/4 D_oe^dag t), |r|^2", mcg),
                 ("cg_update_kernel psi += a p, p = r + b p", upd)]
     else:
-        rows = [("bicg_p_kernel p = r + beta(p - omega v)", 96 * R), ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo p", ainv),
-                ("dslash_kernel<EPI_M_DOTR0> v = M p, <r0|v>", mcg), ("bicg_s_kernel r -= alpha v", 72 * R),
+        rows = [("bicg_p_kernel p = r + beta(p - omega v)", 96 * R * nrhs), ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo p", ainv),
+                ("dslash_kernel<EPI_M_DOTR0> v = M p, <r0|v>", mcg), ("bicg_s_kernel r -= alpha v", 72 * R * nrhs),
                 ("dslash_kernel<EPI_AINV> t = A_ee^-1 D_eo r", ainv), ("dslash_kernel<EPI_M_DOTX> t = M r, <t|r>, |t|^2", m),
-                ("bicg_update_kernel psi += omega r + alpha p, r -= omega t, |r|^2, <r0|r>", 192 * R)]
+                ("bicg_update_kernel psi += omega r + alpha p, r -= omega t, |r|^2, <r0|r>", 192 * R * nrhs)]
     if len(kms) != len(rows):       # symmetric preconditioning adds a clover pass; not the default bench path
         rows = [("launch %d" % i, 0) for i in range(len(kms))]
     total = sum(kms)
@@ -516,6 +520,15 @@ def run_b200(args):
             mrhs = {"nrhs": nr, "ms_per_iteration": ms_b, "ms_per_iteration_per_rhs": ms_b / nr,
                     "gflops": flop_iter * Vh_global * nr / (ms_b * 1e-3) * 1e-9,
                     "speedup_per_rhs_vs_single": ms_step / (ms_b / nr)}
+            try:        # the batched iteration kernel by kernel (same events-behind-every-launch timing as the single-RHS table)
+                kms_b = ctx.dev_time_solver_kernels(solver, max(3, args.steps // 2))
+                pk, _ = peaks()
+                mrhs["kernels_in_loop"] = [{k: v for k, v in row.items() if k != "what"} for row in
+                                           kernel_table(args.solver, kms_b, R, G, Vh, pk, nr)]
+                for row in mrhs["kernels_in_loop"]:
+                    row["kernel"] = row["kernel"].replace("dslash_kernel", "dslash_mrhs_kernel")
+            except Exception as e:  # noqa
+                mrhs["kernels_in_loop"] = {"error": str(e)}
             if world == 1:
                 ctx.dev_time_matpc(out_b, chi_b, +1, 2)
                 barrier()

@@ -757,6 +757,19 @@ __global__ void __launch_bounds__(FINISH_BLOCK) dslash_finish_kernel(const Dslas
   if (EPI == EPI_M_DOTX) reduce_finish<3, FINISH_BLOCK>(a.red, FinBiOmega{a.scal, a.status});
 }
 
+// ... and of a batched step: one CTA per right-hand side (blockIdx.x), each with its own partials, scalars and status.
+template <typename R, int EPI>
+__global__ void __launch_bounds__(FINISH_BLOCK) dslash_mrhs_finish_kernel(const DslashArgs<R> a) {
+  const int rhs = blockIdx.x;
+  double* const scal = a.scal + rhs * S_COUNT;
+  int* const status = a.status + rhs * ST_COUNT;
+  if (a.check_stop && (status[ST_STOP] != 0 || status[ST_BREAKDOWN] != 0)) return;
+  if (EPI == EPI_M_NORM) reduce_finish<1, FINISH_BLOCK>(a.red.template for_rhs<1>(rhs), FinCgD{scal});
+  if (EPI == EPI_M_CG) reduce_finish<1, FINISH_BLOCK>(a.red.template for_rhs<1>(rhs), FinCgCp{scal, status, a.iter, a.check_stop});
+  if (EPI == EPI_M_DOTR0) reduce_finish<2, FINISH_BLOCK>(a.red.template for_rhs<2>(rhs), FinBiAlpha{scal, status});
+  if (EPI == EPI_M_DOTX) reduce_finish<3, FINISH_BLOCK>(a.red.template for_rhs<3>(rhs), FinBiOmega{scal, status});
+}
+
 // ---- multi-RHS variant ------------------------------------------------------------------------------------------
 // CTA = 32 consecutive target sites x NRB right-hand sides (threadIdx.y = right-hand side, one warp each).  All warps
 // of a CTA need the same 8 links and the same clover block per site: the CTA stages them in shared memory once
@@ -915,10 +928,16 @@ __global__ void __launch_bounds__(32 * NRB, (sizeof(R) == 4 ? B200_MRHS_MINB_F :
   }
 
   const int sb = site_block;   // block_offset of a split step is applied inside warp_grid_reduce
-  if (EPI == EPI_M_NORM) warp_grid_reduce<1>(red, a.red.template for_rhs<1>(rhs), sb, FinCgD{a.scal});
-  if (EPI == EPI_M_CG) warp_grid_reduce<1>(red, a.red.template for_rhs<1>(rhs), sb, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
-  if (EPI == EPI_M_DOTR0) warp_grid_reduce<2>(red, a.red.template for_rhs<2>(rhs), sb, FinBiAlpha{a.scal, a.status});
-  if (EPI == EPI_M_DOTX) warp_grid_reduce<3>(red, a.red.template for_rhs<3>(rhs), sb, FinBiOmega{a.scal, a.status});
+  if (a0.red.split) {             // big grids: partials only, dslash_mrhs_finish_kernel behind the step sums them
+    if (EPI == EPI_M_NORM || EPI == EPI_M_CG) warp_partial_store<1>(red, a0.red, rhs, sb);
+    if (EPI == EPI_M_DOTR0) warp_partial_store<2>(red, a0.red, rhs, sb);
+    if (EPI == EPI_M_DOTX) warp_partial_store<3>(red, a0.red, rhs, sb);
+    return;
+  }
+  if (EPI == EPI_M_NORM) warp_grid_reduce<1>(red, a0.red.template for_rhs<1>(rhs), sb, FinCgD{a.scal});
+  if (EPI == EPI_M_CG) warp_grid_reduce<1>(red, a0.red.template for_rhs<1>(rhs), sb, FinCgCp{a.scal, a.status, a.iter, a.check_stop});
+  if (EPI == EPI_M_DOTR0) warp_grid_reduce<2>(red, a0.red.template for_rhs<2>(rhs), sb, FinBiAlpha{a.scal, a.status});
+  if (EPI == EPI_M_DOTX) warp_grid_reduce<3>(red, a0.red.template for_rhs<3>(rhs), sb, FinBiOmega{a.scal, a.status});
 }
 
 }  // namespace b200

@@ -665,22 +665,24 @@ class Engine : public EngineBase {
       // batched right-hand sides: pack + send the faces over NVLink, run the interior while they fly, then the boundary
       rc = halo.start(a.in, gauge, recon, ls, a.isign, a.parity, a.check_stop ? status : nullptr, a.run_if, nb, a.fstride, launches); if (rc) return rc;
       a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
+      const int split_b = split_reduce<EPI>(total);
       if (n_int > 0) {
-        a.box[0] = inner; a.nbox = 1; a.nsites = n_int; a.red = make_red(0, total);
+        a.box[0] = inner; a.nbox = 1; a.nsites = n_int; a.red = make_red(0, total); a.red.split = split_b;
         a.zc_sites = zchunk_sites(inner.nz);
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
       rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, nb, launches); if (rc) return rc;
       for (int k = 0; k < nf; ++k) a.box[k] = faces[k];
-      a.nbox = nf; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total);
-      return launch_one<EPI>(a, nb_face);
+      a.nbox = nf; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total); a.red.split = split_b;
+      rc = launch_one<EPI>(a, nb_face); if (rc) return rc;
+      return launch_finish<EPI>(a);
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr; a.ghost_zfwd = nullptr; a.ghost_zbwd = nullptr;
     a.box[0] = SiteBox{0, g.Lt, 0, g.Lz}; a.nbox = 1; a.nsites = g.Vh;
     a.zc_sites = zchunk_sites(g.Lz);
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
-    if (nb == 1) a.red.split = split_reduce<EPI>(blocks);
+    a.red.split = split_reduce<EPI>(blocks);
     { int rc1 = launch_one<EPI>(a, blocks); if (rc1) return rc1; }
     return launch_finish<EPI>(a);
   }
@@ -693,6 +695,11 @@ class Engine : public EngineBase {
   template <int EPI>
   int launch_finish(const DslashArgs<R>& a) {
     if (!a.red.split) return B200_OK;
+    if (nb > 1) {
+      constexpr int E = (EPI == EPI_M_CGREL ? EPI_M_CG : EPI);     // (the reliable-update epilogue has no batched variant)
+      dslash_mrhs_finish_kernel<R, E><<<nb, FINISH_BLOCK, 0, stream>>>(a);
+      return launched("dslash_mrhs_finish_kernel");
+    }
     dslash_finish_kernel<R, EPI><<<1, FINISH_BLOCK, 0, stream>>>(a);
     return launched("dslash_finish_kernel");
   }

@@ -278,6 +278,23 @@ __device__ __forceinline__ void reduce_finish(const ReduceBuf& rb, Fin fin) {
   }
 }
 
+// Split step of a batched kernel: the warp's partial sums go to slot (rhs, site block) and nothing else happens
+// (dslash_mrhs_finish_kernel sums them).  `rb` is the kernel argument itself, NOT a for_rhs() view: building that view
+// copies the mailbox pointer array, which peer_allreduce indexes by lane, so the copy lives in local memory -- 36 STL.64
+// per thread on the way to a reduction only one warp in 166 000 finishes (ncu, round 2: 288 B of local stores per thread =
+// 3 - 4 GB of extra DRAM writes per batched reducing kernel at 48^3x48).
+template <int N>
+__device__ __forceinline__ void warp_partial_store(const double v[N], const ReduceBuf& rb, int rhs, int site_block) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) rb.partial[((size_t)rhs * N + k) * rb.total_blocks + rb.block_offset + site_block] = x;
+  }
+}
+
 // Warp-synchronous variant for the multi-RHS Dslash kernels, where one WARP (32 consecutive sites of one right-hand
 // side) is the reduction unit: shuffle tree -> one partial per (rhs, site block) -> two-level tickets as above (the
 // warp that draws the last ticket of its group sums the group, the last group finisher sums the group sums, lane-strided
@@ -302,6 +319,12 @@ __device__ __forceinline__ void warp_grid_reduce(double v[N], const ReduceBuf& r
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) rb.partial[(size_t)k * rb.total_blocks + blk] = s[k];
+  }
+  // split step (uniform over the grid): no ticket -- the release atomic behind the stores of the epilogue holds every
+  // warp for an L2 round trip (batched CG, 48^3x96 x 12: EPI_M_NORM 16.9 ms against 12.5 ms for the plain EPI_M) -- a
+  // small kernel behind the step sums the partials of every right-hand side (reduce_finish)
+  if (rb.split) return;
+  if (lane == 0) {
     if (flat) role = (draw_ticket(rb.ticket) == (unsigned int)rb.total_blocks - 1u) ? 2 : 0;
     else role = (draw_ticket(rb.gticket + grp) == (unsigned int)gsize - 1u) ? 1 : 0;
   }

@@ -39,6 +39,19 @@ def test_kernel_table_bicgstab_has_seven_launches():
     assert {k["kernel"] for k in tab} >= {"bicg_p_kernel", "dslash_kernel<EPI_M_DOTR0>", "dslash_kernel<EPI_M_DOTX>", "bicg_update_kernel"}
 
 
+def test_kernel_table_batched_bytes():
+    """nrhs > 1: spinor streams once per right-hand side, links + clover once per batch."""
+    tab = bench.kernel_table("CG", [11.0, 12.5, 11.0, 14.0, 9.0], 8, 18, 1000, 6550.1, nrhs=12)
+    by = {k["kernel"]: k for k in tab}
+    op = (72 + 8 * 18) * 8                                  # 8 links + the clover block of a site: 1728 B
+    assert by["dslash_kernel<EPI_AINV>"]["algorithmic_bytes_per_site"] == 12 * (2112 - op) + op
+    assert by["dslash_kernel<EPI_M_NORM>"]["algorithmic_bytes_per_site"] == 12 * (2304 - op) + op
+    assert by["dslash_kernel<EPI_M_CG>"]["algorithmic_bytes_per_site"] == 12 * (2496 - op) + op
+    assert by["cg_update_kernel"]["algorithmic_bytes_per_site"] == 12 * 960
+    # AINV + M per right-hand side = the 1248 B the bench's multi_rhs.clover_dslash leg quotes
+    assert (by["dslash_kernel<EPI_AINV>"]["algorithmic_bytes_per_site"] + by["dslash_kernel<EPI_M_NORM>"]["algorithmic_bytes_per_site"]) / 12 == 1248
+
+
 def test_expected_records_cover_the_driver_configurations():
     exp = bench.load_expected()
 

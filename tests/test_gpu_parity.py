@@ -373,12 +373,17 @@ def test_multi_rhs_operator_parity(oracle, nrhs, l2_kb, prec, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("split", [False, True], ids=["ticket", "split"])
 @pytest.mark.parametrize("solver", ["CG", "BICGSTAB"])
-def test_multi_rhs_solvers_lockstep(oracle, solver):
+def test_multi_rhs_solvers_lockstep(oracle, solver, split, monkeypatch):
     """12 different right-hand sides solved in lockstep converge independently: each needs the iteration count of its own
     single-RHS solve (+-1: the batched reductions sum in a different, still fixed, order) and reaches the target residual.
-    Includes a zero source (converged before the first iteration) and sources of very different norms."""
+    Includes a zero source (converged before the first iteration) and sources of very different norms.
+    split: the reductions of the batched kernels finished by dslash_mrhs_finish_kernel (one CTA per right-hand side), the path
+    big lattices take; B200_SPLIT_MIN_BLOCKS=0 forces it here."""
     latt = (8, 8, 8, 8)
+    if split:
+        monkeypatch.setenv("B200_SPLIT_MIN_BLOCKS", "0")
     u, op, ctx, cp = setup(oracle, latt, "double", gauge="weak")
     Vh = ctx.Vh
     code = L.B200_SOLVER_CG if solver == "CG" else L.B200_SOLVER_BICGSTAB
