@@ -654,20 +654,31 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
     // all EPI_M* variants: m = A x - 1/4 D in.  Every load is issued before the first store (the stores are
     // volatile asm with a memory clobber, i.e. compiler barriers): a load placed after a store cannot be hoisted
     // and would cost one exposed DRAM round trip each.
-    C m[12], ex[12];
+    // Batched kernels (MR, 168 registers at most): the extra operand (r / r0) is loaded and consumed block by block --
+    // all 12 of its components held across both clover blocks spilled 100 B per thread in EPI_M_CG.  Same sums, same order.
+    C m[12], ex[MR ? 1 : 12];
     const R tw = (R)a.twist;
+    const R cg_a = (EPI == EPI_M_CG || EPI == EPI_M_CGREL) ? (R)a.scal[S_A] : (R)0;
     if (XS) cp_async_wait_all();
-    if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
+    if (!MR && (EPI == EPI_M_CG || EPI == EPI_M_CGREL)) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) ex[k] = ld_stream_rw(a.r + (size_t)k * stride + idx, pol.stream);
     }
-    if (EPI == EPI_M_DOTR0) {
+    if (!MR && EPI == EPI_M_DOTR0) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) ex[k] = ld_stream(a.r0 + (size_t)k * stride + idx, pol.stream);
     }
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      C xi[6], o[6];
+      C xi[6], o[6], exb[6];
+      if (MR && EPI == EPI_M_CG) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) exb[k] = ld_stream_rw(a.r + (size_t)(6 * b + k) * stride + idx, pol.stream);
+      }
+      if (MR && EPI == EPI_M_DOTR0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) exb[k] = ld_stream(a.r0 + (size_t)(6 * b + k) * stride + idx, pol.stream);
+      }
 #pragma unroll
       for (int k = 0; k < 6; ++k) xi[k] = XS ? spx[(6 * b + k) * 32] : ld_stream(a.x + (size_t)(6 * b + k) * stride + idx, pol.stream);
       if (MODE == MODE_ASYM) clover_block<R, MR>(o, xi, cl0 + (size_t)(18 * b) * cs, cs, pol.stream);
@@ -687,26 +698,40 @@ __device__ __forceinline__ void site_epilogue(Cx<R> acc[12], const DslashArgs<R>
           red[1] += (double)mm.x * xi[k].y - (double)mm.y * xi[k].x;
           red[2] += (double)mm.x * mm.x + (double)mm.y * mm.y;
         }
+        if (MR && EPI == EPI_M_CG) {                          // r -= a m, |r|^2 (batched: block by block)
+          C rv = exb[k];
+          rv.x -= cg_a * m[6 * b + k].x; rv.y -= cg_a * m[6 * b + k].y;
+          red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+          m[6 * b + k] = rv;
+        }
+        if (MR && EPI == EPI_M_NORM) red[0] += (double)m[6 * b + k].x * m[6 * b + k].x + (double)m[6 * b + k].y * m[6 * b + k].y;
+        if (MR && EPI == EPI_M_DOTR0) {
+          red[0] += (double)exb[k].x * m[6 * b + k].x + (double)exb[k].y * m[6 * b + k].y;
+          red[1] += (double)exb[k].x * m[6 * b + k].y - (double)exb[k].y * m[6 * b + k].x;
+        }
       }
     }
     if (EPI == EPI_M_CG || EPI == EPI_M_CGREL) {
-      const R cg_a = (R)a.scal[S_A];
+      if (!MR) {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        C rv = ex[k];
-        rv.x -= cg_a * m[k].x; rv.y -= cg_a * m[k].y;
-        red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
-        m[k] = rv;
+        for (int k = 0; k < 12; ++k) {
+          C rv = ex[k];
+          rv.x -= cg_a * m[k].x; rv.y -= cg_a * m[k].y;
+          red[0] += (double)rv.x * rv.x + (double)rv.y * rv.y;
+          m[k] = rv;
+        }
       }
 #pragma unroll
       for (int k = 0; k < 12; ++k) st_stream(a.r + (size_t)k * stride + idx, m[k], pol.stream);
     } else {
+      if (!MR) {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        if (EPI == EPI_M_NORM) red[0] += (double)m[k].x * m[k].x + (double)m[k].y * m[k].y;
-        if (EPI == EPI_M_DOTR0) {                             // <r0|m> = conj(r0) m
-          red[0] += (double)ex[k].x * m[k].x + (double)ex[k].y * m[k].y;
-          red[1] += (double)ex[k].x * m[k].y - (double)ex[k].y * m[k].x;
+        for (int k = 0; k < 12; ++k) {
+          if (EPI == EPI_M_NORM) red[0] += (double)m[k].x * m[k].x + (double)m[k].y * m[k].y;
+          if (EPI == EPI_M_DOTR0) {                             // <r0|m> = conj(r0) m
+            red[0] += (double)ex[k].x * m[k].x + (double)ex[k].y * m[k].y;
+            red[1] += (double)ex[k].x * m[k].y - (double)ex[k].y * m[k].x;
+          }
         }
       }
 #pragma unroll
