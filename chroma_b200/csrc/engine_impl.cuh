@@ -187,6 +187,11 @@ class Engine : public EngineBase {
     if (cfg.pgrid[0] != 1 || cfg.pgrid[1] != 1) { set_error("the process grid may split T and Z only (1 x 1 x Pz x Pt)"); return B200_ERR_ARG; }
     if (cfg.pgrid[2] * cfg.pgrid[3] > 8) { set_error("at most 8 ranks (one NVSwitch node)"); return B200_ERR_ARG; }
     if (cfg.pgrid[2] * cfg.pgrid[3] > 1 && !cfg.have_comm) { set_error("a b200_comm is required for a split lattice"); return B200_ERR_COMM; }
+    // the kernels' division-free site decode (FastDiv, common.cuh) is exact for site counts below 2^28 per checkerboard and rank
+    if ((long long)(cfg.ldims[0] / 2) * cfg.ldims[1] * cfg.ldims[2] * cfg.ldims[3] >= (1ll << 28)) {
+      set_error("local lattice %d x %d x %d x %d has 2^28 or more sites per checkerboard: split it over more ranks", cfg.ldims[0], cfg.ldims[1], cfg.ldims[2], cfg.ldims[3]);
+      return B200_ERR_ARG;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: this engine has no CPU fallback"); return B200_ERR_CUDA; }
     B200_CUDA(cudaSetDevice(cfg.device));

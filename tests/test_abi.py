@@ -55,6 +55,17 @@ def test_no_cpu_fallback(built_lib):
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
 
 
+def test_create_validates_the_lattice_before_touching_a_device(built_lib):
+    """Host-side argument checks of b200_create (engine_impl.cuh::init) come before the device probe: odd extents, a process grid
+    that splits x or y, and a local lattice too big for the kernels' division-free site decode (2^28 sites per checkerboard)."""
+    from chroma_b200 import lib as L
+    from chroma_b200.solver import Context
+    for latt, what in (((4, 4, 4, 6 + 1), "even"), ((128, 128, 128, 256), "2^28")):
+        with pytest.raises(L.B200Error) as e:
+            Context(latt)
+        assert e.value.code == L.B200_ERR_ARG and what in str(e.value), str(e.value)
+
+
 def test_product_never_imports_the_oracle():
     """Nothing under chroma_b200/ may reference oracle/ (the oracle is test infrastructure)."""
     pkg = os.path.join(ROOT, "chroma_b200")
