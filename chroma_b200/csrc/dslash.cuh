@@ -66,7 +66,8 @@ struct DslashArgs {
   size_t fstride;   // elements between consecutive right-hand sides of a batched field (12*Vh)
   size_t gstride;   // same for the T ghost faces (6*S3h)
   size_t gstride_z; // ... and the Z ghost faces (6*SZh)
-  int zc_sites;     // multi-RHS traversal order: != 0 => sweep t inside z-chunks of this many sites per time slice (box 0)
+  int zc_sites;     // traversal order of box 0: != 0 => sweep t inside chunks of this many sites per time slice ...
+  int zc_dz, zc_dy, zc_ncy;   // ... a chunk = zc_dz z-planes x zc_dy y-rows (zc_ncy = Ly / zc_dy chunks side by side in y)
   int mmode;        // OperatorMode of the EPI_M* epilogues (selects the kernel instantiation; single-RHS kernels only)
   L2Policy pol;     // L2 residency descriptors, created once per engine and passed as kernel arguments: they then live in the
                     // constant bank / uniform registers.  (ncu source view, round 2: with createpolicy inside the kernel the
@@ -84,13 +85,15 @@ __device__ __forceinline__ int launch_site(const DslashArgs<R>& a, int local) {
     if (ZC && a.zc_sites) {
       // Traversal order of a batch: the t+-1 neighbours of a site are re-read one time slice later, and one slice of
       // nrhs spinors (127 MB for 12 at 48^3, fp64) does not survive in the 126 MB L2.  So the launch sweeps t inside
-      // z-chunks small enough that three slices of a chunk stay L2-resident (memory layout unchanged: only WHICH site a
-      // thread takes changes).
-      const int slice = g.Lxh * g.Ly * a.box[0].nz, nt = a.box[0].nt;
-      const int per = a.zc_sites * nt;
+      // (z, y) chunks small enough that three slices of a chunk stay L2-resident (memory layout unchanged: only WHICH
+      // site a thread takes changes).  mrhs_site is the division-free twin of this decode.
+      const int nt = a.box[0].nt, per = a.zc_sites * nt;
       const int zc = local / per, rem = local - zc * per;
       const int t = rem / a.zc_sites, w = rem - t * a.zc_sites;
-      local = t * slice + zc * a.zc_sites + w;
+      const int cz = zc / a.zc_ncy, cy = zc - cz * a.zc_ncy;
+      const int rowc = a.zc_dy * g.Lxh;
+      const int zz = w / rowc, r2 = w - zz * rowc;
+      return (((a.box[0].t0 + t) * g.Lz + a.box[0].z0 + cz * a.zc_dz + zz) * g.Ly + cy * a.zc_dy) * g.Lxh + r2;
     }
     return box_site(g, a.box[0], local);
   }
@@ -125,13 +128,14 @@ __device__ __forceinline__ int launch_site_from(const DslashArgs<R>& a, int loca
 struct SiteCoord { int idx, xh, y, z, t; };
 // Launch-invariant divisors of the kernels' site decode (FastDiv, common.cuh), filled on the host per launch and passed
 // as a kernel argument (single-RHS and batched kernels alike).
-struct MrhsDiv { FastDiv lxh, ly, lz, zc, per, row, nz0; };
+struct MrhsDiv { FastDiv lxh, ly, lz, zc, per, row, nz0, ncy, rowc; };
 template <typename R>
 inline MrhsDiv make_mrhs_div(const DslashArgs<R>& a) {
   MrhsDiv d;
   d.lxh = make_fastdiv(a.g.Lxh); d.ly = make_fastdiv(a.g.Ly); d.lz = make_fastdiv(a.g.Lz);
   d.zc = make_fastdiv(a.zc_sites); d.per = make_fastdiv(a.zc_sites * a.box[0].nt);
   d.row = make_fastdiv(a.g.Lxh * a.g.Ly); d.nz0 = make_fastdiv(a.box[0].nz);
+  d.ncy = make_fastdiv(a.zc_ncy); d.rowc = make_fastdiv(a.zc_dy * a.g.Lxh);
   return d;
 }
 // coordinates of the site with cb2 index idx
@@ -155,15 +159,25 @@ __device__ __forceinline__ SiteCoord mrhs_site(const DslashArgs<R>& a, const Mrh
   SiteCoord s;
   if (local < row * b.nz * b.nt) {
     if (a.zc_sites) {
+      // chunked order: chunk (cz, cy) of zc_dz z-planes x zc_dy y-rows, all time slices of a chunk before the next chunk
       const int zc = fast_div(local, dv.per), rem = local - zc * (a.zc_sites * b.nt);
       const int tt = fast_div(rem, dv.zc), w = rem - tt * a.zc_sites;
-      local = tt * (row * b.nz) + zc * a.zc_sites + w;
+      const int cz = fast_div(zc, dv.ncy), cy = zc - cz * a.zc_ncy;
+      const int rowc = a.zc_dy * g.Lxh;
+      const int zz = fast_div(w, dv.rowc), r2 = w - zz * rowc;
+      const int yy = fast_div(r2, dv.lxh);
+      s.xh = r2 - yy * g.Lxh;
+      s.y = cy * a.zc_dy + yy;
+      s.z = b.z0 + cz * a.zc_dz + zz;
+      s.t = b.t0 + tt;
+      s.idx = ((s.t * g.Lz + s.z) * g.Ly + s.y) * g.Lxh + s.xh;
+    } else {
+      const int q = fast_div(local, dv.row), w = local - q * row;      // local = (tt*nz + zz)*row + w
+      const int tt = fast_div(q, dv.nz0), zz = q - tt * b.nz;
+      s.t = b.t0 + tt; s.z = b.z0 + zz;
+      s.y = fast_div(w, dv.lxh); s.xh = w - s.y * g.Lxh;
+      s.idx = (s.t * g.Lz + s.z) * row + w;
     }
-    const int q = fast_div(local, dv.row), w = local - q * row;      // local = (tt*nz + zz)*row + w
-    const int tt = fast_div(q, dv.nz0), zz = q - tt * b.nz;
-    s.t = b.t0 + tt; s.z = b.z0 + zz;
-    s.y = fast_div(w, dv.lxh); s.xh = w - s.y * g.Lxh;
-    s.idx = (s.t * g.Lz + s.z) * row + w;
   } else s = site_coord(g, dv, launch_site<R, false>(a, local));       // the other boxes of a boundary launch
   return s;
 }

@@ -202,6 +202,7 @@ class Engine : public EngineBase {
     num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("B200_MRHS_L2_KB")) l2_budget = atol(e) << 10;
     if (const char* e = getenv("B200_SPLIT_MIN_BLOCKS")) split_min_blocks = atoi(e);
+    if (const char* e = getenv("B200_MRHS_YCHUNK")) y_chunks = atoi(e);
     g.Lxh = cfg.ldims[0] / 2; g.Ly = cfg.ldims[1]; g.Lz = cfg.ldims[2]; g.Lt = cfg.ldims[3];
     g.S3h = g.Lxh * g.Ly * g.Lz;
     g.Vh = g.S3h * g.Lt;
@@ -662,7 +663,7 @@ class Engine : public EngineBase {
         h.n_pack = std::min((halo.pack_threads() + DSLASH_BLOCK - 1) / DSLASH_BLOCK, num_sms); h.n_int = nb_int; h.n_int_sites = n_int;
         a.ghost_fwd = halo.ghost(0); a.ghost_bwd = halo.ghost(1); a.ghost_zfwd = halo.ghost(2); a.ghost_zbwd = halo.ghost(3);
         a.box[0] = inner; for (int k = 0; k < nf; ++k) a.box[1 + k] = faces[k];
-        a.nbox = 1 + nf; a.nsites = g.Vh; a.zc_sites = 0; a.red = make_red(0, total);
+        a.nbox = 1 + nf; a.nsites = g.Vh; set_chunks(a, 0); a.red = make_red(0, total);
         a.red.split = split_reduce<EPI>(total);
         rc = launch_halo<EPI>(a, h, h.n_pack + total); if (rc) return rc;
         return launch_finish<EPI>(a);
@@ -673,18 +674,18 @@ class Engine : public EngineBase {
       const int split_b = split_reduce<EPI>(total);
       if (n_int > 0) {
         a.box[0] = inner; a.nbox = 1; a.nsites = n_int; a.red = make_red(0, total); a.red.split = split_b;
-        a.zc_sites = zchunk_sites(inner.nz);
+        set_chunks(a, inner.nz);
         rc = launch_one<EPI>(a, nb_int); if (rc) return rc;
       }
       rc = halo.wait(a.check_stop ? status : nullptr, a.run_if, nb, launches); if (rc) return rc;
       for (int k = 0; k < nf; ++k) a.box[k] = faces[k];
-      a.nbox = nf; a.nsites = n_face; a.zc_sites = 0; a.red = make_red(nb_int, total); a.red.split = split_b;
+      a.nbox = nf; a.nsites = n_face; set_chunks(a, 0); a.red = make_red(nb_int, total); a.red.split = split_b;
       rc = launch_one<EPI>(a, nb_face); if (rc) return rc;
       return launch_finish<EPI>(a);
     }
     a.ghost_fwd = nullptr; a.ghost_bwd = nullptr; a.ghost_zfwd = nullptr; a.ghost_zbwd = nullptr;
     a.box[0] = SiteBox{0, g.Lt, 0, g.Lz}; a.nbox = 1; a.nsites = g.Vh;
-    a.zc_sites = zchunk_sites(g.Lz);
+    set_chunks(a, g.Lz);
     const int blocks = (g.Vh + bs - 1) / bs;
     a.red = make_red(0, blocks);
     a.red.split = split_reduce<EPI>(blocks);
@@ -737,16 +738,35 @@ class Engine : public EngineBase {
     if (recon == 12) dslash_kernel<R, EPI, true, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, dv);
     else dslash_kernel<R, EPI, false, DSLASH_BLOCK, MODE><<<blocks, DSLASH_BLOCK, 0, stream>>>(a, ls, dv);
   }
-  // z-chunk (in sites per time slice) of the batched traversal order of a box nz planes thick: the largest divisor of
-  // nz for which three time slices of the batch's source spinors fit in ~1/3 of the L2 (B200: 126 MB); 0 = natural order
-  int zchunk_sites(int nz) const {
+  // Traversal order of a box nz planes thick (launch_site / mrhs_site): chunks of dz z-planes x dy y-rows, all time slices
+  // of a chunk before the next chunk, sized so that three time slices of a chunk (all right-hand sides) fit in
+  // `l2_budget` (B200: 126 MB of L2, of which ~32 MB hold neighbour spinors in practice, profiles/r02_mrhs_zchunk_sweep.json).
+  // Among the divisor pairs that fit, the one with the smallest surface wins: a chunk face is where a neighbour spinor is
+  // fetched from DRAM a second time (2/dz + 2/dy extra fetches per site; a direction the chunk spans has no face).
+  // nz = 0 or a box that fits whole: natural order (zc_sites = 0).
+  void set_chunks(DslashArgs<R>& a, int nz) const {
+    a.zc_sites = 0; a.zc_dz = nz; a.zc_dy = g.Ly; a.zc_ncy = 1;
     const long budget = l2_budget;
-    const long plane = (long)g.Lxh * g.Ly * 12 * (long)sizeof(C) * nb;      // one z-plane of one time slice, all right-hand sides
-    if (nz <= 0 || 3 * plane * nz <= budget || budget <= 0) return 0;
-    int zc = 1;
-    for (int d = 1; d <= nz; ++d) if (nz % d == 0 && 3 * plane * d <= budget) zc = d;
-    return zc * g.Lxh * g.Ly;
+    const long rowb = (long)g.Lxh * 12 * (long)sizeof(C) * nb;              // one y-row of one time slice, all right-hand sides
+    if (nz <= 0 || budget <= 0 || 3 * rowb * g.Ly * nz <= budget) return;
+    int bz = 1, by = 1; double best = 1e30; long bvol = 0;
+    for (int dz = 1; dz <= nz; ++dz) {
+      if (nz % dz) continue;
+      for (int dy = 1; dy <= g.Ly; ++dy) {
+        if (g.Ly % dy || 3 * rowb * dz * dy > budget) continue;
+        const double f = (dz < nz ? 2.0 / dz : 0.0) + (dy < g.Ly ? 2.0 / dy : 0.0);
+        const long vol = (long)dz * dy;
+        if (f < best - 1e-12 || (f < best + 1e-12 && vol > bvol)) { best = f; bz = dz; by = dy; bvol = vol; }
+      }
+    }
+    if (!y_chunks) {        // B200_MRHS_YCHUNK=0: z-planes only (the round-1 order)
+      by = g.Ly; bz = 1;
+      for (int dz = 1; dz <= nz; ++dz) if (nz % dz == 0 && 3 * rowb * g.Ly * dz <= budget) bz = dz;
+    }
+    a.zc_dz = bz; a.zc_dy = by; a.zc_ncy = g.Ly / by;
+    a.zc_sites = bz * by * g.Lxh;
   }
+  int y_chunks = 1;
   // batched launch: CTA = 32 sites x NRB right-hand sides; the groups of one site block are adjacent in the grid
   template <int EPI>
   int launch_mrhs(const DslashArgs<R>& a, int site_blocks) {
